@@ -1,0 +1,455 @@
+"""Seeded scene generators for tests and benchmarks (all synthetic or restated recipes).
+
+* golden recipes   : vello_tests/tests/smoke_snapshots.rs:17-52, regression.rs:33-210,
+                     property.rs:21-197, known_issues.rs:21-52
+* tiger            : examples/assets/Ghostscript_Tiger.svg via the draw list pico_svg produces
+                     (examples/scenes/src/pico_svg.rs:134-195, svg.rs `render_svg_rec`), read from
+                     tests/golden/tiger_paths.json.gz (see tests/golden/make_golden.py)
+* paris_like       : BASELINE.md config C3/C4 -- paris-30k.svg is not in the reference, so a seeded
+                     stand-in with the same order of magnitude (30k paths, ~1.5M segments, ~12 MB)
+* beziers_clips    : BASELINE.md config C5
+* robust_paths, funky_paths, fill_types, stroke_styles, many_clips, deep_blend : recipes restated
+  from examples/scenes/src/test_scenes.rs (:1610-1691, :293-333, :699-770, :335-560, :1278-1304,
+  :1241-1276)
+"""
+from __future__ import annotations
+
+import gzip
+import json
+import math
+import os
+from typing import List, Tuple
+
+import numpy as np
+
+from .encoding import (
+    ALPHA_PREMULTIPLIED, ALPHA_STRAIGHT, BLACK, BLUE, COMPOSE_CLEAR, COMPOSE_SRC_OVER, COMPOSE_PLUS, COMPOSE_XOR,
+    Color, EXTEND_PAD, EXTEND_REFLECT, EXTEND_REPEAT, Encoding, FILL_EVEN_ODD, FILL_NON_ZERO, FORMAT_BGRA8,
+    FORMAT_RGBA8, Gradient, Image, LIME, MIX_MULTIPLY, MIX_NORMAL, MIX_SCREEN, MIX_HUE, MIX_DIFFERENCE, QUALITY_HIGH,
+    QUALITY_LOW, QUALITY_MEDIUM, RED, STYLE_CAP_BUTT, STYLE_CAP_ROUND, STYLE_CAP_SQUARE, STYLE_JOIN_BEVEL,
+    STYLE_JOIN_MITER, STYLE_JOIN_ROUND, Scene, Stroke, TAG_LINE_TO_F32, TAG_PATH, TAG_QUAD_TO_F32, TAG_CUBIC_TO_F32,
+    TAG_SUBPATH_END_BIT, TRANSPARENT, WHITE, style_from_stroke, DRAWTAG_COLOR,
+)
+from .shapes import Affine, BezPath, Circle, Line, Rect, RoundedRect
+
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TIGER_FIXTURE = os.path.join(_REPO, "tests", "golden", "tiger_paths.json.gz")
+
+
+# ---------------------------------------------------------------------------------------------
+# golden recipes
+# ---------------------------------------------------------------------------------------------
+def filled_square() -> Tuple[Scene, int, int]:
+    s = Scene()
+    s.fill(FILL_NON_ZERO, Affine.IDENTITY, BLUE, None, Rect.from_center_size((10.0, 10.0), (6.0, 6.0)))
+    return s, 20, 20
+
+
+def filled_circle() -> Tuple[Scene, int, int]:
+    s = Scene()
+    s.fill(FILL_NON_ZERO, Affine.IDENTITY, BLUE, None, Circle(10.0, 10.0, 7.0))
+    return s, 20, 20
+
+
+def simple_square() -> Tuple[Scene, int, int]:
+    s = Scene()
+    s.fill(FILL_NON_ZERO, Affine.IDENTITY, RED, None, Rect.from_center_size((100.0, 100.0), (50.0, 50.0)))
+    return s, 150, 150
+
+
+def gradient_color_alpha(premul: bool) -> Tuple[Scene, int, int]:
+    s = Scene()
+    g = Gradient.linear((0.0, 0.0), (100.0, 0.0),
+                        [(0.0, Color.from_rgba8(255, 255, 0, 0)), (1.0, Color.from_rgba8(0, 0, 255, 255))],
+                        premul_interp=premul)
+    s.fill(FILL_NON_ZERO, Affine.IDENTITY, g, None, Rect(0.0, 0.0, 100.0, 50.0))
+    return s, 100, 50
+
+
+def image_roundtrip(img_rgba: np.ndarray, extend: int) -> Tuple[Scene, int, int]:
+    s = Scene()
+    s.draw_image(Image(img_rgba, quality=QUALITY_LOW, x_extend=extend, y_extend=extend), Affine.IDENTITY)
+    return s, img_rgba.shape[1], img_rgba.shape[0]
+
+
+def layer_size() -> Tuple[Scene, int, int]:
+    s = Scene()
+    s.fill(FILL_NON_ZERO, Affine.IDENTITY, Color.from_rgba8(0, 255, 0), None, Rect.from_origin_size((0.0, 0.0), (60.0, 60.0)))
+    s.fill(FILL_NON_ZERO, Affine.IDENTITY, Color.from_rgba8(255, 0, 0), None, Rect.from_origin_size((20.0, 20.0), (20.0, 20.0)))
+    s.push_layer(FILL_NON_ZERO, MIX_NORMAL, COMPOSE_CLEAR, 1.0, Affine.IDENTITY, Rect.from_origin_size((20.0, 20.0), (20.0, 20.0)))
+    s.pop_layer()
+    return s, 60, 60
+
+
+# ---------------------------------------------------------------------------------------------
+# tiger
+# ---------------------------------------------------------------------------------------------
+def _parse_hex(c: str) -> Color:
+    c = c.strip()
+    if c.startswith("#"):
+        h = c[1:]
+        if len(h) == 3:
+            r, g, b = (int(ch * 2, 16) for ch in h)
+        else:
+            r, g, b = int(h[0:2], 16), int(h[2:4], 16), int(h[4:6], 16)
+        return Color.from_rgba8(r, g, b)
+    return Color(1.0, 0.0, 1.0, 0.5)  # pico_svg falls back to translucent fuchsia
+
+
+def _opacity(c: Color, it: dict, key: str) -> Color:
+    if key in it:
+        v = it[key]
+        a = float(v[:-1]) * 0.01 if v.endswith("%") else float(v)
+        return c.with_alpha(float(np.float32(min(max(a, 0.0), 1.0))))
+    return c
+
+
+def tiger(width: int, height: int, fixture: str = TIGER_FIXTURE) -> Scene:
+    """Ghostscript tiger scaled to fit (scale = min(w, h) / 200, vello_tests/src/lib.rs:293-299)."""
+    with gzip.open(fixture, "rt") as f:
+        doc = json.load(f)
+    scale = min(width, height) / 200.0
+    t = Affine.scale(scale)
+    s = Scene()
+    for it in doc["items"]:
+        path = BezPath.from_svg(it["d"])
+        if it.get("fill") is not None:
+            col = _opacity(_opacity(_parse_hex(it["fill"]), it, "fill-opacity"), it, "opacity")
+            s.fill(FILL_NON_ZERO, t, col, None, path)
+        if it.get("stroke") not in (None, "none"):
+            w = float(it.get("stroke-width", 1.0))
+            col = _opacity(_opacity(_parse_hex(it["stroke"]), it, "stroke-opacity"), it, "opacity")
+            s.stroke(Stroke(w), t, col, None, path)
+    return s
+
+
+# ---------------------------------------------------------------------------------------------
+# bulk (numpy) appenders: identical streams to PathEncoder for well-formed polylines
+# (every consecutive point pair differs by more than 1e-12), without the per-segment Python cost
+# ---------------------------------------------------------------------------------------------
+def _bulk_fill_polygon(e: Encoding, pts: np.ndarray):
+    """pts: (n, 2) f32, n >= 3, first != last. M p0 L p1.. Z PATH (path.rs:508-676)."""
+    n = pts.shape[0]
+    e.path_data.extend(pts.reshape(-1).tolist())
+    e.path_data.extend(pts[0].tolist())
+    e.path_tags.extend([TAG_LINE_TO_F32] * (n - 1))
+    e.path_tags.append(TAG_LINE_TO_F32 | TAG_SUBPATH_END_BIT)
+    e.path_tags.append(TAG_PATH)
+    e.n_path_segments += n
+    e.n_paths += 1
+
+
+def _bulk_stroke_polyline(e: Encoding, pts: np.ndarray):
+    """Open polyline, n >= 2 points: lines, then the quad-to cap marker (path.rs:711-730)."""
+    n = pts.shape[0]
+    f = np.float32
+    p0, p1 = pts[0], pts[1]
+    third = f(1.0) / f(3.0)
+    tan = (p0[0] + third * (p1[0] - p0[0]), p0[1] + third * (p1[1] - p0[1]))
+    e.path_data.extend(pts.reshape(-1).tolist())
+    e.path_data.extend([float(p0[0]), float(p0[1]), float(tan[0]), float(tan[1])])
+    e.path_tags.extend([TAG_LINE_TO_F32] * (n - 1))
+    e.path_tags.append(TAG_QUAD_TO_F32 | TAG_SUBPATH_END_BIT)
+    e.path_tags.append(TAG_PATH)
+    e.n_path_segments += n
+    e.n_paths += 1
+
+
+def _bulk_fill_cubics(e: Encoding, p0: np.ndarray, ctrl: np.ndarray):
+    """Closed loop of cubics: p0 (2,), ctrl (n, 3, 2) with ctrl[-1, 2] == p0."""
+    n = ctrl.shape[0]
+    e.path_data.extend(p0.tolist())
+    e.path_data.extend(ctrl.reshape(-1).tolist())
+    e.path_tags.extend([TAG_CUBIC_TO_F32] * (n - 1))
+    e.path_tags.append(TAG_CUBIC_TO_F32 | TAG_SUBPATH_END_BIT)
+    e.path_tags.append(TAG_PATH)
+    e.n_path_segments += n
+    e.n_paths += 1
+
+
+def _rand_color(rng: np.random.Generator, alpha_prob=0.2) -> Color:
+    r, g, b = (int(v) for v in rng.integers(0, 256, 3))
+    a = int(rng.integers(64, 230)) if rng.random() < alpha_prob else 255
+    return Color.from_rgba8(r, g, b, a)
+
+
+def paris_like(n_paths: int = 30000, size: int = 4096, seed: int = 30000) -> Scene:
+    """Seeded stand-in for paris-30k: 70% filled polygons (8-60 segs, extent log-uniform 4-400 px at
+    4096), 25% stroked polylines (20-200 segs, width 0.5-6), 5% closed cubic blobs; uniform over
+    the canvas; 20% translucent colours. Designed at 4096 and scaled by `size / 4096`."""
+    rng = np.random.default_rng(seed)
+    s = Scene()
+    e = s.encoding
+    t = Affine.scale(size / 4096.0)
+    f32 = np.float32
+    for _ in range(n_paths):
+        kind = rng.random()
+        cx, cy = rng.uniform(0, 4096, 2)
+        extent = math.exp(rng.uniform(math.log(4.0), math.log(400.0)))
+        col = _rand_color(rng)
+        if kind < 0.70:
+            n = int(rng.integers(8, 61))
+            ang = np.sort(rng.uniform(0, 2 * math.pi, n))
+            rad = rng.uniform(0.35, 1.0, n) * (extent * 0.5)
+            pts = np.stack([cx + rad * np.cos(ang), cy + rad * np.sin(ang)], axis=1).astype(f32)
+            e.encode_transform(t)
+            e.encode_fill_style(FILL_NON_ZERO if rng.random() < 0.9 else FILL_EVEN_ODD)
+            _bulk_fill_polygon(e, pts)
+            e.encode_color(col)
+        elif kind < 0.95:
+            n = int(rng.integers(20, 201))
+            step = extent / 16.0 + 1.0
+            heading = rng.uniform(0, 2 * math.pi) + np.cumsum(rng.normal(0, 0.25, n))
+            d = np.stack([np.cos(heading), np.sin(heading)], axis=1) * step
+            pts = (np.array([cx, cy]) + np.cumsum(d, axis=0)).astype(f32)
+            join = (STYLE_JOIN_ROUND, STYLE_JOIN_BEVEL, STYLE_JOIN_MITER)[int(rng.integers(0, 3))]
+            cap = (STYLE_CAP_ROUND, STYLE_CAP_BUTT, STYLE_CAP_SQUARE)[int(rng.integers(0, 3))]
+            st = Stroke(float(f32(rng.uniform(0.5, 6.0))), join=join, start_cap=cap, end_cap=cap)
+            e.encode_transform(t)
+            assert e.encode_stroke_style(st)
+            _bulk_stroke_polyline(e, pts)
+            e.encode_color(col)
+        else:
+            n = int(rng.integers(6, 13))
+            ang = np.linspace(0, 2 * math.pi, n, endpoint=False) + rng.uniform(0, 1)
+            rad = rng.uniform(0.5, 1.0, n) * (extent * 0.5)
+            on = np.stack([cx + rad * np.cos(ang), cy + rad * np.sin(ang)], axis=1)
+            tang = np.stack([-np.sin(ang), np.cos(ang)], axis=1) * (rad * (2 * math.pi / n) * 0.4)[:, None]
+            ctrl = np.zeros((n, 3, 2))
+            for i in range(n):
+                j = (i + 1) % n
+                ctrl[i, 0] = on[i] + tang[i]
+                ctrl[i, 1] = on[j] - tang[j]
+                ctrl[i, 2] = on[j]
+            e.encode_transform(t)
+            e.encode_fill_style(FILL_NON_ZERO)
+            _bulk_fill_cubics(e, on[0].astype(f32), ctrl.astype(f32))
+            e.encode_color(col)
+    return s
+
+
+def beziers_clips(n_paths: int = 100000, n_clips: int = 1000, size: int = 4096, seed: int = 100000,
+                  max_depth: int = 8) -> Scene:
+    """Config C5: cubic paths (4-12 cubics each) interleaved with `n_clips` push_clip_layer/pop pairs
+    nested up to `max_depth`."""
+    rng = np.random.default_rng(seed)
+    s = Scene()
+    e = s.encoding
+    f32 = np.float32
+    t = Affine.scale(size / 4096.0)
+    clip_every = max(1, n_paths // max(1, n_clips))
+    depth = 0
+    pushed = 0
+    for i in range(n_paths):
+        if n_clips and i % clip_every == 0 and pushed < n_clips:
+            if depth >= max_depth or (depth > 0 and rng.random() < 0.35):
+                npop = int(rng.integers(1, depth + 1))
+                for _ in range(npop):
+                    s.pop_layer()
+                depth -= npop
+            cx, cy = rng.uniform(0, 4096, 2)
+            r = rng.uniform(200, 1200)
+            s.push_clip_layer(FILL_NON_ZERO, t, Circle(cx, cy, r) if rng.random() < 0.5 else Rect(cx - r, cy - r, cx + r, cy + r))
+            depth += 1
+            pushed += 1
+        n = int(rng.integers(4, 13))
+        cx, cy = rng.uniform(0, 4096, 2)
+        extent = math.exp(rng.uniform(math.log(8.0), math.log(300.0)))
+        ang = np.linspace(0, 2 * math.pi, n, endpoint=False) + rng.uniform(0, 1)
+        rad = rng.uniform(0.4, 1.0, n) * (extent * 0.5)
+        on = np.stack([cx + rad * np.cos(ang), cy + rad * np.sin(ang)], axis=1)
+        tang = np.stack([-np.sin(ang), np.cos(ang)], axis=1) * (rad * (2 * math.pi / n) * rng.uniform(0.2, 0.7))[:, None]
+        ctrl = np.zeros((n, 3, 2))
+        for k in range(n):
+            j = (k + 1) % n
+            ctrl[k, 0] = on[k] + tang[k]
+            ctrl[k, 1] = on[j] - tang[j]
+            ctrl[k, 2] = on[j]
+        e.encode_transform(t)
+        e.encode_fill_style(FILL_NON_ZERO)
+        _bulk_fill_cubics(e, on[0].astype(f32), ctrl.astype(f32))
+        e.encode_color(_rand_color(rng, 0.3))
+    while depth > 0:
+        s.pop_layer()
+        depth -= 1
+    return s
+
+
+# ---------------------------------------------------------------------------------------------
+# restated test-scene recipes (small; exercise robustness and every draw-object kind)
+# ---------------------------------------------------------------------------------------------
+def robust_paths() -> Tuple[Scene, int, int]:
+    """Tile-boundary-aligned rectangles/triangles and half-pixel slivers, both fill rules."""
+    s = Scene()
+    p = BezPath()
+    for (x0, y0, x1, y1) in [(16, 16, 32, 32), (48, 16, 64, 32), (32, 48, 48, 64), (80, 16, 96.5, 32.5)]:
+        p.move_to(x0, y0); p.line_to(x1, y0); p.line_to(x1, y1); p.line_to(x0, y1); p.close_path()
+    p.move_to(8, 100); p.line_to(8.5, 100); p.line_to(8.5, 116); p.line_to(8, 116); p.close_path()
+    p.move_to(16, 80); p.line_to(48, 80); p.line_to(16, 96); p.close_path()
+    p.move_to(64, 64); p.line_to(96, 64); p.line_to(96, 96); p.close_path()
+    # overlapping squares with opposite winding
+    p.move_to(100, 20); p.line_to(130, 20); p.line_to(130, 50); p.line_to(100, 50); p.close_path()
+    p.move_to(110, 30); p.line_to(110, 60); p.line_to(140, 60); p.line_to(140, 30); p.close_path()
+    s.fill(FILL_NON_ZERO, Affine.IDENTITY, Color.from_rgba8(255, 255, 0), None, p)
+    s.fill(FILL_EVEN_ODD, Affine.translate(0.0, 130.0), Color.from_rgba8(0, 255, 255), None, p)
+    # exact tile-grid aligned big rect and lines on vertical tile edges
+    s.fill(FILL_NON_ZERO, Affine.translate(160.0, 0.0), Color.from_rgba8(200, 80, 200, 160), None, Rect(0, 0, 64, 64))
+    s.fill(FILL_NON_ZERO, Affine.translate(160.0, 80.0), Color.from_rgba8(80, 200, 80), None, Rect(-20, -20, 48, 48))
+    return s, 256, 272
+
+
+def funky_paths() -> Tuple[Scene, int, int]:
+    """Missing move-tos, empty paths, only-move-tos (PathEncoder state machine)."""
+    s = Scene()
+    missing = BezPath([("L", 100.0, 100.0), ("L", 100.0, 200.0), ("Z",), ("L", 0.0, 400.0), ("L", 100.0, 400.0)])
+    only_moves = BezPath([("M", 0.0, 0.0), ("M", 100.0, 100.0)])
+    empty = BezPath()
+    s.fill(FILL_NON_ZERO, Affine.translate(100.0, 100.0), BLUE, None, missing)
+    s.fill(FILL_NON_ZERO, Affine.IDENTITY, BLUE, None, empty)
+    s.fill(FILL_NON_ZERO, Affine.IDENTITY, BLUE, None, only_moves)
+    s.stroke(Stroke(8.0), Affine.translate(100.0, 100.0), Color.from_rgba8(0, 255, 255), None, missing)
+    return s, 320, 560
+
+
+def fill_types() -> Tuple[Scene, int, int]:
+    s = Scene()
+    star = BezPath()
+    for i in range(5):
+        a = -math.pi / 2 + i * 4 * math.pi / 5
+        (star.move_to if i == 0 else star.line_to)(50 + 45 * math.cos(a), 50 + 45 * math.sin(a))
+    star.close_path()
+    arcs = BezPath.from_svg("M10 50 A40 40 0 1 1 90 50 A40 40 0 1 1 10 50 Z M30 50 A20 20 0 1 0 70 50 A20 20 0 1 0 30 50 Z")
+    for i, (rule, shape) in enumerate([(FILL_NON_ZERO, star), (FILL_EVEN_ODD, star), (FILL_NON_ZERO, arcs), (FILL_EVEN_ODD, arcs)]):
+        t = Affine.translate(10.0 + 110.0 * i, 10.0)
+        s.fill(rule, t, Color.from_rgba8(230, 60, 60), None, shape)
+        s.fill(rule, t * Affine.translate(0.0, 110.0) * Affine.rotate(0.06), Color.from_rgba8(40, 40, 230, 128), None, shape)
+    return s, 460, 240
+
+
+def stroke_styles(transform: Affine = Affine.IDENTITY) -> Tuple[Scene, int, int]:
+    s = Scene()
+    zig = BezPath([("M", 10.0, 10.0), ("L", 60.0, 40.0), ("L", 10.0, 70.0), ("L", 60.0, 100.0)])
+    curve = BezPath([("M", 0.0, 0.0), ("C", 40.0, -30.0, 60.0, 60.0, 100.0, 20.0), ("Q", 130.0, -10.0, 150.0, 40.0)])
+    closed = BezPath([("M", 10.0, 10.0), ("L", 90.0, 20.0), ("C", 120.0, 60.0, 40.0, 90.0, 20.0, 60.0), ("Z",)])
+    caps = [STYLE_CAP_BUTT, STYLE_CAP_SQUARE, STYLE_CAP_ROUND]
+    joins = [STYLE_JOIN_BEVEL, STYLE_JOIN_MITER, STYLE_JOIN_ROUND]
+    y = 10.0
+    for ci, cap in enumerate(caps):
+        for ji, join in enumerate(joins):
+            st = Stroke(10.0, join=join, start_cap=cap, end_cap=caps[(ci + 1) % 3], miter_limit=4.0)
+            t = transform * Affine.translate(10.0 + 170.0 * ji, y)
+            s.stroke(st, t, Color.from_rgba8(200, 200 - 60 * ji, 40 + 80 * ci), None, zig)
+            s.stroke(Stroke(3.0, join=join, start_cap=cap, end_cap=cap), t * Affine.translate(70.0, 30.0), WHITE, None, curve)
+        y += 120.0
+    s.stroke(Stroke(6.0, join=STYLE_JOIN_MITER, miter_limit=1.5), transform * Affine.translate(20.0, y), LIME, None, closed)
+    s.stroke(Stroke(6.0, join=STYLE_JOIN_ROUND), transform * Affine.translate(160.0, y), RED, None, closed)
+    s.stroke(Stroke(0.5), transform * Affine.translate(300.0, y), WHITE, None, closed)
+    s.stroke(Stroke(4.0), transform * Affine.translate(420.0, y + 20.0), WHITE, None, Line(0.0, 0.0, 60.0, 60.0))
+    s.stroke(Stroke(5.0), transform * Affine.translate(500.0, y + 50.0), BLUE, None, Circle(0.0, 0.0, 30.0))
+    return s, 560, 480
+
+
+def many_clips(n: int = 40, depth: int = 12) -> Tuple[Scene, int, int]:
+    rng = np.random.default_rng(7)
+    s = Scene()
+    s.fill(FILL_NON_ZERO, Affine.IDENTITY, Color.from_rgba8(30, 30, 60), None, Rect(0, 0, 400, 400))
+    for i in range(n):
+        d = int(rng.integers(1, depth + 1))
+        for k in range(d):
+            cx, cy = rng.uniform(50, 350, 2)
+            r = rng.uniform(60, 220)
+            shape = Circle(cx, cy, r) if (i + k) % 2 == 0 else RoundedRect(cx - r, cy - r * 0.7, cx + r, cy + r * 0.7, 20.0)
+            s.push_clip_layer(FILL_NON_ZERO if k % 3 else FILL_EVEN_ODD, Affine.IDENTITY, shape)
+        x, y = rng.uniform(0, 300, 2)
+        s.fill(FILL_NON_ZERO, Affine.IDENTITY, _rand_color(rng, 0.5), None, Rect(x, y, x + rng.uniform(40, 300), y + rng.uniform(40, 300)))
+        for k in range(d):
+            s.pop_layer()
+    return s, 400, 400
+
+
+def deep_blend(depth: int = 9) -> Tuple[Scene, int, int]:
+    """Nested non-clip blend layers deeper than BLEND_STACK_SPLIT=4 (exercises blend_spill)."""
+    s = Scene()
+    s.fill(FILL_NON_ZERO, Affine.IDENTITY, Color.from_rgba8(240, 240, 240), None, Rect(0, 0, 200, 200))
+    modes = [(MIX_MULTIPLY, COMPOSE_SRC_OVER), (MIX_SCREEN, COMPOSE_SRC_OVER), (MIX_NORMAL, COMPOSE_XOR),
+             (MIX_HUE, COMPOSE_SRC_OVER), (MIX_DIFFERENCE, COMPOSE_SRC_OVER), (MIX_NORMAL, COMPOSE_PLUS)]
+    for i in range(depth):
+        m, c = modes[i % len(modes)]
+        s.push_layer(FILL_NON_ZERO, m, c, 0.9, Affine.IDENTITY, Rect(10 + 8 * i, 10 + 6 * i, 190 - 5 * i, 190 - 7 * i))
+        s.fill(FILL_NON_ZERO, Affine.IDENTITY, Color.from_rgba8((40 * i) % 256, (90 * i + 30) % 256, (160 + 25 * i) % 256, 200),
+               None, Circle(60 + 9 * i, 70 + 8 * i, 50.0))
+    for i in range(depth):
+        s.pop_layer()
+    return s, 200, 200
+
+
+def brushes() -> Tuple[Scene, int, int]:
+    """Every brush kind: linear/radial (all 4 kinds)/sweep gradients with all extends, images at the
+    three qualities, blurred rounded rect, luminance mask layer."""
+    rng = np.random.default_rng(11)
+    s = Scene()
+    stops = [(0.0, Color.from_rgba8(255, 0, 0)), (0.5, Color.from_rgba8(0, 255, 0, 128)), (1.0, Color.from_rgba8(0, 0, 255))]
+    x = 0.0
+    for ext in (EXTEND_PAD, EXTEND_REPEAT, EXTEND_REFLECT):
+        s.fill(FILL_NON_ZERO, Affine.translate(x, 0.0), Gradient.linear((20, 10), (60, 50), stops, ext), None, Rect(0, 0, 100, 80))
+        s.fill(FILL_NON_ZERO, Affine.translate(x, 90.0), Gradient.radial((50, 40), 5.0, (55, 45), 35.0, stops, ext), None, Rect(0, 0, 100, 80))
+        s.fill(FILL_NON_ZERO, Affine.translate(x, 180.0), Gradient.sweep((50, 40), 0.3, 5.0, stops, ext), None, Rect(0, 0, 100, 80))
+        x += 110.0
+    # radial kinds: strip (equal radii), focal on circle, circular (same centre), swapped (r1 == 0)
+    s.fill(FILL_NON_ZERO, Affine.translate(0.0, 270.0), Gradient.radial((20, 40), 20.0, (80, 40), 20.0, stops), None, Rect(0, 0, 100, 80))
+    s.fill(FILL_NON_ZERO, Affine.translate(110.0, 270.0), Gradient.radial((30, 40), 0.0, (60, 40), 30.0, stops), None, Rect(0, 0, 100, 80))
+    s.fill(FILL_NON_ZERO, Affine.translate(220.0, 270.0), Gradient.radial((50, 40), 5.0, (50, 40), 40.0, stops), None, Rect(0, 0, 100, 80))
+    s.fill(FILL_NON_ZERO, Affine.translate(330.0, 270.0), Gradient.radial((40, 40), 30.0, (60, 40), 0.0, stops), None, Rect(0, 0, 100, 80))
+    img = rng.integers(0, 256, (13, 17, 4), dtype=np.uint8)
+    for i, q in enumerate((QUALITY_LOW, QUALITY_MEDIUM, QUALITY_HIGH)):
+        im = Image(img, quality=q, x_extend=(EXTEND_PAD, EXTEND_REPEAT, EXTEND_REFLECT)[i], y_extend=EXTEND_REFLECT,
+                   alpha=0.9, alpha_type=ALPHA_STRAIGHT if i != 1 else ALPHA_PREMULTIPLIED,
+                   format=FORMAT_RGBA8 if i != 2 else FORMAT_BGRA8)
+        t = Affine.translate(340.0, 10.0 + 85.0 * i) * Affine.rotate(0.1 * i) * Affine.scale(4.5)
+        s.fill(FILL_NON_ZERO, Affine.IDENTITY, im, t, Rect(340, 10 + 85 * i, 440, 85 + 85 * i))
+    s.draw_blurred_rounded_rect(Affine.translate(60.0, 400.0), Rect(-40, -25, 40, 25), Color.from_rgba8(250, 200, 30), 8.0, 5.0)
+    s.draw_blurred_rounded_rect(Affine.translate(200.0, 400.0) * Affine.rotate(0.3), Rect(-50, -20, 50, 20), Color.from_rgba8(30, 200, 250, 200), 0.0, 2.0)
+    s.push_luminance_mask_layer(FILL_NON_ZERO, 1.0, Affine.IDENTITY, Rect(280, 360, 440, 440))
+    s.fill(FILL_NON_ZERO, Affine.IDENTITY, Gradient.linear((280, 360), (440, 440), [(0.0, BLACK), (1.0, WHITE)]), None, Rect(280, 360, 440, 440))
+    s.pop_layer()
+    return s, 450, 450
+
+
+def random_small(seed: int, n: int = 40, size: int = 200) -> Tuple[Scene, int, int]:
+    """Mixed random fills / strokes / clips for randomized parity tests."""
+    rng = np.random.default_rng(seed)
+    s = Scene()
+    depth = 0
+    for i in range(n):
+        k = rng.random()
+        p = BezPath()
+        m = int(rng.integers(2, 7))
+        x, y = rng.uniform(-20, size + 20, 2)
+        p.move_to(x, y)
+        for _ in range(m):
+            c = rng.uniform(-40, size + 40, 6)
+            r = rng.random()
+            if r < 0.4:
+                p.line_to(c[0], c[1])
+            elif r < 0.7:
+                p.quad_to(c[0], c[1], c[2], c[3])
+            else:
+                p.curve_to(*c)
+        t = Affine.translate(*rng.uniform(-5, 5, 2)) * Affine.rotate(rng.uniform(-0.3, 0.3)) * Affine.scale(rng.uniform(0.5, 1.5))
+        if k < 0.5:
+            s.fill(FILL_NON_ZERO if rng.random() < 0.5 else FILL_EVEN_ODD, t, _rand_color(rng, 0.5), None, p)
+        elif k < 0.85:
+            st = Stroke(float(rng.uniform(0.3, 12.0)), join=(STYLE_JOIN_BEVEL, STYLE_JOIN_MITER, STYLE_JOIN_ROUND)[int(rng.integers(0, 3))],
+                        start_cap=(STYLE_CAP_BUTT, STYLE_CAP_SQUARE, STYLE_CAP_ROUND)[int(rng.integers(0, 3))],
+                        end_cap=(STYLE_CAP_BUTT, STYLE_CAP_SQUARE, STYLE_CAP_ROUND)[int(rng.integers(0, 3))])
+            if rng.random() < 0.3:
+                p.close_path()
+            s.stroke(st, t, _rand_color(rng, 0.5), None, p)
+        elif depth < 5:
+            s.push_clip_layer(FILL_NON_ZERO, t, p)
+            depth += 1
+        elif depth > 0:
+            s.pop_layer()
+            depth -= 1
+    # leave some clips open on purpose: resolve closes them (resolve.rs:127-141)
+    return s, size, size
