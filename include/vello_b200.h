@@ -1,0 +1,131 @@
+/* vello_b200.h -- C ABI of libvello_b200.so: a Blackwell (sm_100a) drop-in for the GPU compute
+ * path behind vello's `Renderer::render_to_texture`.
+ *
+ * What each entry point replaces in the reference (linebender/vello @ 3fabef93):
+ *
+ *   vb_renderer_new / _free   Renderer::new(&Device, RendererOptions)          vello/src/lib.rs:432-458
+ *                             (shader registry + pipeline build: shaders.rs:48-274, wgpu_engine.rs:163-246)
+ *   vb_render                 Renderer::render_to_texture(dev, queue, &scene, &tex, &RenderParams)
+ *                                                                             vello/src/lib.rs:474-515
+ *                             = Render::render_encoding_coarse + record_fine   vello/src/render.rs:135-629
+ *                             + WgpuEngine::run_recording                      vello/src/wgpu_engine.rs:380-780
+ *                             The inputs are exactly what crosses that seam: the packed scene bytes and
+ *                             `Layout` from Resolver::resolve (vello_encoding/src/resolve.rs:183-399), the
+ *                             gradient ramps (ramp_cache.rs:12,119-155), the image atlas and RenderParams
+ *                             (lib.rs:357-369).
+ *   vb_scene_upload           the `upload("vello.scene")` / ramps / atlas uploads    render.rs:149-232
+ *   vb_render_resident        the 16-18 dispatches + fine, scene already on the device
+ *   vb_frame_stats            Renderer::render_to_texture_async's bump readback  lib.rs:753-763 (the
+ *                             reference leaves "re-run on overflow" as a TODO; here it is implemented)
+ *   vb_run_stages / vb_debug_*   the operator seam `fn(u32 n_wg, &[CpuBinding])`  wgpu_engine.rs:57-61,
+ *                             vello_shaders/src/cpu.rs:57-62 -- used by the stage-level parity tests
+ *
+ * Threading: one host thread per vb_renderer (mirrors `&mut self`; Renderer is Send, not Sync,
+ * lib.rs:351-352). All pointers are plain host or device pointers; no torch / wgpu types.
+ * Errors: 0 = ok, negative = error (vb_strerror). Unlike the reference, bump-arena overflow is
+ * handled (grow and re-run) and, if it persists, REPORTED (VB_E_BUMP_OVERFLOW) instead of silently
+ * leaving the texture unwritten (shared/bump.wgsl:5-9, fine.wgsl:1070-1074).
+ */
+#ifndef VELLO_B200_H
+#define VELLO_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vb_renderer vb_renderer;
+
+typedef struct {
+    int32_t device;        /* CUDA device ordinal */
+    uint32_t timing;       /* 1: record per-stage CUDA events (adds launch gaps; for profiling) */
+    uint32_t max_retries;  /* grow-and-re-run attempts on bump overflow (0 -> default 6) */
+    uint32_t reserved;
+} vb_options;
+
+/* == vello_encoding::Layout (resolve.rs:16-39); offsets in u32 words */
+typedef struct {
+    uint32_t n_draw_objects, n_paths, n_clips, bin_data_start;
+    uint32_t path_tag_base, path_data_base, draw_tag_base, draw_data_base;
+    uint32_t transform_base, style_base;
+} vb_layout;
+
+/* == vello::RenderParams (lib.rs:357-369) + the stripe window extension */
+typedef struct {
+    uint32_t base_color;  /* premultiplied RGBA8, r in the low byte (config.rs:183) */
+    uint32_t width, height;
+    uint32_t aa;          /* AaConfig: 0 Area, 1 Msaa8, 2 Msaa16 (lib.rs:175-193) */
+    uint32_t bin_row0, bin_row1; /* render only bin rows [bin_row0, bin_row1) (256 px each); 0,0 = all.
+                                    The output buffer then holds rows bin_row0*256 .. min(bin_row1*256, height). */
+} vb_params;
+
+enum {
+    VB_STAGE_ID_PATHTAG = 0, VB_STAGE_ID_FLATTEN, VB_STAGE_ID_DRAW, VB_STAGE_ID_CLIP, VB_STAGE_ID_BINNING,
+    VB_STAGE_ID_TILE_ALLOC, VB_STAGE_ID_PATH_COUNT, VB_STAGE_ID_BACKDROP, VB_STAGE_ID_COARSE, VB_STAGE_ID_PATH_TILING,
+    VB_STAGE_ID_FINE, VB_N_STAGE_IDS
+};
+
+typedef struct {
+    /* == BumpAllocators (config.rs:24-37) after the frame */
+    uint32_t failed, binning, ptcl, tile, seg_counts, segments, blend, lines;
+    uint32_t retries;             /* re-runs this frame needed because an arena was too small */
+    uint32_t kernel_launches;     /* kernels launched for the final (successful) attempt */
+    float stage_ms[VB_N_STAGE_IDS]; /* only when options.timing */
+    float total_ms;               /* device time of the final attempt (events), only when options.timing */
+    uint64_t arena_bytes;         /* device memory currently held by the renderer */
+} vb_frame_stats;
+
+#define VB_OK 0
+#define VB_E_INVALID (-1)
+#define VB_E_CUDA (-2)
+#define VB_E_BUMP_OVERFLOW (-3)
+#define VB_E_NO_SCENE (-4)
+#define VB_E_UNKNOWN_BUFFER (-5)
+
+int vb_renderer_new(const vb_options *, vb_renderer **);
+void vb_renderer_free(vb_renderer *);
+const char *vb_strerror(int);
+const char *vb_last_error(vb_renderer *);
+
+/* Copy the packed scene + resources to the device (async on the renderer's stream). `scene` etc. are
+ * HOST pointers; ramps = ramp_h rows of ramp_w (=512) premultiplied RGBA8 texels; atlas = RGBA8. */
+int vb_scene_upload(vb_renderer *, const uint8_t *scene, size_t scene_len, const vb_layout *, const uint32_t *ramps,
+                    uint32_t ramp_w, uint32_t ramp_h, const uint8_t *atlas_rgba8, uint32_t atlas_w, uint32_t atlas_h);
+
+/* Render the uploaded scene. `out` is a DEVICE pointer (RGBA8, un-premultiplied, pitch 4*width) or NULL
+ * to render into the renderer's own target (see vb_target). Blocks until the frame is complete and
+ * arenas were large enough (re-running if not). */
+int vb_render_resident(vb_renderer *, const vb_params *, void *out_device, vb_frame_stats *);
+
+/* Asynchronous variant for pipelined use / benchmarks: enqueue one attempt and return. The frame is
+ * valid iff the following vb_frame_finish returns VB_OK with stats.failed == 0. */
+int vb_render_enqueue(vb_renderer *, const vb_params *, void *out_device);
+int vb_frame_finish(vb_renderer *, vb_frame_stats *);
+
+/* One call = upload + render + (if out_is_device == 0) copy the pixels back to the HOST pointer `out`. */
+int vb_render(vb_renderer *, const uint8_t *scene, size_t scene_len, const vb_layout *, const uint32_t *ramps, uint32_t ramp_w,
+              uint32_t ramp_h, const uint8_t *atlas_rgba8, uint32_t atlas_w, uint32_t atlas_h, const vb_params *, void *out,
+              uint32_t out_is_device, vb_frame_stats *);
+
+/* The renderer-owned target of the last frame (device pointer) and its size in bytes. */
+void *vb_target(vb_renderer *, size_t *bytes);
+/* Copy `bytes` from a device pointer to a host pointer on the renderer's stream, then synchronise. */
+int vb_copy_to_host(vb_renderer *, const void *src_device, void *dst_host, size_t bytes);
+/* cudaStream_t the renderer enqueues on (for event timing by the caller). */
+void *vb_stream(vb_renderer *);
+
+/* ---- stage-level access (parity tests; mirrors the reference's CPU-shader operator seam) ---- */
+/* Run stages first..last (VB_STAGE_ID_*) of the uploaded scene, one attempt, synchronously. */
+int vb_run_stages(vb_renderer *, const vb_params *, int first, int last, void *out_device);
+/* Copy an intermediate buffer to the host: "tag_monoids","path_bboxes","lines","draw_monoids",
+ * "info_bin_data","clip_inp","clip_bboxes","draw_bboxes","bin_headers","paths","tiles","seg_counts",
+ * "segments","ptcl","blend_spill","bump","config". Returns bytes available in *bytes; copies min(cap, bytes). */
+int vb_debug_download(vb_renderer *, const char *name, void *dst, size_t cap, size_t *bytes);
+/* Overwrite an intermediate buffer from the host ("lines" also sets bump.lines; "path_bboxes"). */
+int vb_debug_upload(vb_renderer *, const char *name, const void *src, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,314 @@
+// k_coarse.cu -- per-tile command lists (PTCL).
+//
+// Reference: vello_shaders/shader/coarse.wgsl:156-471 (PTCL layout shared/ptcl.wgsl:6-25, writers
+// coarse.wgsl:68-154), CPU twin cpu/coarse.rs. One CTA = one bin (16x16 tiles), one thread = one
+// tile, as in the WGSL; log-step shared-memory scans are replaced by warp-shuffle scans.
+// The per-tile command SEQUENCE is identical to the reference's; segment slices and dynamic PTCL
+// chunks come from atomic bump allocators, so their absolute offsets are allocation-order
+// dependent (as in the reference). Only bins inside the stripe window are launched.
+#include "vb_device.cuh"
+
+#define CO_THREADS 256
+#define CO_N_SLICE 8
+
+struct TileState {
+    uint32_t cmd_offset, cmd_limit;
+};
+
+__device__ __forceinline__ void co_alloc_cmd(TileState &s, uint32_t size, const VbConfig &cfg, VbBump *bump, uint32_t *ptcl) {
+    if (s.cmd_offset + size >= s.cmd_limit) {
+        const uint32_t ptcl_dyn_start = cfg.width_in_tiles * cfg.height_in_tiles * VB_PTCL_INITIAL_ALLOC;
+        uint32_t new_cmd = ptcl_dyn_start + atomicAdd(&bump->ptcl, VB_PTCL_INCREMENT);
+        if (new_cmd + VB_PTCL_INCREMENT > cfg.ptcl_size) {
+            // Out of PTCL space: park this tile's writes in the (unused) first dynamic chunk slot 0 of
+            // the static area is not safe, so fall back to the tile's own static chunk start; the
+            // frame is discarded and re-run with a bigger arena.
+            new_cmd = 0u;
+            atomicOr(&bump->failed, VB_STAGE_COARSE);
+        }
+        ptcl[s.cmd_offset] = VB_CMD_JUMP;
+        ptcl[s.cmd_offset + 1u] = new_cmd;
+        s.cmd_offset = new_cmd;
+        s.cmd_limit = new_cmd + (VB_PTCL_INCREMENT - VB_PTCL_HEADROOM);
+    }
+}
+
+__device__ __forceinline__ void co_write_path(TileState &s, const VbTile &tile, uint32_t tile_ix, uint32_t draw_flags, const VbConfig &cfg,
+                                              VbBump *bump, uint32_t *ptcl, VbTile *tiles) {
+    const uint32_t n_segs = tile.segment_count_or_ix;
+    if (n_segs != 0u) {
+        uint32_t seg_ix = atomicAdd(&bump->segments, n_segs);
+        tiles[tile_ix].segment_count_or_ix = ~seg_ix;
+        co_alloc_cmd(s, 4u, cfg, bump, ptcl);
+        ptcl[s.cmd_offset] = VB_CMD_FILL;
+        ptcl[s.cmd_offset + 1u] = (n_segs << 1) | (draw_flags & 1u);
+        ptcl[s.cmd_offset + 2u] = seg_ix;
+        ptcl[s.cmd_offset + 3u] = (uint32_t)tile.backdrop;
+        s.cmd_offset += 4u;
+    } else {
+        co_alloc_cmd(s, 1u, cfg, bump, ptcl);
+        ptcl[s.cmd_offset] = VB_CMD_SOLID;
+        s.cmd_offset += 1u;
+    }
+}
+
+__global__ void __launch_bounds__(CO_THREADS)
+k_coarse(VbConfig cfg, const uint32_t *__restrict__ scene, const VbDrawMonoid *__restrict__ draw_monoids,
+         const VbBinHeader *__restrict__ bin_headers, const uint32_t *__restrict__ info_bin_data, const VbPath *__restrict__ paths,
+         VbTile *tiles, VbBump *bump, uint32_t *ptcl) {
+    __shared__ uint32_t sh_bitmaps[CO_N_SLICE][VB_N_TILE];
+    __shared__ uint32_t sh_part_count[CO_THREADS];
+    __shared__ uint32_t sh_part_offsets[CO_THREADS];
+    __shared__ uint32_t sh_drawobj_ix[CO_THREADS];
+    __shared__ uint32_t sh_tile_stride[CO_THREADS];
+    __shared__ uint32_t sh_tile_width[CO_THREADS];
+    __shared__ uint32_t sh_tile_x0y0[CO_THREADS];
+    __shared__ uint32_t sh_tile_count[CO_THREADS];
+    __shared__ uint32_t sh_tile_base[CO_THREADS];
+    __shared__ uint32_t sh_scan[CO_THREADS / 32 + 2];
+
+    const uint32_t lid = threadIdx.x;
+    // Only PRIOR stages abort coarse (coarse.wgsl:164-179); read once per CTA so the decision is
+    // uniform even while other CTAs of this kernel raise VB_STAGE_COARSE.
+    if (lid == 0) sh_scan[0] = bump->failed & (VB_STAGE_BINNING | VB_STAGE_TILE_ALLOC | VB_STAGE_FLATTEN | VB_STAGE_PATH_COUNT);
+    __syncthreads();
+    const uint32_t prior_failed = sh_scan[0];
+    __syncthreads();
+    if (prior_failed != 0u) return;
+    const uint32_t wg_x = blockIdx.x, wg_y = blockIdx.y + cfg.win_by0;
+    const uint32_t width_in_bins = (cfg.width_in_tiles + VB_N_TILE_X - 1u) / VB_N_TILE_X;
+    const uint32_t height_in_bins = (cfg.height_in_tiles + VB_N_TILE_Y - 1u) / VB_N_TILE_Y;
+    const uint32_t bin_ix = width_in_bins * wg_y + wg_x;
+    const uint32_t aligned_n_bins = (width_in_bins * height_in_bins + VB_N_TILE - 1u) & ~(VB_N_TILE - 1u);
+    const uint32_t n_partitions = (cfg.layout.n_draw_objects + VB_N_TILE - 1u) / VB_N_TILE;
+    const uint32_t bin_tile_x = VB_N_TILE_X * wg_x, bin_tile_y = VB_N_TILE_Y * wg_y;
+    const uint32_t tile_x = lid % VB_N_TILE_X, tile_y = lid / VB_N_TILE_X;
+    const uint32_t this_tile_ix = (bin_tile_y + tile_y) * cfg.width_in_tiles + bin_tile_x + tile_x;
+    TileState st;
+    st.cmd_offset = this_tile_ix * VB_PTCL_INITIAL_ALLOC;
+    st.cmd_limit = st.cmd_offset + (VB_PTCL_INITIAL_ALLOC - VB_PTCL_HEADROOM);
+    uint32_t clip_zero_depth = 0u, clip_depth = 0u;
+    uint32_t partition_ix = 0u, rd_ix = 0u, wr_ix = 0u, part_start_ix = 0u, ready_ix = 0u;
+    uint32_t render_blend_depth = 0u, max_blend_depth = 0u;
+    const uint32_t blend_offset = st.cmd_offset;
+    st.cmd_offset += 1u;
+
+    while (true) {
+        for (int i = 0; i < CO_N_SLICE; i++) sh_bitmaps[i][lid] = 0u;
+        while (true) {
+            if (ready_ix == wr_ix && partition_ix < n_partitions) {
+                part_start_ix = ready_ix;
+                uint32_t count = 0u;
+                if (partition_ix + lid < n_partitions) {
+                    VbBinHeader h = bin_headers[(size_t)(partition_ix + lid) * aligned_n_bins + bin_ix];
+                    count = h.element_count;
+                    sh_part_offsets[lid] = h.chunk_offset;
+                }
+                uint32_t total;
+                uint32_t ex = vb_block_excl_scan(count, sh_scan, &total);
+                sh_part_count[lid] = part_start_ix + ex + count;
+                __syncthreads();
+                ready_ix = sh_part_count[CO_THREADS - 1u];
+                partition_ix += CO_THREADS;
+            }
+            uint32_t ix = rd_ix + lid;
+            if (ix >= wr_ix && ix < ready_ix) {
+                uint32_t part_ix = 0u;
+#pragma unroll
+                for (uint32_t i = 0u; i < 8u; i++) {
+                    uint32_t probe = part_ix + (128u >> i);
+                    if (ix >= sh_part_count[probe - 1u]) part_ix = probe;
+                }
+                ix -= part_ix > 0u ? sh_part_count[part_ix - 1u] : part_start_ix;
+                sh_drawobj_ix[lid] = info_bin_data[cfg.layout.bin_data_start + sh_part_offsets[part_ix] + ix];
+            }
+            wr_ix = min(rd_ix + VB_N_TILE, ready_ix);
+            if (wr_ix - rd_ix >= VB_N_TILE || (wr_ix >= ready_ix && partition_ix >= n_partitions)) break;
+            __syncthreads();
+        }
+        __syncthreads();
+        uint32_t tag = VB_DRAWTAG_NOP;
+        uint32_t drawobj_ix = 0u;
+        if (lid + rd_ix < wr_ix) {
+            drawobj_ix = sh_drawobj_ix[lid];
+            tag = vb_scene(scene, cfg, cfg.layout.draw_tag_base + drawobj_ix);
+        }
+        uint32_t tile_count = 0u;
+        if (tag != VB_DRAWTAG_NOP) {
+            const uint32_t path_ix = draw_monoids[drawobj_ix].path_ix;
+            const VbPath path = paths[path_ix];
+            const uint32_t stride = path.bbox[2] - path.bbox[0];
+            sh_tile_stride[lid] = stride;
+            const int32_t dx = (int32_t)path.bbox[0] - (int32_t)bin_tile_x;
+            const int32_t dy = (int32_t)path.bbox[1] - (int32_t)bin_tile_y;
+            const int32_t x0 = vb_clampi(dx, 0, (int32_t)VB_N_TILE_X);
+            const int32_t y0 = vb_clampi(dy, 0, (int32_t)VB_N_TILE_Y);
+            const int32_t x1 = vb_clampi((int32_t)path.bbox[2] - (int32_t)bin_tile_x, 0, (int32_t)VB_N_TILE_X);
+            const int32_t y1 = vb_clampi((int32_t)path.bbox[3] - (int32_t)bin_tile_y, 0, (int32_t)VB_N_TILE_Y);
+            sh_tile_width[lid] = (uint32_t)(x1 - x0);
+            sh_tile_x0y0[lid] = (uint32_t)x0 | ((uint32_t)y0 << 16);
+            tile_count = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0);
+            sh_tile_base[lid] = path.tiles - (uint32_t)(dy * (int32_t)stride + dx);
+        }
+        uint32_t total_tile_count;
+        {
+            uint32_t ex = vb_block_excl_scan(tile_count, sh_scan, &total_tile_count);
+            sh_tile_count[lid] = ex + tile_count;
+        }
+        __syncthreads();
+        for (uint32_t ix = lid; ix < total_tile_count; ix += VB_N_TILE) {
+            uint32_t el_ix = 0u;
+#pragma unroll
+            for (uint32_t i = 0u; i < 8u; i++) {
+                uint32_t probe = el_ix + (128u >> i);
+                if (ix >= sh_tile_count[probe - 1u]) el_ix = probe;
+            }
+            const uint32_t dobj = sh_drawobj_ix[el_ix];
+            const uint32_t dtag = vb_scene(scene, cfg, cfg.layout.draw_tag_base + dobj);
+            const uint32_t seq_ix = ix - (el_ix > 0u ? sh_tile_count[el_ix - 1u] : 0u);
+            const uint32_t width = sh_tile_width[el_ix];
+            const uint32_t x0y0 = sh_tile_x0y0[el_ix];
+            const uint32_t x = (x0y0 & 0xffffu) + seq_ix % width;
+            const uint32_t y = (x0y0 >> 16) + seq_ix / width;
+            const uint32_t tile_ix = sh_tile_base[el_ix] + sh_tile_stride[el_ix] * y + x;
+            const VbTile tile = tiles[tile_ix];
+            const bool is_clip = (dtag & 1u) != 0u;
+            bool is_blend = false;
+            const VbDrawMonoid dm = draw_monoids[dobj];
+            if (is_clip) {
+                const uint32_t BLEND_CLIP = (128u << 8) | 3u;
+                is_blend = vb_scene(scene, cfg, cfg.layout.draw_data_base + dm.scene_offset) != BLEND_CLIP;
+            }
+            const uint32_t draw_flags = info_bin_data[dm.info_offset];
+            const bool even_odd = (draw_flags & 1u) != 0u;
+            const uint32_t n_segs = tile.segment_count_or_ix;
+            const bool backdrop_clear = (even_odd ? (abs(tile.backdrop) & 1) : tile.backdrop) == 0;
+            const bool include_tile = n_segs != 0u || (backdrop_clear == is_clip) || is_blend;
+            if (include_tile) atomicOr(&sh_bitmaps[el_ix / 32u][y * VB_N_TILE_X + x], 1u << (el_ix & 31u));
+        }
+        __syncthreads();
+
+        uint32_t slice_ix = 0u;
+        uint32_t bitmap = sh_bitmaps[0][lid];
+        while (true) {
+            if (bitmap == 0u) {
+                slice_ix += 1u;
+                if (slice_ix == CO_N_SLICE) break;
+                bitmap = sh_bitmaps[slice_ix][lid];
+                if (bitmap == 0u) continue;
+            }
+            const uint32_t el_ix = slice_ix * 32u + (uint32_t)(__ffs((int)bitmap) - 1);
+            const uint32_t dobj = sh_drawobj_ix[el_ix];
+            bitmap &= bitmap - 1u;
+            const uint32_t drawtag = vb_scene(scene, cfg, cfg.layout.draw_tag_base + dobj);
+            const VbDrawMonoid dm = draw_monoids[dobj];
+            const uint32_t dd = cfg.layout.draw_data_base + dm.scene_offset;
+            const uint32_t di = dm.info_offset;
+            const uint32_t draw_flags = info_bin_data[di];
+            if (clip_zero_depth == 0u) {
+                const uint32_t tile_ix = sh_tile_base[el_ix] + sh_tile_stride[el_ix] * tile_y + tile_x;
+                const VbTile tile = tiles[tile_ix];
+                switch (drawtag) {
+                case VB_DRAWTAG_FILL_COLOR:
+                    co_write_path(st, tile, tile_ix, draw_flags, cfg, bump, ptcl, tiles);
+                    co_alloc_cmd(st, 2u, cfg, bump, ptcl);
+                    ptcl[st.cmd_offset] = VB_CMD_COLOR;
+                    ptcl[st.cmd_offset + 1u] = vb_scene(scene, cfg, dd);
+                    st.cmd_offset += 2u;
+                    break;
+                case VB_DRAWTAG_BLURRED_ROUNDED_RECT:
+                    co_write_path(st, tile, tile_ix, draw_flags, cfg, bump, ptcl, tiles);
+                    co_alloc_cmd(st, 3u, cfg, bump, ptcl);
+                    ptcl[st.cmd_offset] = VB_CMD_BLUR_RECT;
+                    ptcl[st.cmd_offset + 1u] = di + 1u;
+                    ptcl[st.cmd_offset + 2u] = vb_scene(scene, cfg, dd);
+                    st.cmd_offset += 3u;
+                    break;
+                case VB_DRAWTAG_FILL_LIN_GRADIENT:
+                case VB_DRAWTAG_FILL_RAD_GRADIENT:
+                case VB_DRAWTAG_FILL_SWEEP_GRADIENT: {
+                    const uint32_t ty = drawtag == VB_DRAWTAG_FILL_LIN_GRADIENT ? VB_CMD_LIN_GRAD
+                                        : drawtag == VB_DRAWTAG_FILL_RAD_GRADIENT ? VB_CMD_RAD_GRAD : VB_CMD_SWEEP_GRAD;
+                    co_write_path(st, tile, tile_ix, draw_flags, cfg, bump, ptcl, tiles);
+                    co_alloc_cmd(st, 3u, cfg, bump, ptcl);
+                    ptcl[st.cmd_offset] = ty;
+                    ptcl[st.cmd_offset + 1u] = vb_scene(scene, cfg, dd);
+                    ptcl[st.cmd_offset + 2u] = di + 1u;
+                    st.cmd_offset += 3u;
+                    break;
+                }
+                case VB_DRAWTAG_FILL_IMAGE:
+                    co_write_path(st, tile, tile_ix, draw_flags, cfg, bump, ptcl, tiles);
+                    co_alloc_cmd(st, 2u, cfg, bump, ptcl);
+                    ptcl[st.cmd_offset] = VB_CMD_IMAGE;
+                    ptcl[st.cmd_offset + 1u] = di + 1u;
+                    st.cmd_offset += 2u;
+                    break;
+                case VB_DRAWTAG_BEGIN_CLIP: {
+                    const bool even_odd = (draw_flags & 1u) != 0u;
+                    const bool backdrop_clear = (even_odd ? (abs(tile.backdrop) & 1) : tile.backdrop) == 0;
+                    if (tile.segment_count_or_ix == 0u && backdrop_clear) {
+                        clip_zero_depth = clip_depth + 1u;
+                    } else {
+                        co_alloc_cmd(st, 1u, cfg, bump, ptcl);
+                        ptcl[st.cmd_offset] = VB_CMD_BEGIN_CLIP;
+                        st.cmd_offset += 1u;
+                        render_blend_depth += 1u;
+                        max_blend_depth = max(max_blend_depth, render_blend_depth);
+                    }
+                    clip_depth += 1u;
+                    break;
+                }
+                case VB_DRAWTAG_END_CLIP:
+                    clip_depth -= 1u;
+                    co_write_path(st, tile, tile_ix, draw_flags, cfg, bump, ptcl, tiles);
+                    co_alloc_cmd(st, 3u, cfg, bump, ptcl);
+                    ptcl[st.cmd_offset] = VB_CMD_END_CLIP;
+                    ptcl[st.cmd_offset + 1u] = vb_scene(scene, cfg, dd);
+                    ptcl[st.cmd_offset + 2u] = vb_scene(scene, cfg, dd + 1u);
+                    st.cmd_offset += 3u;
+                    render_blend_depth -= 1u;
+                    break;
+                default: break;
+                }
+            } else {
+                if (drawtag == VB_DRAWTAG_BEGIN_CLIP) {
+                    clip_depth += 1u;
+                } else if (drawtag == VB_DRAWTAG_END_CLIP) {
+                    if (clip_depth == clip_zero_depth) clip_zero_depth = 0u;
+                    clip_depth -= 1u;
+                }
+            }
+        }
+        rd_ix += VB_N_TILE;
+        if (rd_ix >= ready_ix && partition_ix >= n_partitions) break;
+        __syncthreads();
+    }
+    if (bin_tile_x + tile_x < cfg.width_in_tiles && bin_tile_y + tile_y < cfg.height_in_tiles) {
+        ptcl[st.cmd_offset] = VB_CMD_END;
+        uint32_t blend_ix = 0u;
+        if (max_blend_depth > VB_BLEND_STACK_SPLIT) {
+            const uint32_t scratch_size = (max_blend_depth - VB_BLEND_STACK_SPLIT) * VB_TILE_WIDTH * VB_TILE_HEIGHT;
+            blend_ix = atomicAdd(&bump->blend, scratch_size);
+            if (blend_ix + scratch_size > cfg.blend_size) atomicOr(&bump->failed, VB_STAGE_COARSE);
+        }
+        ptcl[blend_offset] = blend_ix;
+    }
+}
+
+// After coarse: segments arena overflow check (the reference sizes `segments` statically and
+// never checks; path_tiling would write out of bounds).
+__global__ void k_coarse_check(VbConfig cfg, VbBump *bump) {
+    if (bump->segments > cfg.segments_size) atomicOr(&bump->failed, VB_STAGE_FINE_SEGMENTS);
+}
+
+extern "C" void vb_launch_coarse(const VbConfig *cfg, const uint32_t *scene, const VbDrawMonoid *draw_monoids,
+                                 const VbBinHeader *bin_headers, const uint32_t *info_bin_data, const VbPath *paths, VbTile *tiles,
+                                 VbBump *bump, uint32_t *ptcl, cudaStream_t st) {
+    uint32_t width_in_bins = (cfg->width_in_tiles + 15u) / 16u;
+    uint32_t rows = cfg->win_by1 - cfg->win_by0;
+    if (width_in_bins == 0 || rows == 0) return;
+    dim3 grid(width_in_bins, rows);
+    k_coarse<<<grid, CO_THREADS, 0, st>>>(*cfg, scene, draw_monoids, bin_headers, info_bin_data, paths, tiles, bump, ptcl);
+    k_coarse_check<<<1, 1, 0, st>>>(*cfg, bump);
+}

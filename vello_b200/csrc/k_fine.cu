@@ -1,0 +1,862 @@
+// k_fine.cu -- fine rasterisation: interpret each tile's PTCL and write RGBA8 pixels.
+//
+// Reference: vello_shaders/shader/fine.wgsl (area coverage :1005-1059, MSAA :146-709, interpreter
+// :1064-1398), shared/blend.wgsl, mask LUTs vello_encoding/src/mask.rs. The reference has no CPU
+// fine; our oracle (oracle/vbo_fine.c) restates the WGSL and this kernel must match it bit for bit
+// (MSAA: integer sample counts -> exact; area: float sums in slice order).
+//
+// Round-1 structure: one CTA (64 threads = 4x16, 4 horizontally adjacent pixels per thread, exactly
+// the WGSL's decomposition so that per-thread float expressions are identical) per tile; several
+// CTAs are resident per SM. Conventions fixed where WGSL leaves latitude: see oracle/vbo_fine.c.
+// Algorithmic bytes: 4 B/pixel stored + 4 B per PTCL word + 24 B per segment referenced.
+#include <cuda_fp16.h>
+
+#include "vb_detmath.h"
+#include "vb_device.cuh"
+
+#define FI_THREADS 64
+#define PIXELS_PER_THREAD 4
+#define ONE_MINUS_ULP 0.99999994f
+#define ROBUST_EPSILON 2e-7f
+#define GRADIENT_WIDTH 512
+
+struct rgba_t { float r, g, b, a; };
+__device__ __forceinline__ rgba_t RG(float r, float g, float b, float a) { rgba_t c; c.r = r; c.g = g; c.b = b; c.a = a; return c; }
+__device__ __forceinline__ rgba_t rg_scale(rgba_t c, float s) { return RG(c.r * s, c.g * s, c.b * s, c.a * s); }
+__device__ __forceinline__ rgba_t unpack4x8unorm(uint32_t u) {
+    return RG((float)(u & 0xffu) / 255.0f, (float)((u >> 8) & 0xffu) / 255.0f, (float)((u >> 16) & 0xffu) / 255.0f,
+              (float)(u >> 24) / 255.0f);
+}
+__device__ __forceinline__ uint32_t unorm8(float x) { return (uint32_t)floorf(0.5f + 255.0f * fminf(1.0f, fmaxf(0.0f, x))); }
+__device__ __forceinline__ uint32_t pack4x8unorm(rgba_t c) {
+    return unorm8(c.r) | (unorm8(c.g) << 8) | (unorm8(c.b) << 16) | (unorm8(c.a) << 24);
+}
+__device__ __forceinline__ rgba_t over(rgba_t bg, rgba_t fg) {
+    float k = 1.0f - fg.a;
+    return RG(bg.r * k + fg.r, bg.g * k + fg.g, bg.b * k + fg.b, bg.a * k + fg.a);
+}
+
+struct FineArgs {
+    const VbSegment *segments;
+    const uint32_t *ptcl;
+    const uint32_t *info;
+    uint32_t *blend_spill;
+    uint32_t *out; // RGBA8 packed, r in the low byte
+    const uint32_t *ramps;
+    const uint8_t *atlas;
+    const uint32_t *mask_lut;
+};
+
+__device__ __forceinline__ VbSegment ld_segment(const VbSegment *__restrict__ segs, uint32_t ix) {
+    const uint2 *p = reinterpret_cast<const uint2 *>(segs + ix);
+    uint2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    VbSegment s;
+    s.p0[0] = __uint_as_float(a.x); s.p0[1] = __uint_as_float(a.y);
+    s.p1[0] = __uint_as_float(b.x); s.p1[1] = __uint_as_float(b.y);
+    s.y_edge = __uint_as_float(c.x);
+    s._pad = 0;
+    return s;
+}
+
+// ---------------- area coverage: fine.wgsl:1005-1059 ----------------
+__device__ void fill_path_area(const FineArgs &A, uint32_t size_and_rule, uint32_t seg_data, int32_t backdrop, float xyx, float xyy,
+                               float (&area)[PIXELS_PER_THREAD]) {
+    const uint32_t n_segs = size_and_rule >> 1;
+    const bool even_odd = (size_and_rule & 1u) != 0u;
+    const float backdrop_f = (float)backdrop;
+#pragma unroll
+    for (int i = 0; i < PIXELS_PER_THREAD; i++) area[i] = backdrop_f;
+    for (uint32_t s = 0; s < n_segs; s++) {
+        const VbSegment seg = ld_segment(A.segments, seg_data + s);
+        const float y = seg.p0[1] - xyy;
+        const float deltax = seg.p1[0] - seg.p0[0], deltay = seg.p1[1] - seg.p0[1];
+        const float y0 = vb_clampf(y, 0.0f, 1.0f);
+        const float y1 = vb_clampf(y + deltay, 0.0f, 1.0f);
+        const float dy = y0 - y1;
+        if (dy != 0.0f) {
+            const float vec_y_recip = 1.0f / deltay;
+            const float t0 = (y0 - y) * vec_y_recip;
+            const float t1 = (y1 - y) * vec_y_recip;
+            const float startx = seg.p0[0] - xyx;
+            const float x0 = startx + t0 * deltax;
+            const float x1 = startx + t1 * deltax;
+            const float xmin0 = fminf(x0, x1);
+            const float xmax0 = fmaxf(x0, x1);
+#pragma unroll
+            for (int i = 0; i < PIXELS_PER_THREAD; i++) {
+                const float i_f = (float)i;
+                const float xmin = fminf(xmin0 - i_f, 1.0f) - 1.0e-6f;
+                const float xmax = xmax0 - i_f;
+                const float b = fminf(xmax, 1.0f);
+                const float c = fmaxf(b, 0.0f);
+                const float d = fmaxf(xmin, 0.0f);
+                const float a = (b + 0.5f * (d * d - c * c) - xmin) / (xmax - xmin);
+                area[i] += a * dy;
+            }
+        }
+        const float y_edge = vb_signf(deltax) * vb_clampf(xyy - seg.y_edge + 1.0f, 0.0f, 1.0f);
+#pragma unroll
+        for (int i = 0; i < PIXELS_PER_THREAD; i++) area[i] += y_edge;
+    }
+    if (even_odd) {
+#pragma unroll
+        for (int i = 0; i < PIXELS_PER_THREAD; i++) {
+            const float a = area[i];
+            area[i] = fabsf(a - 2.0f * rintf(0.5f * a));
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < PIXELS_PER_THREAD; i++) area[i] = fminf(fabsf(area[i]), 1.0f);
+    }
+}
+
+// ---------------- MSAA coverage: fine.wgsl:146-709 ----------------
+struct MsShared {
+    uint32_t sh_count[FI_THREADS];
+    uint32_t sh_winding_y[4];
+    uint32_t sh_winding_y_prefix[4];
+    uint32_t sh_winding[64];
+    uint32_t sh_samples[1024];
+    uint32_t sh_scan[FI_THREADS / 32 + 2];
+};
+
+template <int AA> // 1 = msaa8, 2 = msaa16
+__device__ void fill_path_ms(const FineArgs &A, MsShared &S, uint32_t size_and_rule, uint32_t seg_data, int32_t backdrop, uint32_t lx,
+                             uint32_t ly, float (&area)[PIXELS_PER_THREAD]) {
+    constexpr uint32_t MASK_WIDTH = AA == 2 ? 64u : 32u;
+    constexpr uint32_t MASK_HEIGHT = MASK_WIDTH;
+    constexpr uint32_t WPP = AA == 2 ? 4u : 2u;
+    const uint32_t n_segs = size_and_rule >> 1;
+    const bool even_odd = (size_and_rule & 1u) != 0u;
+    const uint32_t th_ix = ly * 4u + lx;
+    if (even_odd) {
+        if (th_ix < 16u) {
+            if (th_ix == 0u) S.sh_winding_y[0] = 0u;
+            S.sh_winding[th_ix] = 0u;
+        }
+#pragma unroll
+        for (uint32_t i = 0; i < PIXELS_PER_THREAD; i++) S.sh_samples[th_ix * PIXELS_PER_THREAD + i] = 0u;
+    } else {
+        if (th_ix < 4u) S.sh_winding_y[th_ix] = 0x80808080u;
+        S.sh_winding[th_ix] = 0x80808080u;
+#pragma unroll
+        for (uint32_t i = 0; i < PIXELS_PER_THREAD * WPP; i++) S.sh_samples[th_ix * PIXELS_PER_THREAD * WPP + i] = 0x80808080u;
+    }
+    __syncthreads();
+    const uint32_t n_batch = (n_segs + (FI_THREADS - 1u)) / FI_THREADS;
+    for (uint32_t batch = 0u; batch < n_batch; batch++) {
+        const uint32_t seg_ix = batch * FI_THREADS + th_ix;
+        uint32_t count = 0u;
+        const uint32_t slice_size = min(n_segs - batch * FI_THREADS, (uint32_t)FI_THREADS);
+        if (th_ix < slice_size) {
+            const VbSegment seg = ld_segment(A.segments, seg_data + seg_ix);
+            const float x0 = seg.p0[0], y0 = seg.p0[1], x1 = seg.p1[0], y1 = seg.p1[1];
+            float y_edge_f = 16.0f;
+            const int32_t delta = (x1 <= x0) ? 1 : -1;
+            if (x0 == 0.0f) y_edge_f = y0;
+            else if (x1 == 0.0f) y_edge_f = y1;
+            if (!(y0 == y1 && y0 == floorf(y0))) count = vb_span(x0, x1) + vb_span(y0, y1) - 1u;
+            const uint32_t y_edge = vb_f2u_sat(ceilf(y_edge_f));
+            if (y_edge < 16u) {
+                if (even_odd) atomicXor(&S.sh_winding_y[0], 1u << y_edge);
+                else atomicAdd(&S.sh_winding_y[y_edge >> 2], ((uint32_t)delta) << ((y_edge & 3u) << 3));
+            }
+        }
+        uint32_t total;
+        const uint32_t ex = vb_block_excl_scan(count, S.sh_scan, &total);
+        S.sh_count[th_ix] = ex + count;
+        __syncthreads();
+        for (uint32_t i = th_ix; i < total; i += FI_THREADS) {
+            uint32_t lo = 0u, hi = slice_size;
+            while (hi > lo + 1u) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (i >= S.sh_count[mid - 1u]) lo = mid; else hi = mid;
+            }
+            const uint32_t el_ix = lo;
+            const bool last_pixel = i + 1u == S.sh_count[el_ix];
+            const uint32_t sub_ix = i - (el_ix > 0u ? S.sh_count[el_ix - 1u] : 0u);
+            const VbSegment seg = ld_segment(A.segments, seg_data + batch * FI_THREADS + el_ix);
+            const bool is_down = seg.p1[1] >= seg.p0[1];
+            const float xy0x = is_down ? seg.p0[0] : seg.p1[0], xy0y = is_down ? seg.p0[1] : seg.p1[1];
+            const float xy1x = is_down ? seg.p1[0] : seg.p0[0], xy1y = is_down ? seg.p1[1] : seg.p0[1];
+            const float dx = fabsf(xy1x - xy0x);
+            const float dy = xy1y - xy0y;
+            const float idxdy = 1.0f / (dx + dy);
+            float a = dx * idxdy;
+            const bool is_positive_slope = xy1x >= xy0x;
+            const float x_sign = is_positive_slope ? 1.0f : -1.0f;
+            const float xt0 = floorf(xy0x * x_sign);
+            const float c = xy0x * x_sign - xt0;
+            const float y0i = floorf(xy0y);
+            const float ytop = y0i + 1.0f;
+            const float b = fminf((dy * c + dx * (ytop - xy0y)) * idxdy, ONE_MINUS_ULP);
+            const uint32_t count_x = vb_span(xy0x, xy1x) - 1u;
+            const uint32_t count_full = count_x + vb_span(xy0y, xy1y);
+            const float robust_err = floorf(a * ((float)count_full - 1.0f) + b) - (float)count_x;
+            if (robust_err != 0.0f) a -= ROBUST_EPSILON * vb_signf(robust_err);
+            const int32_t x0i = vb_f2i_sat(xt0 * x_sign + 0.5f * (x_sign - 1.0f));
+            const float zf = a * (float)sub_ix + b;
+            const float z = floorf(zf);
+            const int32_t x = x0i + vb_f2i_sat(x_sign * z);
+            const int32_t y = vb_f2i_sat(y0i) + (int32_t)sub_ix - vb_f2i_sat(z);
+            bool is_delta, is_bump = false;
+            if (sub_ix == 0u) {
+                is_delta = y0i == xy0y;
+                is_bump = even_odd ? (xy0x == 0.0f) : (xy0x == 0.0f && y0i != xy0y);
+            } else {
+                const float zp = floorf(a * (float)(sub_ix - 1u) + b);
+                is_delta = z == zp;
+                is_bump = is_positive_slope && !is_delta;
+            }
+            const uint32_t pix_ix = (uint32_t)y * 16u + (uint32_t)x;
+            if ((uint32_t)x < 15u && (uint32_t)y < 16u && is_delta) {
+                if (even_odd) {
+                    atomicXor(&S.sh_winding[y], 2u << (uint32_t)x);
+                } else {
+                    const uint32_t delta_pix = pix_ix + 1u;
+                    atomicAdd(&S.sh_winding[delta_pix >> 2], (is_down ? 1u : 0xffffffffu) << ((delta_pix & 3u) << 3));
+                }
+            }
+            const uint32_t mask_block = (uint32_t)is_positive_slope * (MASK_WIDTH * MASK_HEIGHT / 2u);
+            const float half_height = (float)(MASK_HEIGHT / 2u);
+            const float mask_row = floorf(fminf(a * half_height, half_height - 1.0f)) * (float)MASK_WIDTH;
+            const float mask_col = floorf((zf - z) * (float)MASK_WIDTH);
+            const uint32_t mask_ix = mask_block + vb_f2u_sat(mask_row + mask_col);
+            if (pix_ix >= 256u) continue;
+            if (AA == 1) {
+                uint32_t mask = (__ldg(A.mask_lut + ((mask_ix / 4u) & 255u)) >> ((mask_ix % 4u) * 8u)) & 0xffu;
+                if (sub_ix == 0u && !is_bump) {
+                    const uint32_t sh = vb_f2u_sat(rintf(8.0f * (xy0y - (float)y)));
+                    mask &= sh < 32u ? (0xffu << sh) : 0u;
+                }
+                if (last_pixel && xy1x != 0.0f) {
+                    const uint32_t sh = vb_f2u_sat(rintf(8.0f * (xy1y - (float)y)));
+                    mask &= ~(sh < 32u ? (0xffu << sh) : 0u);
+                }
+                if (even_odd) {
+                    if (is_bump) mask ^= 0xffu;
+                    atomicXor(&S.sh_samples[pix_ix], mask);
+                } else {
+                    const uint32_t mask_a = mask ^ (mask << 7);
+                    const uint32_t mask_b = mask_a ^ (mask_a << 14);
+                    const uint32_t m0 = mask_b & 0x1010101u, m1 = (mask_b >> 4) & 0x1010101u;
+                    uint32_t m0s = is_down ? (0u - m0) : m0;
+                    uint32_t m1s = is_down ? (0u - m1) : m1;
+                    if (is_bump) {
+                        const uint32_t bd = is_down ? 0x1010101u : (0u - 0x1010101u);
+                        m0s += bd; m1s += bd;
+                    }
+                    atomicAdd(&S.sh_samples[pix_ix * 2u], m0s);
+                    atomicAdd(&S.sh_samples[pix_ix * 2u + 1u], m1s);
+                }
+            } else {
+                uint32_t mask = (__ldg(A.mask_lut + ((mask_ix / 2u) & 2047u)) >> ((mask_ix % 2u) * 16u)) & 0xffffu;
+                if (sub_ix == 0u && !is_bump) {
+                    const uint32_t sh = vb_f2u_sat(rintf(16.0f * (xy0y - (float)y)));
+                    mask &= sh < 32u ? (0xffffu << sh) : 0u;
+                }
+                if (last_pixel && xy1x != 0.0f) {
+                    const uint32_t sh = vb_f2u_sat(rintf(16.0f * (xy1y - (float)y)));
+                    mask &= ~(sh < 32u ? (0xffffu << sh) : 0u);
+                }
+                if (even_odd) {
+                    if (is_bump) mask ^= 0xffffu;
+                    atomicXor(&S.sh_samples[pix_ix], mask);
+                } else {
+                    const uint32_t mask0 = mask & 0xffu;
+                    const uint32_t mask0_a = mask0 ^ (mask0 << 7);
+                    const uint32_t mask0_b = mask0_a ^ (mask0_a << 14);
+                    const uint32_t e0 = mask0_b & 0x1010101u, e1 = (mask0_b >> 4) & 0x1010101u;
+                    const uint32_t mask1 = (mask >> 8) & 0xffu;
+                    const uint32_t mask1_a = mask1 ^ (mask1 << 7);
+                    const uint32_t mask1_b = mask1_a ^ (mask1_a << 14);
+                    const uint32_t e2 = mask1_b & 0x1010101u, e3 = (mask1_b >> 4) & 0x1010101u;
+                    uint32_t s0 = is_down ? (0u - e0) : e0, s1 = is_down ? (0u - e1) : e1;
+                    uint32_t s2 = is_down ? (0u - e2) : e2, s3 = is_down ? (0u - e3) : e3;
+                    if (is_bump) {
+                        const uint32_t bd = is_down ? 0x1010101u : (0u - 0x1010101u);
+                        s0 += bd; s1 += bd; s2 += bd; s3 += bd;
+                    }
+                    atomicAdd(&S.sh_samples[pix_ix * 4u], s0);
+                    atomicAdd(&S.sh_samples[pix_ix * 4u + 1u], s1);
+                    atomicAdd(&S.sh_samples[pix_ix * 4u + 2u], s2);
+                    atomicAdd(&S.sh_samples[pix_ix * 4u + 3u], s3);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (even_odd) {
+        uint32_t scan_x = S.sh_winding[ly];
+        scan_x ^= scan_x << 1; scan_x ^= scan_x << 2; scan_x ^= scan_x << 4; scan_x ^= scan_x << 8;
+        uint32_t scan_y = S.sh_winding_y[0];
+        scan_y ^= scan_y << 1; scan_y ^= scan_y << 2; scan_y ^= scan_y << 4; scan_y ^= scan_y << 8;
+        const uint32_t row_parity = (scan_y >> ly) ^ (uint32_t)backdrop;
+#pragma unroll
+        for (uint32_t i = 0; i < PIXELS_PER_THREAD; i++) {
+            const uint32_t pix_ix = th_ix * PIXELS_PER_THREAD + i;
+            const uint32_t samples = S.sh_samples[pix_ix];
+            const uint32_t pix_parity = row_parity ^ (scan_x >> (pix_ix % 16u));
+            const uint32_t pix_mask = 0u - (pix_parity & 1u);
+            if (AA == 2) area[i] = (float)__popc((samples ^ pix_mask) & 0xffffu) * 0.0625f;
+            else area[i] = (float)__popc((samples ^ pix_mask) & 0xffu) * 0.125f;
+        }
+        __syncthreads();
+        return;
+    }
+    const uint32_t major = th_ix;
+    uint32_t packed_w = S.sh_winding[major];
+    packed_w += (packed_w - 0x808080u) << 8;
+    packed_w += (packed_w - 0x8080u) << 16;
+    uint32_t packed_y = S.sh_winding_y[ly >> 2];
+    packed_y += (packed_y - 0x808080u) << 8;
+    packed_y += (packed_y - 0x8080u) << 16;
+    uint32_t wind_y = (packed_y >> ((ly & 3u) << 3)) - 0x80u;
+    __syncthreads(); // every thread has read sh_winding / sh_winding_y before they are overwritten
+    if ((ly & 3u) == 3u && lx == 0u) S.sh_winding_y_prefix[ly >> 2] = wind_y;
+    const uint32_t prefix_x = ((packed_w >> 24) - 0x80u) * 0x1010101u;
+    S.sh_winding[major] = prefix_x;
+    __syncthreads();
+    for (uint32_t i = (major & ~3u); i < major; i++) packed_w += S.sh_winding[i];
+    for (uint32_t i = 0u; i < (ly >> 2); i++) wind_y += S.sh_winding_y_prefix[i];
+#pragma unroll
+    for (uint32_t i = 0u; i < PIXELS_PER_THREAD; i++) {
+        const uint32_t pix_ix = th_ix * PIXELS_PER_THREAD + i;
+        const uint32_t expected_zero = (((packed_w >> (i * 8u)) + wind_y) & 0xffu) - (uint32_t)backdrop;
+        if (expected_zero >= 256u) {
+            area[i] = 1.0f;
+        } else if (AA == 1) {
+            const uint32_t samples0 = S.sh_samples[pix_ix * 2u], samples1 = S.sh_samples[pix_ix * 2u + 1u];
+            const uint32_t xored0 = (expected_zero * 0x1010101u) ^ samples0;
+            const uint32_t xored0_2 = xored0 | (xored0 * 2u);
+            const uint32_t xored1 = (expected_zero * 0x1010101u) ^ samples1;
+            const uint32_t xored1_2 = xored1 | (xored1 >> 1);
+            const uint32_t xored2 = (xored0_2 & 0xAAAAAAAAu) | (xored1_2 & 0x55555555u);
+            const uint32_t xored4 = xored2 | (xored2 * 4u);
+            const uint32_t xored8 = xored4 | (xored4 * 16u);
+            area[i] = (float)__popc(xored8 & 0xC0C0C0C0u) * 0.125f;
+        } else {
+            const uint32_t sm0 = S.sh_samples[pix_ix * 4u], sm1 = S.sh_samples[pix_ix * 4u + 1u];
+            const uint32_t sm2 = S.sh_samples[pix_ix * 4u + 2u], sm3 = S.sh_samples[pix_ix * 4u + 3u];
+            const uint32_t ez = expected_zero * 0x1010101u;
+            const uint32_t xored0 = ez ^ sm0;
+            const uint32_t xored0_2 = xored0 | (xored0 * 2u);
+            const uint32_t xored1 = ez ^ sm1;
+            const uint32_t xored1_2 = xored1 | (xored1 >> 1);
+            const uint32_t xored01 = (xored0_2 & 0xAAAAAAAAu) | (xored1_2 & 0x55555555u);
+            const uint32_t xored01_4 = xored01 | (xored01 * 4u);
+            const uint32_t xored2 = ez ^ sm2;
+            const uint32_t xored2_2 = xored2 | (xored2 * 2u);
+            const uint32_t xored3 = ez ^ sm3;
+            const uint32_t xored3_2 = xored3 | (xored3 >> 1);
+            const uint32_t xored23 = (xored2_2 & 0xAAAAAAAAu) | (xored3_2 & 0x55555555u);
+            const uint32_t xored23_4 = xored23 | (xored23 >> 2);
+            const uint32_t xored4 = (xored01_4 & 0xCCCCCCCCu) | (xored23_4 & 0x33333333u);
+            const uint32_t xored8 = xored4 | (xored4 * 16u);
+            area[i] = (float)__popc(xored8 & 0xF0F0F0F0u) * 0.0625f;
+        }
+    }
+    __syncthreads();
+}
+
+// ---------------- blend.wgsl ----------------
+struct v3 { float x, y, z; };
+__device__ __forceinline__ v3 V3(float x, float y, float z) { v3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ float color_dodge(float cb, float cs) {
+    if (cb == 0.0f) return 0.0f;
+    if (cs == 1.0f) return 1.0f;
+    return fminf(1.0f, cb / (1.0f - cs));
+}
+__device__ float color_burn(float cb, float cs) {
+    if (cb == 1.0f) return 1.0f;
+    if (cs == 0.0f) return 0.0f;
+    return 1.0f - fminf(1.0f, (1.0f - cb) / cs);
+}
+__device__ __forceinline__ float screen1(float cb, float cs) { return cb + cs - (cb * cs); }
+__device__ float hard_light1(float cb, float cs) { return cs <= 0.5f ? cb * 2.0f * cs : screen1(cb, 2.0f * cs - 1.0f); }
+__device__ float soft_light1(float cb, float cs) {
+    float d = cb <= 0.25f ? ((16.0f * cb - 12.0f) * cb + 4.0f) * cb : sqrtf(cb);
+    return cs <= 0.5f ? cb - (1.0f - 2.0f * cs) * cb * (1.0f - cb) : cb + (2.0f * cs - 1.0f) * (d - cb);
+}
+__device__ __forceinline__ float sat3(v3 c) { return fmaxf(c.x, fmaxf(c.y, c.z)) - fminf(c.x, fminf(c.y, c.z)); }
+__device__ __forceinline__ float dot3(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float lum(v3 c) { return dot3(c, V3(0.3f, 0.59f, 0.11f)); }
+__device__ __forceinline__ float svg_lum(v3 c) { return dot3(c, V3(0.2125f, 0.7154f, 0.0721f)); }
+__device__ v3 clip_color(v3 c) {
+    float l = lum(c);
+    float n = fminf(c.x, fminf(c.y, c.z));
+    float x = fmaxf(c.x, fmaxf(c.y, c.z));
+    if (n < 0.0f) c = V3(l + (((c.x - l) * l) / (l - n)), l + (((c.y - l) * l) / (l - n)), l + (((c.z - l) * l) / (l - n)));
+    if (x > 1.0f)
+        c = V3(l + (((c.x - l) * (1.0f - l)) / (x - l)), l + (((c.y - l) * (1.0f - l)) / (x - l)),
+               l + (((c.z - l) * (1.0f - l)) / (x - l)));
+    return c;
+}
+__device__ v3 set_lum(v3 c, float l) {
+    float d = l - lum(c);
+    return clip_color(V3(c.x + d, c.y + d, c.z + d));
+}
+__device__ void set_sat_inner(float &cmin, float &cmid, float &cmax, float s) {
+    if (cmax > cmin) {
+        cmid = ((cmid - cmin) * s) / (cmax - cmin);
+        cmax = s;
+    } else {
+        cmid = 0.0f;
+        cmax = 0.0f;
+    }
+    cmin = 0.0f;
+}
+__device__ v3 set_sat(v3 c, float s) {
+    float r = c.x, g = c.y, b = c.z;
+    if (r <= g) {
+        if (g <= b) set_sat_inner(r, g, b, s);
+        else if (r <= b) set_sat_inner(r, b, g, s);
+        else set_sat_inner(b, r, g, s);
+    } else {
+        if (r <= b) set_sat_inner(g, r, b, s);
+        else if (g <= b) set_sat_inner(g, b, r, s);
+        else set_sat_inner(b, g, r, s);
+    }
+    return V3(r, g, b);
+}
+__device__ v3 blend_mix(v3 cb, v3 cs, uint32_t mode) {
+    switch (mode) {
+    case 1: return V3(cb.x * cs.x, cb.y * cs.y, cb.z * cs.z);
+    case 2: return V3(screen1(cb.x, cs.x), screen1(cb.y, cs.y), screen1(cb.z, cs.z));
+    case 3: return V3(hard_light1(cs.x, cb.x), hard_light1(cs.y, cb.y), hard_light1(cs.z, cb.z));
+    case 4: return V3(fminf(cb.x, cs.x), fminf(cb.y, cs.y), fminf(cb.z, cs.z));
+    case 5: return V3(fmaxf(cb.x, cs.x), fmaxf(cb.y, cs.y), fmaxf(cb.z, cs.z));
+    case 6: return V3(color_dodge(cb.x, cs.x), color_dodge(cb.y, cs.y), color_dodge(cb.z, cs.z));
+    case 7: return V3(color_burn(cb.x, cs.x), color_burn(cb.y, cs.y), color_burn(cb.z, cs.z));
+    case 8: return V3(hard_light1(cb.x, cs.x), hard_light1(cb.y, cs.y), hard_light1(cb.z, cs.z));
+    case 9: return V3(soft_light1(cb.x, cs.x), soft_light1(cb.y, cs.y), soft_light1(cb.z, cs.z));
+    case 10: return V3(fabsf(cb.x - cs.x), fabsf(cb.y - cs.y), fabsf(cb.z - cs.z));
+    case 11: return V3(cb.x + cs.x - 2.0f * cb.x * cs.x, cb.y + cs.y - 2.0f * cb.y * cs.y, cb.z + cs.z - 2.0f * cb.z * cs.z);
+    case 12: return set_lum(set_sat(cs, sat3(cb)), lum(cb));
+    case 13: return set_lum(set_sat(cb, sat3(cs)), lum(cb));
+    case 14: return set_lum(cs, lum(cb));
+    case 15: return set_lum(cb, lum(cs));
+    default: return cs;
+    }
+}
+__device__ rgba_t blend_compose(v3 cb, v3 cs, float ab, float as_, uint32_t mode) {
+    float fa = 0.0f, fb = 0.0f;
+    switch (mode) {
+    case 1: fa = 1.0f; fb = 0.0f; break;
+    case 2: fa = 0.0f; fb = 1.0f; break;
+    case 3: fa = 1.0f; fb = 1.0f - as_; break;
+    case 4: fa = 1.0f - ab; fb = 1.0f; break;
+    case 5: fa = ab; fb = 0.0f; break;
+    case 6: fa = 0.0f; fb = as_; break;
+    case 7: fa = 1.0f - ab; fb = 0.0f; break;
+    case 8: fa = 0.0f; fb = 1.0f - as_; break;
+    case 9: fa = ab; fb = 1.0f - as_; break;
+    case 10: fa = 1.0f - ab; fb = as_; break;
+    case 11: fa = 1.0f - ab; fb = 1.0f - as_; break;
+    case 12: fa = 1.0f; fb = 1.0f; break;
+    case 13:
+        return RG(fminf(1.0f, as_ * cs.x + ab * cb.x), fminf(1.0f, as_ * cs.y + ab * cb.y), fminf(1.0f, as_ * cs.z + ab * cb.z),
+                  fminf(1.0f, as_ + ab));
+    default: break;
+    }
+    float as_fa = as_ * fa, ab_fb = ab * fb;
+    return RG(as_fa * cs.x + ab_fb * cb.x, as_fa * cs.y + ab_fb * cb.y, as_fa * cs.z + ab_fb * cb.z, fminf(as_fa + ab_fb, 1.0f));
+}
+__device__ __forceinline__ v3 unpremultiply(rgba_t c) {
+    float inv = 1.0f / fmaxf(c.a, 1e-15f);
+    return V3(c.r * inv, c.g * inv, c.b * inv);
+}
+__device__ __forceinline__ float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
+__device__ rgba_t blend_mix_compose(rgba_t backdrop, rgba_t src, uint32_t mode) {
+    if ((mode & 0x7fffu) == 3u) return over(backdrop, src);
+    v3 cs = unpremultiply(src);
+    v3 cb = unpremultiply(backdrop);
+    v3 mixed = blend_mix(cb, cs, mode >> 8);
+    cs = V3(mixf(cs.x, mixed.x, backdrop.a), mixf(cs.y, mixed.y, backdrop.a), mixf(cs.z, mixed.z, backdrop.a));
+    uint32_t compose_mode = mode & 0xffu;
+    if (compose_mode == 3u) {
+        return RG(mixf(backdrop.r, cs.x, src.a), mixf(backdrop.g, cs.y, src.a), mixf(backdrop.b, cs.z, src.a),
+                  src.a + backdrop.a * (1.0f - src.a));
+    }
+    return blend_compose(cb, cs, backdrop.a, src.a, compose_mode);
+}
+
+// ---------------- gradients / images ----------------
+__device__ __forceinline__ float extend_mode_normalized(float t, uint32_t mode) {
+    if (mode == 0u) return vb_clampf(t, 0.0f, 1.0f);
+    if (mode == 1u) return t - floorf(t);
+    return fabsf(t - 2.0f * rintf(0.5f * t));
+}
+__device__ __forceinline__ float extend_mode(float t, uint32_t mode, float mx) {
+    if (mode == 0u) return vb_clampf(t, 0.0f, mx);
+    return extend_mode_normalized(t / mx, mode) * mx;
+}
+__device__ __forceinline__ rgba_t ramp_load(const FineArgs &A, const VbConfig &cfg, int32_t x, uint32_t index) {
+    if (index >= cfg.n_ramps || x < 0 || x >= GRADIENT_WIDTH) return RG(0, 0, 0, 0);
+    return unpack4x8unorm(__ldg(A.ramps + (size_t)index * GRADIENT_WIDTH + (uint32_t)x));
+}
+__device__ __forceinline__ rgba_t atlas_load(const FineArgs &A, const VbConfig &cfg, float fx, float fy) {
+    int32_t x = vb_f2i_sat(fx), y = vb_f2i_sat(fy);
+    if (x < 0 || y < 0 || (uint32_t)x >= cfg.atlas_w || (uint32_t)y >= cfg.atlas_h) return RG(0, 0, 0, 0);
+    uint32_t p = __ldg(reinterpret_cast<const uint32_t *>(A.atlas) + (size_t)y * cfg.atlas_w + (uint32_t)x);
+    return unpack4x8unorm(p);
+}
+__device__ __forceinline__ rgba_t maybe_premul(rgba_t p, uint32_t alpha_type) {
+    if (alpha_type == 1u) return p;
+    return RG(p.r * p.a, p.g * p.a, p.b * p.a, p.a);
+}
+__device__ __forceinline__ rgba_t pixel_format(rgba_t p, uint32_t format) { return format == 1u ? RG(p.b, p.g, p.r, p.a) : p; }
+__device__ float erf7(float x) {
+    float y = vb_clampf(x * 1.1283791671f, -100.0f, 100.0f);
+    float yy = y * y;
+    float z = y + (0.24295f + (0.03395f + 0.0104f * yy) * yy) * (y * yy);
+    return z / sqrtf(1.0f + z * z);
+}
+__device__ __forceinline__ float hypot_w(float a, float b) { return sqrtf(a * a + b * b); }
+__device__ __forceinline__ float single_weight(float t, float a, float b, float c, float d) { return t * (t * (t * d + c) + b) + a; }
+__device__ void cubic_weights(float fr, float (&w)[4]) {
+    w[0] = single_weight(fr, (1.0f / 6.0f) / 3.0f, -(3.0f / 6.0f) / 3.0f - 1.0f / 3.0f, (3.0f / 6.0f) / 3.0f + 2.0f * 1.0f / 3.0f,
+                         -(1.0f / 6.0f) / 3.0f - 1.0f / 3.0f);
+    w[1] = single_weight(fr, 1.0f - (2.0f / 6.0f) / 3.0f, 0.0f, -3.0f + (12.0f / 6.0f) / 3.0f + 1.0f / 3.0f,
+                         2.0f - (9.0f / 6.0f) / 3.0f - 1.0f / 3.0f);
+    w[2] = single_weight(fr, (1.0f / 6.0f) / 3.0f, (3.0f / 6.0f) / 3.0f + 1.0f / 3.0f, 3.0f - (15.0f / 6.0f) / 3.0f - 2.0f * 1.0f / 3.0f,
+                         -2.0f + (9.0f / 6.0f) / 3.0f + 1.0f / 3.0f);
+    w[3] = single_weight(fr, 0.0f, 0.0f, -1.0f / 3.0f, (1.0f / 6.0f) / 3.0f + 1.0f / 3.0f);
+}
+__device__ rgba_t bicubic_sample(const FineArgs &A, const VbConfig &cfg, float cx, float cy, float ox, float oy, float mx, float my,
+                                 uint32_t alpha_type) {
+    float fxx = (cx + 0.5f) - floorf(cx + 0.5f), fyy = (cy + 0.5f) - floorf(cy + 0.5f);
+    float wx[4], wy[4];
+    cubic_weights(fxx, wx);
+    cubic_weights(fyy, wy);
+    const float offs[4] = {-1.5f, -0.5f, 0.5f, 1.5f};
+    rgba_t r = RG(0, 0, 0, 0);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        rgba_t acc = RG(0, 0, 0, 0);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            rgba_t s = maybe_premul(atlas_load(A, cfg, vb_clampf(cx + offs[i], ox, mx), vb_clampf(cy + offs[j], oy, my)), alpha_type);
+            if (i == 0) acc = rg_scale(s, wx[0]);
+            else acc = RG(acc.r + wx[i] * s.r, acc.g + wx[i] * s.g, acc.b + wx[i] * s.b, acc.a + wx[i] * s.a);
+        }
+        if (j == 0) r = rg_scale(acc, wy[0]);
+        else r = RG(r.r + wy[j] * acc.r, r.g + wy[j] * acc.g, r.b + wy[j] * acc.b, r.a + wy[j] * acc.a);
+    }
+    float a = vb_clampf(r.a, 0.0f, 1.0f);
+    return RG(vb_clampf(r.r, 0.0f, a), vb_clampf(r.g, 0.0f, a), vb_clampf(r.b, 0.0f, a), a);
+}
+
+// ---------------- the interpreter: fine.wgsl:1064-1398 ----------------
+template <int AA>
+__global__ void __launch_bounds__(FI_THREADS)
+k_fine(VbConfig cfg, FineArgs A) {
+    __shared__ MsShared S; // only touched by the MSAA variants
+    const uint32_t *__restrict__ ptcl = A.ptcl;
+    const uint32_t *__restrict__ info = A.info;
+    if (__ldg(ptcl) == ~0u) return; // upstream failure flag (path_tiling_setup.wgsl:25)
+    const uint32_t tile_x = blockIdx.x, tile_y = blockIdx.y + cfg.win_ty0;
+    const uint32_t lx = threadIdx.x & 3u, ly = threadIdx.x >> 2;
+    const uint32_t tile_ix = tile_y * cfg.width_in_tiles + tile_x;
+    const uint32_t gx = tile_x * 16u + lx * PIXELS_PER_THREAD, gy = tile_y * 16u + ly;
+    const float xyx = (float)gx, xyy = (float)gy;
+    const float local_x = (float)(lx * PIXELS_PER_THREAD), local_y = (float)ly;
+    rgba_t rgba[PIXELS_PER_THREAD];
+    float area[PIXELS_PER_THREAD];
+    const rgba_t base = unpack4x8unorm(cfg.base_color);
+#pragma unroll
+    for (int i = 0; i < PIXELS_PER_THREAD; i++) { rgba[i] = base; area[i] = 0.0f; }
+    uint32_t blend_stack[VB_BLEND_STACK_SPLIT][PIXELS_PER_THREAD];
+    uint32_t clip_depth = 0u;
+    uint32_t cmd_ix = tile_ix * VB_PTCL_INITIAL_ALLOC;
+    const uint32_t blend_offset = __ldg(ptcl + cmd_ix);
+    cmd_ix += 1u;
+    for (;;) {
+        const uint32_t tag = __ldg(ptcl + cmd_ix);
+        if (tag == VB_CMD_END) break;
+        switch (tag) {
+        case VB_CMD_FILL: {
+            const uint32_t sr = __ldg(ptcl + cmd_ix + 1), sd = __ldg(ptcl + cmd_ix + 2);
+            const int32_t bd = (int32_t)__ldg(ptcl + cmd_ix + 3);
+            if (AA == 0) fill_path_area(A, sr, sd, bd, local_x, local_y, area);
+            else fill_path_ms<AA == 0 ? 1 : AA>(A, S, sr, sd, bd, lx, ly, area);
+            cmd_ix += 4u;
+            break;
+        }
+        case VB_CMD_SOLID:
+#pragma unroll
+            for (int i = 0; i < PIXELS_PER_THREAD; i++) area[i] = 1.0f;
+            cmd_ix += 1u;
+            break;
+        case VB_CMD_COLOR: {
+            const rgba_t fg = unpack4x8unorm(__ldg(ptcl + cmd_ix + 1));
+#pragma unroll
+            for (int i = 0; i < PIXELS_PER_THREAD; i++) rgba[i] = over(rgba[i], rg_scale(fg, area[i]));
+            cmd_ix += 2u;
+            break;
+        }
+        case VB_CMD_BEGIN_CLIP: {
+            if (clip_depth < VB_BLEND_STACK_SPLIT) {
+#pragma unroll
+                for (int i = 0; i < PIXELS_PER_THREAD; i++) {
+                    // static indexing keeps blend_stack in registers
+#pragma unroll
+                    for (uint32_t d = 0; d < VB_BLEND_STACK_SPLIT; d++)
+                        if (d == clip_depth) blend_stack[d][i] = pack4x8unorm(rgba[i]);
+                    rgba[i] = RG(0, 0, 0, 0);
+                }
+            } else {
+                const uint32_t base_ix = blend_offset + (clip_depth - VB_BLEND_STACK_SPLIT) * 256u + lx * PIXELS_PER_THREAD + ly * 16u;
+#pragma unroll
+                for (int i = 0; i < PIXELS_PER_THREAD; i++) {
+                    if (base_ix + i < cfg.blend_size) A.blend_spill[base_ix + i] = pack4x8unorm(rgba[i]);
+                    rgba[i] = RG(0, 0, 0, 0);
+                }
+            }
+            clip_depth += 1u;
+            cmd_ix += 1u;
+            break;
+        }
+        case VB_CMD_END_CLIP: {
+            const uint32_t blend = __ldg(ptcl + cmd_ix + 1);
+            const float alpha = __uint_as_float(__ldg(ptcl + cmd_ix + 2));
+            clip_depth -= 1u;
+#pragma unroll
+            for (int i = 0; i < PIXELS_PER_THREAD; i++) {
+                uint32_t bg_rgba = 0u;
+                if (clip_depth < VB_BLEND_STACK_SPLIT) {
+#pragma unroll
+                    for (uint32_t d = 0; d < VB_BLEND_STACK_SPLIT; d++)
+                        if (d == clip_depth) bg_rgba = blend_stack[d][i];
+                } else {
+                    const uint32_t ix = blend_offset + (clip_depth - VB_BLEND_STACK_SPLIT) * 256u + lx * PIXELS_PER_THREAD + ly * 16u + i;
+                    bg_rgba = ix < cfg.blend_size ? A.blend_spill[ix] : 0u;
+                }
+                const rgba_t bg = unpack4x8unorm(bg_rgba);
+                const rgba_t fg = rg_scale(rg_scale(rgba[i], area[i]), alpha);
+                if (blend == 0x10000u) {
+                    if (area[i] == 0.0f) { rgba[i] = bg; continue; }
+                    const float luminance = vb_clampf(svg_lum(unpremultiply(fg)) * fg.a, 0.0f, 1.0f);
+                    rgba[i] = rg_scale(bg, luminance);
+                } else {
+                    rgba[i] = blend_mix_compose(bg, fg, blend);
+                }
+            }
+            cmd_ix += 3u;
+            break;
+        }
+        case VB_CMD_JUMP:
+            cmd_ix = __ldg(ptcl + cmd_ix + 1);
+            break;
+        case VB_CMD_BLUR_RECT: {
+            const uint32_t io = __ldg(ptcl + cmd_ix + 1);
+            const rgba_t blur_rgba = unpack4x8unorm(__ldg(ptcl + cmd_ix + 2));
+            const float m0 = __uint_as_float(info[io]), m1 = __uint_as_float(info[io + 1]), m2 = __uint_as_float(info[io + 2]),
+                        m3 = __uint_as_float(info[io + 3]);
+            const float tx = __uint_as_float(info[io + 4]), ty = __uint_as_float(info[io + 5]);
+            const float bw = __uint_as_float(info[io + 6]), bh = __uint_as_float(info[io + 7]), bradius = __uint_as_float(info[io + 8]);
+            const float std_dev = fmaxf(__uint_as_float(info[io + 9]), 1e-5f);
+            const float inv_std_dev = 1.0f / std_dev;
+            const float min_edge = fminf(bw, bh);
+            const float radius_max = 0.5f * min_edge;
+            const float r0 = fminf(hypot_w(bradius, std_dev * 1.15f), radius_max);
+            const float r1 = fminf(hypot_w(bradius, std_dev * 2.0f), radius_max);
+            const float exponent = 2.0f * r1 / r0;
+            const float inv_exponent = 1.0f / exponent;
+            const float ew = 0.5f * inv_std_dev * bw, eh = 0.5f * inv_std_dev * bh;
+            const float delta = 1.25f * std_dev * (vb_expf(-(ew * ew)) - vb_expf(-(eh * eh)));
+            const float width = bw + fminf(delta, 0.0f);
+            const float height = bh - fmaxf(delta, 0.0f);
+            const float scale = 0.5f * erf7(inv_std_dev * 0.5f * (fmaxf(width, height) - 0.5f * bradius));
+#pragma unroll
+            for (int i = 0; i < PIXELS_PER_THREAD; i++) {
+                const float px = xyx + (float)i, py = xyy;
+                const float x = (m0 * px + m2 * py) + tx;
+                const float y = (m1 * px + m3 * py) + ty;
+                const float y0 = fabsf(y) - (height * 0.5f - r1);
+                const float y1 = fmaxf(y0, 0.0f);
+                const float x0 = fabsf(x) - (width * 0.5f - r1);
+                const float x1 = fmaxf(x0, 0.0f);
+                const float d_pos = vb_powf_pos(vb_powf_pos(x1, exponent) + vb_powf_pos(y1, exponent), inv_exponent);
+                const float d_neg = fminf(fmaxf(x0, y0), 0.0f);
+                const float d = d_pos + d_neg - r1;
+                const float alpha = scale * (erf7(inv_std_dev * (min_edge + d)) - erf7(inv_std_dev * d));
+                rgba[i] = over(rgba[i], rg_scale(rg_scale(blur_rgba, alpha), area[i]));
+            }
+            cmd_ix += 3u;
+            break;
+        }
+        case VB_CMD_LIN_GRAD: {
+            const uint32_t index_mode = __ldg(ptcl + cmd_ix + 1), io = __ldg(ptcl + cmd_ix + 2);
+            const uint32_t index = index_mode >> 2, ext = index_mode & 3u;
+            const float line_x = __uint_as_float(info[io]), line_y = __uint_as_float(info[io + 1]), line_c = __uint_as_float(info[io + 2]);
+            const float d = (line_x * xyx + line_y * xyy) + line_c;
+#pragma unroll
+            for (int i = 0; i < PIXELS_PER_THREAD; i++) {
+                const float my_d = d + line_x * (float)i;
+                const int32_t x = vb_f2i_sat(rintf(extend_mode_normalized(my_d, ext) * (float)(GRADIENT_WIDTH - 1)));
+                rgba[i] = over(rgba[i], rg_scale(ramp_load(A, cfg, x, index), area[i]));
+            }
+            cmd_ix += 3u;
+            break;
+        }
+        case VB_CMD_RAD_GRAD: {
+            const uint32_t index_mode = __ldg(ptcl + cmd_ix + 1), io = __ldg(ptcl + cmd_ix + 2);
+            const uint32_t index = index_mode >> 2, ext = index_mode & 3u;
+            const float m0 = __uint_as_float(info[io]), m1 = __uint_as_float(info[io + 1]), m2 = __uint_as_float(info[io + 2]),
+                        m3 = __uint_as_float(info[io + 3]);
+            const float tx = __uint_as_float(info[io + 4]), ty = __uint_as_float(info[io + 5]);
+            const float focal_x = __uint_as_float(info[io + 6]), radius = __uint_as_float(info[io + 7]);
+            const uint32_t flags_kind = info[io + 8];
+            const uint32_t flags = flags_kind >> 3, kind = flags_kind & 7u;
+            const bool is_strip = kind == 2u, is_circular = kind == 1u, is_focal_on_circle = kind == 3u;
+            const bool is_swapped = (flags & 1u) != 0u;
+            const float r1_recip = is_circular ? 0.0f : 1.0f / radius;
+            const float less_scale = (is_swapped || (1.0f - focal_x) < 0.0f) ? -1.0f : 1.0f;
+            const float t_sign = vb_signf(1.0f - focal_x);
+#pragma unroll
+            for (int i = 0; i < PIXELS_PER_THREAD; i++) {
+                const float px = xyx + (float)i, py = xyy;
+                const float x = (m0 * px + m2 * py) + tx;
+                const float y = (m1 * px + m3 * py) + ty;
+                const float xx = x * x, yy = y * y;
+                float t = 0.0f;
+                bool is_valid = true;
+                if (is_strip) {
+                    const float a = radius - yy;
+                    t = sqrtf(a) + x;
+                    is_valid = a >= 0.0f;
+                } else if (is_focal_on_circle) {
+                    t = (xx + yy) / x;
+                    is_valid = t >= 0.0f && x != 0.0f;
+                } else if (radius > 1.0f) {
+                    t = sqrtf(xx + yy) - x * r1_recip;
+                } else {
+                    const float a = xx - yy;
+                    t = less_scale * sqrtf(a) - x * r1_recip;
+                    is_valid = a >= 0.0f && t >= 0.0f;
+                }
+                if (is_valid) {
+                    t = extend_mode_normalized(focal_x + t_sign * t, ext);
+                    if (is_swapped) t = 1.0f - t;
+                    const int32_t rx = vb_f2i_sat(rintf(t * (float)(GRADIENT_WIDTH - 1)));
+                    rgba[i] = over(rgba[i], rg_scale(ramp_load(A, cfg, rx, index), area[i]));
+                }
+            }
+            cmd_ix += 3u;
+            break;
+        }
+        case VB_CMD_SWEEP_GRAD: {
+            const uint32_t index_mode = __ldg(ptcl + cmd_ix + 1), io = __ldg(ptcl + cmd_ix + 2);
+            const uint32_t index = index_mode >> 2, ext = index_mode & 3u;
+            const float m0 = __uint_as_float(info[io]), m1 = __uint_as_float(info[io + 1]), m2 = __uint_as_float(info[io + 2]),
+                        m3 = __uint_as_float(info[io + 3]);
+            const float tx = __uint_as_float(info[io + 4]), ty = __uint_as_float(info[io + 5]);
+            const float t0 = __uint_as_float(info[io + 6]), t1 = __uint_as_float(info[io + 7]);
+            const float scale = 1.0f / (t1 - t0);
+#pragma unroll
+            for (int i = 0; i < PIXELS_PER_THREAD; i++) {
+                const float px = xyx + (float)i, py = xyy;
+                const float x = (m0 * px + m2 * py) + tx;
+                const float y = (m1 * px + m3 * py) + ty;
+                const float xabs = fabsf(x), yabs = fabsf(y);
+                const float slope = fminf(xabs, yabs) / fmaxf(xabs, yabs);
+                const float s = slope * slope;
+                float phi = slope * (0.15912117063999176025390625f +
+                                     s * (-5.185396969318389892578125e-2f +
+                                          s * (2.476101927459239959716796875e-2f + s * (-7.0547382347285747528076171875e-3f))));
+                if (xabs < yabs) phi = 1.0f / 4.0f - phi;
+                if (x < 0.0f) phi = 1.0f / 2.0f - phi;
+                if (y < 0.0f) phi = 1.0f - phi;
+                if (phi != phi) phi = 0.0f;
+                phi = (phi - t0) * scale;
+                const float t = extend_mode_normalized(phi, ext);
+                const int32_t rx = vb_f2i_sat(rintf(t * (float)(GRADIENT_WIDTH - 1)));
+                rgba[i] = over(rgba[i], rg_scale(ramp_load(A, cfg, rx, index), area[i]));
+            }
+            cmd_ix += 3u;
+            break;
+        }
+        case VB_CMD_IMAGE: {
+            const uint32_t io = __ldg(ptcl + cmd_ix + 1);
+            const float m0 = __uint_as_float(info[io]), m1 = __uint_as_float(info[io + 1]), m2 = __uint_as_float(info[io + 2]),
+                        m3 = __uint_as_float(info[io + 3]);
+            const float tx = __uint_as_float(info[io + 4]), ty = __uint_as_float(info[io + 5]);
+            const uint32_t xy = info[io + 6], wh = info[io + 7], sa = info[io + 8];
+            const float alpha = (float)(sa & 0xFFu) / 255.0f;
+            const uint32_t format = sa >> 15, alpha_type = (sa >> 14) & 1u, quality = (sa >> 12) & 3u;
+            const uint32_t x_ext = (sa >> 10) & 3u, y_ext = (sa >> 8) & 3u;
+            const float ox = (float)(xy >> 16), oy = (float)(xy & 0xffffu);
+            const float ew = (float)(wh >> 16), eh = (float)(wh & 0xffffu);
+            const float mx = ox + ew - 1.0f, my = oy + eh - 1.0f;
+#pragma unroll 1
+            for (int i = 0; i < PIXELS_PER_THREAD; i++) {
+                if (area[i] == 0.0f) continue;
+                const float px = (xyx + (float)i) + 0.5f, py = xyy + 0.5f;
+                float u = (m0 * px + m2 * py) + tx;
+                float v = (m1 * px + m3 * py) + ty;
+                u = extend_mode(u, x_ext, ew);
+                v = extend_mode(v, y_ext, eh);
+                rgba_t fg;
+                if (quality == 0u) {
+                    u = u + ox; v = v + oy;
+                    fg = maybe_premul(atlas_load(A, cfg, vb_clampf(u, ox, mx), vb_clampf(v, oy, my)), alpha_type);
+                } else if (quality == 2u) {
+                    u = u + ox; v = v + oy;
+                    fg = bicubic_sample(A, cfg, u, v, ox, oy, mx, my, alpha_type);
+                } else {
+                    u = (u + ox) - 0.5f; v = (v + oy) - 0.5f;
+                    const float uc = vb_clampf(u, ox, mx), vc = vb_clampf(v, oy, my);
+                    const float qx0 = floorf(uc), qy0 = floorf(vc), qx1 = ceilf(uc), qy1 = ceilf(vc);
+                    const float fu = u - floorf(u), fv = v - floorf(v);
+                    const rgba_t a = maybe_premul(atlas_load(A, cfg, qx0, qy0), alpha_type);
+                    const rgba_t b = maybe_premul(atlas_load(A, cfg, qx0, qy1), alpha_type);
+                    const rgba_t c = maybe_premul(atlas_load(A, cfg, qx1, qy0), alpha_type);
+                    const rgba_t d = maybe_premul(atlas_load(A, cfg, qx1, qy1), alpha_type);
+                    const rgba_t ab = RG(mixf(a.r, b.r, fv), mixf(a.g, b.g, fv), mixf(a.b, b.b, fv), mixf(a.a, b.a, fv));
+                    const rgba_t cd = RG(mixf(c.r, d.r, fv), mixf(c.g, d.g, fv), mixf(c.b, d.b, fv), mixf(c.a, d.a, fv));
+                    fg = RG(mixf(ab.r, cd.r, fu), mixf(ab.g, cd.g, fu), mixf(ab.b, cd.b, fu), mixf(ab.a, cd.a, fu));
+                }
+                const rgba_t fg_i = pixel_format(rg_scale(rg_scale(fg, area[i]), alpha), format);
+                rgba[i] = over(rgba[i], fg_i);
+            }
+            cmd_ix += 2u;
+            break;
+        }
+        default:
+            cmd_ix += 1u;
+            break;
+        }
+    }
+    if (gy < cfg.target_height && gy >= cfg.out_row0) {
+        uint32_t px[PIXELS_PER_THREAD];
+#pragma unroll
+        for (int i = 0; i < PIXELS_PER_THREAD; i++) {
+            const rgba_t fg = rgba[i];
+            const float a_inv = 1.0f / fmaxf(fg.a, 1e-6f);
+            px[i] = unorm8(fg.r * a_inv) | (unorm8(fg.g * a_inv) << 8) | (unorm8(fg.b * a_inv) << 16) | (unorm8(fg.a) << 24);
+        }
+        uint32_t *row = A.out + (size_t)(gy - cfg.out_row0) * cfg.out_pitch_px;
+        if (gx + 3u < cfg.target_width && (cfg.out_pitch_px & 3u) == 0u && ((uintptr_t)A.out & 15u) == 0u) {
+            *reinterpret_cast<uint4 *>(row + gx) = make_uint4(px[0], px[1], px[2], px[3]); // 128-bit row store
+        } else {
+#pragma unroll
+            for (int i = 0; i < PIXELS_PER_THREAD; i++)
+                if (gx + i < cfg.target_width) row[gx + i] = px[i];
+        }
+    }
+}
+
+extern "C" void vb_launch_fine(const VbConfig *cfg, int aa, const VbSegment *segments, const uint32_t *ptcl, const uint32_t *info,
+                               uint32_t *blend_spill, uint32_t *out, const uint32_t *ramps, const uint8_t *atlas,
+                               const uint32_t *mask_lut8, const uint32_t *mask_lut16, cudaStream_t st) {
+    uint32_t rows = cfg->win_ty1 - cfg->win_ty0;
+    if (cfg->width_in_tiles == 0 || rows == 0) return;
+    dim3 grid(cfg->width_in_tiles, rows);
+    FineArgs A;
+    A.segments = segments; A.ptcl = ptcl; A.info = info; A.blend_spill = blend_spill; A.out = out; A.ramps = ramps; A.atlas = atlas;
+    A.mask_lut = aa == 2 ? mask_lut16 : mask_lut8;
+    if (aa == 0) k_fine<0><<<grid, FI_THREADS, 0, st>>>(*cfg, A);
+    else if (aa == 1) k_fine<1><<<grid, FI_THREADS, 0, st>>>(*cfg, A);
+    else k_fine<2><<<grid, FI_THREADS, 0, st>>>(*cfg, A);
+}

@@ -1,0 +1,123 @@
+// k_tile.cu -- tile_alloc and backdrop.
+//
+// Reference: vello_shaders/shader/tile_alloc.wgsl:36-123 (CPU twin cpu/tile_alloc.rs),
+// backdrop_dyn.wgsl:29-86 (CPU twin cpu/backdrop.rs).
+//
+// B200 design: tile_alloc's per-workgroup atomicAdd(bump.tile) becomes a decoupled look-back scan,
+// so `Path.tiles` offsets are deterministic and equal to the serial CPU shader's -- `tiles[]` can be
+// compared byte for byte. Each CTA zeroes the tile range it allocated with coalesced 8 B stores.
+// Extension: tile rows are clamped to the stripe window [win_ty0, win_ty1).
+#include "vb_device.cuh"
+
+#define TA_THREADS 256
+
+__global__ void __launch_bounds__(TA_THREADS)
+k_tile_alloc(VbConfig cfg, const uint32_t *__restrict__ scene, const VbBbox4 *__restrict__ draw_bboxes, VbBump *bump, VbPath *paths,
+             VbTile *tiles, uint32_t *lb_mem, uint32_t n_parts) {
+    __shared__ uint32_t sh_ticket;
+    __shared__ uint32_t sh_scan[TA_THREADS / 32 + 2];
+    __shared__ uint32_t sh_base;
+    if (bump->failed & (VB_STAGE_BINNING | VB_STAGE_FLATTEN)) return; // uniform: set only by earlier kernels
+    VbLookback lb = vb_lookback_view(lb_mem, n_parts, 1);
+    const uint32_t part = vb_take_ticket(lb, &sh_ticket);
+    const uint32_t drawobj_ix = part * TA_THREADS + threadIdx.x;
+    const float SX = 1.0f / 16.0f, SY = 1.0f / 16.0f;
+    uint32_t drawtag = VB_DRAWTAG_NOP;
+    if (drawobj_ix < cfg.layout.n_draw_objects) drawtag = vb_scene(scene, cfg, cfg.layout.draw_tag_base + drawobj_ix);
+    int32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    if (drawtag != VB_DRAWTAG_NOP && drawtag != VB_DRAWTAG_END_CLIP) {
+        VbBbox4 b = draw_bboxes[drawobj_ix];
+        if (b.x0 < b.x1 && b.y0 < b.y1) {
+            x0 = vb_f2i_sat(floorf(b.x0 * SX));
+            y0 = vb_f2i_sat(floorf(b.y0 * SY));
+            x1 = vb_f2i_sat(ceilf(b.x1 * SX));
+            y1 = vb_f2i_sat(ceilf(b.y1 * SY));
+        }
+    }
+    const uint32_t ux0 = (uint32_t)vb_clampi(x0, 0, (int32_t)cfg.width_in_tiles);
+    const uint32_t ux1 = (uint32_t)vb_clampi(x1, 0, (int32_t)cfg.width_in_tiles);
+    const uint32_t uy0 = (uint32_t)vb_clampi(y0, (int32_t)cfg.win_ty0, (int32_t)cfg.win_ty1);
+    const uint32_t uy1 = (uint32_t)vb_clampi(y1, (int32_t)cfg.win_ty0, (int32_t)cfg.win_ty1);
+    const uint32_t tile_count = (ux1 - ux0) * (uy1 - uy0);
+    uint32_t total;
+    const uint32_t local_off = vb_block_excl_scan(tile_count, sh_scan, &total);
+    if (threadIdx.x < 32) {
+        uint32_t agg[1] = {total}, excl[1];
+        vb_lookback<1>(lb, part, agg, excl);
+        if (threadIdx.x == 0) {
+            sh_base = excl[0];
+            if (part == n_parts - 1) {
+                bump->tile = excl[0] + total;
+                if (excl[0] + total > cfg.tiles_size) atomicOr(&bump->failed, VB_STAGE_TILE_ALLOC);
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t base = sh_base;
+    if (drawobj_ix < cfg.layout.n_draw_objects) {
+        VbPath p;
+        p.bbox[0] = ux0; p.bbox[1] = uy0; p.bbox[2] = ux1; p.bbox[3] = uy1;
+        p.tiles = base + local_off;
+        p._pad[0] = p._pad[1] = p._pad[2] = 0;
+        paths[drawobj_ix] = p;
+    }
+    const uint32_t end = min(base + total, cfg.tiles_size);
+    uint2 *t2 = reinterpret_cast<uint2 *>(tiles);
+    for (uint32_t i = base + threadIdx.x; i < end; i += TA_THREADS) t2[i] = make_uint2(0u, 0u);
+}
+
+// backdrop: per (path, tile row) inclusive prefix sum along x. One thread per row, rows found by
+// binary search over the CTA's row-count prefix (same balancing as backdrop_dyn.wgsl:52-84).
+#define BD_THREADS 256
+__global__ void __launch_bounds__(BD_THREADS)
+k_backdrop(VbConfig cfg, const VbBump *__restrict__ bump, const VbPath *__restrict__ paths, VbTile *tiles) {
+    __shared__ uint32_t sh_row_width[BD_THREADS];
+    __shared__ uint32_t sh_row_count[BD_THREADS];
+    __shared__ uint32_t sh_offset[BD_THREADS];
+    __shared__ uint32_t sh_scan[BD_THREADS / 32 + 2];
+    if (bump->failed != 0u) return;
+    const uint32_t drawobj_ix = blockIdx.x * BD_THREADS + threadIdx.x;
+    uint32_t row_count = 0u;
+    sh_row_width[threadIdx.x] = 0u;
+    if (drawobj_ix < cfg.layout.n_draw_objects) {
+        VbPath p = paths[drawobj_ix];
+        sh_row_width[threadIdx.x] = p.bbox[2] - p.bbox[0];
+        row_count = p.bbox[3] - p.bbox[1];
+        sh_offset[threadIdx.x] = p.tiles;
+    }
+    uint32_t total_rows;
+    uint32_t ex = vb_block_excl_scan(row_count, sh_scan, &total_rows);
+    sh_row_count[threadIdx.x] = ex + row_count; // inclusive
+    __syncthreads();
+    for (uint32_t row = threadIdx.x; row < total_rows; row += BD_THREADS) {
+        uint32_t el_ix = 0u;
+#pragma unroll
+        for (uint32_t i = 0u; i < 8u; i++) {
+            uint32_t probe = el_ix + (128u >> i);
+            if (row >= sh_row_count[probe - 1u]) el_ix = probe;
+        }
+        uint32_t width = sh_row_width[el_ix];
+        if (width > 0u) {
+            uint32_t seq_ix = row - (el_ix > 0u ? sh_row_count[el_ix - 1u] : 0u);
+            uint32_t tile_ix = sh_offset[el_ix] + seq_ix * width;
+            int32_t sum = tiles[tile_ix].backdrop;
+            for (uint32_t x = 1u; x < width; x++) {
+                tile_ix += 1u;
+                sum += tiles[tile_ix].backdrop;
+                tiles[tile_ix].backdrop = sum;
+            }
+        }
+    }
+}
+
+extern "C" void vb_launch_tile_alloc(const VbConfig *cfg, const uint32_t *scene, const VbBbox4 *draw_bboxes, VbBump *bump,
+                                     VbPath *paths, VbTile *tiles, uint32_t *lb_mem, uint32_t n_parts, cudaStream_t st) {
+    if (n_parts == 0) return;
+    k_tile_alloc<<<n_parts, TA_THREADS, 0, st>>>(*cfg, scene, draw_bboxes, bump, paths, tiles, lb_mem, n_parts);
+}
+extern "C" uint32_t vb_tile_alloc_parts(uint32_t n_draw) { return (n_draw + TA_THREADS - 1) / TA_THREADS; }
+extern "C" void vb_launch_backdrop(const VbConfig *cfg, const VbBump *bump, const VbPath *paths, VbTile *tiles, cudaStream_t st) {
+    uint32_t n = cfg->layout.n_draw_objects;
+    if (n == 0) return;
+    k_backdrop<<<(n + BD_THREADS - 1) / BD_THREADS, BD_THREADS, 0, st>>>(*cfg, bump, paths, tiles);
+}

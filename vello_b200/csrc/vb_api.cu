@@ -1,0 +1,635 @@
+// vb_api.cu -- host orchestration + the extern "C" ABI declared in include/vello_b200.h.
+//
+// Replaces vello/src/render.rs (graph: stage order, bindings, buffer lifetimes) and
+// vello/src/wgpu_engine.rs (engine) with a CUDA-stream pipeline. Unlike the reference
+// (config.rs:398-408 fixed `1 << 21` arenas; lib.rs:762 "TODO: re-run on overflow") every
+// bump-allocated arena is sized from the scene and grown + re-run when a frame overflows.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/vello_b200.h"
+#include "vb_device.cuh"
+#include "vb_types.h"
+
+// ---- stage launchers (k_*.cu) --------------------------------------------------------------
+extern "C" {
+void vb_launch_pathtag(const VbConfig *, const uint32_t *, VbTagMonoid *, uint32_t *, uint32_t, cudaStream_t);
+uint32_t vb_pathtag_parts(uint32_t);
+void vb_launch_flatten(const VbConfig *, const uint32_t *, const VbTagMonoid *, VbPathBbox *, VbBump *, VbLineSoup *, uint32_t *, uint32_t,
+                       cudaStream_t);
+uint32_t vb_flatten_parts(uint32_t);
+void vb_launch_draw(const VbConfig *, const uint32_t *, const VbPathBbox *, VbDrawMonoid *, uint32_t *, VbClipInp *, uint32_t *, uint32_t,
+                    cudaStream_t);
+uint32_t vb_draw_parts(uint32_t);
+void vb_launch_clip(uint32_t, const VbClipInp *, const VbPathBbox *, VbDrawMonoid *, VbBbox4 *, int32_t *, cudaStream_t);
+size_t vb_clip_scratch_words(uint32_t);
+void vb_launch_binning(const VbConfig *, const VbDrawMonoid *, const VbPathBbox *, const VbBbox4 *, VbBbox4 *, VbBump *, uint32_t *,
+                       VbBinHeader *, cudaStream_t);
+void vb_launch_tile_alloc(const VbConfig *, const uint32_t *, const VbBbox4 *, VbBump *, VbPath *, VbTile *, uint32_t *, uint32_t,
+                          cudaStream_t);
+uint32_t vb_tile_alloc_parts(uint32_t);
+void vb_launch_backdrop(const VbConfig *, const VbBump *, const VbPath *, VbTile *, cudaStream_t);
+void vb_launch_path_count(const VbConfig *, VbBump *, const VbLineSoup *, const VbPath *, VbTile *, VbSegmentCount *, uint32_t,
+                          cudaStream_t);
+void vb_launch_coarse(const VbConfig *, const uint32_t *, const VbDrawMonoid *, const VbBinHeader *, const uint32_t *, const VbPath *,
+                      VbTile *, VbBump *, uint32_t *, cudaStream_t);
+void vb_launch_path_tiling(const VbConfig *, const VbBump *, const VbSegmentCount *, const VbLineSoup *, const VbPath *, const VbTile *,
+                           VbSegment *, uint32_t, cudaStream_t);
+void vb_launch_fine(const VbConfig *, int, const VbSegment *, const uint32_t *, const uint32_t *, uint32_t *, uint32_t *, const uint32_t *,
+                    const uint8_t *, const uint32_t *, const uint32_t *, cudaStream_t);
+}
+
+// path_tiling_setup.wgsl:21-26: a failed frame is flagged to fine through ptcl[0]
+__global__ void k_flag_failure(const VbBump *bump, uint32_t *ptcl) {
+    if (bump->failed != 0u) ptcl[0] = ~0u;
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0; // bytes
+};
+
+struct vb_renderer {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool timing = false;
+    uint32_t max_retries = 6;
+    std::string err;
+    int sm_count = 148;
+
+    // scene
+    bool have_scene = false;
+    VbLayout layout{};
+    size_t scene_words = 0;
+    uint32_t n_ramps = 0, atlas_w = 0, atlas_h = 0;
+    DevBuf scene, ramps, atlas, mask8, mask16;
+
+    // fixed-size intermediates
+    DevBuf tag_monoids, path_bboxes, draw_monoids, info_bin_data, clip_inp, clip_bboxes, clip_scratch, draw_bboxes, bin_headers, paths,
+        ctl, target;
+    // bump arenas (capacities in elements live in cap_*)
+    DevBuf lines, tiles, seg_counts, segments, ptcl, blend_spill;
+    uint32_t cap_lines = 0, cap_binning = 0, cap_tiles = 0, cap_seg_counts = 0, cap_segments = 0, cap_blend = 0, cap_ptcl = 0;
+
+    // per-frame
+    VbConfig cfg{};
+    vb_params params{};
+    void *out_dev = nullptr;
+    VbBump *h_bump = nullptr; // pinned
+    uint32_t retries = 0, launches = 0;
+    size_t ctl_words = 0;
+    uint32_t parts_pathtag = 0, parts_flatten = 0, parts_draw = 0, parts_tile = 0;
+    size_t off_lb_pathtag = 0, off_lb_flatten = 0, off_lb_draw = 0, off_lb_tile = 0;
+    cudaEvent_t ev[VB_N_STAGE_IDS + 1]{};
+    bool ev_ok = false;
+    bool frame_pending = false;
+};
+
+#define CK(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            r->err = std::string(#call) + ": " + cudaGetErrorString(e_);                          \
+            return VB_E_CUDA;                                                                     \
+        }                                                                                         \
+    } while (0)
+
+static int ensure(vb_renderer *r, DevBuf &b, size_t bytes) {
+    if (bytes < 256) bytes = 256;
+    if (b.cap >= bytes) return VB_OK;
+    if (b.p) CK(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = (bytes + 255) & ~(size_t)255;
+    CK(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return VB_OK;
+}
+static size_t arena_bytes(const vb_renderer *r) {
+    const DevBuf *all[] = {&r->scene, &r->ramps, &r->atlas, &r->mask8, &r->mask16, &r->tag_monoids, &r->path_bboxes, &r->draw_monoids,
+                           &r->info_bin_data, &r->clip_inp, &r->clip_bboxes, &r->clip_scratch, &r->draw_bboxes, &r->bin_headers, &r->paths,
+                           &r->ctl, &r->target, &r->lines, &r->tiles, &r->seg_counts, &r->segments, &r->ptcl, &r->blend_spill};
+    size_t s = 0;
+    for (auto b : all) s += b->cap;
+    return s;
+}
+
+// mask LUTs: vello_encoding/src/mask.rs:10-98 (f64 maths like the reference)
+static uint32_t one_mask(double slope, double translation, bool is_pos, const uint8_t *pattern, int n) {
+    if (is_pos) translation = 1. - translation;
+    uint32_t result = 0;
+    for (int i = 0; i < n; i++) {
+        double y = (i + 0.5) * (1.0 / n);
+        double x = (pattern[i] + 0.5) * (1.0 / n);
+        if (!is_pos) y = 1. - y;
+        if ((x - (1.0 - translation)) * (1. - slope) - (y - translation) * slope >= 0.) result |= 1u << i;
+    }
+    return result;
+}
+static void make_mask_luts(std::vector<uint32_t> &l8, std::vector<uint32_t> &l16) {
+    static const uint8_t P8[8] = {0, 5, 3, 7, 1, 4, 6, 2};
+    static const uint8_t P16[16] = {1, 8, 4, 11, 15, 7, 3, 12, 0, 9, 5, 13, 2, 10, 6, 14};
+    l8.assign(256, 0);
+    l16.assign(2048, 0);
+    for (int i = 0; i < 32 * 32; i++) {
+        int u = i % 32, v = i / 32;
+        l8[i / 4] |= one_mask(((v % 16) + 0.5) * (1.0 / 16), (u + 0.5) * (1.0 / 32), v >= 16, P8, 8) << ((i % 4) * 8);
+    }
+    for (int i = 0; i < 64 * 64; i++) {
+        int u = i % 64, v = i / 64;
+        l16[i / 2] |= one_mask(((v % 32) + 0.5) * (1.0 / 32), (u + 0.5) * (1.0 / 64), v >= 32, P16, 16) << ((i % 2) * 16);
+    }
+}
+
+extern "C" int vb_renderer_new(const vb_options *opt, vb_renderer **out) {
+    if (!out) return VB_E_INVALID;
+    vb_renderer *r = new vb_renderer();
+    r->device = opt ? opt->device : 0;
+    r->timing = opt && opt->timing;
+    if (opt && opt->max_retries) r->max_retries = opt->max_retries;
+    cudaError_t e = cudaSetDevice(r->device);
+    if (e != cudaSuccess) {
+        fprintf(stderr, "vello_b200: cudaSetDevice(%d): %s\n", r->device, cudaGetErrorString(e));
+        delete r;
+        return VB_E_CUDA;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, r->device) == cudaSuccess) r->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMallocHost((void **)&r->h_bump, sizeof(VbBump)) != cudaSuccess) {
+        delete r;
+        return VB_E_CUDA;
+    }
+    memset(r->h_bump, 0, sizeof(VbBump));
+    for (auto &ev : r->ev) cudaEventCreate(&ev);
+    r->ev_ok = true;
+    std::vector<uint32_t> l8, l16;
+    make_mask_luts(l8, l16);
+    if (ensure(r, r->mask8, l8.size() * 4) || ensure(r, r->mask16, l16.size() * 4)) {
+        delete r;
+        return VB_E_CUDA;
+    }
+    cudaMemcpy(r->mask8.p, l8.data(), l8.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(r->mask16.p, l16.data(), l16.size() * 4, cudaMemcpyHostToDevice);
+    *out = r;
+    return VB_OK;
+}
+
+extern "C" void vb_renderer_free(vb_renderer *r) {
+    if (!r) return;
+    cudaSetDevice(r->device);
+    if (r->stream) cudaStreamSynchronize(r->stream);
+    DevBuf *all[] = {&r->scene, &r->ramps, &r->atlas, &r->mask8, &r->mask16, &r->tag_monoids, &r->path_bboxes, &r->draw_monoids,
+                     &r->info_bin_data, &r->clip_inp, &r->clip_bboxes, &r->clip_scratch, &r->draw_bboxes, &r->bin_headers, &r->paths,
+                     &r->ctl, &r->target, &r->lines, &r->tiles, &r->seg_counts, &r->segments, &r->ptcl, &r->blend_spill};
+    for (auto b : all)
+        if (b->p) cudaFree(b->p);
+    if (r->h_bump) cudaFreeHost(r->h_bump);
+    if (r->ev_ok)
+        for (auto &ev : r->ev) cudaEventDestroy(ev);
+    if (r->stream) cudaStreamDestroy(r->stream);
+    delete r;
+}
+
+extern "C" const char *vb_strerror(int code) {
+    switch (code) {
+    case VB_OK: return "ok";
+    case VB_E_INVALID: return "invalid argument";
+    case VB_E_CUDA: return "CUDA error (see vb_last_error)";
+    case VB_E_BUMP_OVERFLOW: return "bump arena overflow persisted after grow-and-retry";
+    case VB_E_NO_SCENE: return "no scene uploaded";
+    case VB_E_UNKNOWN_BUFFER: return "unknown buffer name";
+    default: return "unknown error";
+    }
+}
+extern "C" const char *vb_last_error(vb_renderer *r) { return r ? r->err.c_str() : ""; }
+extern "C" void *vb_stream(vb_renderer *r) { return r ? (void *)r->stream : nullptr; }
+extern "C" void *vb_target(vb_renderer *r, size_t *bytes) {
+    if (!r) return nullptr;
+    if (bytes) *bytes = r->target.cap;
+    return r->target.p;
+}
+extern "C" int vb_copy_to_host(vb_renderer *r, const void *src_device, void *dst_host, size_t bytes) {
+    if (!r || !src_device || !dst_host) return VB_E_INVALID;
+    CK(cudaSetDevice(r->device));
+    CK(cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost, r->stream));
+    CK(cudaStreamSynchronize(r->stream));
+    return VB_OK;
+}
+
+extern "C" int vb_scene_upload(vb_renderer *r, const uint8_t *scene, size_t scene_len, const vb_layout *layout, const uint32_t *ramps,
+                               uint32_t ramp_w, uint32_t ramp_h, const uint8_t *atlas, uint32_t atlas_w, uint32_t atlas_h) {
+    if (!r || !layout || (scene_len && !scene) || (scene_len & 3)) return VB_E_INVALID;
+    if (ramp_h && ramp_w != 512) return VB_E_INVALID;
+    CK(cudaSetDevice(r->device));
+    memcpy(&r->layout, layout, sizeof(VbLayout));
+    r->scene_words = scene_len / 4;
+    int rc;
+    if ((rc = ensure(r, r->scene, scene_len + 64))) return rc;
+    if (scene_len) CK(cudaMemcpyAsync(r->scene.p, scene, scene_len, cudaMemcpyHostToDevice, r->stream));
+    r->n_ramps = ramp_h;
+    if ((rc = ensure(r, r->ramps, (size_t)ramp_h * 512 * 4))) return rc;
+    if (ramp_h) CK(cudaMemcpyAsync(r->ramps.p, ramps, (size_t)ramp_h * 512 * 4, cudaMemcpyHostToDevice, r->stream));
+    r->atlas_w = atlas ? atlas_w : 0;
+    r->atlas_h = atlas ? atlas_h : 0;
+    if ((rc = ensure(r, r->atlas, (size_t)r->atlas_w * r->atlas_h * 4))) return rc;
+    if (r->atlas_w && r->atlas_h)
+        CK(cudaMemcpyAsync(r->atlas.p, atlas, (size_t)r->atlas_w * r->atlas_h * 4, cudaMemcpyHostToDevice, r->stream));
+    r->have_scene = true;
+    return VB_OK;
+}
+
+static uint32_t grow(uint32_t need) {
+    uint64_t g = (uint64_t)need + need / 4 + 1024;
+    return g > 0xfffffff0ull ? 0xfffffff0u : (uint32_t)g;
+}
+
+// Compute the config for these params, size the fixed buffers, and (first time / after growth) the arenas.
+static int prepare(vb_renderer *r, const vb_params *p) {
+    VbConfig &c = r->cfg;
+    memset(&c, 0, sizeof c);
+    c.width_in_tiles = (p->width + 15u) / 16u;
+    c.height_in_tiles = (p->height + 15u) / 16u;
+    c.target_width = p->width;
+    c.target_height = p->height;
+    c.base_color = p->base_color;
+    c.layout = r->layout;
+    const uint32_t hb = (c.height_in_tiles + 15u) / 16u, wb = (c.width_in_tiles + 15u) / 16u;
+    c.win_by0 = 0;
+    c.win_by1 = hb;
+    if (p->bin_row1 > p->bin_row0) {
+        c.win_by0 = p->bin_row0 < hb ? p->bin_row0 : hb;
+        c.win_by1 = p->bin_row1 < hb ? p->bin_row1 : hb;
+    }
+    c.win_ty0 = c.win_by0 * 16u;
+    c.win_ty1 = c.win_by1 * 16u < c.height_in_tiles ? c.win_by1 * 16u : c.height_in_tiles;
+    c.n_tag_words = r->layout.path_data_base - r->layout.path_tag_base;
+    c.scene_words = (uint32_t)r->scene_words;
+    c.n_ramps = r->n_ramps;
+    c.atlas_w = r->atlas_w;
+    c.atlas_h = r->atlas_h;
+    c.out_pitch_px = p->width;
+    c.out_row0 = c.win_ty0 * 16u;
+    r->params = *p;
+
+    const VbLayout &L = r->layout;
+    const uint32_t n_draw = L.n_draw_objects, n_paths = L.n_paths, n_clips = L.n_clips;
+    const uint32_t n_tiles = c.width_in_tiles * c.height_in_tiles;
+    const uint32_t n_bins = wb * hb, aligned_n_bins = (n_bins + 255u) & ~255u;
+    int rc;
+    if ((rc = ensure(r, r->tag_monoids, (size_t)c.n_tag_words * sizeof(VbTagMonoid)))) return rc;
+    if ((rc = ensure(r, r->path_bboxes, (size_t)n_paths * sizeof(VbPathBbox)))) return rc;
+    if ((rc = ensure(r, r->draw_monoids, (size_t)n_draw * sizeof(VbDrawMonoid)))) return rc;
+    if ((rc = ensure(r, r->clip_inp, (size_t)n_clips * sizeof(VbClipInp)))) return rc;
+    if ((rc = ensure(r, r->clip_bboxes, (size_t)n_clips * sizeof(VbBbox4)))) return rc;
+    if ((rc = ensure(r, r->clip_scratch, vb_clip_scratch_words(n_clips) * 4))) return rc;
+    if ((rc = ensure(r, r->draw_bboxes, (size_t)n_draw * sizeof(VbBbox4)))) return rc;
+    if ((rc = ensure(r, r->bin_headers, (size_t)((n_draw + 255u) / 256u) * aligned_n_bins * sizeof(VbBinHeader)))) return rc;
+    if ((rc = ensure(r, r->paths, (size_t)((n_draw + 255u) & ~255u) * sizeof(VbPath)))) return rc;
+
+    // first-guess arena capacities (elements); they only ever grow
+    const uint32_t n_tags = c.n_tag_words * 4u;
+    auto atleast = [](uint32_t &cap, uint64_t v) {
+        if (v > 0xfffffff0ull) v = 0xfffffff0ull;
+        if (cap < (uint32_t)v) cap = (uint32_t)v;
+    };
+    atleast(r->cap_lines, (uint64_t)n_tags * 2 + 4096);
+    atleast(r->cap_binning, (uint64_t)n_draw * 4 + 4096);
+    atleast(r->cap_tiles, (uint64_t)n_draw * 16 + 4096);
+    atleast(r->cap_seg_counts, (uint64_t)r->cap_lines * 2);
+    atleast(r->cap_segments, (uint64_t)r->cap_seg_counts);
+    atleast(r->cap_blend, 256);
+    atleast(r->cap_ptcl, (uint64_t)n_tiles * VB_PTCL_INITIAL_ALLOC + (uint64_t)VB_PTCL_INCREMENT * (64 + n_tiles / 8));
+    if (r->cap_ptcl < n_tiles * VB_PTCL_INITIAL_ALLOC + VB_PTCL_INCREMENT)
+        r->cap_ptcl = n_tiles * VB_PTCL_INITIAL_ALLOC + VB_PTCL_INCREMENT;
+    if ((rc = ensure(r, r->lines, (size_t)r->cap_lines * sizeof(VbLineSoup)))) return rc;
+    if ((rc = ensure(r, r->info_bin_data, ((size_t)L.bin_data_start + r->cap_binning) * 4))) return rc;
+    if ((rc = ensure(r, r->tiles, (size_t)r->cap_tiles * sizeof(VbTile)))) return rc;
+    if ((rc = ensure(r, r->seg_counts, (size_t)r->cap_seg_counts * sizeof(VbSegmentCount)))) return rc;
+    if ((rc = ensure(r, r->segments, (size_t)r->cap_segments * sizeof(VbSegment)))) return rc;
+    if ((rc = ensure(r, r->blend_spill, (size_t)r->cap_blend * 4))) return rc;
+    if ((rc = ensure(r, r->ptcl, (size_t)r->cap_ptcl * 4))) return rc;
+    c.lines_size = r->cap_lines;
+    c.binning_size = r->cap_binning;
+    c.tiles_size = r->cap_tiles;
+    c.seg_counts_size = r->cap_seg_counts;
+    c.segments_size = r->cap_segments;
+    c.blend_size = r->cap_blend;
+    c.ptcl_size = r->cap_ptcl;
+
+    // control block: [bump (8 words, padded to 16)] [look-back states]
+    r->parts_pathtag = vb_pathtag_parts(c.n_tag_words);
+    r->parts_flatten = vb_flatten_parts(c.n_tag_words);
+    r->parts_draw = vb_draw_parts(n_draw);
+    r->parts_tile = vb_tile_alloc_parts(n_draw);
+    size_t off = 16;
+    r->off_lb_pathtag = off; off += vb_lookback_words(r->parts_pathtag, 5);
+    r->off_lb_flatten = off; off += vb_lookback_words(r->parts_flatten, 1);
+    r->off_lb_draw = off; off += vb_lookback_words(r->parts_draw, 4);
+    r->off_lb_tile = off; off += vb_lookback_words(r->parts_tile, 1);
+    r->ctl_words = off;
+    if ((rc = ensure(r, r->ctl, off * 4))) return rc;
+    return VB_OK;
+}
+
+static void rec(vb_renderer *r, int i) {
+    if (r->timing) cudaEventRecord(r->ev[i], r->stream);
+}
+
+// Enqueue stages first..last. Does not synchronise.
+static int enqueue(vb_renderer *r, int first, int last, void *out_dev) {
+    const VbConfig &c = r->cfg;
+    cudaStream_t st = r->stream;
+    uint32_t *ctl = (uint32_t *)r->ctl.p;
+    VbBump *bump = (VbBump *)ctl;
+    uint32_t launches = 0;
+    const uint32_t n_draw = c.layout.n_draw_objects;
+    if (first == 0) {
+        CK(cudaMemsetAsync(ctl, 0, r->ctl_words * 4, st));
+        launches++;
+    }
+    rec(r, 0);
+    for (int s = first; s <= last; s++) {
+        switch (s) {
+        case VB_STAGE_ID_PATHTAG:
+            vb_launch_pathtag(&c, (const uint32_t *)r->scene.p, (VbTagMonoid *)r->tag_monoids.p, ctl + r->off_lb_pathtag, r->parts_pathtag, st);
+            launches += r->parts_pathtag ? 1 : 0;
+            break;
+        case VB_STAGE_ID_FLATTEN:
+            vb_launch_flatten(&c, (const uint32_t *)r->scene.p, (const VbTagMonoid *)r->tag_monoids.p, (VbPathBbox *)r->path_bboxes.p, bump,
+                              (VbLineSoup *)r->lines.p, ctl + r->off_lb_flatten, r->parts_flatten, st);
+            launches += (c.layout.n_paths ? 1 : 0) + (r->parts_flatten ? 1 : 0);
+            break;
+        case VB_STAGE_ID_DRAW:
+            vb_launch_draw(&c, (const uint32_t *)r->scene.p, (const VbPathBbox *)r->path_bboxes.p, (VbDrawMonoid *)r->draw_monoids.p,
+                           (uint32_t *)r->info_bin_data.p, (VbClipInp *)r->clip_inp.p, ctl + r->off_lb_draw, r->parts_draw, st);
+            launches += r->parts_draw ? 1 : 0;
+            break;
+        case VB_STAGE_ID_CLIP:
+            vb_launch_clip(c.layout.n_clips, (const VbClipInp *)r->clip_inp.p, (const VbPathBbox *)r->path_bboxes.p,
+                           (VbDrawMonoid *)r->draw_monoids.p, (VbBbox4 *)r->clip_bboxes.p, (int32_t *)r->clip_scratch.p, st);
+            launches += c.layout.n_clips ? 3 : 0;
+            break;
+        case VB_STAGE_ID_BINNING:
+            vb_launch_binning(&c, (const VbDrawMonoid *)r->draw_monoids.p, (const VbPathBbox *)r->path_bboxes.p,
+                              (const VbBbox4 *)r->clip_bboxes.p, (VbBbox4 *)r->draw_bboxes.p, bump, (uint32_t *)r->info_bin_data.p,
+                              (VbBinHeader *)r->bin_headers.p, st);
+            launches += n_draw ? 1 : 0;
+            break;
+        case VB_STAGE_ID_TILE_ALLOC:
+            vb_launch_tile_alloc(&c, (const uint32_t *)r->scene.p, (const VbBbox4 *)r->draw_bboxes.p, bump, (VbPath *)r->paths.p,
+                                 (VbTile *)r->tiles.p, ctl + r->off_lb_tile, r->parts_tile, st);
+            launches += r->parts_tile ? 1 : 0;
+            break;
+        case VB_STAGE_ID_PATH_COUNT: {
+            // grid from the arena capacity; the kernel strides over bump.lines read on the device
+            uint64_t blocks = ((uint64_t)c.lines_size + 255) / 256;
+            uint32_t grid = (uint32_t)(blocks < (uint64_t)r->sm_count * 16 ? blocks : (uint64_t)r->sm_count * 16);
+            vb_launch_path_count(&c, bump, (const VbLineSoup *)r->lines.p, (const VbPath *)r->paths.p, (VbTile *)r->tiles.p,
+                                 (VbSegmentCount *)r->seg_counts.p, grid, st);
+            launches += 2;
+            break;
+        }
+        case VB_STAGE_ID_BACKDROP:
+            vb_launch_backdrop(&c, bump, (const VbPath *)r->paths.p, (VbTile *)r->tiles.p, st);
+            launches += n_draw ? 1 : 0;
+            break;
+        case VB_STAGE_ID_COARSE:
+            vb_launch_coarse(&c, (const uint32_t *)r->scene.p, (const VbDrawMonoid *)r->draw_monoids.p, (const VbBinHeader *)r->bin_headers.p,
+                             (const uint32_t *)r->info_bin_data.p, (const VbPath *)r->paths.p, (VbTile *)r->tiles.p, bump,
+                             (uint32_t *)r->ptcl.p, st);
+            launches += 2;
+            break;
+        case VB_STAGE_ID_PATH_TILING: {
+            uint64_t blocks = ((uint64_t)c.seg_counts_size + 255) / 256;
+            uint32_t grid = (uint32_t)(blocks < (uint64_t)r->sm_count * 16 ? blocks : (uint64_t)r->sm_count * 16);
+            vb_launch_path_tiling(&c, bump, (const VbSegmentCount *)r->seg_counts.p, (const VbLineSoup *)r->lines.p,
+                                  (const VbPath *)r->paths.p, (const VbTile *)r->tiles.p, (VbSegment *)r->segments.p, grid, st);
+            k_flag_failure<<<1, 1, 0, st>>>(bump, (uint32_t *)r->ptcl.p);
+            launches += 2;
+            break;
+        }
+        case VB_STAGE_ID_FINE:
+            vb_launch_fine(&c, (int)r->params.aa, (const VbSegment *)r->segments.p, (const uint32_t *)r->ptcl.p,
+                           (const uint32_t *)r->info_bin_data.p, (uint32_t *)r->blend_spill.p, (uint32_t *)out_dev,
+                           (const uint32_t *)r->ramps.p, (const uint8_t *)r->atlas.p, (const uint32_t *)r->mask8.p,
+                           (const uint32_t *)r->mask16.p, st);
+            launches += 1;
+            break;
+        default: return VB_E_INVALID;
+        }
+        rec(r, s + 1);
+    }
+    CK(cudaMemcpyAsync(r->h_bump, bump, sizeof(VbBump), cudaMemcpyDeviceToHost, st));
+    CK(cudaGetLastError());
+    r->launches = launches;
+    return VB_OK;
+}
+
+static int pick_out(vb_renderer *r, void *out_device, void **out) {
+    if (out_device) {
+        *out = out_device;
+        return VB_OK;
+    }
+    const VbConfig &c = r->cfg;
+    size_t rows = (size_t)(c.win_ty1 - c.win_ty0) * 16u;
+    int rc = ensure(r, r->target, (size_t)c.out_pitch_px * 4u * rows);
+    *out = r->target.p;
+    return rc;
+}
+
+extern "C" int vb_render_enqueue(vb_renderer *r, const vb_params *p, void *out_device) {
+    if (!r || !p) return VB_E_INVALID;
+    if (!r->have_scene) return VB_E_NO_SCENE;
+    CK(cudaSetDevice(r->device));
+    int rc = prepare(r, p);
+    if (rc) return rc;
+    void *out;
+    if ((rc = pick_out(r, out_device, &out))) return rc;
+    r->out_dev = out;
+    rc = enqueue(r, 0, VB_N_STAGE_IDS - 1, out);
+    r->frame_pending = rc == VB_OK;
+    return rc;
+}
+
+static void fill_stats(vb_renderer *r, vb_frame_stats *s) {
+    if (!s) return;
+    memset(s, 0, sizeof *s);
+    memcpy(s, r->h_bump, sizeof(VbBump));
+    s->retries = r->retries;
+    s->kernel_launches = r->launches;
+    s->arena_bytes = arena_bytes(r);
+    if (r->timing) {
+        for (int i = 0; i < VB_N_STAGE_IDS; i++) cudaEventElapsedTime(&s->stage_ms[i], r->ev[i], r->ev[i + 1]);
+        cudaEventElapsedTime(&s->total_ms, r->ev[0], r->ev[VB_N_STAGE_IDS]);
+    }
+}
+
+// After a failed attempt: enlarge whatever overflowed, using the counters the kernels kept counting.
+static void grow_arenas(vb_renderer *r) {
+    const VbBump &b = *r->h_bump;
+    const VbConfig &c = r->cfg;
+    if (b.lines > r->cap_lines) r->cap_lines = grow(b.lines);
+    if (b.binning > r->cap_binning) r->cap_binning = grow(b.binning);
+    if (b.tile > r->cap_tiles) r->cap_tiles = grow(b.tile);
+    if (b.seg_counts > r->cap_seg_counts) r->cap_seg_counts = grow(b.seg_counts);
+    if (b.segments > r->cap_segments) r->cap_segments = grow(b.segments);
+    if (b.blend > r->cap_blend) r->cap_blend = grow(b.blend);
+    uint64_t ptcl_need = (uint64_t)c.width_in_tiles * c.height_in_tiles * VB_PTCL_INITIAL_ALLOC + b.ptcl + VB_PTCL_INCREMENT;
+    if (ptcl_need > r->cap_ptcl) r->cap_ptcl = grow((uint32_t)(ptcl_need > 0xf0000000ull ? 0xf0000000ull : ptcl_need));
+    if (r->cap_seg_counts < r->cap_lines) r->cap_seg_counts = r->cap_lines;
+    if (r->cap_segments < r->cap_seg_counts && (b.failed & VB_STAGE_PATH_COUNT)) r->cap_segments = r->cap_seg_counts;
+}
+
+extern "C" int vb_frame_finish(vb_renderer *r, vb_frame_stats *stats) {
+    if (!r) return VB_E_INVALID;
+    CK(cudaSetDevice(r->device));
+    CK(cudaStreamSynchronize(r->stream));
+    r->frame_pending = false;
+    fill_stats(r, stats);
+    return r->h_bump->failed ? VB_E_BUMP_OVERFLOW : VB_OK;
+}
+
+extern "C" int vb_render_resident(vb_renderer *r, const vb_params *p, void *out_device, vb_frame_stats *stats) {
+    if (!r || !p) return VB_E_INVALID;
+    if (!r->have_scene) return VB_E_NO_SCENE;
+    r->retries = 0;
+    for (uint32_t attempt = 0;; attempt++) {
+        int rc = vb_render_enqueue(r, p, out_device);
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(r->stream));
+        r->frame_pending = false;
+        if (r->h_bump->failed == 0) break;
+        if (attempt >= r->max_retries) {
+            fill_stats(r, stats);
+            r->err = "bump overflow persisted";
+            return VB_E_BUMP_OVERFLOW;
+        }
+        grow_arenas(r);
+        r->retries++;
+    }
+    fill_stats(r, stats);
+    return VB_OK;
+}
+
+extern "C" int vb_render(vb_renderer *r, const uint8_t *scene, size_t scene_len, const vb_layout *layout, const uint32_t *ramps,
+                         uint32_t ramp_w, uint32_t ramp_h, const uint8_t *atlas, uint32_t atlas_w, uint32_t atlas_h, const vb_params *p,
+                         void *out, uint32_t out_is_device, vb_frame_stats *stats) {
+    if (!r || !p || !out) return VB_E_INVALID;
+    int rc = vb_scene_upload(r, scene, scene_len, layout, ramps, ramp_w, ramp_h, atlas, atlas_w, atlas_h);
+    if (rc) return rc;
+    rc = vb_render_resident(r, p, out_is_device ? out : nullptr, stats);
+    if (rc) return rc;
+    if (!out_is_device) {
+        const VbConfig &c = r->cfg;
+        size_t row0 = c.out_row0, row1 = (size_t)c.win_ty1 * 16u;
+        if (row1 > c.target_height) row1 = c.target_height;
+        size_t rows = row1 > row0 ? row1 - row0 : 0;
+        CK(cudaMemcpyAsync(out, r->target.p, rows * c.out_pitch_px * 4u, cudaMemcpyDeviceToHost, r->stream));
+        CK(cudaStreamSynchronize(r->stream));
+    }
+    return VB_OK;
+}
+
+extern "C" int vb_run_stages(vb_renderer *r, const vb_params *p, int first, int last, void *out_device) {
+    if (!r || !p || first < 0 || last >= VB_N_STAGE_IDS || first > last) return VB_E_INVALID;
+    if (!r->have_scene) return VB_E_NO_SCENE;
+    CK(cudaSetDevice(r->device));
+    int rc = prepare(r, p);
+    if (rc) return rc;
+    void *out = nullptr;
+    if (last == VB_STAGE_ID_FINE) {
+        if ((rc = pick_out(r, out_device, &out))) return rc;
+        r->out_dev = out;
+    }
+    rc = enqueue(r, first, last, out);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(r->stream));
+    return VB_OK;
+}
+
+struct NamedBuf {
+    const char *name;
+    DevBuf *buf;
+    size_t bytes;
+};
+static std::vector<NamedBuf> named(vb_renderer *r) {
+    const VbConfig &c = r->cfg;
+    const VbLayout &L = r->layout;
+    const VbBump &b = *r->h_bump;
+    auto mn = [](uint64_t a, uint64_t b2) { return a < b2 ? a : b2; };
+    const uint32_t wb = (c.width_in_tiles + 15u) / 16u, hb = (c.height_in_tiles + 15u) / 16u;
+    const uint32_t aligned_n_bins = (wb * hb + 255u) & ~255u;
+    uint64_t ptcl_words = mn((uint64_t)c.width_in_tiles * c.height_in_tiles * VB_PTCL_INITIAL_ALLOC + b.ptcl, c.ptcl_size);
+    return {
+        {"tag_monoids", &r->tag_monoids, (size_t)c.n_tag_words * sizeof(VbTagMonoid)},
+        {"path_bboxes", &r->path_bboxes, (size_t)L.n_paths * sizeof(VbPathBbox)},
+        {"lines", &r->lines, (size_t)mn(b.lines, c.lines_size) * sizeof(VbLineSoup)},
+        {"draw_monoids", &r->draw_monoids, (size_t)L.n_draw_objects * sizeof(VbDrawMonoid)},
+        {"info_bin_data", &r->info_bin_data, ((size_t)L.bin_data_start + mn(b.binning, c.binning_size)) * 4},
+        {"clip_inp", &r->clip_inp, (size_t)L.n_clips * sizeof(VbClipInp)},
+        {"clip_bboxes", &r->clip_bboxes, (size_t)L.n_clips * sizeof(VbBbox4)},
+        {"draw_bboxes", &r->draw_bboxes, (size_t)L.n_draw_objects * sizeof(VbBbox4)},
+        {"bin_headers", &r->bin_headers, (size_t)((L.n_draw_objects + 255u) / 256u) * aligned_n_bins * sizeof(VbBinHeader)},
+        {"paths", &r->paths, (size_t)L.n_draw_objects * sizeof(VbPath)},
+        {"tiles", &r->tiles, (size_t)mn(b.tile, c.tiles_size) * sizeof(VbTile)},
+        {"seg_counts", &r->seg_counts, (size_t)mn(b.seg_counts, c.seg_counts_size) * sizeof(VbSegmentCount)},
+        {"segments", &r->segments, (size_t)mn(b.segments, c.segments_size) * sizeof(VbSegment)},
+        {"ptcl", &r->ptcl, (size_t)ptcl_words * 4},
+        {"blend_spill", &r->blend_spill, (size_t)mn(b.blend, c.blend_size) * 4},
+    };
+}
+
+extern "C" int vb_debug_download(vb_renderer *r, const char *name, void *dst, size_t cap, size_t *bytes) {
+    if (!r || !name) return VB_E_INVALID;
+    CK(cudaSetDevice(r->device));
+    CK(cudaStreamSynchronize(r->stream));
+    if (!strcmp(name, "bump")) {
+        if (bytes) *bytes = sizeof(VbBump);
+        if (dst && cap >= sizeof(VbBump)) CK(cudaMemcpy(dst, r->ctl.p, sizeof(VbBump), cudaMemcpyDeviceToHost));
+        return VB_OK;
+    }
+    if (!strcmp(name, "config")) {
+        if (bytes) *bytes = sizeof(VbConfig);
+        if (dst && cap >= sizeof(VbConfig)) memcpy(dst, &r->cfg, sizeof(VbConfig));
+        return VB_OK;
+    }
+    for (auto &nb : named(r))
+        if (!strcmp(name, nb.name)) {
+            if (bytes) *bytes = nb.bytes;
+            size_t n = nb.bytes < cap ? nb.bytes : cap;
+            if (dst && n) CK(cudaMemcpy(dst, nb.buf->p, n, cudaMemcpyDeviceToHost));
+            return VB_OK;
+        }
+    return VB_E_UNKNOWN_BUFFER;
+}
+
+extern "C" int vb_debug_upload(vb_renderer *r, const char *name, const void *src, size_t bytes) {
+    if (!r || !name || !src) return VB_E_INVALID;
+    CK(cudaSetDevice(r->device));
+    CK(cudaStreamSynchronize(r->stream));
+    if (!strcmp(name, "lines")) {
+        uint32_t n = (uint32_t)(bytes / sizeof(VbLineSoup));
+        if (n > r->cap_lines) {
+            r->cap_lines = grow(n);
+            int rc = ensure(r, r->lines, (size_t)r->cap_lines * sizeof(VbLineSoup));
+            if (rc) return rc;
+        }
+        CK(cudaMemcpy(r->lines.p, src, (size_t)n * sizeof(VbLineSoup), cudaMemcpyHostToDevice));
+        VbBump *bump = (VbBump *)r->ctl.p;
+        CK(cudaMemcpy(&bump->lines, &n, 4, cudaMemcpyHostToDevice));
+        r->h_bump->lines = n;
+        return VB_OK;
+    }
+    if (!strcmp(name, "path_bboxes")) {
+        if (bytes > r->path_bboxes.cap) return VB_E_INVALID;
+        CK(cudaMemcpy(r->path_bboxes.p, src, bytes, cudaMemcpyHostToDevice));
+        return VB_OK;
+    }
+    return VB_E_UNKNOWN_BUFFER;
+}
