@@ -27,8 +27,8 @@ DTYPES = {
                               ("info_offset", "<u4")]),
     "info_bin_data": np.dtype("<u4"),
     "clip_inp": np.dtype([("ix", "<u4"), ("path_ix", "<i4")]),
-    "clip_bboxes": np.dtype(("<f4", 4)),
-    "draw_bboxes": np.dtype(("<f4", 4)),
+    "clip_bboxes": np.dtype([("x0", "<f4"), ("y0", "<f4"), ("x1", "<f4"), ("y1", "<f4")]),
+    "draw_bboxes": np.dtype([("x0", "<f4"), ("y0", "<f4"), ("x1", "<f4"), ("y1", "<f4")]),
     "bin_headers": np.dtype([("element_count", "<u4"), ("chunk_offset", "<u4")]),
     "paths": np.dtype([("bbox", "<u4", 4), ("tiles", "<u4"), ("pad", "<u4", 3)]),
     "tiles": np.dtype([("backdrop", "<i4"), ("segment_count_or_ix", "<u4")]),

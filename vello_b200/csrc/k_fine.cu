@@ -566,7 +566,13 @@ k_fine(VbConfig cfg, FineArgs A) {
     const rgba_t base = unpack4x8unorm(cfg.base_color);
 #pragma unroll
     for (int i = 0; i < PIXELS_PER_THREAD; i++) { rgba[i] = base; area[i] = 0.0f; }
+    // Zero-initialised on purpose: with undefined initial contents the optimiser may fold the
+    // `d == clip_depth ? new : old` selects below and clobber live stack levels.
     uint32_t blend_stack[VB_BLEND_STACK_SPLIT][PIXELS_PER_THREAD];
+#pragma unroll
+    for (uint32_t d = 0; d < VB_BLEND_STACK_SPLIT; d++)
+#pragma unroll
+        for (int i = 0; i < PIXELS_PER_THREAD; i++) blend_stack[d][i] = 0u;
     uint32_t clip_depth = 0u;
     uint32_t cmd_ix = tile_ix * VB_PTCL_INITIAL_ALLOC;
     const uint32_t blend_offset = __ldg(ptcl + cmd_ix);
