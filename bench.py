@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s on the paris-30k-like scene at 4096x4096 MSAA16 (BASELINE.json configs[2]) and the
+fine-stage HBM roofline, next to the CPU baseline (the oracle = restated reference CPU shaders).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W          (one rank per GPU, bin-row stripes, no data-path collective)
+    python bench.py --impl reference ...                (the CPU arm: oracle on the host cores)
+
+One step = one frame of the hot path (pathtag .. fine) over the synthetic scene.
+`value`  : frames/s with the packed scene already resident in HBM (vb_render_resident).
+`e2e`    : frames/s through the one-call C ABI `vb_render` with pinned HOST buffers: scene H2D + render +
+           full image D2H inside the timed region.
+Timing   : CUDA events on the renderer's stream around every step; L2 is flushed (256 MiB write) between
+           steps outside the event pairs; max over ranks; clocks sampled with nvidia-smi during the run.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(name="paris-like-30k 4096x4096 MSAA16", n_paths=30000, size=4096, seed=30000, aa=2)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_scene(args):
+    from vello_b200 import scenes
+    from vello_b200.encoding import resolve
+    t = time.time()
+    sc = scenes.paris_like(args.paths, args.size, args.seed)
+    packed = resolve(sc.encoding)
+    return packed, time.time() - t
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        return rank, world, local, dist
+    return rank, world, local, None
+
+
+def stripe_for(rank, world, height):
+    """Bin-row stripe [b0, b1) of `rank` (bins are 256 px tall); contiguous, as even as possible."""
+    n_bins = (height + 255) // 256
+    base, rem = divmod(n_bins, world)
+    b0 = rank * base + min(rank, rem)
+    b1 = b0 + base + (1 if rank < rem else 0)
+    return b0, b1
+
+
+def run_cpu_arm(args, packed, as_reference):
+    """Time the oracle (restated reference CPU shaders + fine) on the host cores."""
+    from oracle.vbo import Oracle
+    from vello_b200.encoding import BLACK
+    cores = os.cpu_count() or 1
+    o = Oracle(threads=cores)
+    # bounded sample: one full frame is ~3-5 s of CPU work on 8 cores, so the reference arm runs at most
+    # one warm-up frame and stops after ~2 minutes of timed frames
+    steps = max(1, min(args.steps, 20) if as_reference else 1)
+    warm = min(args.warmup, 1) if as_reference else 0
+    times = []
+    for i in range(warm + steps):
+        t = time.perf_counter()
+        o.render(packed, args.size, args.size, BLACK.premul_rgba8_u32(), args.aa)
+        dt = time.perf_counter() - t
+        if i >= warm:
+            times.append(dt)
+        if sum(times) > 120:
+            break
+    fps = len(times) / sum(times)
+    return fps, dict(value=fps, unit="frames/s", cores=cores, kind="port",
+                     sample=f"{len(times)} full frame(s) of the workload; coarse stages serial (as RendererOptions::use_cpu), fine on {cores} threads"), \
+        1000.0 * sum(times) / len(times), len(times)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--paths", type=int, default=WORKLOAD["n_paths"])
+    ap.add_argument("--size", type=int, default=WORKLOAD["size"])
+    ap.add_argument("--seed", type=int, default=WORKLOAD["seed"])
+    ap.add_argument("--aa", type=int, default=WORKLOAD["aa"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-only", action="store_true", help="just run warmup+steps resident frames (for ncu)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if not args.profile_only else args.warmup
+
+    config = {"workload": f"paris-like-{args.paths // 1000}k {args.size}x{args.size} " + ["Area", "MSAA8", "MSAA16"][args.aa],
+              "n_paths": args.paths, "seed": args.seed, "parallelism": f"bin-row stripes x{args.gpus}",
+              "l2": "flushed between steps (256 MiB write) outside the per-step CUDA-event pairs"}
+
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        if rank != 0:
+            return
+        packed, _ = build_scene(args)
+        fps, cb, ms, n = run_cpu_arm(args, packed, True)
+        print(json.dumps({"impl": "reference", "metric": "frames/sec paris-30k@4K", "value": fps, "unit": "frames/s",
+                          "n_gpus": args.gpus, "steps": n, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                          "cpu_baseline": cb, "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return
+
+    rank, world, local, dist = dist_setup(args.gpus)
+    import torch
+    from vello_b200.config import RenderParams
+    from vello_b200.encoding import BLACK
+    from vello_b200.renderer import Renderer, RendererOptions, FrameStats, _Layout, _Params
+
+    packed, gen_s = build_scene(args)
+    params = RenderParams(BLACK, args.size, args.size, args.aa)
+    bin_rows = stripe_for(rank, world, args.size) if world > 1 else (0, 0)
+    torch.cuda.set_device(local)
+    r = Renderer(RendererOptions(device=local))
+    r.upload(packed)
+    h0, h1 = r.stripe_rows(params, bin_rows)
+    out = torch.empty((max(h1 - h0, 1), args.size, 4), dtype=torch.uint8, device=f"cuda:{local}")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
+    stream = torch.cuda.ExternalStream(r.stream, device=f"cuda:{local}")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident-scene throughput ("value") -------------------------------------------------
+    st = r.render_resident(params, out.data_ptr(), bin_rows)  # sizes the arenas (may retry)
+    for _ in range(args.warmup):
+        r.render_resident(params, out.data_ptr(), bin_rows)
+    if args.profile_only:
+        for _ in range(args.steps):
+            r.render_resident(params, out.data_ptr(), bin_rows)
+        return
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches = 0
+    t_wall = time.perf_counter()
+    for a, b in evs:
+        flush.fill_(1)          # L2 flush on the default stream ...
+        torch.cuda.synchronize()  # ... finished before the step starts
+        a.record(stream)
+        r.enqueue(params, out.data_ptr(), bin_rows)
+        b.record(stream)
+        s = r.finish()
+        assert s.failed == 0
+        launches += int(s.kernel_launches)
+    barrier()
+    wall = time.perf_counter() - t_wall
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=f"cuda:{local}")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    fps = args.steps / (total_ms / 1000.0)
+
+    # ---- end-to-end through vb_render with pinned host buffers ("e2e") ---------------------------
+    scene_h = torch.from_numpy(np.ascontiguousarray(packed.scene)).pin_memory()
+    ramps_h = torch.from_numpy(np.ascontiguousarray(packed.ramps.reshape(-1))).pin_memory() if packed.ramps.size else None
+    atlas_np = np.ascontiguousarray(packed.atlas)
+    out_h = torch.empty((max(h1 - h0, 1), args.size, 4), dtype=torch.uint8).pin_memory()
+    lay = _Layout(*[int(v) for v in packed.layout.as_array()])
+    ps = _Params(BLACK.premul_rgba8_u32(), args.size, args.size, args.aa, bin_rows[0], bin_rows[1])
+    fs = FrameStats()
+
+    def e2e_step():
+        rc = r.lib.vb_render(r.handle, scene_h.data_ptr(), scene_h.numel() * 4, C.byref(lay),
+                             ramps_h.data_ptr() if ramps_h is not None else None, 512, packed.ramps.shape[0],
+                             atlas_np.ctypes.data, atlas_np.shape[1], atlas_np.shape[0], C.byref(ps), out_h.data_ptr(), 0, C.byref(fs))
+        assert rc == 0 and fs.failed == 0
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, args.steps // 2)
+    for _ in range(e2e_steps):
+        e2e_step()  # vb_render synchronises internally: host wall clock == device completion
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_fps = e2e_steps / float(t.item())
+    h2d = int(packed.scene.nbytes + packed.ramps.nbytes + packed.atlas.nbytes)
+    d2h = int((h1 - h0) * args.size * 4 + 32)
+
+    if rank != 0:
+        return
+
+    # ---- roofline of the dominant kernel (fine), measured live with per-stage CUDA events ----------
+    rt = Renderer(RendererOptions(device=local, timing=True))
+    rt.upload(packed)
+    rt.render_resident(params, out.data_ptr(), bin_rows)
+    stage_ms = {}
+    n_t = 10
+    for _ in range(n_t):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        sd = rt.render_resident(params, out.data_ptr(), bin_rows).as_dict()
+        for k, v in sd["stage_ms"].items():
+            stage_ms[k] = stage_ms.get(k, 0.0) + v / n_t
+    ptcl_words, seg_refs, fill_cmds = rt.fine_traffic()
+    px = (h1 - h0) * args.size
+    seg_bytes = 24 * seg_refs * (2 if args.aa else 1)  # MSAA reads each segment twice (count + rasterise), fine.wgsl:177,225
+    alg_bytes = 4 * px + 4 * ptcl_words + 24 * seg_refs  # each datum once
+    fine_s = stage_ms["fine"] / 1000.0
+    peak, peak_src = measured_peaks()
+    achieved = alg_bytes / fine_s / 1e9
+    roofline = {"kernel": f"k_fine<{args.aa}>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes": alg_bytes, "bytes_breakdown": {"pixels": 4 * px, "ptcl": 4 * ptcl_words, "segments": 24 * seg_refs},
+                "fine_ms": stage_ms["fine"], "note": "MSAA16 fine is shared-memory-atomic / ALU bound (SURVEY.md 8d caveat); "
+                "segments re-read from L2 by the second MSAA pass are not counted"}
+    tp = os.path.join(ROOT, "profiles", "fine_traffic.json")
+    if os.path.exists(tp):
+        try:
+            roofline["traffic"] = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    rt.close()
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        _, cpu_baseline, _, _ = run_cpu_arm(args, packed, False)
+
+    line = {"metric": "frames/sec paris-30k@4K", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "stage_ms": stage_ms, "bump": {k: int(getattr(st, k)) for k in ("lines", "tile", "seg_counts", "segments", "ptcl", "binning")},
+            "scene_bytes": int(packed.scene.nbytes), "wall_s_timed_region": wall, "scene_build_s": gen_s}
+    print(json.dumps(line))
+    r.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

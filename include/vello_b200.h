@@ -125,6 +125,10 @@ int vb_debug_download(vb_renderer *, const char *name, void *dst, size_t cap, si
 /* Overwrite an intermediate buffer from the host ("lines" also sets bump.lines; "path_bboxes"). */
 int vb_debug_upload(vb_renderer *, const char *name, const void *src, size_t bytes);
 
+/* Traffic statistics of the last frame's `fine` (for the roofline): PTCL words its interpreters read,
+ * segments referenced by CMD_FILL, number of CMD_FILL commands. */
+int vb_debug_fine_traffic(vb_renderer *, uint64_t *ptcl_words, uint64_t *segment_refs, uint64_t *fill_cmds);
+
 #ifdef __cplusplus
 }
 #endif

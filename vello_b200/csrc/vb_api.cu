@@ -49,6 +49,31 @@ __global__ void k_flag_failure(const VbBump *bump, uint32_t *ptcl) {
     if (bump->failed != 0u) ptcl[0] = ~0u;
 }
 
+// Statistics for the roofline of `fine`: PTCL words each tile's interpreter reads and segments it
+// references (one thread per tile walks its command stream, as fine does).
+__global__ void k_ptcl_stats(VbConfig cfg, const uint32_t *__restrict__ ptcl, unsigned long long *out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t wt = cfg.width_in_tiles, rows = cfg.win_ty1 - cfg.win_ty0;
+    if (t >= wt * rows) return;
+    uint32_t tile_ix = (cfg.win_ty0 + t / wt) * wt + t % wt;
+    uint32_t ix = tile_ix * VB_PTCL_INITIAL_ALLOC + 1u;
+    unsigned long long words = 1, segs = 0, fills = 0;
+    for (uint32_t guard = 0; guard < (1u << 24); guard++) {
+        uint32_t tag = ptcl[ix];
+        uint32_t size = 1;
+        if (tag == VB_CMD_END) { words += 1; break; }
+        if (tag == VB_CMD_JUMP) { words += 2; ix = ptcl[ix + 1]; continue; }
+        if (tag == VB_CMD_FILL) { size = 4; segs += ptcl[ix + 1] >> 1; fills++; }
+        else if (tag == VB_CMD_COLOR || tag == VB_CMD_IMAGE) size = 2;
+        else if (tag == VB_CMD_LIN_GRAD || tag == VB_CMD_RAD_GRAD || tag == VB_CMD_SWEEP_GRAD || tag == VB_CMD_END_CLIP || tag == VB_CMD_BLUR_RECT) size = 3;
+        words += size;
+        ix += size;
+    }
+    atomicAdd(out, words);
+    atomicAdd(out + 1, segs);
+    atomicAdd(out + 2, fills);
+}
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0; // bytes
@@ -607,6 +632,24 @@ extern "C" int vb_debug_download(vb_renderer *r, const char *name, void *dst, si
             return VB_OK;
         }
     return VB_E_UNKNOWN_BUFFER;
+}
+
+extern "C" int vb_debug_fine_traffic(vb_renderer *r, uint64_t *ptcl_words, uint64_t *segment_refs, uint64_t *fill_cmds) {
+    if (!r) return VB_E_INVALID;
+    CK(cudaSetDevice(r->device));
+    CK(cudaStreamSynchronize(r->stream));
+    unsigned long long *d = nullptr, h[3] = {0, 0, 0};
+    CK(cudaMalloc(&d, sizeof h));
+    CK(cudaMemset(d, 0, sizeof h));
+    uint32_t n = r->cfg.width_in_tiles * (r->cfg.win_ty1 - r->cfg.win_ty0);
+    if (n) k_ptcl_stats<<<(n + 127) / 128, 128, 0, r->stream>>>(r->cfg, (const uint32_t *)r->ptcl.p, d);
+    CK(cudaStreamSynchronize(r->stream));
+    CK(cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    if (ptcl_words) *ptcl_words = h[0];
+    if (segment_refs) *segment_refs = h[1];
+    if (fill_cmds) *fill_cmds = h[2];
+    return VB_OK;
 }
 
 extern "C" int vb_debug_upload(vb_renderer *r, const char *name, const void *src, size_t bytes) {

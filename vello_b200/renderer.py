@@ -87,13 +87,14 @@ def load_library() -> C.CDLL:
     lib.vb_run_stages.argtypes = [vp, C.POINTER(_Params), C.c_int, C.c_int, vp]
     lib.vb_debug_download.argtypes = [vp, C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.vb_debug_upload.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
+    lib.vb_debug_fine_traffic.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     _lib = lib
     return lib
 
 
 EXPORTED_SYMBOLS = ["vb_renderer_new", "vb_renderer_free", "vb_strerror", "vb_last_error", "vb_scene_upload",
                     "vb_render_resident", "vb_render_enqueue", "vb_frame_finish", "vb_render", "vb_target", "vb_copy_to_host", "vb_stream",
-                    "vb_run_stages", "vb_debug_download", "vb_debug_upload"]
+                    "vb_run_stages", "vb_debug_download", "vb_debug_upload", "vb_debug_fine_traffic"]
 
 
 @dataclass
@@ -224,6 +225,12 @@ class Renderer:
     def upload_buffer(self, name: str, arr: np.ndarray):
         a = np.ascontiguousarray(arr)
         self._check(self.lib.vb_debug_upload(self.handle, name.encode(), a.ctypes.data, a.nbytes), f"upload {name}")
+
+    def fine_traffic(self):
+        """(ptcl_words, segment_refs, fill_cmds) of the last frame -- inputs of the fine roofline."""
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self._check(self.lib.vb_debug_fine_traffic(self.handle, C.byref(a), C.byref(b), C.byref(c)), "vb_debug_fine_traffic")
+        return int(a.value), int(b.value), int(c.value)
 
     def download_target(self, params: RenderParams, bin_rows=(0, 0), device_ptr: int = 0) -> np.ndarray:
         """Copy the last frame's target (or `device_ptr`) to the host."""
