@@ -5,17 +5,24 @@
 // fine; our oracle (oracle/vbo_fine.c) restates the WGSL and this kernel must match it bit for bit
 // (MSAA: integer sample counts -> exact; area: float sums in slice order).
 //
-// Round-1 structure: one CTA (64 threads = 4x16, 4 horizontally adjacent pixels per thread, exactly
-// the WGSL's decomposition so that per-thread float expressions are identical) per tile; several
-// CTAs are resident per SM. Conventions fixed where WGSL leaves latitude: see oracle/vbo_fine.c.
+// B200 design (v2): ONE WARP PER TILE. The WGSL uses a 64-thread workgroup per tile and ~10
+// workgroup barriers per CMD_FILL; with ~5 segments per fill on map-like scenes the barriers and the
+// 1024-word clear / 256-pixel resolve per fill dominate. Here a warp owns the tile (lane = 8
+// horizontally adjacent pixels = two of the WGSL's 4-pixel groups, so every per-group float
+// expression is unchanged), all synchronisation is __syncwarp / shuffles, and the MSAA state is kept
+// CLEAN between fills: a 256-bit `touched` bitmap records which pixels received sample masks, the
+// resolve reads and re-clears only those, and untouched pixels resolve to 0 or 1 from the winding
+// words alone. The integer arithmetic per touched pixel is the WGSL's, word for word.
+// Conventions fixed where WGSL leaves latitude: see oracle/vbo_fine.c.
 // Algorithmic bytes: 4 B/pixel stored + 4 B per PTCL word + 24 B per segment referenced.
 #include <cuda_fp16.h>
 
 #include "vb_detmath.h"
 #include "vb_device.cuh"
 
-#define FI_THREADS 64
-#define PIXELS_PER_THREAD 4
+#define FI_WARPS 2                 // tiles per CTA (independent warps)
+#define FI_THREADS (32 * FI_WARPS)
+#define PX 8                       // pixels per lane
 #define ONE_MINUS_ULP 0.99999994f
 #define ROBUST_EPSILON 2e-7f
 #define GRADIENT_WIDTH 512
@@ -59,13 +66,14 @@ __device__ __forceinline__ VbSegment ld_segment(const VbSegment *__restrict__ se
 }
 
 // ---------------- area coverage: fine.wgsl:1005-1059 ----------------
-__device__ void fill_path_area(const FineArgs &A, uint32_t size_and_rule, uint32_t seg_data, int32_t backdrop, float xyx, float xyy,
-                               float (&area)[PIXELS_PER_THREAD]) {
+// lane = row `ly`, pixels 8*h .. 8*h+7 = WGSL thread groups (2h, ly) and (2h+1, ly): xy.x = 4 * group.
+__device__ void fill_path_area(const FineArgs &A, uint32_t size_and_rule, uint32_t seg_data, int32_t backdrop, float lx0, float xyy,
+                               float (&area)[PX]) {
     const uint32_t n_segs = size_and_rule >> 1;
     const bool even_odd = (size_and_rule & 1u) != 0u;
     const float backdrop_f = (float)backdrop;
 #pragma unroll
-    for (int i = 0; i < PIXELS_PER_THREAD; i++) area[i] = backdrop_f;
+    for (int i = 0; i < PX; i++) area[i] = backdrop_f;
     for (uint32_t s = 0; s < n_segs; s++) {
         const VbSegment seg = ld_segment(A.segments, seg_data + s);
         const float y = seg.p0[1] - xyy;
@@ -77,108 +85,124 @@ __device__ void fill_path_area(const FineArgs &A, uint32_t size_and_rule, uint32
             const float vec_y_recip = 1.0f / deltay;
             const float t0 = (y0 - y) * vec_y_recip;
             const float t1 = (y1 - y) * vec_y_recip;
-            const float startx = seg.p0[0] - xyx;
-            const float x0 = startx + t0 * deltax;
-            const float x1 = startx + t1 * deltax;
-            const float xmin0 = fminf(x0, x1);
-            const float xmax0 = fmaxf(x0, x1);
 #pragma unroll
-            for (int i = 0; i < PIXELS_PER_THREAD; i++) {
-                const float i_f = (float)i;
-                const float xmin = fminf(xmin0 - i_f, 1.0f) - 1.0e-6f;
-                const float xmax = xmax0 - i_f;
-                const float b = fminf(xmax, 1.0f);
-                const float c = fmaxf(b, 0.0f);
-                const float d = fmaxf(xmin, 0.0f);
-                const float a = (b + 0.5f * (d * d - c * c) - xmin) / (xmax - xmin);
-                area[i] += a * dy;
+            for (int q = 0; q < 2; q++) {
+                const float startx = seg.p0[0] - (lx0 + 4.0f * (float)q);
+                const float x0 = startx + t0 * deltax;
+                const float x1 = startx + t1 * deltax;
+                const float xmin0 = fminf(x0, x1);
+                const float xmax0 = fmaxf(x0, x1);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float i_f = (float)i;
+                    const float xmin = fminf(xmin0 - i_f, 1.0f) - 1.0e-6f;
+                    const float xmax = xmax0 - i_f;
+                    const float b = fminf(xmax, 1.0f);
+                    const float c = fmaxf(b, 0.0f);
+                    const float d = fmaxf(xmin, 0.0f);
+                    const float a = (b + 0.5f * (d * d - c * c) - xmin) / (xmax - xmin);
+                    area[q * 4 + i] += a * dy;
+                }
             }
         }
         const float y_edge = vb_signf(deltax) * vb_clampf(xyy - seg.y_edge + 1.0f, 0.0f, 1.0f);
 #pragma unroll
-        for (int i = 0; i < PIXELS_PER_THREAD; i++) area[i] += y_edge;
+        for (int i = 0; i < PX; i++) area[i] += y_edge;
     }
     if (even_odd) {
 #pragma unroll
-        for (int i = 0; i < PIXELS_PER_THREAD; i++) {
+        for (int i = 0; i < PX; i++) {
             const float a = area[i];
             area[i] = fabsf(a - 2.0f * rintf(0.5f * a));
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < PIXELS_PER_THREAD; i++) area[i] = fminf(fabsf(area[i]), 1.0f);
+        for (int i = 0; i < PX; i++) area[i] = fminf(fabsf(area[i]), 1.0f);
     }
 }
 
-// ---------------- MSAA coverage: fine.wgsl:146-709 ----------------
-struct MsShared {
-    uint32_t sh_count[FI_THREADS];
-    uint32_t sh_winding_y[4];
-    uint32_t sh_winding_y_prefix[4];
-    uint32_t sh_winding[64];
-    uint32_t sh_samples[1024];
-    uint32_t sh_scan[FI_THREADS / 32 + 2];
+// ---------------- MSAA coverage: fine.wgsl:146-709, one warp per tile ----------------
+// Per-warp shared state. INVARIANT between fills: samples == 0x80808080 (biased zero), eo_samples == 0,
+// winding == 0x80808080, winding_y == 0x80808080, eo_* == 0, touched == 0.
+template <int AA>
+struct WarpMs {
+    static constexpr uint32_t WPP = AA == 2 ? 4u : 2u; // sample words per pixel (non-zero rule)
+    uint32_t samples[256 * (AA == 2 ? 4 : 2)];
+    uint32_t eo_samples[256];
+    uint32_t winding[64];
+    uint32_t eo_winding[16];
+    uint32_t winding_y[4];
+    uint32_t eo_winding_y[4];
+    uint32_t touched[8];
+    uint32_t counts[32];
 };
 
+template <int AA>
+__device__ __forceinline__ void ms_init(WarpMs<AA> &S, uint32_t lane) {
+    for (uint32_t i = lane; i < 256u * WarpMs<AA>::WPP; i += 32u) S.samples[i] = 0x80808080u;
+    for (uint32_t i = lane; i < 256u; i += 32u) S.eo_samples[i] = 0u;
+    S.winding[lane] = 0x80808080u;
+    S.winding[lane + 32u] = 0x80808080u;
+    if (lane < 16u) S.eo_winding[lane] = 0u;
+    if (lane < 4u) { S.winding_y[lane] = 0x80808080u; S.eo_winding_y[lane] = 0u; }
+    if (lane < 8u) S.touched[lane] = 0u;
+    __syncwarp();
+}
+
 template <int AA> // 1 = msaa8, 2 = msaa16
-__device__ void fill_path_ms(const FineArgs &A, MsShared &S, uint32_t size_and_rule, uint32_t seg_data, int32_t backdrop, uint32_t lx,
-                             uint32_t ly, float (&area)[PIXELS_PER_THREAD]) {
+__device__ void fill_path_ms(const FineArgs &A, WarpMs<AA> &S, uint32_t size_and_rule, uint32_t seg_data, int32_t backdrop, uint32_t lane,
+                             float (&area)[PX]) {
     constexpr uint32_t MASK_WIDTH = AA == 2 ? 64u : 32u;
     constexpr uint32_t MASK_HEIGHT = MASK_WIDTH;
-    constexpr uint32_t WPP = AA == 2 ? 4u : 2u;
     const uint32_t n_segs = size_and_rule >> 1;
     const bool even_odd = (size_and_rule & 1u) != 0u;
-    const uint32_t th_ix = ly * 4u + lx;
-    if (even_odd) {
-        if (th_ix < 16u) {
-            if (th_ix == 0u) S.sh_winding_y[0] = 0u;
-            S.sh_winding[th_ix] = 0u;
-        }
-#pragma unroll
-        for (uint32_t i = 0; i < PIXELS_PER_THREAD; i++) S.sh_samples[th_ix * PIXELS_PER_THREAD + i] = 0u;
-    } else {
-        if (th_ix < 4u) S.sh_winding_y[th_ix] = 0x80808080u;
-        S.sh_winding[th_ix] = 0x80808080u;
-#pragma unroll
-        for (uint32_t i = 0; i < PIXELS_PER_THREAD * WPP; i++) S.sh_samples[th_ix * PIXELS_PER_THREAD * WPP + i] = 0x80808080u;
-    }
-    __syncthreads();
-    const uint32_t n_batch = (n_segs + (FI_THREADS - 1u)) / FI_THREADS;
-    for (uint32_t batch = 0u; batch < n_batch; batch++) {
-        const uint32_t seg_ix = batch * FI_THREADS + th_ix;
+    const uint32_t ly = lane >> 1, h = lane & 1u;
+
+    // ---- accumulate: batches of 32 segments; every lane first counts its segment's pixel touches, then the
+    // touches are spread over the lanes (prefix sum + binary search, as fine.wgsl:196-224)
+    for (uint32_t batch_start = 0u; batch_start < n_segs; batch_start += 32u) {
+        const uint32_t slice_size = min(n_segs - batch_start, 32u);
+        float sx0 = 0.f, sy0 = 0.f, sx1 = 0.f, sy1 = 0.f;
         uint32_t count = 0u;
-        const uint32_t slice_size = min(n_segs - batch * FI_THREADS, (uint32_t)FI_THREADS);
-        if (th_ix < slice_size) {
-            const VbSegment seg = ld_segment(A.segments, seg_data + seg_ix);
-            const float x0 = seg.p0[0], y0 = seg.p0[1], x1 = seg.p1[0], y1 = seg.p1[1];
+        if (lane < slice_size) {
+            const VbSegment seg = ld_segment(A.segments, seg_data + batch_start + lane);
+            sx0 = seg.p0[0]; sy0 = seg.p0[1]; sx1 = seg.p1[0]; sy1 = seg.p1[1];
             float y_edge_f = 16.0f;
-            const int32_t delta = (x1 <= x0) ? 1 : -1;
-            if (x0 == 0.0f) y_edge_f = y0;
-            else if (x1 == 0.0f) y_edge_f = y1;
-            if (!(y0 == y1 && y0 == floorf(y0))) count = vb_span(x0, x1) + vb_span(y0, y1) - 1u;
+            const int32_t delta = (sx1 <= sx0) ? 1 : -1;
+            if (sx0 == 0.0f) y_edge_f = sy0;
+            else if (sx1 == 0.0f) y_edge_f = sy1;
+            if (!(sy0 == sy1 && sy0 == floorf(sy0))) count = vb_span(sx0, sx1) + vb_span(sy0, sy1) - 1u;
             const uint32_t y_edge = vb_f2u_sat(ceilf(y_edge_f));
             if (y_edge < 16u) {
-                if (even_odd) atomicXor(&S.sh_winding_y[0], 1u << y_edge);
-                else atomicAdd(&S.sh_winding_y[y_edge >> 2], ((uint32_t)delta) << ((y_edge & 3u) << 3));
+                if (even_odd) atomicXor(&S.eo_winding_y[0], 1u << y_edge);
+                else atomicAdd(&S.winding_y[y_edge >> 2], ((uint32_t)delta) << ((y_edge & 3u) << 3));
             }
         }
-        uint32_t total;
-        const uint32_t ex = vb_block_excl_scan(count, S.sh_scan, &total);
-        S.sh_count[th_ix] = ex + count;
-        __syncthreads();
-        for (uint32_t i = th_ix; i < total; i += FI_THREADS) {
-            uint32_t lo = 0u, hi = slice_size;
-            while (hi > lo + 1u) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (i >= S.sh_count[mid - 1u]) lo = mid; else hi = mid;
+        const uint32_t incl = vb_warp_incl_scan(count);
+        const uint32_t total = __shfl_sync(VB_FULL, incl, 31);
+        S.counts[lane] = incl;
+        __syncwarp();
+        for (uint32_t base = 0u; base < total; base += 32u) {
+            const uint32_t i = base + lane;
+            const bool active = i < total;
+            uint32_t lo = 0u;
+            if (active) {
+                uint32_t hi = slice_size;
+                while (hi > lo + 1u) {
+                    const uint32_t m = (lo + hi) >> 1;
+                    if (i >= S.counts[m - 1u]) lo = m; else hi = m;
+                }
             }
             const uint32_t el_ix = lo;
-            const bool last_pixel = i + 1u == S.sh_count[el_ix];
-            const uint32_t sub_ix = i - (el_ix > 0u ? S.sh_count[el_ix - 1u] : 0u);
-            const VbSegment seg = ld_segment(A.segments, seg_data + batch * FI_THREADS + el_ix);
-            const bool is_down = seg.p1[1] >= seg.p0[1];
-            const float xy0x = is_down ? seg.p0[0] : seg.p1[0], xy0y = is_down ? seg.p0[1] : seg.p1[1];
-            const float xy1x = is_down ? seg.p1[0] : seg.p0[0], xy1y = is_down ? seg.p1[1] : seg.p0[1];
+            // fetch the owning lane's segment (all lanes take part in the shuffles)
+            const float p0x = __shfl_sync(VB_FULL, sx0, el_ix), p0y = __shfl_sync(VB_FULL, sy0, el_ix);
+            const float p1x = __shfl_sync(VB_FULL, sx1, el_ix), p1y = __shfl_sync(VB_FULL, sy1, el_ix);
+            if (!active) continue;
+            const bool last_pixel = i + 1u == S.counts[el_ix];
+            const uint32_t sub_ix = i - (el_ix > 0u ? S.counts[el_ix - 1u] : 0u);
+            const bool is_down = p1y >= p0y;
+            const float xy0x = is_down ? p0x : p1x, xy0y = is_down ? p0y : p1y;
+            const float xy1x = is_down ? p1x : p0x, xy1y = is_down ? p1y : p0y;
             const float dx = fabsf(xy1x - xy0x);
             const float dy = xy1y - xy0y;
             const float idxdy = 1.0f / (dx + dy);
@@ -211,10 +235,10 @@ __device__ void fill_path_ms(const FineArgs &A, MsShared &S, uint32_t size_and_r
             const uint32_t pix_ix = (uint32_t)y * 16u + (uint32_t)x;
             if ((uint32_t)x < 15u && (uint32_t)y < 16u && is_delta) {
                 if (even_odd) {
-                    atomicXor(&S.sh_winding[y], 2u << (uint32_t)x);
+                    atomicXor(&S.eo_winding[y], 2u << (uint32_t)x);
                 } else {
                     const uint32_t delta_pix = pix_ix + 1u;
-                    atomicAdd(&S.sh_winding[delta_pix >> 2], (is_down ? 1u : 0xffffffffu) << ((delta_pix & 3u) << 3));
+                    atomicAdd(&S.winding[delta_pix >> 2], (is_down ? 1u : 0xffffffffu) << ((delta_pix & 3u) << 3));
                 }
             }
             const uint32_t mask_block = (uint32_t)is_positive_slope * (MASK_WIDTH * MASK_HEIGHT / 2u);
@@ -223,8 +247,9 @@ __device__ void fill_path_ms(const FineArgs &A, MsShared &S, uint32_t size_and_r
             const float mask_col = floorf((zf - z) * (float)MASK_WIDTH);
             const uint32_t mask_ix = mask_block + vb_f2u_sat(mask_row + mask_col);
             if (pix_ix >= 256u) continue;
+            uint32_t mask;
             if (AA == 1) {
-                uint32_t mask = (__ldg(A.mask_lut + ((mask_ix / 4u) & 255u)) >> ((mask_ix % 4u) * 8u)) & 0xffu;
+                mask = (__ldg(A.mask_lut + ((mask_ix / 4u) & 255u)) >> ((mask_ix % 4u) * 8u)) & 0xffu;
                 if (sub_ix == 0u && !is_bump) {
                     const uint32_t sh = vb_f2u_sat(rintf(8.0f * (xy0y - (float)y)));
                     mask &= sh < 32u ? (0xffu << sh) : 0u;
@@ -233,24 +258,8 @@ __device__ void fill_path_ms(const FineArgs &A, MsShared &S, uint32_t size_and_r
                     const uint32_t sh = vb_f2u_sat(rintf(8.0f * (xy1y - (float)y)));
                     mask &= ~(sh < 32u ? (0xffu << sh) : 0u);
                 }
-                if (even_odd) {
-                    if (is_bump) mask ^= 0xffu;
-                    atomicXor(&S.sh_samples[pix_ix], mask);
-                } else {
-                    const uint32_t mask_a = mask ^ (mask << 7);
-                    const uint32_t mask_b = mask_a ^ (mask_a << 14);
-                    const uint32_t m0 = mask_b & 0x1010101u, m1 = (mask_b >> 4) & 0x1010101u;
-                    uint32_t m0s = is_down ? (0u - m0) : m0;
-                    uint32_t m1s = is_down ? (0u - m1) : m1;
-                    if (is_bump) {
-                        const uint32_t bd = is_down ? 0x1010101u : (0u - 0x1010101u);
-                        m0s += bd; m1s += bd;
-                    }
-                    atomicAdd(&S.sh_samples[pix_ix * 2u], m0s);
-                    atomicAdd(&S.sh_samples[pix_ix * 2u + 1u], m1s);
-                }
             } else {
-                uint32_t mask = (__ldg(A.mask_lut + ((mask_ix / 2u) & 2047u)) >> ((mask_ix % 2u) * 16u)) & 0xffffu;
+                mask = (__ldg(A.mask_lut + ((mask_ix / 2u) & 2047u)) >> ((mask_ix % 2u) * 16u)) & 0xffffu;
                 if (sub_ix == 0u && !is_bump) {
                     const uint32_t sh = vb_f2u_sat(rintf(16.0f * (xy0y - (float)y)));
                     mask &= sh < 32u ? (0xffffu << sh) : 0u;
@@ -259,104 +268,159 @@ __device__ void fill_path_ms(const FineArgs &A, MsShared &S, uint32_t size_and_r
                     const uint32_t sh = vb_f2u_sat(rintf(16.0f * (xy1y - (float)y)));
                     mask &= ~(sh < 32u ? (0xffffu << sh) : 0u);
                 }
-                if (even_odd) {
-                    if (is_bump) mask ^= 0xffffu;
-                    atomicXor(&S.sh_samples[pix_ix], mask);
-                } else {
-                    const uint32_t mask0 = mask & 0xffu;
-                    const uint32_t mask0_a = mask0 ^ (mask0 << 7);
-                    const uint32_t mask0_b = mask0_a ^ (mask0_a << 14);
-                    const uint32_t e0 = mask0_b & 0x1010101u, e1 = (mask0_b >> 4) & 0x1010101u;
-                    const uint32_t mask1 = (mask >> 8) & 0xffu;
-                    const uint32_t mask1_a = mask1 ^ (mask1 << 7);
-                    const uint32_t mask1_b = mask1_a ^ (mask1_a << 14);
-                    const uint32_t e2 = mask1_b & 0x1010101u, e3 = (mask1_b >> 4) & 0x1010101u;
-                    uint32_t s0 = is_down ? (0u - e0) : e0, s1 = is_down ? (0u - e1) : e1;
-                    uint32_t s2 = is_down ? (0u - e2) : e2, s3 = is_down ? (0u - e3) : e3;
-                    if (is_bump) {
-                        const uint32_t bd = is_down ? 0x1010101u : (0u - 0x1010101u);
-                        s0 += bd; s1 += bd; s2 += bd; s3 += bd;
-                    }
-                    atomicAdd(&S.sh_samples[pix_ix * 4u], s0);
-                    atomicAdd(&S.sh_samples[pix_ix * 4u + 1u], s1);
-                    atomicAdd(&S.sh_samples[pix_ix * 4u + 2u], s2);
-                    atomicAdd(&S.sh_samples[pix_ix * 4u + 3u], s3);
+            }
+            atomicOr(&S.touched[pix_ix >> 5], 1u << (pix_ix & 31u));
+            if (even_odd) {
+                if (is_bump) mask ^= (AA == 1 ? 0xffu : 0xffffu);
+                atomicXor(&S.eo_samples[pix_ix], mask);
+            } else if (AA == 1) {
+                const uint32_t mask_a = mask ^ (mask << 7);
+                const uint32_t mask_b = mask_a ^ (mask_a << 14);
+                const uint32_t m0 = mask_b & 0x1010101u, m1 = (mask_b >> 4) & 0x1010101u;
+                uint32_t m0s = is_down ? (0u - m0) : m0;
+                uint32_t m1s = is_down ? (0u - m1) : m1;
+                if (is_bump) {
+                    const uint32_t bd = is_down ? 0x1010101u : (0u - 0x1010101u);
+                    m0s += bd; m1s += bd;
                 }
+                atomicAdd(&S.samples[pix_ix * 2u], m0s);
+                atomicAdd(&S.samples[pix_ix * 2u + 1u], m1s);
+            } else {
+                const uint32_t mask0 = mask & 0xffu;
+                const uint32_t mask0_a = mask0 ^ (mask0 << 7);
+                const uint32_t mask0_b = mask0_a ^ (mask0_a << 14);
+                const uint32_t e0 = mask0_b & 0x1010101u, e1 = (mask0_b >> 4) & 0x1010101u;
+                const uint32_t mask1 = (mask >> 8) & 0xffu;
+                const uint32_t mask1_a = mask1 ^ (mask1 << 7);
+                const uint32_t mask1_b = mask1_a ^ (mask1_a << 14);
+                const uint32_t e2 = mask1_b & 0x1010101u, e3 = (mask1_b >> 4) & 0x1010101u;
+                uint32_t s0 = is_down ? (0u - e0) : e0, s1 = is_down ? (0u - e1) : e1;
+                uint32_t s2 = is_down ? (0u - e2) : e2, s3 = is_down ? (0u - e3) : e3;
+                if (is_bump) {
+                    const uint32_t bd = is_down ? 0x1010101u : (0u - 0x1010101u);
+                    s0 += bd; s1 += bd; s2 += bd; s3 += bd;
+                }
+                atomicAdd(&S.samples[pix_ix * 4u], s0);
+                atomicAdd(&S.samples[pix_ix * 4u + 1u], s1);
+                atomicAdd(&S.samples[pix_ix * 4u + 2u], s2);
+                atomicAdd(&S.samples[pix_ix * 4u + 3u], s3);
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
+
+    // ---- resolve: lane owns row ly, pixels 8h..8h+7
+    const uint32_t tb = (S.touched[ly >> 1] >> ((ly & 1u) * 16u + h * 8u)) & 0xffu;
     if (even_odd) {
-        uint32_t scan_x = S.sh_winding[ly];
+        uint32_t scan_x = S.eo_winding[ly];
         scan_x ^= scan_x << 1; scan_x ^= scan_x << 2; scan_x ^= scan_x << 4; scan_x ^= scan_x << 8;
-        uint32_t scan_y = S.sh_winding_y[0];
+        uint32_t scan_y = S.eo_winding_y[0];
         scan_y ^= scan_y << 1; scan_y ^= scan_y << 2; scan_y ^= scan_y << 4; scan_y ^= scan_y << 8;
         const uint32_t row_parity = (scan_y >> ly) ^ (uint32_t)backdrop;
 #pragma unroll
-        for (uint32_t i = 0; i < PIXELS_PER_THREAD; i++) {
-            const uint32_t pix_ix = th_ix * PIXELS_PER_THREAD + i;
-            const uint32_t samples = S.sh_samples[pix_ix];
-            const uint32_t pix_parity = row_parity ^ (scan_x >> (pix_ix % 16u));
+        for (uint32_t i = 0; i < PX; i++) {
+            const uint32_t px = h * 8u + i;
+            const uint32_t pix_ix = ly * 16u + px;
+            uint32_t samples = 0u;
+            if ((tb >> i) & 1u) {
+                samples = S.eo_samples[pix_ix];
+                S.eo_samples[pix_ix] = 0u;
+            }
+            const uint32_t pix_parity = row_parity ^ (scan_x >> px);
             const uint32_t pix_mask = 0u - (pix_parity & 1u);
             if (AA == 2) area[i] = (float)__popc((samples ^ pix_mask) & 0xffffu) * 0.0625f;
             else area[i] = (float)__popc((samples ^ pix_mask) & 0xffu) * 0.125f;
         }
-        __syncthreads();
+        __syncwarp();
+        if (lane < 16u) S.eo_winding[lane] = 0u;
+        if (lane == 0u) S.eo_winding_y[0] = 0u;
+        if (lane < 8u) S.touched[lane] = 0u;
+        __syncwarp();
         return;
     }
-    const uint32_t major = th_ix;
-    uint32_t packed_w = S.sh_winding[major];
-    packed_w += (packed_w - 0x808080u) << 8;
-    packed_w += (packed_w - 0x8080u) << 16;
-    uint32_t packed_y = S.sh_winding_y[ly >> 2];
-    packed_y += (packed_y - 0x808080u) << 8;
-    packed_y += (packed_y - 0x8080u) << 16;
-    uint32_t wind_y = (packed_y >> ((ly & 3u) << 3)) - 0x80u;
-    __syncthreads(); // every thread has read sh_winding / sh_winding_y before they are overwritten
-    if ((ly & 3u) == 3u && lx == 0u) S.sh_winding_y_prefix[ly >> 2] = wind_y;
-    const uint32_t prefix_x = ((packed_w >> 24) - 0x80u) * 0x1010101u;
-    S.sh_winding[major] = prefix_x;
-    __syncthreads();
-    for (uint32_t i = (major & ~3u); i < major; i++) packed_w += S.sh_winding[i];
-    for (uint32_t i = 0u; i < (ly >> 2); i++) wind_y += S.sh_winding_y_prefix[i];
+    // winding of the 4 words of this row, exactly as fine.wgsl:399-425
+    uint32_t pw[4], pfx[4];
 #pragma unroll
-    for (uint32_t i = 0u; i < PIXELS_PER_THREAD; i++) {
-        const uint32_t pix_ix = th_ix * PIXELS_PER_THREAD + i;
-        const uint32_t expected_zero = (((packed_w >> (i * 8u)) + wind_y) & 0xffu) - (uint32_t)backdrop;
-        if (expected_zero >= 256u) {
-            area[i] = 1.0f;
+    for (uint32_t k = 0; k < 4; k++) {
+        uint32_t w = S.winding[ly * 4u + k];
+        w += (w - 0x808080u) << 8;
+        w += (w - 0x8080u) << 16;
+        pw[k] = w;
+        pfx[k] = ((w >> 24) - 0x80u) * 0x1010101u;
+    }
+    uint32_t packed_w[2];
+    packed_w[0] = pw[h * 2u];
+    packed_w[1] = pw[h * 2u + 1u];
+    if (h == 1u) { packed_w[0] += pfx[0]; packed_w[0] += pfx[1]; packed_w[1] += pfx[0]; packed_w[1] += pfx[1]; packed_w[1] += pfx[2]; }
+    else { packed_w[1] += pfx[0]; }
+    uint32_t wind_y;
+    {
+        uint32_t py[4];
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) {
+            uint32_t w = S.winding_y[k];
+            w += (w - 0x808080u) << 8;
+            w += (w - 0x8080u) << 16;
+            py[k] = w;
+        }
+        wind_y = (py[ly >> 2] >> ((ly & 3u) << 3)) - 0x80u;
+        for (uint32_t k = 0; k < (ly >> 2); k++) wind_y += (py[k] >> 24) - 0x80u;
+    }
+#pragma unroll
+    for (uint32_t i = 0; i < PX; i++) {
+        const uint32_t pix_ix = ly * 16u + h * 8u + i;
+        const uint32_t expected_zero = (((packed_w[i >> 2] >> ((i & 3u) * 8u)) + wind_y) & 0xffu) - (uint32_t)backdrop;
+        if (!((tb >> i) & 1u)) {
+            // untouched pixel: all samples are the biased zero 0x80 -> every sample differs from `expected`
+            // unless expected == 0x80 (same result as the full SWAR reduction, incl. expected_zero >= 256)
+            area[i] = expected_zero == 0x80u ? 0.0f : 1.0f;
         } else if (AA == 1) {
-            const uint32_t samples0 = S.sh_samples[pix_ix * 2u], samples1 = S.sh_samples[pix_ix * 2u + 1u];
-            const uint32_t xored0 = (expected_zero * 0x1010101u) ^ samples0;
-            const uint32_t xored0_2 = xored0 | (xored0 * 2u);
-            const uint32_t xored1 = (expected_zero * 0x1010101u) ^ samples1;
-            const uint32_t xored1_2 = xored1 | (xored1 >> 1);
-            const uint32_t xored2 = (xored0_2 & 0xAAAAAAAAu) | (xored1_2 & 0x55555555u);
-            const uint32_t xored4 = xored2 | (xored2 * 4u);
-            const uint32_t xored8 = xored4 | (xored4 * 16u);
-            area[i] = (float)__popc(xored8 & 0xC0C0C0C0u) * 0.125f;
+            const uint32_t samples0 = S.samples[pix_ix * 2u], samples1 = S.samples[pix_ix * 2u + 1u];
+            S.samples[pix_ix * 2u] = 0x80808080u;
+            S.samples[pix_ix * 2u + 1u] = 0x80808080u;
+            if (expected_zero >= 256u) {
+                area[i] = 1.0f;
+            } else {
+                const uint32_t xored0 = (expected_zero * 0x1010101u) ^ samples0;
+                const uint32_t xored0_2 = xored0 | (xored0 * 2u);
+                const uint32_t xored1 = (expected_zero * 0x1010101u) ^ samples1;
+                const uint32_t xored1_2 = xored1 | (xored1 >> 1);
+                const uint32_t xored2 = (xored0_2 & 0xAAAAAAAAu) | (xored1_2 & 0x55555555u);
+                const uint32_t xored4 = xored2 | (xored2 * 4u);
+                const uint32_t xored8 = xored4 | (xored4 * 16u);
+                area[i] = (float)__popc(xored8 & 0xC0C0C0C0u) * 0.125f;
+            }
         } else {
-            const uint32_t sm0 = S.sh_samples[pix_ix * 4u], sm1 = S.sh_samples[pix_ix * 4u + 1u];
-            const uint32_t sm2 = S.sh_samples[pix_ix * 4u + 2u], sm3 = S.sh_samples[pix_ix * 4u + 3u];
-            const uint32_t ez = expected_zero * 0x1010101u;
-            const uint32_t xored0 = ez ^ sm0;
-            const uint32_t xored0_2 = xored0 | (xored0 * 2u);
-            const uint32_t xored1 = ez ^ sm1;
-            const uint32_t xored1_2 = xored1 | (xored1 >> 1);
-            const uint32_t xored01 = (xored0_2 & 0xAAAAAAAAu) | (xored1_2 & 0x55555555u);
-            const uint32_t xored01_4 = xored01 | (xored01 * 4u);
-            const uint32_t xored2 = ez ^ sm2;
-            const uint32_t xored2_2 = xored2 | (xored2 * 2u);
-            const uint32_t xored3 = ez ^ sm3;
-            const uint32_t xored3_2 = xored3 | (xored3 >> 1);
-            const uint32_t xored23 = (xored2_2 & 0xAAAAAAAAu) | (xored3_2 & 0x55555555u);
-            const uint32_t xored23_4 = xored23 | (xored23 >> 2);
-            const uint32_t xored4 = (xored01_4 & 0xCCCCCCCCu) | (xored23_4 & 0x33333333u);
-            const uint32_t xored8 = xored4 | (xored4 * 16u);
-            area[i] = (float)__popc(xored8 & 0xF0F0F0F0u) * 0.0625f;
+            const uint4 sm = *reinterpret_cast<const uint4 *>(&S.samples[pix_ix * 4u]);
+            *reinterpret_cast<uint4 *>(&S.samples[pix_ix * 4u]) = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+            if (expected_zero >= 256u) {
+                area[i] = 1.0f;
+            } else {
+                const uint32_t ez = expected_zero * 0x1010101u;
+                const uint32_t xored0 = ez ^ sm.x;
+                const uint32_t xored0_2 = xored0 | (xored0 * 2u);
+                const uint32_t xored1 = ez ^ sm.y;
+                const uint32_t xored1_2 = xored1 | (xored1 >> 1);
+                const uint32_t xored01 = (xored0_2 & 0xAAAAAAAAu) | (xored1_2 & 0x55555555u);
+                const uint32_t xored01_4 = xored01 | (xored01 * 4u);
+                const uint32_t xored2 = ez ^ sm.z;
+                const uint32_t xored2_2 = xored2 | (xored2 * 2u);
+                const uint32_t xored3 = ez ^ sm.w;
+                const uint32_t xored3_2 = xored3 | (xored3 >> 1);
+                const uint32_t xored23 = (xored2_2 & 0xAAAAAAAAu) | (xored3_2 & 0x55555555u);
+                const uint32_t xored23_4 = xored23 | (xored23 >> 2);
+                const uint32_t xored4 = (xored01_4 & 0xCCCCCCCCu) | (xored23_4 & 0x33333333u);
+                const uint32_t xored8 = xored4 | (xored4 * 16u);
+                area[i] = (float)__popc(xored8 & 0xF0F0F0F0u) * 0.0625f;
+            }
         }
     }
-    __syncthreads();
+    __syncwarp();
+    S.winding[lane] = 0x80808080u;
+    S.winding[lane + 32u] = 0x80808080u;
+    if (lane < 4u) S.winding_y[lane] = 0x80808080u;
+    if (lane < 8u) S.touched[lane] = 0u;
+    __syncwarp();
 }
 
 // ---------------- blend.wgsl ----------------
@@ -549,34 +613,47 @@ __device__ rgba_t bicubic_sample(const FineArgs &A, const VbConfig &cfg, float c
 
 // ---------------- the interpreter: fine.wgsl:1064-1398 ----------------
 template <int AA>
+struct FineShared { WarpMs<AA == 0 ? 1 : AA> w[FI_WARPS]; };
+template <>
+struct FineShared<0> { uint32_t unused; };
+
+template <int AA>
 __global__ void __launch_bounds__(FI_THREADS)
 k_fine(VbConfig cfg, FineArgs A) {
-    __shared__ MsShared S; // only touched by the MSAA variants
+    __shared__ FineShared<AA> SH;
     const uint32_t *__restrict__ ptcl = A.ptcl;
     const uint32_t *__restrict__ info = A.info;
     if (__ldg(ptcl) == ~0u) return; // upstream failure flag (path_tiling_setup.wgsl:25)
-    const uint32_t tile_x = blockIdx.x, tile_y = blockIdx.y + cfg.win_ty0;
-    const uint32_t lx = threadIdx.x & 3u, ly = threadIdx.x >> 2;
+    const uint32_t lane = vb_lane(), warp = threadIdx.x >> 5;
+    const uint32_t n_win_tiles = cfg.width_in_tiles * (cfg.win_ty1 - cfg.win_ty0);
+    const uint32_t t = blockIdx.x * FI_WARPS + warp;
+    if (t >= n_win_tiles) return;
+    const uint32_t tile_x = t % cfg.width_in_tiles, tile_y = cfg.win_ty0 + t / cfg.width_in_tiles;
+    const uint32_t ly = lane >> 1, h = lane & 1u;
     const uint32_t tile_ix = tile_y * cfg.width_in_tiles + tile_x;
-    const uint32_t gx = tile_x * 16u + lx * PIXELS_PER_THREAD, gy = tile_y * 16u + ly;
-    const float xyx = (float)gx, xyy = (float)gy;
-    const float local_x = (float)(lx * PIXELS_PER_THREAD), local_y = (float)ly;
-    rgba_t rgba[PIXELS_PER_THREAD];
-    float area[PIXELS_PER_THREAD];
+    const uint32_t gx = tile_x * 16u + h * 8u, gy = tile_y * 16u + ly;
+    const float xyy = (float)gy;
+    const float local_x = (float)(h * 8u), local_y = (float)ly;
+    // xy.x of the two WGSL thread groups this lane covers
+    const float xyx0 = (float)gx, xyx1 = (float)(gx + 4u);
+    rgba_t rgba[PX];
+    float area[PX];
     const rgba_t base = unpack4x8unorm(cfg.base_color);
 #pragma unroll
-    for (int i = 0; i < PIXELS_PER_THREAD; i++) { rgba[i] = base; area[i] = 0.0f; }
-    // Zero-initialised on purpose: with undefined initial contents the optimiser may fold the
-    // `d == clip_depth ? new : old` selects below and clobber live stack levels.
-    uint32_t blend_stack[VB_BLEND_STACK_SPLIT][PIXELS_PER_THREAD];
+    for (int i = 0; i < PX; i++) { rgba[i] = base; area[i] = 0.0f; }
+    // first BLEND_STACK_SPLIT levels of the blend stack: thread-private (local memory, L1 resident); deeper
+    // levels spill to blend_spill exactly as in the reference
+    uint32_t blend_stack[VB_BLEND_STACK_SPLIT][PX];
 #pragma unroll
     for (uint32_t d = 0; d < VB_BLEND_STACK_SPLIT; d++)
 #pragma unroll
-        for (int i = 0; i < PIXELS_PER_THREAD; i++) blend_stack[d][i] = 0u;
+        for (int i = 0; i < PX; i++) blend_stack[d][i] = 0u; // never leave it undefined (see git history: select folding)
     uint32_t clip_depth = 0u;
     uint32_t cmd_ix = tile_ix * VB_PTCL_INITIAL_ALLOC;
     const uint32_t blend_offset = __ldg(ptcl + cmd_ix);
     cmd_ix += 1u;
+    if (AA != 0) ms_init(reinterpret_cast<WarpMs<AA == 0 ? 1 : AA> *>(&SH)[warp], lane);
+#define PXX(i) ((((i) < 4) ? xyx0 : xyx1) + (float)((i) & 3))
     for (;;) {
         const uint32_t tag = __ldg(ptcl + cmd_ix);
         if (tag == VB_CMD_END) break;
@@ -585,36 +662,33 @@ k_fine(VbConfig cfg, FineArgs A) {
             const uint32_t sr = __ldg(ptcl + cmd_ix + 1), sd = __ldg(ptcl + cmd_ix + 2);
             const int32_t bd = (int32_t)__ldg(ptcl + cmd_ix + 3);
             if (AA == 0) fill_path_area(A, sr, sd, bd, local_x, local_y, area);
-            else fill_path_ms<AA == 0 ? 1 : AA>(A, S, sr, sd, bd, lx, ly, area);
+            else fill_path_ms<AA == 0 ? 1 : AA>(A, reinterpret_cast<WarpMs<AA == 0 ? 1 : AA> *>(&SH)[warp], sr, sd, bd, lane, area);
             cmd_ix += 4u;
             break;
         }
         case VB_CMD_SOLID:
 #pragma unroll
-            for (int i = 0; i < PIXELS_PER_THREAD; i++) area[i] = 1.0f;
+            for (int i = 0; i < PX; i++) area[i] = 1.0f;
             cmd_ix += 1u;
             break;
         case VB_CMD_COLOR: {
             const rgba_t fg = unpack4x8unorm(__ldg(ptcl + cmd_ix + 1));
 #pragma unroll
-            for (int i = 0; i < PIXELS_PER_THREAD; i++) rgba[i] = over(rgba[i], rg_scale(fg, area[i]));
+            for (int i = 0; i < PX; i++) rgba[i] = over(rgba[i], rg_scale(fg, area[i]));
             cmd_ix += 2u;
             break;
         }
         case VB_CMD_BEGIN_CLIP: {
             if (clip_depth < VB_BLEND_STACK_SPLIT) {
 #pragma unroll
-                for (int i = 0; i < PIXELS_PER_THREAD; i++) {
-                    // static indexing keeps blend_stack in registers
-#pragma unroll
-                    for (uint32_t d = 0; d < VB_BLEND_STACK_SPLIT; d++)
-                        if (d == clip_depth) blend_stack[d][i] = pack4x8unorm(rgba[i]);
+                for (int i = 0; i < PX; i++) {
+                    blend_stack[clip_depth][i] = pack4x8unorm(rgba[i]);
                     rgba[i] = RG(0, 0, 0, 0);
                 }
             } else {
-                const uint32_t base_ix = blend_offset + (clip_depth - VB_BLEND_STACK_SPLIT) * 256u + lx * PIXELS_PER_THREAD + ly * 16u;
+                const uint32_t base_ix = blend_offset + (clip_depth - VB_BLEND_STACK_SPLIT) * 256u + h * 8u + ly * 16u;
 #pragma unroll
-                for (int i = 0; i < PIXELS_PER_THREAD; i++) {
+                for (int i = 0; i < PX; i++) {
                     if (base_ix + i < cfg.blend_size) A.blend_spill[base_ix + i] = pack4x8unorm(rgba[i]);
                     rgba[i] = RG(0, 0, 0, 0);
                 }
@@ -628,14 +702,12 @@ k_fine(VbConfig cfg, FineArgs A) {
             const float alpha = __uint_as_float(__ldg(ptcl + cmd_ix + 2));
             clip_depth -= 1u;
 #pragma unroll
-            for (int i = 0; i < PIXELS_PER_THREAD; i++) {
-                uint32_t bg_rgba = 0u;
+            for (int i = 0; i < PX; i++) {
+                uint32_t bg_rgba;
                 if (clip_depth < VB_BLEND_STACK_SPLIT) {
-#pragma unroll
-                    for (uint32_t d = 0; d < VB_BLEND_STACK_SPLIT; d++)
-                        if (d == clip_depth) bg_rgba = blend_stack[d][i];
+                    bg_rgba = blend_stack[clip_depth][i];
                 } else {
-                    const uint32_t ix = blend_offset + (clip_depth - VB_BLEND_STACK_SPLIT) * 256u + lx * PIXELS_PER_THREAD + ly * 16u + i;
+                    const uint32_t ix = blend_offset + (clip_depth - VB_BLEND_STACK_SPLIT) * 256u + h * 8u + ly * 16u + i;
                     bg_rgba = ix < cfg.blend_size ? A.blend_spill[ix] : 0u;
                 }
                 const rgba_t bg = unpack4x8unorm(bg_rgba);
@@ -674,9 +746,9 @@ k_fine(VbConfig cfg, FineArgs A) {
             const float width = bw + fminf(delta, 0.0f);
             const float height = bh - fmaxf(delta, 0.0f);
             const float scale = 0.5f * erf7(inv_std_dev * 0.5f * (fmaxf(width, height) - 0.5f * bradius));
-#pragma unroll
-            for (int i = 0; i < PIXELS_PER_THREAD; i++) {
-                const float px = xyx + (float)i, py = xyy;
+#pragma unroll 1
+            for (int i = 0; i < PX; i++) {
+                const float px = PXX(i), py = xyy;
                 const float x = (m0 * px + m2 * py) + tx;
                 const float y = (m1 * px + m3 * py) + ty;
                 const float y0 = fabsf(y) - (height * 0.5f - r1);
@@ -696,10 +768,11 @@ k_fine(VbConfig cfg, FineArgs A) {
             const uint32_t index_mode = __ldg(ptcl + cmd_ix + 1), io = __ldg(ptcl + cmd_ix + 2);
             const uint32_t index = index_mode >> 2, ext = index_mode & 3u;
             const float line_x = __uint_as_float(info[io]), line_y = __uint_as_float(info[io + 1]), line_c = __uint_as_float(info[io + 2]);
-            const float d = (line_x * xyx + line_y * xyy) + line_c;
+            const float d0 = (line_x * xyx0 + line_y * xyy) + line_c;
+            const float d1 = (line_x * xyx1 + line_y * xyy) + line_c;
 #pragma unroll
-            for (int i = 0; i < PIXELS_PER_THREAD; i++) {
-                const float my_d = d + line_x * (float)i;
+            for (int i = 0; i < PX; i++) {
+                const float my_d = (i < 4 ? d0 : d1) + line_x * (float)(i & 3);
                 const int32_t x = vb_f2i_sat(rintf(extend_mode_normalized(my_d, ext) * (float)(GRADIENT_WIDTH - 1)));
                 rgba[i] = over(rgba[i], rg_scale(ramp_load(A, cfg, x, index), area[i]));
             }
@@ -720,32 +793,32 @@ k_fine(VbConfig cfg, FineArgs A) {
             const float r1_recip = is_circular ? 0.0f : 1.0f / radius;
             const float less_scale = (is_swapped || (1.0f - focal_x) < 0.0f) ? -1.0f : 1.0f;
             const float t_sign = vb_signf(1.0f - focal_x);
-#pragma unroll
-            for (int i = 0; i < PIXELS_PER_THREAD; i++) {
-                const float px = xyx + (float)i, py = xyy;
+#pragma unroll 1
+            for (int i = 0; i < PX; i++) {
+                const float px = PXX(i), py = xyy;
                 const float x = (m0 * px + m2 * py) + tx;
                 const float y = (m1 * px + m3 * py) + ty;
                 const float xx = x * x, yy = y * y;
-                float t = 0.0f;
+                float tt = 0.0f;
                 bool is_valid = true;
                 if (is_strip) {
                     const float a = radius - yy;
-                    t = sqrtf(a) + x;
+                    tt = sqrtf(a) + x;
                     is_valid = a >= 0.0f;
                 } else if (is_focal_on_circle) {
-                    t = (xx + yy) / x;
-                    is_valid = t >= 0.0f && x != 0.0f;
+                    tt = (xx + yy) / x;
+                    is_valid = tt >= 0.0f && x != 0.0f;
                 } else if (radius > 1.0f) {
-                    t = sqrtf(xx + yy) - x * r1_recip;
+                    tt = sqrtf(xx + yy) - x * r1_recip;
                 } else {
                     const float a = xx - yy;
-                    t = less_scale * sqrtf(a) - x * r1_recip;
-                    is_valid = a >= 0.0f && t >= 0.0f;
+                    tt = less_scale * sqrtf(a) - x * r1_recip;
+                    is_valid = a >= 0.0f && tt >= 0.0f;
                 }
                 if (is_valid) {
-                    t = extend_mode_normalized(focal_x + t_sign * t, ext);
-                    if (is_swapped) t = 1.0f - t;
-                    const int32_t rx = vb_f2i_sat(rintf(t * (float)(GRADIENT_WIDTH - 1)));
+                    tt = extend_mode_normalized(focal_x + t_sign * tt, ext);
+                    if (is_swapped) tt = 1.0f - tt;
+                    const int32_t rx = vb_f2i_sat(rintf(tt * (float)(GRADIENT_WIDTH - 1)));
                     rgba[i] = over(rgba[i], rg_scale(ramp_load(A, cfg, rx, index), area[i]));
                 }
             }
@@ -760,9 +833,9 @@ k_fine(VbConfig cfg, FineArgs A) {
             const float tx = __uint_as_float(info[io + 4]), ty = __uint_as_float(info[io + 5]);
             const float t0 = __uint_as_float(info[io + 6]), t1 = __uint_as_float(info[io + 7]);
             const float scale = 1.0f / (t1 - t0);
-#pragma unroll
-            for (int i = 0; i < PIXELS_PER_THREAD; i++) {
-                const float px = xyx + (float)i, py = xyy;
+#pragma unroll 1
+            for (int i = 0; i < PX; i++) {
+                const float px = PXX(i), py = xyy;
                 const float x = (m0 * px + m2 * py) + tx;
                 const float y = (m1 * px + m3 * py) + ty;
                 const float xabs = fabsf(x), yabs = fabsf(y);
@@ -776,8 +849,8 @@ k_fine(VbConfig cfg, FineArgs A) {
                 if (y < 0.0f) phi = 1.0f - phi;
                 if (phi != phi) phi = 0.0f;
                 phi = (phi - t0) * scale;
-                const float t = extend_mode_normalized(phi, ext);
-                const int32_t rx = vb_f2i_sat(rintf(t * (float)(GRADIENT_WIDTH - 1)));
+                const float tt = extend_mode_normalized(phi, ext);
+                const int32_t rx = vb_f2i_sat(rintf(tt * (float)(GRADIENT_WIDTH - 1)));
                 rgba[i] = over(rgba[i], rg_scale(ramp_load(A, cfg, rx, index), area[i]));
             }
             cmd_ix += 3u;
@@ -796,9 +869,9 @@ k_fine(VbConfig cfg, FineArgs A) {
             const float ew = (float)(wh >> 16), eh = (float)(wh & 0xffffu);
             const float mx = ox + ew - 1.0f, my = oy + eh - 1.0f;
 #pragma unroll 1
-            for (int i = 0; i < PIXELS_PER_THREAD; i++) {
+            for (int i = 0; i < PX; i++) {
                 if (area[i] == 0.0f) continue;
-                const float px = (xyx + (float)i) + 0.5f, py = xyy + 0.5f;
+                const float px = PXX(i) + 0.5f, py = xyy + 0.5f;
                 float u = (m0 * px + m2 * py) + tx;
                 float v = (m1 * px + m3 * py) + ty;
                 u = extend_mode(u, x_ext, ew);
@@ -834,20 +907,24 @@ k_fine(VbConfig cfg, FineArgs A) {
             break;
         }
     }
+#undef PXX
     if (gy < cfg.target_height && gy >= cfg.out_row0) {
-        uint32_t px[PIXELS_PER_THREAD];
+        uint32_t px[PX];
 #pragma unroll
-        for (int i = 0; i < PIXELS_PER_THREAD; i++) {
+        for (int i = 0; i < PX; i++) {
             const rgba_t fg = rgba[i];
             const float a_inv = 1.0f / fmaxf(fg.a, 1e-6f);
             px[i] = unorm8(fg.r * a_inv) | (unorm8(fg.g * a_inv) << 8) | (unorm8(fg.b * a_inv) << 16) | (unorm8(fg.a) << 24);
         }
         uint32_t *row = A.out + (size_t)(gy - cfg.out_row0) * cfg.out_pitch_px;
-        if (gx + 3u < cfg.target_width && (cfg.out_pitch_px & 3u) == 0u && ((uintptr_t)A.out & 15u) == 0u) {
-            *reinterpret_cast<uint4 *>(row + gx) = make_uint4(px[0], px[1], px[2], px[3]); // 128-bit row store
+        if (gx + 7u < cfg.target_width && (cfg.out_pitch_px & 3u) == 0u && ((uintptr_t)A.out & 15u) == 0u) {
+            // two 128-bit stores: 32 contiguous bytes of one pixel row per lane
+            uint4 *dst = reinterpret_cast<uint4 *>(row + gx);
+            dst[0] = make_uint4(px[0], px[1], px[2], px[3]);
+            dst[1] = make_uint4(px[4], px[5], px[6], px[7]);
         } else {
 #pragma unroll
-            for (int i = 0; i < PIXELS_PER_THREAD; i++)
+            for (int i = 0; i < PX; i++)
                 if (gx + i < cfg.target_width) row[gx + i] = px[i];
         }
     }
@@ -857,8 +934,9 @@ extern "C" void vb_launch_fine(const VbConfig *cfg, int aa, const VbSegment *seg
                                uint32_t *blend_spill, uint32_t *out, const uint32_t *ramps, const uint8_t *atlas,
                                const uint32_t *mask_lut8, const uint32_t *mask_lut16, cudaStream_t st) {
     uint32_t rows = cfg->win_ty1 - cfg->win_ty0;
-    if (cfg->width_in_tiles == 0 || rows == 0) return;
-    dim3 grid(cfg->width_in_tiles, rows);
+    uint32_t n = cfg->width_in_tiles * rows;
+    if (n == 0) return;
+    uint32_t grid = (n + FI_WARPS - 1) / FI_WARPS;
     FineArgs A;
     A.segments = segments; A.ptcl = ptcl; A.info = info; A.blend_spill = blend_spill; A.out = out; A.ramps = ramps; A.atlas = atlas;
     A.mask_lut = aa == 2 ? mask_lut16 : mask_lut8;
