@@ -110,13 +110,7 @@ def dist_setup(n_gpus):
     return rank, world, local, None
 
 
-def stripe_for(rank, world, height):
-    """Bin-row stripe [b0, b1) of `rank` (bins are 256 px tall); contiguous, as even as possible."""
-    n_bins = (height + 255) // 256
-    base, rem = divmod(n_bins, world)
-    b0 = rank * base + min(rank, rem)
-    b1 = b0 + base + (1 if rank < rem else 0)
-    return b0, b1
+from vello_b200.stripes import stripe_for  # noqa: E402  (bin-row stripe of a rank)
 
 
 def run_cpu_arm(args, packed, as_reference):

@@ -65,6 +65,12 @@ k_coarse(VbConfig cfg, const uint32_t *__restrict__ scene, const VbDrawMonoid *_
     __shared__ uint32_t sh_tile_x0y0[CO_THREADS];
     __shared__ uint32_t sh_tile_count[CO_THREADS];
     __shared__ uint32_t sh_tile_base[CO_THREADS];
+    // per-draw-object fields cached once per 256-element chunk (the WGSL re-reads them from global memory for
+    // every (draw, tile) pair: 3-4 dependent loads per pair -> 1)
+    __shared__ uint32_t sh_tag[CO_THREADS];    // draw tag
+    __shared__ uint32_t sh_dd[CO_THREADS];     // draw data word offset
+    __shared__ uint32_t sh_di[CO_THREADS];     // info word offset
+    __shared__ uint32_t sh_dflags[CO_THREADS]; // bit0 even-odd, bit1 non-trivial blend (clip objects)
     __shared__ uint32_t sh_scan[CO_THREADS / 32 + 2];
 
     const uint32_t lid = threadIdx.x;
@@ -134,8 +140,16 @@ k_coarse(VbConfig cfg, const uint32_t *__restrict__ scene, const VbDrawMonoid *_
             tag = vb_scene(scene, cfg, cfg.layout.draw_tag_base + drawobj_ix);
         }
         uint32_t tile_count = 0u;
+        sh_tag[lid] = tag;
         if (tag != VB_DRAWTAG_NOP) {
-            const uint32_t path_ix = draw_monoids[drawobj_ix].path_ix;
+            const VbDrawMonoid dm0 = draw_monoids[drawobj_ix];
+            const uint32_t path_ix = dm0.path_ix;
+            const uint32_t dd0 = cfg.layout.draw_data_base + dm0.scene_offset;
+            uint32_t fl = info_bin_data[dm0.info_offset] & 1u;
+            if ((tag & 1u) != 0u && vb_scene(scene, cfg, dd0) != ((128u << 8) | 3u)) fl |= 2u;
+            sh_dd[lid] = dd0;
+            sh_di[lid] = dm0.info_offset;
+            sh_dflags[lid] = fl;
             const VbPath path = paths[path_ix];
             const uint32_t stride = path.bbox[2] - path.bbox[0];
             sh_tile_stride[lid] = stride;
@@ -163,8 +177,7 @@ k_coarse(VbConfig cfg, const uint32_t *__restrict__ scene, const VbDrawMonoid *_
                 uint32_t probe = el_ix + (128u >> i);
                 if (ix >= sh_tile_count[probe - 1u]) el_ix = probe;
             }
-            const uint32_t dobj = sh_drawobj_ix[el_ix];
-            const uint32_t dtag = vb_scene(scene, cfg, cfg.layout.draw_tag_base + dobj);
+            const uint32_t dtag = sh_tag[el_ix];
             const uint32_t seq_ix = ix - (el_ix > 0u ? sh_tile_count[el_ix - 1u] : 0u);
             const uint32_t width = sh_tile_width[el_ix];
             const uint32_t x0y0 = sh_tile_x0y0[el_ix];
@@ -173,14 +186,9 @@ k_coarse(VbConfig cfg, const uint32_t *__restrict__ scene, const VbDrawMonoid *_
             const uint32_t tile_ix = sh_tile_base[el_ix] + sh_tile_stride[el_ix] * y + x;
             const VbTile tile = tiles[tile_ix];
             const bool is_clip = (dtag & 1u) != 0u;
-            bool is_blend = false;
-            const VbDrawMonoid dm = draw_monoids[dobj];
-            if (is_clip) {
-                const uint32_t BLEND_CLIP = (128u << 8) | 3u;
-                is_blend = vb_scene(scene, cfg, cfg.layout.draw_data_base + dm.scene_offset) != BLEND_CLIP;
-            }
-            const uint32_t draw_flags = info_bin_data[dm.info_offset];
-            const bool even_odd = (draw_flags & 1u) != 0u;
+            const uint32_t fl = sh_dflags[el_ix];
+            const bool is_blend = (fl & 2u) != 0u;
+            const bool even_odd = (fl & 1u) != 0u;
             const uint32_t n_segs = tile.segment_count_or_ix;
             const bool backdrop_clear = (even_odd ? (abs(tile.backdrop) & 1) : tile.backdrop) == 0;
             const bool include_tile = n_segs != 0u || (backdrop_clear == is_clip) || is_blend;
@@ -198,13 +206,11 @@ k_coarse(VbConfig cfg, const uint32_t *__restrict__ scene, const VbDrawMonoid *_
                 if (bitmap == 0u) continue;
             }
             const uint32_t el_ix = slice_ix * 32u + (uint32_t)(__ffs((int)bitmap) - 1);
-            const uint32_t dobj = sh_drawobj_ix[el_ix];
             bitmap &= bitmap - 1u;
-            const uint32_t drawtag = vb_scene(scene, cfg, cfg.layout.draw_tag_base + dobj);
-            const VbDrawMonoid dm = draw_monoids[dobj];
-            const uint32_t dd = cfg.layout.draw_data_base + dm.scene_offset;
-            const uint32_t di = dm.info_offset;
-            const uint32_t draw_flags = info_bin_data[di];
+            const uint32_t drawtag = sh_tag[el_ix];
+            const uint32_t dd = sh_dd[el_ix];
+            const uint32_t di = sh_di[el_ix];
+            const uint32_t draw_flags = sh_dflags[el_ix] & 1u; // only the fill-rule bit is defined (drawtag.wgsl:42)
             if (clip_zero_depth == 0u) {
                 const uint32_t tile_ix = sh_tile_base[el_ix] + sh_tile_stride[el_ix] * tile_y + tile_x;
                 const VbTile tile = tiles[tile_ix];

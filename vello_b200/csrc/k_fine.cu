@@ -643,11 +643,10 @@ k_fine(VbConfig cfg, FineArgs A) {
     for (int i = 0; i < PX; i++) { rgba[i] = base; area[i] = 0.0f; }
     // first BLEND_STACK_SPLIT levels of the blend stack: thread-private (local memory, L1 resident); deeper
     // levels spill to blend_spill exactly as in the reference
+    // Dynamically indexed -> lives in local memory; every level is stored by BEGIN_CLIP before END_CLIP loads it.
+    // (Do not turn this into a register array updated through `d == clip_depth ? new : old` selects without
+    // initialising it: the optimiser folds selects on undefined values and clobbers live levels.)
     uint32_t blend_stack[VB_BLEND_STACK_SPLIT][PX];
-#pragma unroll
-    for (uint32_t d = 0; d < VB_BLEND_STACK_SPLIT; d++)
-#pragma unroll
-        for (int i = 0; i < PX; i++) blend_stack[d][i] = 0u; // never leave it undefined (see git history: select folding)
     uint32_t clip_depth = 0u;
     uint32_t cmd_ix = tile_ix * VB_PTCL_INITIAL_ALLOC;
     const uint32_t blend_offset = __ldg(ptcl + cmd_ix);

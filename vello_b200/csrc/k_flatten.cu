@@ -35,18 +35,27 @@ __device__ __forceinline__ fv2 fx_apply(const FXform &t, fv2 p) { // flatten.wgs
     return F2(fmaf(t.m0, p.x, fmaf(t.m2, p.y, t.tx)), fmaf(t.m1, p.x, fmaf(t.m3, p.y, t.ty)));
 }
 
-template <bool EMIT>
+// MODE 0: count lines only. MODE 1: count, accumulate the bbox and stash the first FL_CACHE lines of this thread
+// in shared memory (most tags produce <= FL_CACHE lines, so the geometry is computed once). MODE 2: emit to global.
+#define FL_CACHE 6
+template <int MODE>
 struct Flat {
     VbLineSoup *lines;
     uint32_t lines_size;
-    uint32_t ix; // next line slot (EMIT) / running count (!EMIT)
+    uint32_t ix; // next line slot (MODE 2) / running count (MODE 0, 1)
     float bx0, by0, bx1, by1;
+    float4 *cache; // MODE 1: &cache[0][threadIdx.x], stride FL_THREADS
     __device__ __forceinline__ void write_line(uint32_t path_ix, fv2 p0, fv2 p1) {
-        if (EMIT) {
+        if (MODE != 0) {
             bx0 = fminf(bx0, fminf(p0.x, p1.x));
             by0 = fminf(by0, fminf(p0.y, p1.y));
             bx1 = fmaxf(bx1, fmaxf(p0.x, p1.x));
             by1 = fmaxf(by1, fmaxf(p0.y, p1.y));
+        }
+        if (MODE == 1) {
+            if (ix < FL_CACHE) cache[ix * FL_THREADS] = make_float4(p0.x, p0.y, p1.x, p1.y);
+        }
+        if (MODE == 2) {
             if (ix < lines_size) {
                 uint2 *dst = reinterpret_cast<uint2 *>(lines + ix);
                 dst[0] = make_uint2(path_ix, 0u);
@@ -57,7 +66,7 @@ struct Flat {
         ix++;
     }
     __device__ __forceinline__ void line_xf(uint32_t path_ix, fv2 p0, fv2 p1, const FXform &t) {
-        if (EMIT) write_line(path_ix, fx_apply(t, p0), fx_apply(t, p1));
+        if (MODE != 0) write_line(path_ix, fx_apply(t, p0), fx_apply(t, p1));
         else ix++;
     }
 };
@@ -269,7 +278,7 @@ __device__ fv2 cubic_end_tangent(fv2 p0, fv2 p1, fv2 p2, fv2 p3) {
 
 struct CubicPoints { fv2 p0, p1, p2, p3; };
 
-template <bool EMIT>
+template <int EMIT>
 __device__ void flatten_euler(Flat<EMIT> &f, const CubicPoints &cubic, uint32_t path_ix, const FXform &local_to_device,
                               float offset, fv2 start_p, fv2 end_p) { // flatten.wgsl:326-481
     fv2 p0, p1, p2, p3;
@@ -350,7 +359,7 @@ __device__ void flatten_euler(Flat<EMIT> &f, const CubicPoints &cubic, uint32_t 
             }
             float n = vb_clampf(ceilf(n_frac * scale_multiplier), 1.0f, 100.0f);
             uint32_t n_u = vb_f2u_sat(n);
-            if (EMIT) {
+            if (EMIT != 0) {
                 for (uint32_t i = 0u; i < n_u; i++) {
                     fv2 lp1;
                     if (i + 1u == n_u && t1 == 1.0f) {
@@ -389,7 +398,7 @@ __device__ void flatten_euler(Flat<EMIT> &f, const CubicPoints &cubic, uint32_t 
     }
 }
 
-template <bool EMIT>
+template <int EMIT>
 __device__ void flatten_arc(Flat<EMIT> &f, uint32_t path_ix, fv2 begin, fv2 end, fv2 center, float angle, const FXform &t) {
     fv2 p0 = fx_apply(t, begin);
     fv2 r = begin - center;
@@ -398,7 +407,7 @@ __device__ void flatten_arc(Flat<EMIT> &f, uint32_t path_ix, fv2 begin, fv2 end,
     float radius = fmaxf(tol, flen(p0 - fx_apply(t, center)));
     float theta = fmaxf(MIN_THETA, 2.f * vb_acosf(1.f - tol / radius));
     uint32_t n_lines = max(1u, vb_f2u_sat(ceilf(angle / theta)));
-    if (!EMIT) { f.ix += n_lines; return; }
+    if (EMIT == 0) { f.ix += n_lines; return; }
     float s, c;
     vb_sincosf(theta, &s, &c);
     for (uint32_t i = 0u; i + 1u < n_lines; i++) {
@@ -423,7 +432,7 @@ __device__ void flatten_arc(Flat<EMIT> &f, uint32_t path_ix, fv2 begin, fv2 end,
 #define STYLE_FLAGS_JOIN_MITER 0x10000000u
 #define STYLE_FLAGS_JOIN_ROUND 0x20000000u
 
-template <bool EMIT>
+template <int EMIT>
 __device__ void draw_cap(Flat<EMIT> &f, uint32_t path_ix, uint32_t cap_style, fv2 point, fv2 cap0, fv2 cap1, fv2 offset_tangent,
                          const FXform &t) { // flatten.wgsl:521-545 (slot order of the WGSL)
     if (cap_style == STYLE_FLAGS_CAP_ROUND) {
@@ -445,7 +454,7 @@ __device__ void draw_cap(Flat<EMIT> &f, uint32_t path_ix, uint32_t cap_style, fv
 
 __device__ __forceinline__ float f16_bits_to_f32(uint32_t h) { return __half2float(__ushort_as_half((unsigned short)(h & 0xffffu))); }
 
-template <bool EMIT>
+template <int EMIT>
 __device__ void draw_join(Flat<EMIT> &f, uint32_t path_ix, uint32_t style_flags, fv2 p0, fv2 tan_prev, fv2 tan_next, fv2 n_prev,
                           fv2 n_next, const FXform &t) { // flatten.wgsl:547-631
     fv2 front0 = p0 + n_prev;
@@ -576,7 +585,7 @@ __device__ CubicPoints read_path_segment(const VbConfig &cfg, const uint32_t *__
 }
 
 // Everything one tag byte produces. EMIT=false only counts lines.
-template <bool EMIT>
+template <int EMIT>
 __device__ void flatten_tag(Flat<EMIT> &f, const VbConfig &cfg, const uint32_t *__restrict__ scene,
                             const VbTagMonoid *__restrict__ tag_monoids, const PathTagData &tag, uint32_t ix, uint32_t style_flags) {
     uint32_t seg_type = tag.tag_byte & 3u;
@@ -674,10 +683,13 @@ k_flatten(VbConfig cfg, const uint32_t *__restrict__ scene, const VbTagMonoid *_
             path_bboxes[tag.path_ix].trans_ix = tag.trans_ix;
         }
     }
-    // pass 1: count
-    Flat<false> fc;
+    // pass 1: count + cache
+    __shared__ float4 sh_cache[FL_CACHE][FL_THREADS];
+    Flat<1> fc;
     fc.lines = nullptr; fc.lines_size = 0; fc.ix = 0;
-    flatten_tag<false>(fc, cfg, scene, tag_monoids, tag, ix, style_flags);
+    fc.bx0 = 1e31f; fc.by0 = 1e31f; fc.bx1 = -1e31f; fc.by1 = -1e31f;
+    fc.cache = &sh_cache[0][threadIdx.x];
+    flatten_tag<1>(fc, cfg, scene, tag_monoids, tag, ix, style_flags);
     uint32_t total;
     uint32_t local_off = vb_block_excl_scan(fc.ix, sh_scan, &total);
     if (threadIdx.x < 32) {
@@ -693,18 +705,36 @@ k_flatten(VbConfig cfg, const uint32_t *__restrict__ scene, const VbTagMonoid *_
         }
     }
     __syncthreads();
-    // pass 2: emit into [base + local_off, ...)
     if (fc.ix != 0u) {
-        Flat<true> fe;
-        fe.lines = lines; fe.lines_size = cfg.lines_size; fe.ix = sh_base + local_off;
-        fe.bx0 = 1e31f; fe.by0 = 1e31f; fe.bx1 = -1e31f; fe.by1 = -1e31f;
-        flatten_tag<true>(fe, cfg, scene, tag_monoids, tag, ix, style_flags);
-        if ((fe.bx1 > fe.bx0 || fe.by1 > fe.by0) && tag.path_ix < n_paths) {
+        const uint32_t out0 = sh_base + local_off;
+        float bx0 = fc.bx0, by0 = fc.by0, bx1 = fc.bx1, by1 = fc.by1;
+        if (fc.ix <= FL_CACHE) {
+            // pass 2a: copy the cached lines to their final slots
+            for (uint32_t k = 0; k < fc.ix; k++) {
+                const uint32_t o = out0 + k;
+                if (o < cfg.lines_size) {
+                    const float4 l = sh_cache[k][threadIdx.x];
+                    uint2 *dst = reinterpret_cast<uint2 *>(lines + o);
+                    dst[0] = make_uint2(tag.path_ix, 0u);
+                    dst[1] = make_uint2(__float_as_uint(l.x), __float_as_uint(l.y));
+                    dst[2] = make_uint2(__float_as_uint(l.z), __float_as_uint(l.w));
+                }
+            }
+        } else {
+            // pass 2b: too many lines for the cache -> recompute, emitting straight to global memory
+            Flat<2> fe;
+            fe.lines = lines; fe.lines_size = cfg.lines_size; fe.ix = out0;
+            fe.bx0 = 1e31f; fe.by0 = 1e31f; fe.bx1 = -1e31f; fe.by1 = -1e31f;
+            fe.cache = nullptr;
+            flatten_tag<2>(fe, cfg, scene, tag_monoids, tag, ix, style_flags);
+            bx0 = fe.bx0; by0 = fe.by0; bx1 = fe.bx1; by1 = fe.by1;
+        }
+        if ((bx1 > bx0 || by1 > by0) && tag.path_ix < n_paths) {
             VbPathBbox *o = path_bboxes + tag.path_ix;
-            atomicMin(&o->x0, vb_f2i_sat(floorf(fe.bx0)));
-            atomicMin(&o->y0, vb_f2i_sat(floorf(fe.by0)));
-            atomicMax(&o->x1, vb_f2i_sat(ceilf(fe.bx1)));
-            atomicMax(&o->y1, vb_f2i_sat(ceilf(fe.by1)));
+            atomicMin(&o->x0, vb_f2i_sat(floorf(bx0)));
+            atomicMin(&o->y0, vb_f2i_sat(floorf(by0)));
+            atomicMax(&o->x1, vb_f2i_sat(ceilf(bx1)));
+            atomicMax(&o->y1, vb_f2i_sat(ceilf(by1)));
         }
     }
 }

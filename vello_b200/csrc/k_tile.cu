@@ -66,46 +66,70 @@ k_tile_alloc(VbConfig cfg, const uint32_t *__restrict__ scene, const VbBbox4 *__
     for (uint32_t i = base + threadIdx.x; i < end; i += TA_THREADS) t2[i] = make_uint2(0u, 0u);
 }
 
-// backdrop: per (path, tile row) inclusive prefix sum along x. One thread per row, rows found by
-// binary search over the CTA's row-count prefix (same balancing as backdrop_dyn.wgsl:52-84).
+// backdrop: per (path, tile row) inclusive prefix sum along x (backdrop_dyn.wgsl:66-84).
+// B200 design: the WGSL assigns one thread per row, walking 8-byte tiles at a stride of the row width
+// (uncoalesced). Here a CTA takes 256 consecutive paths, cuts every path's row-major tile rectangle into chunks of
+// whole rows (<= ~1024 tiles), and its warps take chunks round-robin (binary search over the CTA's chunk prefix, the
+// same balancing idea as backdrop_dyn.wgsl:52-84). A warp sweeps its chunk 32 consecutive tiles at a time
+// (coalesced) with a segmented warp-shuffle scan whose segments are the rows. Integer sums: identical results.
 #define BD_THREADS 256
+#define BD_CHUNK_TILES 1024u
 __global__ void __launch_bounds__(BD_THREADS)
 k_backdrop(VbConfig cfg, const VbBump *__restrict__ bump, const VbPath *__restrict__ paths, VbTile *tiles) {
-    __shared__ uint32_t sh_row_width[BD_THREADS];
-    __shared__ uint32_t sh_row_count[BD_THREADS];
+    __shared__ uint32_t sh_chunks[BD_THREADS];   // inclusive prefix of chunk counts
+    __shared__ uint32_t sh_width[BD_THREADS];
+    __shared__ uint32_t sh_height[BD_THREADS];
     __shared__ uint32_t sh_offset[BD_THREADS];
     __shared__ uint32_t sh_scan[BD_THREADS / 32 + 2];
     if (bump->failed != 0u) return;
-    const uint32_t drawobj_ix = blockIdx.x * BD_THREADS + threadIdx.x;
-    uint32_t row_count = 0u;
-    sh_row_width[threadIdx.x] = 0u;
-    if (drawobj_ix < cfg.layout.n_draw_objects) {
-        VbPath p = paths[drawobj_ix];
-        sh_row_width[threadIdx.x] = p.bbox[2] - p.bbox[0];
-        row_count = p.bbox[3] - p.bbox[1];
-        sh_offset[threadIdx.x] = p.tiles;
+    const uint32_t p = blockIdx.x * BD_THREADS + threadIdx.x;
+    uint32_t width = 0u, height = 0u, n_chunks = 0u;
+    if (p < cfg.layout.n_draw_objects) {
+        const VbPath path = paths[p];
+        width = path.bbox[2] - path.bbox[0];
+        height = path.bbox[3] - path.bbox[1];
+        sh_offset[threadIdx.x] = path.tiles;
+        if (width > 1u && height > 0u) {
+            const uint32_t rows_per_chunk = max(1u, BD_CHUNK_TILES / width);
+            n_chunks = (height + rows_per_chunk - 1u) / rows_per_chunk;
+        }
     }
-    uint32_t total_rows;
-    uint32_t ex = vb_block_excl_scan(row_count, sh_scan, &total_rows);
-    sh_row_count[threadIdx.x] = ex + row_count; // inclusive
+    sh_width[threadIdx.x] = width;
+    sh_height[threadIdx.x] = height;
+    uint32_t total;
+    const uint32_t ex = vb_block_excl_scan(n_chunks, sh_scan, &total);
+    sh_chunks[threadIdx.x] = ex + n_chunks;
     __syncthreads();
-    for (uint32_t row = threadIdx.x; row < total_rows; row += BD_THREADS) {
-        uint32_t el_ix = 0u;
+    const uint32_t lane = vb_lane();
+    for (uint32_t c = threadIdx.x >> 5; c < total; c += BD_THREADS / 32) {
+        uint32_t el = 0u;
 #pragma unroll
         for (uint32_t i = 0u; i < 8u; i++) {
-            uint32_t probe = el_ix + (128u >> i);
-            if (row >= sh_row_count[probe - 1u]) el_ix = probe;
+            const uint32_t probe = el + (128u >> i);
+            if (c >= sh_chunks[probe - 1u]) el = probe;
         }
-        uint32_t width = sh_row_width[el_ix];
-        if (width > 0u) {
-            uint32_t seq_ix = row - (el_ix > 0u ? sh_row_count[el_ix - 1u] : 0u);
-            uint32_t tile_ix = sh_offset[el_ix] + seq_ix * width;
-            int32_t sum = tiles[tile_ix].backdrop;
-            for (uint32_t x = 1u; x < width; x++) {
-                tile_ix += 1u;
-                sum += tiles[tile_ix].backdrop;
-                tiles[tile_ix].backdrop = sum;
+        const uint32_t w = sh_width[el];
+        const uint32_t rows_per_chunk = max(1u, BD_CHUNK_TILES / w);
+        const uint32_t chunk_in_path = c - (el > 0u ? sh_chunks[el - 1u] : 0u);
+        const uint32_t r0 = chunk_in_path * rows_per_chunk;
+        const uint32_t r1 = min(r0 + rows_per_chunk, sh_height[el]);
+        const uint32_t base = sh_offset[el] + r0 * w;
+        const uint32_t n = (r1 - r0) * w;
+        int32_t carry = 0;
+        for (uint32_t off = 0u; off < n; off += 32u) {
+            const uint32_t idx = off + lane;
+            const bool valid = idx < n;
+            int32_t v = valid ? tiles[base + idx].backdrop : 0;
+            const uint32_t x = idx % w;             // column inside the row
+            const uint32_t reach = min(x, lane);    // elements of my row to my left inside this 32-tile group
+#pragma unroll
+            for (uint32_t o = 1u; o < 32u; o <<= 1) {
+                const int32_t t = __shfl_up_sync(VB_FULL, v, o);
+                if (o <= reach) v += t;
             }
+            if (x > lane) v += carry;               // my row started in an earlier group
+            if (valid && x != 0u) tiles[base + idx].backdrop = v;
+            carry = __shfl_sync(VB_FULL, v, 31);
         }
     }
 }
