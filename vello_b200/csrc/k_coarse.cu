@@ -6,6 +6,10 @@
 // The per-tile command SEQUENCE is identical to the reference's; segment slices and dynamic PTCL
 // chunks come from atomic bump allocators, so their absolute offsets are allocation-order
 // dependent (as in the reference). Only bins inside the stripe window are launched.
+// Parallelism: the WGSL launches one workgroup per bin (256 at 4096^2 -- far fewer than a B200 can hold), and the
+// per-bin coverage loop is a chain of dependent global loads. Here every bin is split into four 8x8-tile QUADRANTS,
+// each handled by its own CTA (all 256 threads share the (draw, tile) coverage loop, threads 0..63 own a tile each for
+// emission), and the coverage loop keeps two independent tile loads in flight.
 #include "vb_device.cuh"
 
 #define CO_THREADS 256
@@ -81,14 +85,16 @@ k_coarse(VbConfig cfg, const uint32_t *__restrict__ scene, const VbDrawMonoid *_
     const uint32_t prior_failed = sh_scan[0];
     __syncthreads();
     if (prior_failed != 0u) return;
-    const uint32_t wg_x = blockIdx.x, wg_y = blockIdx.y + cfg.win_by0;
+    const uint32_t wg_x = blockIdx.x >> 1, wg_y = (blockIdx.y >> 1) + cfg.win_by0;
+    const int32_t qx0 = (int32_t)(blockIdx.x & 1u) * 8, qy0 = (int32_t)(blockIdx.y & 1u) * 8; // quadrant origin in bin tiles
     const uint32_t width_in_bins = (cfg.width_in_tiles + VB_N_TILE_X - 1u) / VB_N_TILE_X;
     const uint32_t height_in_bins = (cfg.height_in_tiles + VB_N_TILE_Y - 1u) / VB_N_TILE_Y;
     const uint32_t bin_ix = width_in_bins * wg_y + wg_x;
     const uint32_t aligned_n_bins = (width_in_bins * height_in_bins + VB_N_TILE - 1u) & ~(VB_N_TILE - 1u);
     const uint32_t n_partitions = (cfg.layout.n_draw_objects + VB_N_TILE - 1u) / VB_N_TILE;
     const uint32_t bin_tile_x = VB_N_TILE_X * wg_x, bin_tile_y = VB_N_TILE_Y * wg_y;
-    const uint32_t tile_x = lid % VB_N_TILE_X, tile_y = lid / VB_N_TILE_X;
+    const bool owns_tile = lid < 64u;
+    const uint32_t tile_x = (uint32_t)qx0 + (lid & 7u), tile_y = (uint32_t)qy0 + ((lid >> 3) & 7u);
     const uint32_t this_tile_ix = (bin_tile_y + tile_y) * cfg.width_in_tiles + bin_tile_x + tile_x;
     TileState st;
     st.cmd_offset = this_tile_ix * VB_PTCL_INITIAL_ALLOC;
@@ -155,10 +161,10 @@ k_coarse(VbConfig cfg, const uint32_t *__restrict__ scene, const VbDrawMonoid *_
             sh_tile_stride[lid] = stride;
             const int32_t dx = (int32_t)path.bbox[0] - (int32_t)bin_tile_x;
             const int32_t dy = (int32_t)path.bbox[1] - (int32_t)bin_tile_y;
-            const int32_t x0 = vb_clampi(dx, 0, (int32_t)VB_N_TILE_X);
-            const int32_t y0 = vb_clampi(dy, 0, (int32_t)VB_N_TILE_Y);
-            const int32_t x1 = vb_clampi((int32_t)path.bbox[2] - (int32_t)bin_tile_x, 0, (int32_t)VB_N_TILE_X);
-            const int32_t y1 = vb_clampi((int32_t)path.bbox[3] - (int32_t)bin_tile_y, 0, (int32_t)VB_N_TILE_Y);
+            const int32_t x0 = vb_clampi(dx, qx0, qx0 + 8);
+            const int32_t y0 = vb_clampi(dy, qy0, qy0 + 8);
+            const int32_t x1 = vb_clampi((int32_t)path.bbox[2] - (int32_t)bin_tile_x, qx0, qx0 + 8);
+            const int32_t y1 = vb_clampi((int32_t)path.bbox[3] - (int32_t)bin_tile_y, qy0, qy0 + 8);
             sh_tile_width[lid] = (uint32_t)(x1 - x0);
             sh_tile_x0y0[lid] = (uint32_t)x0 | ((uint32_t)y0 << 16);
             tile_count = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0);
@@ -170,35 +176,54 @@ k_coarse(VbConfig cfg, const uint32_t *__restrict__ scene, const VbDrawMonoid *_
             sh_tile_count[lid] = ex + tile_count;
         }
         __syncthreads();
-        for (uint32_t ix = lid; ix < total_tile_count; ix += VB_N_TILE) {
-            uint32_t el_ix = 0u;
+        for (uint32_t ix0 = lid; ix0 < total_tile_count; ix0 += 2u * VB_N_TILE) {
+            uint32_t el[2], tix[2], bit[2];
+            VbTile tl[2];
+            bool ok[2];
 #pragma unroll
-            for (uint32_t i = 0u; i < 8u; i++) {
-                uint32_t probe = el_ix + (128u >> i);
-                if (ix >= sh_tile_count[probe - 1u]) el_ix = probe;
+            for (int u = 0; u < 2; u++) {
+                const uint32_t ix = ix0 + (uint32_t)u * VB_N_TILE;
+                ok[u] = ix < total_tile_count;
+                uint32_t el_ix = 0u;
+                if (ok[u]) {
+#pragma unroll
+                    for (uint32_t i = 0u; i < 8u; i++) {
+                        uint32_t probe = el_ix + (128u >> i);
+                        if (ix >= sh_tile_count[probe - 1u]) el_ix = probe;
+                    }
+                }
+                el[u] = el_ix;
+                const uint32_t seq_ix = ix - (el_ix > 0u ? sh_tile_count[el_ix - 1u] : 0u);
+                const uint32_t width = ok[u] ? sh_tile_width[el_ix] : 1u;
+                const uint32_t x0y0 = sh_tile_x0y0[el_ix];
+                const uint32_t x = (x0y0 & 0xffffu) + seq_ix % width;
+                const uint32_t y = (x0y0 >> 16) + seq_ix / width;
+                tix[u] = sh_tile_base[el_ix] + sh_tile_stride[el_ix] * y + x;
+                bit[u] = (y - (uint32_t)qy0) * 8u + (x - (uint32_t)qx0);
             }
-            const uint32_t dtag = sh_tag[el_ix];
-            const uint32_t seq_ix = ix - (el_ix > 0u ? sh_tile_count[el_ix - 1u] : 0u);
-            const uint32_t width = sh_tile_width[el_ix];
-            const uint32_t x0y0 = sh_tile_x0y0[el_ix];
-            const uint32_t x = (x0y0 & 0xffffu) + seq_ix % width;
-            const uint32_t y = (x0y0 >> 16) + seq_ix / width;
-            const uint32_t tile_ix = sh_tile_base[el_ix] + sh_tile_stride[el_ix] * y + x;
-            const VbTile tile = tiles[tile_ix];
-            const bool is_clip = (dtag & 1u) != 0u;
-            const uint32_t fl = sh_dflags[el_ix];
-            const bool is_blend = (fl & 2u) != 0u;
-            const bool even_odd = (fl & 1u) != 0u;
-            const uint32_t n_segs = tile.segment_count_or_ix;
-            const bool backdrop_clear = (even_odd ? (abs(tile.backdrop) & 1) : tile.backdrop) == 0;
-            const bool include_tile = n_segs != 0u || (backdrop_clear == is_clip) || is_blend;
-            if (include_tile) atomicOr(&sh_bitmaps[el_ix / 32u][y * VB_N_TILE_X + x], 1u << (el_ix & 31u));
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+                if (ok[u]) tl[u] = tiles[tix[u]]; // independent loads in flight
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                if (!ok[u]) continue;
+                const uint32_t el_ix = el[u];
+                const uint32_t dtag = sh_tag[el_ix];
+                const bool is_clip = (dtag & 1u) != 0u;
+                const uint32_t fl = sh_dflags[el_ix];
+                const bool is_blend = (fl & 2u) != 0u;
+                const bool even_odd = (fl & 1u) != 0u;
+                const uint32_t n_segs = tl[u].segment_count_or_ix;
+                const bool backdrop_clear = (even_odd ? (abs(tl[u].backdrop) & 1) : tl[u].backdrop) == 0;
+                const bool include_tile = n_segs != 0u || (backdrop_clear == is_clip) || is_blend;
+                if (include_tile) atomicOr(&sh_bitmaps[el_ix / 32u][bit[u]], 1u << (el_ix & 31u));
+            }
         }
         __syncthreads();
 
         uint32_t slice_ix = 0u;
-        uint32_t bitmap = sh_bitmaps[0][lid];
-        while (true) {
+        uint32_t bitmap = owns_tile ? sh_bitmaps[0][lid] : 0u;
+        while (owns_tile) {
             if (bitmap == 0u) {
                 slice_ix += 1u;
                 if (slice_ix == CO_N_SLICE) break;
@@ -290,7 +315,7 @@ k_coarse(VbConfig cfg, const uint32_t *__restrict__ scene, const VbDrawMonoid *_
         if (rd_ix >= ready_ix && partition_ix >= n_partitions) break;
         __syncthreads();
     }
-    if (bin_tile_x + tile_x < cfg.width_in_tiles && bin_tile_y + tile_y < cfg.height_in_tiles) {
+    if (owns_tile && bin_tile_x + tile_x < cfg.width_in_tiles && bin_tile_y + tile_y < cfg.height_in_tiles) {
         ptcl[st.cmd_offset] = VB_CMD_END;
         uint32_t blend_ix = 0u;
         if (max_blend_depth > VB_BLEND_STACK_SPLIT) {
@@ -314,7 +339,7 @@ extern "C" void vb_launch_coarse(const VbConfig *cfg, const uint32_t *scene, con
     uint32_t width_in_bins = (cfg->width_in_tiles + 15u) / 16u;
     uint32_t rows = cfg->win_by1 - cfg->win_by0;
     if (width_in_bins == 0 || rows == 0) return;
-    dim3 grid(width_in_bins, rows);
+    dim3 grid(width_in_bins * 2u, rows * 2u); // four quadrant CTAs per bin
     k_coarse<<<grid, CO_THREADS, 0, st>>>(*cfg, scene, draw_monoids, bin_headers, info_bin_data, paths, tiles, bump, ptcl);
     k_coarse_check<<<1, 1, 0, st>>>(*cfg, bump);
 }

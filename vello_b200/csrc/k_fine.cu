@@ -43,6 +43,18 @@ __device__ __forceinline__ rgba_t over(rgba_t bg, rgba_t fg) {
     return RG(bg.r * k + fg.r, bg.g * k + fg.g, bg.b * k + fg.b, bg.a * k + fg.a);
 }
 
+// byte / 255.0f for the warp-uniform unpacks (CMD_COLOR, base colour): filled on the host with the same IEEE
+// division, so values are identical to unpack4x8unorm()'s.
+__constant__ float c_unorm[256];
+__device__ __forceinline__ rgba_t unpack4x8unorm_uniform(uint32_t u) {
+    return RG(c_unorm[u & 0xffu], c_unorm[(u >> 8) & 0xffu], c_unorm[(u >> 16) & 0xffu], c_unorm[u >> 24]);
+}
+extern "C" int vb_fine_init_constants(void) {
+    float h[256];
+    for (int i = 0; i < 256; i++) h[i] = (float)i / 255.0f;
+    return (int)cudaMemcpyToSymbol(c_unorm, h, sizeof h);
+}
+
 struct FineArgs {
     const VbSegment *segments;
     const uint32_t *ptcl;
@@ -162,11 +174,14 @@ __device__ void fill_path_ms(const FineArgs &A, WarpMs<AA> &S, uint32_t size_and
     // touches are spread over the lanes (prefix sum + binary search, as fine.wgsl:196-224)
     for (uint32_t batch_start = 0u; batch_start < n_segs; batch_start += 32u) {
         const uint32_t slice_size = min(n_segs - batch_start, 32u);
-        float sx0 = 0.f, sy0 = 0.f, sx1 = 0.f, sy1 = 0.f;
+        // per-segment line setup, computed ONCE by the owning lane (the WGSL recomputes it for every pixel touch)
+        float s_a = 0.f, s_b = 0.f, s_y0i = 0.f, s_xy0y = 0.f, s_xy1y = 0.f;
+        int32_t s_x0i = 0;
+        uint32_t s_flags = 0u; // bit0 is_down, bit1 is_positive_slope, bit2 xy0.x == 0, bit3 xy1.x != 0, bit4 y0i == xy0.y
         uint32_t count = 0u;
         if (lane < slice_size) {
             const VbSegment seg = ld_segment(A.segments, seg_data + batch_start + lane);
-            sx0 = seg.p0[0]; sy0 = seg.p0[1]; sx1 = seg.p1[0]; sy1 = seg.p1[1];
+            const float sx0 = seg.p0[0], sy0 = seg.p0[1], sx1 = seg.p1[0], sy1 = seg.p1[1];
             float y_edge_f = 16.0f;
             const int32_t delta = (sx1 <= sx0) ? 1 : -1;
             if (sx0 == 0.0f) y_edge_f = sy0;
@@ -177,6 +192,28 @@ __device__ void fill_path_ms(const FineArgs &A, WarpMs<AA> &S, uint32_t size_and
                 if (even_odd) atomicXor(&S.eo_winding_y[0], 1u << y_edge);
                 else atomicAdd(&S.winding_y[y_edge >> 2], ((uint32_t)delta) << ((y_edge & 3u) << 3));
             }
+            const bool is_down = sy1 >= sy0;
+            const float xy0x = is_down ? sx0 : sx1, xy0y = is_down ? sy0 : sy1;
+            const float xy1x = is_down ? sx1 : sx0, xy1y = is_down ? sy1 : sy0;
+            const float dx = fabsf(xy1x - xy0x);
+            const float dy = xy1y - xy0y;
+            const float idxdy = 1.0f / (dx + dy);
+            float a = dx * idxdy;
+            const bool is_positive_slope = xy1x >= xy0x;
+            const float x_sign = is_positive_slope ? 1.0f : -1.0f;
+            const float xt0 = floorf(xy0x * x_sign);
+            const float c = xy0x * x_sign - xt0;
+            const float y0i = floorf(xy0y);
+            const float ytop = y0i + 1.0f;
+            const float b = fminf((dy * c + dx * (ytop - xy0y)) * idxdy, ONE_MINUS_ULP);
+            const uint32_t count_x = vb_span(xy0x, xy1x) - 1u;
+            const uint32_t count_full = count_x + vb_span(xy0y, xy1y);
+            const float robust_err = floorf(a * ((float)count_full - 1.0f) + b) - (float)count_x;
+            if (robust_err != 0.0f) a -= ROBUST_EPSILON * vb_signf(robust_err);
+            s_a = a; s_b = b; s_y0i = y0i; s_xy0y = xy0y; s_xy1y = xy1y;
+            s_x0i = vb_f2i_sat(xt0 * x_sign + 0.5f * (x_sign - 1.0f));
+            s_flags = (is_down ? 1u : 0u) | (is_positive_slope ? 2u : 0u) | (xy0x == 0.0f ? 4u : 0u) | (xy1x != 0.0f ? 8u : 0u) |
+                      (y0i == xy0y ? 16u : 0u);
         }
         const uint32_t incl = vb_warp_incl_scan(count);
         const uint32_t total = __shfl_sync(VB_FULL, incl, 31);
@@ -194,39 +231,26 @@ __device__ void fill_path_ms(const FineArgs &A, WarpMs<AA> &S, uint32_t size_and
                 }
             }
             const uint32_t el_ix = lo;
-            // fetch the owning lane's segment (all lanes take part in the shuffles)
-            const float p0x = __shfl_sync(VB_FULL, sx0, el_ix), p0y = __shfl_sync(VB_FULL, sy0, el_ix);
-            const float p1x = __shfl_sync(VB_FULL, sx1, el_ix), p1y = __shfl_sync(VB_FULL, sy1, el_ix);
+            // fetch the owning lane's setup (all lanes take part in the shuffles)
+            const float a = __shfl_sync(VB_FULL, s_a, el_ix), b = __shfl_sync(VB_FULL, s_b, el_ix);
+            const float y0i = __shfl_sync(VB_FULL, s_y0i, el_ix);
+            const float xy0y = __shfl_sync(VB_FULL, s_xy0y, el_ix), xy1y = __shfl_sync(VB_FULL, s_xy1y, el_ix);
+            const int32_t x0i = __shfl_sync(VB_FULL, s_x0i, el_ix);
+            const uint32_t fl = __shfl_sync(VB_FULL, s_flags, el_ix);
             if (!active) continue;
+            const bool is_down = (fl & 1u) != 0u, is_positive_slope = (fl & 2u) != 0u;
+            const bool xy0x_zero = (fl & 4u) != 0u, xy1x_nonzero = (fl & 8u) != 0u, y0i_eq = (fl & 16u) != 0u;
+            const float x_sign = is_positive_slope ? 1.0f : -1.0f;
             const bool last_pixel = i + 1u == S.counts[el_ix];
             const uint32_t sub_ix = i - (el_ix > 0u ? S.counts[el_ix - 1u] : 0u);
-            const bool is_down = p1y >= p0y;
-            const float xy0x = is_down ? p0x : p1x, xy0y = is_down ? p0y : p1y;
-            const float xy1x = is_down ? p1x : p0x, xy1y = is_down ? p1y : p0y;
-            const float dx = fabsf(xy1x - xy0x);
-            const float dy = xy1y - xy0y;
-            const float idxdy = 1.0f / (dx + dy);
-            float a = dx * idxdy;
-            const bool is_positive_slope = xy1x >= xy0x;
-            const float x_sign = is_positive_slope ? 1.0f : -1.0f;
-            const float xt0 = floorf(xy0x * x_sign);
-            const float c = xy0x * x_sign - xt0;
-            const float y0i = floorf(xy0y);
-            const float ytop = y0i + 1.0f;
-            const float b = fminf((dy * c + dx * (ytop - xy0y)) * idxdy, ONE_MINUS_ULP);
-            const uint32_t count_x = vb_span(xy0x, xy1x) - 1u;
-            const uint32_t count_full = count_x + vb_span(xy0y, xy1y);
-            const float robust_err = floorf(a * ((float)count_full - 1.0f) + b) - (float)count_x;
-            if (robust_err != 0.0f) a -= ROBUST_EPSILON * vb_signf(robust_err);
-            const int32_t x0i = vb_f2i_sat(xt0 * x_sign + 0.5f * (x_sign - 1.0f));
             const float zf = a * (float)sub_ix + b;
             const float z = floorf(zf);
             const int32_t x = x0i + vb_f2i_sat(x_sign * z);
             const int32_t y = vb_f2i_sat(y0i) + (int32_t)sub_ix - vb_f2i_sat(z);
             bool is_delta, is_bump = false;
             if (sub_ix == 0u) {
-                is_delta = y0i == xy0y;
-                is_bump = even_odd ? (xy0x == 0.0f) : (xy0x == 0.0f && y0i != xy0y);
+                is_delta = y0i_eq;
+                is_bump = even_odd ? xy0x_zero : (xy0x_zero && !y0i_eq);
             } else {
                 const float zp = floorf(a * (float)(sub_ix - 1u) + b);
                 is_delta = z == zp;
@@ -254,7 +278,7 @@ __device__ void fill_path_ms(const FineArgs &A, WarpMs<AA> &S, uint32_t size_and
                     const uint32_t sh = vb_f2u_sat(rintf(8.0f * (xy0y - (float)y)));
                     mask &= sh < 32u ? (0xffu << sh) : 0u;
                 }
-                if (last_pixel && xy1x != 0.0f) {
+                if (last_pixel && xy1x_nonzero) {
                     const uint32_t sh = vb_f2u_sat(rintf(8.0f * (xy1y - (float)y)));
                     mask &= ~(sh < 32u ? (0xffu << sh) : 0u);
                 }
@@ -264,7 +288,7 @@ __device__ void fill_path_ms(const FineArgs &A, WarpMs<AA> &S, uint32_t size_and
                     const uint32_t sh = vb_f2u_sat(rintf(16.0f * (xy0y - (float)y)));
                     mask &= sh < 32u ? (0xffffu << sh) : 0u;
                 }
-                if (last_pixel && xy1x != 0.0f) {
+                if (last_pixel && xy1x_nonzero) {
                     const uint32_t sh = vb_f2u_sat(rintf(16.0f * (xy1y - (float)y)));
                     mask &= ~(sh < 32u ? (0xffffu << sh) : 0u);
                 }
@@ -638,7 +662,7 @@ k_fine(VbConfig cfg, FineArgs A) {
     const float xyx0 = (float)gx, xyx1 = (float)(gx + 4u);
     rgba_t rgba[PX];
     float area[PX];
-    const rgba_t base = unpack4x8unorm(cfg.base_color);
+    const rgba_t base = unpack4x8unorm_uniform(cfg.base_color);
 #pragma unroll
     for (int i = 0; i < PX; i++) { rgba[i] = base; area[i] = 0.0f; }
     // first BLEND_STACK_SPLIT levels of the blend stack: thread-private (local memory, L1 resident); deeper
@@ -671,7 +695,7 @@ k_fine(VbConfig cfg, FineArgs A) {
             cmd_ix += 1u;
             break;
         case VB_CMD_COLOR: {
-            const rgba_t fg = unpack4x8unorm(__ldg(ptcl + cmd_ix + 1));
+            const rgba_t fg = unpack4x8unorm_uniform(__ldg(ptcl + cmd_ix + 1));
 #pragma unroll
             for (int i = 0; i < PX; i++) rgba[i] = over(rgba[i], rg_scale(fg, area[i]));
             cmd_ix += 2u;
@@ -727,7 +751,7 @@ k_fine(VbConfig cfg, FineArgs A) {
             break;
         case VB_CMD_BLUR_RECT: {
             const uint32_t io = __ldg(ptcl + cmd_ix + 1);
-            const rgba_t blur_rgba = unpack4x8unorm(__ldg(ptcl + cmd_ix + 2));
+            const rgba_t blur_rgba = unpack4x8unorm_uniform(__ldg(ptcl + cmd_ix + 2));
             const float m0 = __uint_as_float(info[io]), m1 = __uint_as_float(info[io + 1]), m2 = __uint_as_float(info[io + 2]),
                         m3 = __uint_as_float(info[io + 3]);
             const float tx = __uint_as_float(info[io + 4]), ty = __uint_as_float(info[io + 5]);

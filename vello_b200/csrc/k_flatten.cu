@@ -660,15 +660,21 @@ __global__ void k_bbox_clear(uint32_t n_paths, VbPathBbox *path_bboxes) {
     }
 }
 
+// One look-back PARTITION PER WARP (32 tags): flatten's per-thread work varies by 10-100x (a fill line vs a stroked
+// curve with round joins), so CTA-wide barriers leave most warps waiting for the slowest thread (ncu: "barrier" was the
+// dominant stall with 256-tag partitions). With warp partitions there is no __syncthreads at all: a warp counts,
+// scans with shuffles, resolves its base by look-back and emits.
 __global__ void __launch_bounds__(FL_THREADS)
 k_flatten(VbConfig cfg, const uint32_t *__restrict__ scene, const VbTagMonoid *__restrict__ tag_monoids,
           VbPathBbox *path_bboxes, VbBump *bump, VbLineSoup *lines, uint32_t *lb_mem, uint32_t n_parts) {
-    __shared__ uint32_t sh_ticket;
-    __shared__ uint32_t sh_scan[FL_THREADS / 32 + 2];
-    __shared__ uint32_t sh_base;
+    __shared__ float4 sh_cache[FL_CACHE][FL_THREADS];
     VbLookback lb = vb_lookback_view(lb_mem, n_parts, 1);
-    const uint32_t part = vb_take_ticket(lb, &sh_ticket);
-    const uint32_t ix = part * FL_THREADS + threadIdx.x;
+    const uint32_t lane = vb_lane();
+    uint32_t part = 0u;
+    if (lane == 0u) part = atomicAdd(lb.ticket, 1u);
+    part = __shfl_sync(VB_FULL, part, 0);
+    if (part >= n_parts) return;
+    const uint32_t ix = part * 32u + lane;
     const uint32_t n_tags = cfg.n_tag_words * 4u;
     const uint32_t n_paths = cfg.layout.n_paths;
 
@@ -684,29 +690,24 @@ k_flatten(VbConfig cfg, const uint32_t *__restrict__ scene, const VbTagMonoid *_
         }
     }
     // pass 1: count + cache
-    __shared__ float4 sh_cache[FL_CACHE][FL_THREADS];
     Flat<1> fc;
     fc.lines = nullptr; fc.lines_size = 0; fc.ix = 0;
     fc.bx0 = 1e31f; fc.by0 = 1e31f; fc.bx1 = -1e31f; fc.by1 = -1e31f;
     fc.cache = &sh_cache[0][threadIdx.x];
     flatten_tag<1>(fc, cfg, scene, tag_monoids, tag, ix, style_flags);
-    uint32_t total;
-    uint32_t local_off = vb_block_excl_scan(fc.ix, sh_scan, &total);
-    if (threadIdx.x < 32) {
-        uint32_t agg[1] = {total}, excl[1];
-        vb_lookback<1>(lb, part, agg, excl);
-        if (threadIdx.x == 0) {
-            sh_base = excl[0];
-            if (part == n_parts - 1) {
-                uint32_t n_lines = excl[0] + total;
-                bump->lines = n_lines;
-                if (n_lines > cfg.lines_size) atomicOr(&bump->failed, VB_STAGE_FLATTEN);
-            }
-        }
+    __syncwarp();
+    const uint32_t incl = vb_warp_incl_scan(fc.ix);
+    const uint32_t total = __shfl_sync(VB_FULL, incl, 31);
+    uint32_t agg[1] = {total}, excl[1];
+    vb_lookback<1>(lb, part, agg, excl);
+    const uint32_t base = excl[0];
+    if (lane == 0u && part == n_parts - 1u) {
+        const uint32_t n_lines = base + total;
+        bump->lines = n_lines;
+        if (n_lines > cfg.lines_size) atomicOr(&bump->failed, VB_STAGE_FLATTEN);
     }
-    __syncthreads();
     if (fc.ix != 0u) {
-        const uint32_t out0 = sh_base + local_off;
+        const uint32_t out0 = base + incl - fc.ix;
         float bx0 = fc.bx0, by0 = fc.by0, bx1 = fc.bx1, by1 = fc.by1;
         if (fc.ix <= FL_CACHE) {
             // pass 2a: copy the cached lines to their final slots
@@ -744,6 +745,10 @@ extern "C" void vb_launch_flatten(const VbConfig *cfg, const uint32_t *scene, co
                                   cudaStream_t st) {
     uint32_t n_paths = cfg->layout.n_paths;
     if (n_paths) k_bbox_clear<<<(n_paths + 255) / 256, 256, 0, st>>>(n_paths, path_bboxes);
-    if (n_parts) k_flatten<<<n_parts, FL_THREADS, 0, st>>>(*cfg, scene, tag_monoids, path_bboxes, bump, lines, lb_mem, n_parts);
+    if (n_parts) {
+        const uint32_t warps_per_cta = FL_THREADS / 32;
+        k_flatten<<<(n_parts + warps_per_cta - 1) / warps_per_cta, FL_THREADS, 0, st>>>(*cfg, scene, tag_monoids, path_bboxes, bump, lines,
+                                                                                       lb_mem, n_parts);
+    }
 }
-extern "C" uint32_t vb_flatten_parts(uint32_t n_tag_words) { return (n_tag_words * 4u + FL_THREADS - 1) / FL_THREADS; }
+extern "C" uint32_t vb_flatten_parts(uint32_t n_tag_words) { return (n_tag_words * 4u + 31u) / 32u; }

@@ -68,12 +68,13 @@ k_tile_alloc(VbConfig cfg, const uint32_t *__restrict__ scene, const VbBbox4 *__
 
 // backdrop: per (path, tile row) inclusive prefix sum along x (backdrop_dyn.wgsl:66-84).
 // B200 design: the WGSL assigns one thread per row, walking 8-byte tiles at a stride of the row width
-// (uncoalesced). Here a CTA takes 256 consecutive paths, cuts every path's row-major tile rectangle into chunks of
+// (uncoalesced). Here a CTA takes 32 consecutive paths, cuts every path's row-major tile rectangle into chunks of
 // whole rows (<= ~1024 tiles), and its warps take chunks round-robin (binary search over the CTA's chunk prefix, the
 // same balancing idea as backdrop_dyn.wgsl:52-84). A warp sweeps its chunk 32 consecutive tiles at a time
 // (coalesced) with a segmented warp-shuffle scan whose segments are the rows. Integer sums: identical results.
 #define BD_THREADS 256
-#define BD_CHUNK_TILES 1024u
+#define BD_PATHS 32u      // paths per CTA: small, so that the grid has enough CTAs to fill the machine
+#define BD_CHUNK_TILES 512u
 __global__ void __launch_bounds__(BD_THREADS)
 k_backdrop(VbConfig cfg, const VbBump *__restrict__ bump, const VbPath *__restrict__ paths, VbTile *tiles) {
     __shared__ uint32_t sh_chunks[BD_THREADS];   // inclusive prefix of chunk counts
@@ -82,9 +83,9 @@ k_backdrop(VbConfig cfg, const VbBump *__restrict__ bump, const VbPath *__restri
     __shared__ uint32_t sh_offset[BD_THREADS];
     __shared__ uint32_t sh_scan[BD_THREADS / 32 + 2];
     if (bump->failed != 0u) return;
-    const uint32_t p = blockIdx.x * BD_THREADS + threadIdx.x;
+    const uint32_t p = blockIdx.x * BD_PATHS + threadIdx.x;
     uint32_t width = 0u, height = 0u, n_chunks = 0u;
-    if (p < cfg.layout.n_draw_objects) {
+    if (threadIdx.x < BD_PATHS && p < cfg.layout.n_draw_objects) {
         const VbPath path = paths[p];
         width = path.bbox[2] - path.bbox[0];
         height = path.bbox[3] - path.bbox[1];
@@ -143,5 +144,5 @@ extern "C" uint32_t vb_tile_alloc_parts(uint32_t n_draw) { return (n_draw + TA_T
 extern "C" void vb_launch_backdrop(const VbConfig *cfg, const VbBump *bump, const VbPath *paths, VbTile *tiles, cudaStream_t st) {
     uint32_t n = cfg->layout.n_draw_objects;
     if (n == 0) return;
-    k_backdrop<<<(n + BD_THREADS - 1) / BD_THREADS, BD_THREADS, 0, st>>>(*cfg, bump, paths, tiles);
+    k_backdrop<<<(n + BD_PATHS - 1) / BD_PATHS, BD_THREADS, 0, st>>>(*cfg, bump, paths, tiles);
 }

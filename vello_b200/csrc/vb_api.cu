@@ -44,6 +44,8 @@ void vb_launch_fine(const VbConfig *, int, const VbSegment *, const uint32_t *, 
                     const uint8_t *, const uint32_t *, const uint32_t *, cudaStream_t);
 }
 
+extern "C" int vb_fine_init_constants(void);
+
 // path_tiling_setup.wgsl:21-26: a failed frame is flagged to fine through ptcl[0]
 __global__ void k_flag_failure(const VbBump *bump, uint32_t *ptcl) {
     if (bump->failed != 0u) ptcl[0] = ~0u;
@@ -193,6 +195,10 @@ extern "C" int vb_renderer_new(const vb_options *opt, vb_renderer **out) {
     memset(r->h_bump, 0, sizeof(VbBump));
     for (auto &ev : r->ev) cudaEventCreate(&ev);
     r->ev_ok = true;
+    if (vb_fine_init_constants() != 0) {
+        delete r;
+        return VB_E_CUDA;
+    }
     std::vector<uint32_t> l8, l16;
     make_mask_luts(l8, l16);
     if (ensure(r, r->mask8, l8.size() * 4) || ensure(r, r->mask16, l16.size() * 4)) {
