@@ -10,7 +10,12 @@
 // per-bin coverage loop is a chain of dependent global loads. Here every bin is split into four 8x8-tile QUADRANTS,
 // each handled by its own CTA (all 256 threads share the (draw, tile) coverage loop, threads 0..63 own a tile each for
 // emission), and the coverage loop keeps two independent tile loads in flight.
+#include <cooperative_groups.h>
+#include <cooperative_groups/scan.h>
+
 #include "vb_device.cuh"
+
+namespace cg = cooperative_groups;
 
 #define CO_THREADS 256
 #define CO_N_SLICE 8
@@ -41,7 +46,18 @@ __device__ __forceinline__ void co_write_path(TileState &s, const VbTile &tile, 
                                               VbBump *bump, uint32_t *ptcl, VbTile *tiles) {
     const uint32_t n_segs = tile.segment_count_or_ix;
     if (n_segs != 0u) {
-        uint32_t seg_ix = atomicAdd(&bump->segments, n_segs);
+        // Every CMD_FILL of the frame allocates from ONE counter (about a million times on a map-like scene): as
+        // separate same-address atomics they serialise in L2 and dominated this kernel. Aggregate over the lanes
+        // that happen to be here together (opportunistic warp aggregation): one atomic per group.
+        uint32_t seg_ix;
+        {
+            cg::coalesced_group g = cg::coalesced_threads();
+            const uint32_t pre = cg::exclusive_scan(g, n_segs);
+            uint32_t base = 0u;
+            if (g.thread_rank() == g.size() - 1u) base = atomicAdd(&bump->segments, pre + n_segs);
+            base = g.shfl(base, g.size() - 1u);
+            seg_ix = base + pre;
+        }
         tiles[tile_ix].segment_count_or_ix = ~seg_ix;
         co_alloc_cmd(s, 4u, cfg, bump, ptcl);
         ptcl[s.cmd_offset] = VB_CMD_FILL;

@@ -20,6 +20,8 @@
 __global__ void __launch_bounds__(PC_THREADS)
 k_path_count(VbConfig cfg, VbBump *bump, const VbLineSoup *__restrict__ lines, const VbPath *__restrict__ paths, VbTile *tile,
              VbSegmentCount *seg_counts) {
+    __shared__ uint32_t sh_scan[PC_THREADS / 32 + 2];
+    __shared__ uint32_t sh_base;
     if (bump->failed != 0u) return;
     const uint32_t n_lines = min(bump->lines, cfg.lines_size);
     for (uint32_t line_base = blockIdx.x * PC_THREADS; line_base < n_lines; line_base += gridDim.x * PC_THREADS) {
@@ -124,14 +126,14 @@ k_path_count(VbConfig cfg, VbBump *bump, const VbLineSoup *__restrict__ lines, c
             }
         }
         const uint32_t n = active ? imax - imin : 0u;
-        // warp-aggregated worklist allocation
-        const uint32_t incl = vb_warp_incl_scan(n);
-        uint32_t warp_base = 0u;
-        const uint32_t warp_total = __shfl_sync(VB_FULL, incl, 31);
-        if (vb_lane() == 31u && warp_total != 0u) warp_base = atomicAdd(&bump->seg_counts, warp_total);
-        warp_base = __shfl_sync(VB_FULL, warp_base, 31);
+        // CTA-aggregated worklist allocation: one same-address atomic per 256 lines
+        uint32_t cta_total;
+        const uint32_t excl = vb_block_excl_scan(n, sh_scan, &cta_total);
+        if (threadIdx.x == 0 && cta_total != 0u) sh_base = atomicAdd(&bump->seg_counts, cta_total);
+        __syncthreads();
+        const uint32_t cta_base = sh_base;
         if (n != 0u) {
-            const uint32_t seg_base = warp_base + incl - n;
+            const uint32_t seg_base = cta_base + excl;
             float last_z = floorf(a * ((float)imin - 1.0f) + b);
             for (uint32_t i = imin; i < imax; i++) {
                 const float zf = a * (float)i + b;
