@@ -660,24 +660,26 @@ __global__ void k_bbox_clear(uint32_t n_paths, VbPathBbox *path_bboxes) {
     }
 }
 
-// One look-back PARTITION PER WARP (32 tags): flatten's per-thread work varies by 10-100x (a fill line vs a stroked
-// curve with round joins), so CTA-wide barriers leave most warps waiting for the slowest thread (ncu: "barrier" was the
-// dominant stall with 256-tag partitions). With warp partitions there is no __syncthreads at all: a warp counts,
-// scans with shuffles, resolves its base by look-back and emits.
+// Three small kernels instead of one look-back pass. flatten's per-thread work varies by 10-100x (a fill line vs a
+// stroked curve with round joins); with a single-pass look-back every warp that has finished counting sits on its
+// registers until ALL earlier partitions have published, so the slowest tag in flight gates the whole machine
+// (ncu r1: 18 % issue utilisation, stalls = barrier / look-back spin). Instead:
+//   A  k_flatten        : each thread flattens its tag ONCE, lines go to a scratch arena at an offset taken with one
+//                         atomicAdd per warp (lane order inside the warp = tag order); per-warp {count, scratch offset}
+//   B  k_flatten_scan   : exclusive scan of the per-warp counts (one CTA; ~50k values)
+//   C  k_flatten_reorder: per warp, block-copy scratch[src .. src+count) -> lines[dst ..): final order = tag order,
+//                         deterministic and identical to the serial CPU shader, independent of the atomics' order.
+#define FL_MAX_CACHE 12 // lines a thread keeps in registers/local before it learns its offset; beyond that: 2nd pass
 __global__ void __launch_bounds__(FL_THREADS)
 k_flatten(VbConfig cfg, const uint32_t *__restrict__ scene, const VbTagMonoid *__restrict__ tag_monoids,
-          VbPathBbox *path_bboxes, VbBump *bump, VbLineSoup *lines, uint32_t *lb_mem, uint32_t n_parts) {
-    __shared__ float4 sh_cache[FL_CACHE][FL_THREADS];
-    VbLookback lb = vb_lookback_view(lb_mem, n_parts, 1);
+          VbPathBbox *path_bboxes, VbBump *bump, VbLineSoup *scratch, uint32_t *part_count, uint32_t *part_src, uint32_t *scratch_ctr,
+          uint32_t n_parts) {
     const uint32_t lane = vb_lane();
-    uint32_t part = 0u;
-    if (lane == 0u) part = atomicAdd(lb.ticket, 1u);
-    part = __shfl_sync(VB_FULL, part, 0);
+    const uint32_t part = blockIdx.x * (FL_THREADS / 32) + (threadIdx.x >> 5);
     if (part >= n_parts) return;
     const uint32_t ix = part * 32u + lane;
     const uint32_t n_tags = cfg.n_tag_words * 4u;
     const uint32_t n_paths = cfg.layout.n_paths;
-
     PathTagData tag;
     tag.tag_byte = 0; tag.trans_ix = 0; tag.pathseg_offset = 0; tag.style_ix = 0; tag.path_ix = 0;
     uint32_t style_flags = 0;
@@ -689,7 +691,8 @@ k_flatten(VbConfig cfg, const uint32_t *__restrict__ scene, const VbTagMonoid *_
             path_bboxes[tag.path_ix].trans_ix = tag.trans_ix;
         }
     }
-    // pass 1: count + cache
+    // pass 1: count (cheap for the common tags: the geometry of the first FL_CACHE lines is kept in shared memory)
+    __shared__ float4 sh_cache[FL_CACHE][FL_THREADS];
     Flat<1> fc;
     fc.lines = nullptr; fc.lines_size = 0; fc.ix = 0;
     fc.bx0 = 1e31f; fc.by0 = 1e31f; fc.bx1 = -1e31f; fc.by1 = -1e31f;
@@ -698,33 +701,30 @@ k_flatten(VbConfig cfg, const uint32_t *__restrict__ scene, const VbTagMonoid *_
     __syncwarp();
     const uint32_t incl = vb_warp_incl_scan(fc.ix);
     const uint32_t total = __shfl_sync(VB_FULL, incl, 31);
-    uint32_t agg[1] = {total}, excl[1];
-    vb_lookback<1>(lb, part, agg, excl);
-    const uint32_t base = excl[0];
-    if (lane == 0u && part == n_parts - 1u) {
-        const uint32_t n_lines = base + total;
-        bump->lines = n_lines;
-        if (n_lines > cfg.lines_size) atomicOr(&bump->failed, VB_STAGE_FLATTEN);
+    uint32_t base = 0u;
+    if (lane == 31u && total != 0u) base = atomicAdd(scratch_ctr, total);
+    base = __shfl_sync(VB_FULL, base, 31);
+    if (lane == 0u) {
+        part_count[part] = total;
+        part_src[part] = base;
     }
     if (fc.ix != 0u) {
         const uint32_t out0 = base + incl - fc.ix;
         float bx0 = fc.bx0, by0 = fc.by0, bx1 = fc.bx1, by1 = fc.by1;
         if (fc.ix <= FL_CACHE) {
-            // pass 2a: copy the cached lines to their final slots
             for (uint32_t k = 0; k < fc.ix; k++) {
                 const uint32_t o = out0 + k;
                 if (o < cfg.lines_size) {
                     const float4 l = sh_cache[k][threadIdx.x];
-                    uint2 *dst = reinterpret_cast<uint2 *>(lines + o);
+                    uint2 *dst = reinterpret_cast<uint2 *>(scratch + o);
                     dst[0] = make_uint2(tag.path_ix, 0u);
                     dst[1] = make_uint2(__float_as_uint(l.x), __float_as_uint(l.y));
                     dst[2] = make_uint2(__float_as_uint(l.z), __float_as_uint(l.w));
                 }
             }
         } else {
-            // pass 2b: too many lines for the cache -> recompute, emitting straight to global memory
             Flat<2> fe;
-            fe.lines = lines; fe.lines_size = cfg.lines_size; fe.ix = out0;
+            fe.lines = scratch; fe.lines_size = cfg.lines_size; fe.ix = out0;
             fe.bx0 = 1e31f; fe.by0 = 1e31f; fe.bx1 = -1e31f; fe.by1 = -1e31f;
             fe.cache = nullptr;
             flatten_tag<2>(fe, cfg, scene, tag_monoids, tag, ix, style_flags);
@@ -740,15 +740,58 @@ k_flatten(VbConfig cfg, const uint32_t *__restrict__ scene, const VbTagMonoid *_
     }
 }
 
+// B: exclusive scan of part_count (in place -> destination offsets); publishes bump.lines.
+#define FS_THREADS 1024
+__global__ void __launch_bounds__(FS_THREADS)
+k_flatten_scan(VbConfig cfg, uint32_t n_parts, uint32_t *part_count, uint32_t *part_dst, VbBump *bump) {
+    __shared__ uint32_t sh_scan[FS_THREADS / 32 + 2];
+    uint32_t carry = 0u;
+    for (uint32_t base = 0u; base < n_parts; base += FS_THREADS) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n_parts ? part_count[i] : 0u;
+        uint32_t total;
+        const uint32_t ex = vb_block_excl_scan(v, sh_scan, &total);
+        if (i < n_parts) part_dst[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) {
+        bump->lines = carry;
+        if (carry > cfg.lines_size) atomicOr(&bump->failed, VB_STAGE_FLATTEN);
+    }
+}
+
+// C: per partition, copy its block of lines from the scratch arena to its final position (8-byte words, coalesced).
+#define FR_THREADS 256
+__global__ void __launch_bounds__(FR_THREADS)
+k_flatten_reorder(VbConfig cfg, uint32_t n_parts, const uint32_t *__restrict__ part_count, const uint32_t *__restrict__ part_src,
+                  const uint32_t *__restrict__ part_dst, const VbLineSoup *__restrict__ scratch, VbLineSoup *lines) {
+    const uint32_t lane = vb_lane();
+    const uint32_t warps = gridDim.x * (FR_THREADS / 32);
+    for (uint32_t part = blockIdx.x * (FR_THREADS / 32) + (threadIdx.x >> 5); part < n_parts; part += warps) {
+        const uint32_t n = part_count[part];
+        if (n == 0u) continue;
+        const uint32_t src = part_src[part], dst = part_dst[part];
+        if (src + n > cfg.lines_size || dst + n > cfg.lines_size) continue; // overflowed frame: will be re-run
+        const uint2 *s = reinterpret_cast<const uint2 *>(scratch + src);
+        uint2 *d = reinterpret_cast<uint2 *>(lines + dst);
+        for (uint32_t k = lane; k < n * 3u; k += 32u) d[k] = __ldg(s + k);
+    }
+}
+
 extern "C" void vb_launch_flatten(const VbConfig *cfg, const uint32_t *scene, const VbTagMonoid *tag_monoids,
-                                  VbPathBbox *path_bboxes, VbBump *bump, VbLineSoup *lines, uint32_t *lb_mem, uint32_t n_parts,
-                                  cudaStream_t st) {
+                                  VbPathBbox *path_bboxes, VbBump *bump, VbLineSoup *lines, VbLineSoup *scratch, uint32_t *part_mem /* 3*n_parts */,
+                                  uint32_t *scratch_ctr, uint32_t n_parts, cudaStream_t st) {
     uint32_t n_paths = cfg->layout.n_paths;
     if (n_paths) k_bbox_clear<<<(n_paths + 255) / 256, 256, 0, st>>>(n_paths, path_bboxes);
     if (n_parts) {
+        uint32_t *part_count = part_mem, *part_src = part_mem + n_parts, *part_dst = part_mem + 2 * (size_t)n_parts;
         const uint32_t warps_per_cta = FL_THREADS / 32;
-        k_flatten<<<(n_parts + warps_per_cta - 1) / warps_per_cta, FL_THREADS, 0, st>>>(*cfg, scene, tag_monoids, path_bboxes, bump, lines,
-                                                                                       lb_mem, n_parts);
+        k_flatten<<<(n_parts + warps_per_cta - 1) / warps_per_cta, FL_THREADS, 0, st>>>(*cfg, scene, tag_monoids, path_bboxes, bump, scratch,
+                                                                                       part_count, part_src, scratch_ctr, n_parts);
+        k_flatten_scan<<<1, FS_THREADS, 0, st>>>(*cfg, n_parts, part_count, part_dst, bump);
+        uint32_t blocks = (n_parts + (FR_THREADS / 32) - 1) / (FR_THREADS / 32);
+        if (blocks > 148u * 8u) blocks = 148u * 8u;
+        k_flatten_reorder<<<blocks, FR_THREADS, 0, st>>>(*cfg, n_parts, part_count, part_src, part_dst, scratch, lines);
     }
 }
 extern "C" uint32_t vb_flatten_parts(uint32_t n_tag_words) { return (n_tag_words * 4u + 31u) / 32u; }
