@@ -31,10 +31,11 @@ static inline uint32_t unorm8(float x) { return (uint32_t)floorf(0.5f + 255.0f *
 static inline uint32_t pack4x8unorm(rgba_t c) {
     return unorm8(c.r) | (unorm8(c.g) << 8) | (unorm8(c.b) << 16) | (unorm8(c.a) << 24);
 }
-/* rgba = rgba * (1 - fg.a) + fg  (fine.wgsl:1117) */
+/* rgba = rgba * (1 - fg.a) + fg  (fine.wgsl:1117), evaluated as a fused multiply-add: WGSL lets the implementation
+ * contract a*b+c, and GPU back ends do; this is one of the conventions shared with the CUDA kernel. */
 static inline rgba_t over(rgba_t bg, rgba_t fg) {
     float k = 1.0f - fg.a;
-    return RG(bg.r * k + fg.r, bg.g * k + fg.g, bg.b * k + fg.b, bg.a * k + fg.a);
+    return RG(fmaf(bg.r, k, fg.r), fmaf(bg.g, k, fg.g), fmaf(bg.b, k, fg.b), fmaf(bg.a, k, fg.a));
 }
 
 typedef struct {

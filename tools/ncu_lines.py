@@ -3,7 +3,7 @@ usage: python tools/ncu_lines.py rep.ncu-rep cubin mangled_kernel_name [top]"""
 import csv, io, re, subprocess, sys
 rep, cubin, kname = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + (["-k", "regex:" + sys.argv[5]] if len(sys.argv) > 5 else []), capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr = rows[1]; c = {h: i for i, h in enumerate(hdr)}
 sass = [(r[c["Source"]].strip(), float(r[c["Instructions Executed"]] or 0), float(r[c["# Samples"]] or 0)) for r in rows[2:] if len(r) > 5]

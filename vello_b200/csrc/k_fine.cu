@@ -40,7 +40,7 @@ __device__ __forceinline__ uint32_t pack4x8unorm(rgba_t c) {
 }
 __device__ __forceinline__ rgba_t over(rgba_t bg, rgba_t fg) {
     float k = 1.0f - fg.a;
-    return RG(bg.r * k + fg.r, bg.g * k + fg.g, bg.b * k + fg.b, bg.a * k + fg.a);
+    return RG(fmaf(bg.r, k, fg.r), fmaf(bg.g, k, fg.g), fmaf(bg.b, k, fg.b), fmaf(bg.a, k, fg.a)); // explicit FMA (see oracle)
 }
 
 // byte / 255.0f for the warp-uniform unpacks (CMD_COLOR, base colour): filled on the host with the same IEEE
@@ -642,7 +642,7 @@ template <>
 struct FineShared<0> { uint32_t unused; };
 
 template <int AA>
-__global__ void __launch_bounds__(FI_THREADS)
+__global__ void __launch_bounds__(FI_THREADS, 16)
 k_fine(VbConfig cfg, FineArgs A) {
     __shared__ FineShared<AA> SH;
     const uint32_t *__restrict__ ptcl = A.ptcl;
@@ -678,12 +678,15 @@ k_fine(VbConfig cfg, FineArgs A) {
     if (AA != 0) ms_init(reinterpret_cast<WarpMs<AA == 0 ? 1 : AA> *>(&SH)[warp], lane);
 #define PXX(i) ((((i) < 4) ? xyx0 : xyx1) + (float)((i) & 3))
     for (;;) {
+        // fetch the command word and its (up to 3) operands together: one load latency per command instead of two
+        // (the ptcl arena has slack words at its end so this never reads out of bounds)
         const uint32_t tag = __ldg(ptcl + cmd_ix);
+        const uint32_t w1 = __ldg(ptcl + cmd_ix + 1), w2 = __ldg(ptcl + cmd_ix + 2), w3 = __ldg(ptcl + cmd_ix + 3);
         if (tag == VB_CMD_END) break;
         switch (tag) {
         case VB_CMD_FILL: {
-            const uint32_t sr = __ldg(ptcl + cmd_ix + 1), sd = __ldg(ptcl + cmd_ix + 2);
-            const int32_t bd = (int32_t)__ldg(ptcl + cmd_ix + 3);
+            const uint32_t sr = w1, sd = w2;
+            const int32_t bd = (int32_t)w3;
             if (AA == 0) fill_path_area(A, sr, sd, bd, local_x, local_y, area);
             else fill_path_ms<AA == 0 ? 1 : AA>(A, reinterpret_cast<WarpMs<AA == 0 ? 1 : AA> *>(&SH)[warp], sr, sd, bd, lane, area);
             cmd_ix += 4u;
@@ -695,7 +698,7 @@ k_fine(VbConfig cfg, FineArgs A) {
             cmd_ix += 1u;
             break;
         case VB_CMD_COLOR: {
-            const rgba_t fg = unpack4x8unorm_uniform(__ldg(ptcl + cmd_ix + 1));
+            const rgba_t fg = unpack4x8unorm_uniform(w1);
 #pragma unroll
             for (int i = 0; i < PX; i++) rgba[i] = over(rgba[i], rg_scale(fg, area[i]));
             cmd_ix += 2u;
@@ -721,8 +724,8 @@ k_fine(VbConfig cfg, FineArgs A) {
             break;
         }
         case VB_CMD_END_CLIP: {
-            const uint32_t blend = __ldg(ptcl + cmd_ix + 1);
-            const float alpha = __uint_as_float(__ldg(ptcl + cmd_ix + 2));
+            const uint32_t blend = w1;
+            const float alpha = __uint_as_float(w2);
             clip_depth -= 1u;
 #pragma unroll
             for (int i = 0; i < PX; i++) {
@@ -747,11 +750,11 @@ k_fine(VbConfig cfg, FineArgs A) {
             break;
         }
         case VB_CMD_JUMP:
-            cmd_ix = __ldg(ptcl + cmd_ix + 1);
+            cmd_ix = w1;
             break;
         case VB_CMD_BLUR_RECT: {
-            const uint32_t io = __ldg(ptcl + cmd_ix + 1);
-            const rgba_t blur_rgba = unpack4x8unorm_uniform(__ldg(ptcl + cmd_ix + 2));
+            const uint32_t io = w1;
+            const rgba_t blur_rgba = unpack4x8unorm_uniform(w2);
             const float m0 = __uint_as_float(info[io]), m1 = __uint_as_float(info[io + 1]), m2 = __uint_as_float(info[io + 2]),
                         m3 = __uint_as_float(info[io + 3]);
             const float tx = __uint_as_float(info[io + 4]), ty = __uint_as_float(info[io + 5]);
@@ -788,7 +791,7 @@ k_fine(VbConfig cfg, FineArgs A) {
             break;
         }
         case VB_CMD_LIN_GRAD: {
-            const uint32_t index_mode = __ldg(ptcl + cmd_ix + 1), io = __ldg(ptcl + cmd_ix + 2);
+            const uint32_t index_mode = w1, io = w2;
             const uint32_t index = index_mode >> 2, ext = index_mode & 3u;
             const float line_x = __uint_as_float(info[io]), line_y = __uint_as_float(info[io + 1]), line_c = __uint_as_float(info[io + 2]);
             const float d0 = (line_x * xyx0 + line_y * xyy) + line_c;
@@ -803,7 +806,7 @@ k_fine(VbConfig cfg, FineArgs A) {
             break;
         }
         case VB_CMD_RAD_GRAD: {
-            const uint32_t index_mode = __ldg(ptcl + cmd_ix + 1), io = __ldg(ptcl + cmd_ix + 2);
+            const uint32_t index_mode = w1, io = w2;
             const uint32_t index = index_mode >> 2, ext = index_mode & 3u;
             const float m0 = __uint_as_float(info[io]), m1 = __uint_as_float(info[io + 1]), m2 = __uint_as_float(info[io + 2]),
                         m3 = __uint_as_float(info[io + 3]);
@@ -849,7 +852,7 @@ k_fine(VbConfig cfg, FineArgs A) {
             break;
         }
         case VB_CMD_SWEEP_GRAD: {
-            const uint32_t index_mode = __ldg(ptcl + cmd_ix + 1), io = __ldg(ptcl + cmd_ix + 2);
+            const uint32_t index_mode = w1, io = w2;
             const uint32_t index = index_mode >> 2, ext = index_mode & 3u;
             const float m0 = __uint_as_float(info[io]), m1 = __uint_as_float(info[io + 1]), m2 = __uint_as_float(info[io + 2]),
                         m3 = __uint_as_float(info[io + 3]);
@@ -880,7 +883,7 @@ k_fine(VbConfig cfg, FineArgs A) {
             break;
         }
         case VB_CMD_IMAGE: {
-            const uint32_t io = __ldg(ptcl + cmd_ix + 1);
+            const uint32_t io = w1;
             const float m0 = __uint_as_float(info[io]), m1 = __uint_as_float(info[io + 1]), m2 = __uint_as_float(info[io + 2]),
                         m3 = __uint_as_float(info[io + 3]);
             const float tx = __uint_as_float(info[io + 4]), ty = __uint_as_float(info[io + 5]);

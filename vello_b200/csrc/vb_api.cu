@@ -345,7 +345,7 @@ static int prepare(vb_renderer *r, const vb_params *p) {
     if ((rc = ensure(r, r->seg_counts, (size_t)r->cap_seg_counts * sizeof(VbSegmentCount)))) return rc;
     if ((rc = ensure(r, r->segments, (size_t)r->cap_segments * sizeof(VbSegment)))) return rc;
     if ((rc = ensure(r, r->blend_spill, (size_t)r->cap_blend * 4))) return rc;
-    if ((rc = ensure(r, r->ptcl, (size_t)r->cap_ptcl * 4))) return rc;
+    if ((rc = ensure(r, r->ptcl, (size_t)r->cap_ptcl * 4 + 64))) return rc; // + slack for fine's 4-word command fetch
     c.lines_size = r->cap_lines;
     c.binning_size = r->cap_binning;
     c.tiles_size = r->cap_tiles;
