@@ -114,6 +114,10 @@ struct vb_renderer {
     size_t off_lb_pathtag = 0, off_lb_flatten = 0, off_lb_draw = 0, off_lb_tile = 0;
     cudaEvent_t ev[VB_N_STAGE_IDS + 1]{};
     bool ev_ok = false;
+    // read-back pipeline of vb_render (host output): fine runs in row bands, each band's D2H copy overlaps the next band
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t band_ev[8]{};
+    void *host_out = nullptr; // set by vb_render for the duration of one frame
     bool frame_pending = false;
 };
 
@@ -194,6 +198,11 @@ extern "C" int vb_renderer_new(const vb_options *opt, vb_renderer **out) {
     }
     memset(r->h_bump, 0, sizeof(VbBump));
     for (auto &ev : r->ev) cudaEventCreate(&ev);
+    for (auto &ev : r->band_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete r;
+        return VB_E_CUDA;
+    }
     r->ev_ok = true;
     if (vb_fine_init_constants() != 0) {
         delete r;
@@ -221,8 +230,11 @@ extern "C" void vb_renderer_free(vb_renderer *r) {
     for (auto b : all)
         if (b->p) cudaFree(b->p);
     if (r->h_bump) cudaFreeHost(r->h_bump);
-    if (r->ev_ok)
+    if (r->ev_ok) {
         for (auto &ev : r->ev) cudaEventDestroy(ev);
+        for (auto &ev : r->band_ev) cudaEventDestroy(ev);
+    }
+    if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
     if (r->stream) cudaStreamDestroy(r->stream);
     delete r;
 }
@@ -448,13 +460,36 @@ static int enqueue(vb_renderer *r, int first, int last, void *out_dev) {
             launches += 2;
             break;
         }
-        case VB_STAGE_ID_FINE:
-            vb_launch_fine(&c, (int)r->params.aa, (const VbSegment *)r->segments.p, (const uint32_t *)r->ptcl.p,
-                           (const uint32_t *)r->info_bin_data.p, (uint32_t *)r->blend_spill.p, (uint32_t *)out_dev,
-                           (const uint32_t *)r->ramps.p, (const uint8_t *)r->atlas.p, (const uint32_t *)r->mask8.p,
-                           (const uint32_t *)r->mask16.p, st);
-            launches += 1;
+        case VB_STAGE_ID_FINE: {
+            // With a host destination (vb_render) fine is launched in up to 4 bands of tile rows and each band's
+            // device->host copy is queued on a second stream behind an event, so the read-back of band k overlaps
+            // the rasterisation of band k+1 (only the last band's copy is exposed).
+            const uint32_t rows = c.win_ty1 - c.win_ty0;
+            uint32_t n_bands = (r->host_out && rows >= 32u) ? 4u : 1u;
+            const uint32_t band_rows = (rows + n_bands - 1u) / n_bands;
+            for (uint32_t b = 0; b < n_bands; b++) {
+                VbConfig cb = c;
+                cb.win_ty0 = c.win_ty0 + b * band_rows;
+                cb.win_ty1 = cb.win_ty0 + band_rows < c.win_ty1 ? cb.win_ty0 + band_rows : c.win_ty1;
+                if (cb.win_ty0 >= cb.win_ty1) break;
+                vb_launch_fine(&cb, (int)r->params.aa, (const VbSegment *)r->segments.p, (const uint32_t *)r->ptcl.p,
+                               (const uint32_t *)r->info_bin_data.p, (uint32_t *)r->blend_spill.p, (uint32_t *)out_dev,
+                               (const uint32_t *)r->ramps.p, (const uint8_t *)r->atlas.p, (const uint32_t *)r->mask8.p,
+                               (const uint32_t *)r->mask16.p, st);
+                launches += 1;
+                if (r->host_out) {
+                    size_t y0 = (size_t)cb.win_ty0 * 16u, y1 = (size_t)cb.win_ty1 * 16u;
+                    if (y1 > c.target_height) y1 = c.target_height;
+                    if (y1 > y0) {
+                        const size_t off = (y0 - c.out_row0) * c.out_pitch_px * 4u, bytes = (y1 - y0) * c.out_pitch_px * 4u;
+                        CK(cudaEventRecord(r->band_ev[b], st));
+                        CK(cudaStreamWaitEvent(r->copy_stream, r->band_ev[b], 0));
+                        CK(cudaMemcpyAsync((char *)r->host_out + off, (const char *)out_dev + off, bytes, cudaMemcpyDeviceToHost, r->copy_stream));
+                    }
+                }
+            }
             break;
+        }
         default: return VB_E_INVALID;
         }
         rec(r, s + 1);
@@ -557,17 +592,18 @@ extern "C" int vb_render(vb_renderer *r, const uint8_t *scene, size_t scene_len,
     if (!r || !p || !out) return VB_E_INVALID;
     int rc = vb_scene_upload(r, scene, scene_len, layout, ramps, ramp_w, ramp_h, atlas, atlas_w, atlas_h);
     if (rc) return rc;
+    r->host_out = out_is_device ? nullptr : out;
     rc = vb_render_resident(r, p, out_is_device ? out : nullptr, stats);
-    if (rc) return rc;
+    r->host_out = nullptr;
     if (!out_is_device) {
-        const VbConfig &c = r->cfg;
-        size_t row0 = c.out_row0, row1 = (size_t)c.win_ty1 * 16u;
-        if (row1 > c.target_height) row1 = c.target_height;
-        size_t rows = row1 > row0 ? row1 - row0 : 0;
-        CK(cudaMemcpyAsync(out, r->target.p, rows * c.out_pitch_px * 4u, cudaMemcpyDeviceToHost, r->stream));
-        CK(cudaStreamSynchronize(r->stream));
+        // the band copies were queued behind the fine bands; a re-run after an arena overflow simply copies again
+        cudaError_t e = cudaStreamSynchronize(r->copy_stream);
+        if (rc == VB_OK && e != cudaSuccess) {
+            r->err = std::string("copy stream: ") + cudaGetErrorString(e);
+            return VB_E_CUDA;
+        }
     }
-    return VB_OK;
+    return rc;
 }
 
 extern "C" int vb_run_stages(vb_renderer *r, const vb_params *p, int first, int last, void *out_device) {
