@@ -102,6 +102,7 @@ def dist_setup(n_gpus):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the single JSON line (no NCCL version banner)
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
