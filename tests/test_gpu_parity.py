@@ -191,3 +191,41 @@ def test_oracle_lines_into_gpu_tile_stages(renderer, oracle):
     renderer.run_stages(p, "draw", "fine")
     img = renderer.download_target(p)
     assert np.array_equal(img, ref)
+
+
+def test_flatten_fill_line_fast_path_extremes(renderer, oracle):
+    """k_flatten short-cuts line-to segments of fills (one line, no Euler machinery). The oracle has no such
+    shortcut, so bit-identical `lines` on adversarial inputs -- tiny segments at large coordinates, skewed /
+    scaled transforms, near-degenerate and huge lines, coordinates beyond the guard -- proves the equivalence."""
+    from vello_b200.encoding import FILL_NON_ZERO, FILL_EVEN_ODD
+    from vello_b200.shapes import Affine, BezPath
+    from oracle.vbo import DTYPES
+    rng = np.random.default_rng(123)
+    s = Scene()
+    for k in range(400):
+        p = BezPath()
+        mag = [1.0, 100.0, 4000.0, 60000.0, 3.0e5, 2.0e7][k % 6]
+        step = [1e-4, 1e-3, 1e-2, 0.3, 5.0, 300.0, 5e4][k % 7]
+        x, y = rng.uniform(-mag, mag, 2)
+        p.move_to(x, y)
+        for _ in range(int(rng.integers(2, 9))):
+            x += rng.normal(0, step)
+            y += rng.normal(0, step)
+            p.line_to(x, y)
+        p.close_path()
+        if k % 5 == 0:
+            t = Affine((rng.normal(0, 2), rng.normal(0, 2), rng.normal(0, 2), rng.normal(0, 2), rng.normal(0, 50), rng.normal(0, 50)))
+        elif k % 5 == 1:
+            t = Affine.scale(float(rng.uniform(1e-3, 50)))
+        else:
+            t = Affine.translate(*rng.uniform(-10, 10, 2))
+        s.fill(FILL_NON_ZERO if k % 2 else FILL_EVEN_ODD, t, Color.from_rgba8(200, 50, 50, 128), None, p)
+    packed = resolve(s.encoding)
+    p = RenderParams(BLACK, 256, 256, AA_AREA)
+    renderer.upload(packed)
+    renderer.run_stages(p, "pathtag", "flatten")
+    oracle.bind(packed, 256, 256)
+    oracle.run("pathtag", "flatten")
+    g, c = renderer.download("lines", DTYPES["lines"]), oracle.buffer("lines")
+    assert g.shape == c.shape and g.tobytes() == c.tobytes()
+    assert renderer.download("path_bboxes", DTYPES["path_bboxes"]).tobytes() == oracle.buffer("path_bboxes").tobytes()

@@ -645,6 +645,26 @@ __device__ void flatten_tag(Flat<EMIT> &f, const VbConfig &cfg, const uint32_t *
             }
         }
     } else {
+        // Fast path for a line-to in a fill (the bulk of map-like scenes). For a degree-raised line the general
+        // algorithm provably accepts the whole range at the first step and emits exactly ONE line (p0', p3'):
+        //  * err = O(angle^2) * chord, and the tangent angles of a degree-raised line are pure rounding noise
+        //    (~3 ulp(coord)/chord); for chords shorter than that noise err <= 2 * chord <= 0.024 px  -> accepted;
+        //  * n = ceil(n_frac * sqrt(chord/2)) with n_frac <= sqrt(|k0|) ~ sqrt(3 ulp/chord) -> n_frac*mult <= sqrt(1.5 ulp) < 1;
+        //  * the single line runs from t_start = p0' to t_end = p3' (t1 == 1 exactly).
+        // The bounds need ulp(coord) <= 2^-8, hence the |coord| < 65536 guard; anything else takes the general path.
+        // tests/test_gpu_parity.py compares `lines` bit-for-bit with the oracle, which has no such shortcut.
+        if (seg_type == 1u) {
+            const fv2 q0 = fx_apply(transform, pts.p0), q1 = fx_apply(transform, pts.p1);
+            const fv2 q2 = fx_apply(transform, pts.p2), q3 = fx_apply(transform, pts.p3);
+            const float lim = 65536.0f;
+            if (fabsf(q0.x) < lim && fabsf(q0.y) < lim && fabsf(q3.x) < lim && fabsf(q3.y) < lim && fabsf(q1.x) < lim && fabsf(q1.y) < lim &&
+                fabsf(q2.x) < lim && fabsf(q2.y) < lim) {
+                if (feq(q0, q1) && feq(q0, q2) && feq(q0, q3)) return;
+                if (EMIT != 0) f.write_line(path_ix, q0, q3);
+                else f.ix++;
+                return;
+            }
+        }
         flatten_euler<EMIT>(f, pts, path_ix, transform, 0.f, pts.p0, pts.p3);
     }
 }
@@ -740,18 +760,28 @@ k_flatten(VbConfig cfg, const uint32_t *__restrict__ scene, const VbTagMonoid *_
     }
 }
 
-// B: exclusive scan of part_count (in place -> destination offsets); publishes bump.lines.
+// B: exclusive scan of part_count -> destination offsets; publishes bump.lines. One CTA, 8 values per thread per pass.
 #define FS_THREADS 1024
+#define FS_PER_THREAD 8
 __global__ void __launch_bounds__(FS_THREADS)
-k_flatten_scan(VbConfig cfg, uint32_t n_parts, uint32_t *part_count, uint32_t *part_dst, VbBump *bump) {
+k_flatten_scan(VbConfig cfg, uint32_t n_parts, const uint32_t *__restrict__ part_count, uint32_t *part_dst, VbBump *bump) {
     __shared__ uint32_t sh_scan[FS_THREADS / 32 + 2];
     uint32_t carry = 0u;
-    for (uint32_t base = 0u; base < n_parts; base += FS_THREADS) {
-        const uint32_t i = base + threadIdx.x;
-        const uint32_t v = i < n_parts ? part_count[i] : 0u;
+    for (uint32_t base = 0u; base < n_parts; base += FS_THREADS * FS_PER_THREAD) {
+        const uint32_t i0 = base + threadIdx.x * FS_PER_THREAD;
+        uint32_t v[FS_PER_THREAD], sum = 0u;
+#pragma unroll
+        for (int k = 0; k < FS_PER_THREAD; k++) {
+            v[k] = i0 + k < n_parts ? part_count[i0 + k] : 0u;
+            sum += v[k];
+        }
         uint32_t total;
-        const uint32_t ex = vb_block_excl_scan(v, sh_scan, &total);
-        if (i < n_parts) part_dst[i] = carry + ex;
+        uint32_t run = carry + vb_block_excl_scan(sum, sh_scan, &total);
+#pragma unroll
+        for (int k = 0; k < FS_PER_THREAD; k++) {
+            if (i0 + k < n_parts) part_dst[i0 + k] = run;
+            run += v[k];
+        }
         carry += total;
     }
     if (threadIdx.x == 0) {

@@ -461,11 +461,11 @@ static int enqueue(vb_renderer *r, int first, int last, void *out_dev) {
             break;
         }
         case VB_STAGE_ID_FINE: {
-            // With a host destination (vb_render) fine is launched in up to 4 bands of tile rows and each band's
+            // With a host destination (vb_render) fine is launched in up to 8 bands of tile rows and each band's
             // device->host copy is queued on a second stream behind an event, so the read-back of band k overlaps
             // the rasterisation of band k+1 (only the last band's copy is exposed).
             const uint32_t rows = c.win_ty1 - c.win_ty0;
-            uint32_t n_bands = (r->host_out && rows >= 32u) ? 4u : 1u;
+            uint32_t n_bands = (r->host_out && rows >= 64u) ? 8u : 1u;
             const uint32_t band_rows = (rows + n_bands - 1u) / n_bands;
             for (uint32_t b = 0; b < n_bands; b++) {
                 VbConfig cb = c;
