@@ -45,7 +45,12 @@ def build_scene(args):
     from vello_b200 import scenes
     from vello_b200.encoding import resolve
     t = time.time()
-    sc = scenes.paris_like(args.paths, args.size, args.seed)
+    if args.scene == "tiger":        # BASELINE.json configs[1]: tiger at args.size x args.height
+        sc = scenes.tiger(args.size, args.height or args.size)
+    elif args.scene == "beziers":    # configs[4]: cubic paths + nested clips
+        sc = scenes.beziers_clips(args.paths, max(1, args.paths // 100), args.size, seed=100000)
+    else:                            # configs[2] (default, the headline workload)
+        sc = scenes.paris_like(args.paths, args.size, args.seed)
     packed = resolve(sc.encoding)
     return packed, time.time() - t
 
@@ -127,7 +132,7 @@ def run_cpu_arm(args, packed, as_reference):
     times = []
     for i in range(warm + steps):
         t = time.perf_counter()
-        o.render(packed, args.size, args.size, BLACK.premul_rgba8_u32(), args.aa)
+        o.render(packed, args.size, args.height or args.size, BLACK.premul_rgba8_u32(), args.aa)
         dt = time.perf_counter() - t
         if i >= warm:
             times.append(dt)
@@ -149,12 +154,16 @@ def main():
     ap.add_argument("--size", type=int, default=WORKLOAD["size"])
     ap.add_argument("--seed", type=int, default=WORKLOAD["seed"])
     ap.add_argument("--aa", type=int, default=WORKLOAD["aa"])
+    ap.add_argument("--scene", default="paris", choices=["paris", "tiger", "beziers"], help="paris = the headline workload")
+    ap.add_argument("--height", type=int, default=0, help="frame height (default: --size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-only", action="store_true", help="just run warmup+steps resident frames (for ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if not args.profile_only else args.warmup
 
-    config = {"workload": f"paris-like-{args.paths // 1000}k {args.size}x{args.size} " + ["Area", "MSAA8", "MSAA16"][args.aa],
+    H = args.height or args.size
+    wl = {"paris": f"paris-like-{args.paths // 1000}k", "tiger": "Ghostscript tiger", "beziers": f"beziers-{args.paths // 1000}k+clips"}[args.scene]
+    config = {"workload": f"{wl} {args.size}x{H} " + ["Area", "MSAA8", "MSAA16"][args.aa],
               "n_paths": args.paths, "seed": args.seed, "parallelism": f"bin-row stripes x{args.gpus}",
               "l2": "flushed between steps (256 MiB write) outside the per-step CUDA-event pairs"}
 
@@ -178,8 +187,8 @@ def main():
     from vello_b200.renderer import Renderer, RendererOptions, FrameStats, _Layout, _Params
 
     packed, gen_s = build_scene(args)
-    params = RenderParams(BLACK, args.size, args.size, args.aa)
-    bin_rows = stripe_for(rank, world, args.size) if world > 1 else (0, 0)
+    params = RenderParams(BLACK, args.size, H, args.aa)
+    bin_rows = stripe_for(rank, world, H) if world > 1 else (0, 0)
     torch.cuda.set_device(local)
     r = Renderer(RendererOptions(device=local))
     r.upload(packed)
@@ -233,7 +242,7 @@ def main():
     atlas_np = np.ascontiguousarray(packed.atlas)
     out_h = torch.empty((max(h1 - h0, 1), args.size, 4), dtype=torch.uint8).pin_memory()
     lay = _Layout(*[int(v) for v in packed.layout.as_array()])
-    ps = _Params(BLACK.premul_rgba8_u32(), args.size, args.size, args.aa, bin_rows[0], bin_rows[1])
+    ps = _Params(BLACK.premul_rgba8_u32(), args.size, H, args.aa, bin_rows[0], bin_rows[1])
     fs = FrameStats()
 
     def e2e_step():
