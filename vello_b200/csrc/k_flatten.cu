@@ -13,12 +13,15 @@
 //  * Transcendentals come from vb_detmath.h (IEEE-only) and the TU is compiled with -fmad=false,
 //    so `lines` is bit-identical to the oracle's, and so is everything downstream.
 // Algorithmic bytes: 1 B tag + 20/4 B monoid + <= 32 B coords per segment, 24 B per line out.
+#include <cooperative_groups.h>
 #include <cuda_fp16.h>
 
 #include "vb_detmath.h"
 #include "vb_device.cuh"
 
 #define FL_THREADS 256
+
+namespace cg = cooperative_groups;
 
 struct fv2 { float x, y; };
 __device__ __forceinline__ fv2 F2(float x, float y) { fv2 r; r.x = x; r.y = y; return r; }
@@ -35,39 +38,94 @@ __device__ __forceinline__ fv2 fx_apply(const FXform &t, fv2 p) { // flatten.wgs
     return F2(fmaf(t.m0, p.x, fmaf(t.m2, p.y, t.tx)), fmaf(t.m1, p.x, fmaf(t.m3, p.y, t.ty)));
 }
 
-// MODE 0: count lines only. MODE 1: count, accumulate the bbox and stash the first FL_CACHE lines of this thread
-// in shared memory (most tags produce <= FL_CACHE lines, so the geometry is computed once). MODE 2: emit to global.
-#define FL_CACHE 6
-template <int MODE>
+// One pass over the tags, then one pass over the LINES.
+//  * k_flatten (thread per tag) runs the control flow of the reference -- subdivision into Euler segments, caps,
+//    joins -- but does not evaluate long runs of lines itself: an Euler segment or arc of >= FL_DEFER_MIN lines
+//    becomes a 96 B FlJob record ("these n lines, at tag-relative offset rel"). Short output (the one line of a
+//    line-to, cap / join lines) is kept in a small shared-memory cache and leaves as 32 B FlLit records.
+//  * k_flatten_scan turns per-warp line counts into final offsets (tag order == the serial CPU shader's order).
+//  * k_flatten_place (thread per LINE) scatters the literals and expands the jobs, 32 jobs per warp with a
+//    load-balanced lane <-> line mapping, so the cost of a frame no longer hangs on its slowest tag.
+// Every point is a pure function of (job, i); whoever evaluates it gets the same bits.
+#define FL_CACHE 6     // literal lines a thread keeps in shared memory
+#define FL_DEFER_MIN 3 // runs of at least this many lines are deferred to k_flatten_place
+#define FL_ARC_MAX 64  // arcs longer than this are emitted in place (line i costs i rotations when deferred)
+
+struct FlLit { uint32_t tag_ix, rel, path_ix, pad; float x0, y0, x1, y1; }; // 32 B
+struct FlJob {                                                             // 96 B = 6 x 16 B
+    float p0x, p0y, p1x, p1y;      // Euler: chord end points (local space) | arc: begin, end (local space)
+    float th0, k0, k1, ch;         // Euler: EulerParams                    | arc: centre.x, centre.y, cos, sin
+    float noff, n, integral, int0; // Euler: normalized offset, float(n), integral, int0
+    float a, b, lp0x, lp0y;        // Euler: a, b | both: start point of line 0, DEVICE space
+    float tex, tey;                // Euler: t_end (local space)
+    uint32_t tag_ix, rel;          // destination = offset of the tag + rel
+    uint32_t path_ix, trans_ix, meta, pad;
+};
+static_assert(sizeof(FlLit) == 32 && sizeof(FlJob) == 96, "record layout");
+#define FJ_N(m) ((m) & 0xffu)
+#define FJ_ROBUST(m) (((m) >> 8) & 3u)
+#define FJ_TEND 0x400u  // the last line ends at t_end exactly
+#define FJ_NEG 0x800u   // negative offset: swap the end points of every line
+#define FJ_IDENT 0x1000u // points are already in device space
+#define FJ_ARC 0x2000u
+
+struct FlCtx {
+    FlLit *lits;
+    FlJob *jobs;
+    uint32_t lits_cap, jobs_cap;
+    uint32_t *ctrs; // [0] literal records, [1] jobs
+};
+
+__device__ __forceinline__ uint32_t fl_alloc(uint32_t *ctr) { // one atomic per converged group of lanes
+    cg::coalesced_group g = cg::coalesced_threads();
+    uint32_t base = 0u;
+    if (g.thread_rank() == 0u) base = atomicAdd(ctr, g.size());
+    return g.shfl(base, 0) + g.thread_rank();
+}
+
 struct Flat {
-    VbLineSoup *lines;
-    uint32_t lines_size;
-    uint32_t ix; // next line slot (MODE 2) / running count (MODE 0, 1)
-    float bx0, by0, bx1, by1;
-    float4 *cache; // MODE 1: &cache[0][threadIdx.x], stride FL_THREADS
-    __device__ __forceinline__ void write_line(uint32_t path_ix, fv2 p0, fv2 p1) {
-        if (MODE != 0) {
-            bx0 = fminf(bx0, fminf(p0.x, p1.x));
-            by0 = fminf(by0, fminf(p0.y, p1.y));
-            bx1 = fmaxf(bx1, fmaxf(p0.x, p1.x));
-            by1 = fmaxf(by1, fmaxf(p0.y, p1.y));
-        }
-        if (MODE == 1) {
-            if (ix < FL_CACHE) cache[ix * FL_THREADS] = make_float4(p0.x, p0.y, p1.x, p1.y);
-        }
-        if (MODE == 2) {
-            if (ix < lines_size) {
-                uint2 *dst = reinterpret_cast<uint2 *>(lines + ix);
-                dst[0] = make_uint2(path_ix, 0u);
-                dst[1] = make_uint2(__float_as_uint(p0.x), __float_as_uint(p0.y));
-                dst[2] = make_uint2(__float_as_uint(p1.x), __float_as_uint(p1.y));
+    FlCtx c;
+    uint32_t tag_ix, path_ix, trans_ix;
+    uint32_t ix;   // lines of this tag so far
+    uint32_t nlit; // of which literal (cached or spilled)
+    float bx0, by0, bx1, by1; // bbox of the literal lines
+    bool force;    // a job was deferred: the tag's bbox is known to be non-degenerate
+    float4 *cache; // &cache[0][threadIdx.x], stride FL_THREADS
+    uint32_t *cache_rel;
+    __device__ __forceinline__ void write_line(fv2 p0, fv2 p1) { // device-space end points
+        bx0 = fminf(bx0, fminf(p0.x, p1.x));
+        by0 = fminf(by0, fminf(p0.y, p1.y));
+        bx1 = fmaxf(bx1, fmaxf(p0.x, p1.x));
+        by1 = fmaxf(by1, fmaxf(p0.y, p1.y));
+        if (nlit < FL_CACHE) {
+            cache[nlit * FL_THREADS] = make_float4(p0.x, p0.y, p1.x, p1.y);
+            cache_rel[nlit * FL_THREADS] = ix;
+        } else {
+            const uint32_t slot = fl_alloc(c.ctrs);
+            if (slot < c.lits_cap) {
+                uint4 *dst = reinterpret_cast<uint4 *>(c.lits + slot);
+                dst[0] = make_uint4(tag_ix, ix, path_ix, 0u);
+                dst[1] = make_uint4(__float_as_uint(p0.x), __float_as_uint(p0.y), __float_as_uint(p1.x), __float_as_uint(p1.y));
             }
         }
+        nlit++;
         ix++;
     }
-    __device__ __forceinline__ void line_xf(uint32_t path_ix, fv2 p0, fv2 p1, const FXform &t) {
-        if (MODE != 0) write_line(path_ix, fx_apply(t, p0), fx_apply(t, p1));
-        else ix++;
+    __device__ __forceinline__ void line_xf(fv2 p0, fv2 p1, const FXform &t) { write_line(fx_apply(t, p0), fx_apply(t, p1)); }
+    __device__ __forceinline__ void push_job(FlJob &j, uint32_t n_lines) {
+        j.tag_ix = tag_ix; j.rel = ix; j.path_ix = path_ix; j.trans_ix = trans_ix; j.pad = 0u;
+        const uint32_t slot = fl_alloc(c.ctrs + 1);
+        if (slot < c.jobs_cap) {
+            float4 *dst = reinterpret_cast<float4 *>(c.jobs + slot);
+            dst[0] = make_float4(j.p0x, j.p0y, j.p1x, j.p1y);
+            dst[1] = make_float4(j.th0, j.k0, j.k1, j.ch);
+            dst[2] = make_float4(j.noff, j.n, j.integral, j.int0);
+            dst[3] = make_float4(j.a, j.b, j.lp0x, j.lp0y);
+            dst[4] = make_float4(j.tex, j.tey, __uint_as_float(j.tag_ix), __uint_as_float(j.rel));
+            dst[5] = make_float4(__uint_as_float(j.path_ix), __uint_as_float(j.trans_ix), __uint_as_float(j.meta), 0.f);
+        }
+        ix += n_lines;
+        force = true;
     }
 };
 
@@ -278,9 +336,25 @@ __device__ fv2 cubic_end_tangent(fv2 p0, fv2 p1, fv2 p2, fv2 p3) {
 
 struct CubicPoints { fv2 p0, p1, p2, p3; };
 
-template <int EMIT>
-__device__ void flatten_euler(Flat<EMIT> &f, const CubicPoints &cubic, uint32_t path_ix, const FXform &local_to_device,
-                              float offset, fv2 start_p, fv2 end_p) { // flatten.wgsl:326-481
+// End point (local space) of line i of an Euler-segment job: the body of the inner loop of flatten.wgsl:441-466.
+__device__ fv2 fl_euler_point(const FlJob &j, uint32_t i) {
+    if (i + 1u == FJ_N(j.meta) && (j.meta & FJ_TEND) != 0u) return F2(j.tex, j.tey);
+    float t = (float)(i + 1u) / j.n;
+    float s = t;
+    const uint32_t robust = FJ_ROBUST(j.meta);
+    if (robust != 1u) {
+        float u = j.integral * t + j.int0;
+        float inv;
+        if (robust == 2u) inv = vb_pow_2_3(fabsf(u)) * vb_signf(u);
+        else inv = espc_int_inv_approx(u);
+        s = (inv - j.b) / j.a;
+    }
+    EulerParams ep = {j.th0, j.k0, j.k1, j.ch};
+    return es_seg_eval_with_offset(F2(j.p0x, j.p0y), F2(j.p1x, j.p1y), ep, s, j.noff);
+}
+
+__device__ void flatten_euler(Flat &f, const CubicPoints &cubic, const FXform &local_to_device, float offset, fv2 start_p,
+                              fv2 end_p) { // flatten.wgsl:326-481
     fv2 p0, p1, p2, p3;
     float scale;
     FXform transform;
@@ -334,11 +408,11 @@ __device__ void flatten_euler(Flat<EMIT> &f, const CubicPoints &cubic, uint32_t 
             float dist_scaled = normalized_offset * ep.ch;
             float scale_multiplier = sqrtf(0.125f * scale * cp.chord_len / (ep.ch * tol));
             float a = 0.0f, b = 0.0f, integral = 0.0f, int0 = 0.0f, n_frac;
-            int robust = 0;
+            uint32_t robust = 0u;
             if (fabsf(k1) < K1_THRESH) {
                 float k = ep.k0;
                 n_frac = sqrtf(fabsf(k * (k * dist_scaled + 1.0f)));
-                robust = 1;
+                robust = 1u;
             } else if (fabsf(dist_scaled) < DIST_THRESH) {
                 a = k1;
                 b = k0;
@@ -346,7 +420,7 @@ __device__ void flatten_euler(Flat<EMIT> &f, const CubicPoints &cubic, uint32_t 
                 float int1 = pow_1_5_signed(a + b);
                 integral = int1 - int0;
                 n_frac = (2.f / 3.f) * integral / a;
-                robust = 2;
+                robust = 2u;
             } else {
                 a = -2.0f * dist_scaled * k1;
                 b = -1.0f - 2.0f * dist_scaled * k0;
@@ -359,30 +433,34 @@ __device__ void flatten_euler(Flat<EMIT> &f, const CubicPoints &cubic, uint32_t 
             }
             float n = vb_clampf(ceilf(n_frac * scale_multiplier), 1.0f, 100.0f);
             uint32_t n_u = vb_f2u_sat(n);
-            if (EMIT != 0) {
+            FlJob j;
+            j.p0x = this_p0.x; j.p0y = this_p0.y; j.p1x = this_pq1.p.x; j.p1y = this_pq1.p.y;
+            j.th0 = ep.th0; j.k0 = ep.k0; j.k1 = ep.k1; j.ch = ep.ch;
+            j.noff = normalized_offset; j.n = n; j.integral = integral; j.int0 = int0;
+            j.a = a; j.b = b;
+            j.tex = t_end.x; j.tey = t_end.y;
+            j.meta = n_u | (robust << 8) | (t1 == 1.0f ? FJ_TEND : 0u) | (offset >= 0.f ? 0u : FJ_NEG) | (offset == 0.f ? FJ_IDENT : 0u);
+            bool deferred = false;
+            if (n_u >= FL_DEFER_MIN) {
+                // The tag's bbox is only published when it is non-degenerate (flatten.wgsl:916); deferring is safe
+                // when the run itself already spans two distinct device-space points.
+                const fv2 last = fl_euler_point(j, n_u - 1u);
+                const fv2 d0 = fx_apply(transform, lp0), d1 = fx_apply(transform, last);
+                if (!feq(d0, d1)) {
+                    j.lp0x = d0.x; j.lp0y = d0.y;
+                    f.push_job(j, n_u);
+                    lp0 = last;
+                    deferred = true;
+                }
+            }
+            if (!deferred) {
                 for (uint32_t i = 0u; i < n_u; i++) {
-                    fv2 lp1;
-                    if (i + 1u == n_u && t1 == 1.0f) {
-                        lp1 = t_end;
-                    } else {
-                        float t = (float)(i + 1u) / n;
-                        float s = t;
-                        if (robust != 1) {
-                            float u = integral * t + int0;
-                            float inv;
-                            if (robust == 2) inv = vb_pow_2_3(fabsf(u)) * vb_signf(u);
-                            else inv = espc_int_inv_approx(u);
-                            s = (inv - b) / a;
-                        }
-                        lp1 = es_seg_eval_with_offset(this_p0, this_pq1.p, ep, s, normalized_offset);
-                    }
+                    const fv2 lp1 = fl_euler_point(j, i);
                     fv2 l0 = offset >= 0.f ? lp0 : lp1;
                     fv2 l1 = offset >= 0.f ? lp1 : lp0;
-                    f.line_xf(path_ix, l0, l1, transform);
+                    f.line_xf(l0, l1, transform);
                     lp0 = lp1;
                 }
-            } else {
-                f.ix += n_u;
             }
             last_p = this_pq1.p;
             last_q = this_pq1.q;
@@ -398,8 +476,17 @@ __device__ void flatten_euler(Flat<EMIT> &f, const CubicPoints &cubic, uint32_t 
     }
 }
 
-template <int EMIT>
-__device__ void flatten_arc(Flat<EMIT> &f, uint32_t path_ix, fv2 begin, fv2 end, fv2 center, float angle, const FXform &t) {
+// Device-space end point of line i of an arc job (flatten.wgsl:494-519): i + 1 rotations of the start radius.
+__device__ fv2 fl_arc_point(const FlJob &j, uint32_t i, const FXform &t) {
+    if (i + 1u == FJ_N(j.meta)) return fx_apply(t, F2(j.p1x, j.p1y));
+    const fv2 center = F2(j.th0, j.k0);
+    const float c = j.k1, s = j.ch;
+    fv2 r = F2(j.p0x, j.p0y) - center;
+    for (uint32_t k = 0u; k <= i; k++) r = F2(c * r.x + s * r.y, -s * r.x + c * r.y);
+    return fx_apply(t, center + r);
+}
+
+__device__ void flatten_arc(Flat &f, fv2 begin, fv2 end, fv2 center, float angle, const FXform &t) {
     fv2 p0 = fx_apply(t, begin);
     fv2 r = begin - center;
     const float MIN_THETA = 0.0001f;
@@ -407,17 +494,26 @@ __device__ void flatten_arc(Flat<EMIT> &f, uint32_t path_ix, fv2 begin, fv2 end,
     float radius = fmaxf(tol, flen(p0 - fx_apply(t, center)));
     float theta = fmaxf(MIN_THETA, 2.f * vb_acosf(1.f - tol / radius));
     uint32_t n_lines = max(1u, vb_f2u_sat(ceilf(angle / theta)));
-    if (EMIT == 0) { f.ix += n_lines; return; }
     float s, c;
     vb_sincosf(theta, &s, &c);
+    if (n_lines >= FL_DEFER_MIN && n_lines <= FL_ARC_MAX && !feq(p0, fx_apply(t, end))) {
+        FlJob j;
+        j.p0x = begin.x; j.p0y = begin.y; j.p1x = end.x; j.p1y = end.y;
+        j.th0 = center.x; j.k0 = center.y; j.k1 = c; j.ch = s;
+        j.noff = 0.f; j.n = 0.f; j.integral = 0.f; j.int0 = 0.f; j.a = 0.f; j.b = 0.f;
+        j.lp0x = p0.x; j.lp0y = p0.y; j.tex = 0.f; j.tey = 0.f;
+        j.meta = n_lines | FJ_ARC;
+        f.push_job(j, n_lines);
+        return;
+    }
     for (uint32_t i = 0u; i + 1u < n_lines; i++) {
         r = F2(c * r.x + s * r.y, -s * r.x + c * r.y);
         fv2 p1 = fx_apply(t, center + r);
-        f.write_line(path_ix, p0, p1);
+        f.write_line(p0, p1);
         p0 = p1;
     }
     fv2 p1 = fx_apply(t, end);
-    f.write_line(path_ix, p0, p1);
+    f.write_line(p0, p1);
 }
 
 #define STYLE_FLAGS_STYLE 0x80000000u
@@ -432,11 +528,10 @@ __device__ void flatten_arc(Flat<EMIT> &f, uint32_t path_ix, fv2 begin, fv2 end,
 #define STYLE_FLAGS_JOIN_MITER 0x10000000u
 #define STYLE_FLAGS_JOIN_ROUND 0x20000000u
 
-template <int EMIT>
-__device__ void draw_cap(Flat<EMIT> &f, uint32_t path_ix, uint32_t cap_style, fv2 point, fv2 cap0, fv2 cap1, fv2 offset_tangent,
+__device__ void draw_cap(Flat &f, uint32_t cap_style, fv2 point, fv2 cap0, fv2 cap1, fv2 offset_tangent,
                          const FXform &t) { // flatten.wgsl:521-545 (slot order of the WGSL)
     if (cap_style == STYLE_FLAGS_CAP_ROUND) {
-        flatten_arc<EMIT>(f, path_ix, cap0, cap1, point, 3.1415927f, t);
+        flatten_arc(f, cap0, cap1, point, 3.1415927f, t);
         return;
     }
     fv2 start = cap0, end = cap1;
@@ -444,18 +539,17 @@ __device__ void draw_cap(Flat<EMIT> &f, uint32_t path_ix, uint32_t cap_style, fv
         fv2 v = offset_tangent;
         fv2 p0 = start + v;
         fv2 p1 = end + v;
-        f.line_xf(path_ix, p0, p1, t);
-        f.line_xf(path_ix, start, p0, t);
-        f.line_xf(path_ix, p1, end, t);
+        f.line_xf(p0, p1, t);
+        f.line_xf(start, p0, t);
+        f.line_xf(p1, end, t);
         return;
     }
-    f.line_xf(path_ix, start, end, t);
+    f.line_xf(start, end, t);
 }
 
 __device__ __forceinline__ float f16_bits_to_f32(uint32_t h) { return __half2float(__ushort_as_half((unsigned short)(h & 0xffffu))); }
 
-template <int EMIT>
-__device__ void draw_join(Flat<EMIT> &f, uint32_t path_ix, uint32_t style_flags, fv2 p0, fv2 tan_prev, fv2 tan_next, fv2 n_prev,
+__device__ void draw_join(Flat &f, uint32_t style_flags, fv2 p0, fv2 tan_prev, fv2 tan_next, fv2 n_prev,
                           fv2 n_next, const FXform &t) { // flatten.wgsl:547-631
     fv2 front0 = p0 + n_prev;
     fv2 front1 = p0 + n_next;
@@ -465,8 +559,8 @@ __device__ void draw_join(Flat<EMIT> &f, uint32_t path_ix, uint32_t style_flags,
     float d = fdot(tan_prev, tan_next);
     switch (style_flags & STYLE_FLAGS_JOIN_MASK) {
     case STYLE_FLAGS_JOIN_BEVEL:
-        f.line_xf(path_ix, front0, front1, t);
-        f.line_xf(path_ix, back0, back1, t);
+        f.line_xf(front0, front1, t);
+        f.line_xf(back0, back1, t);
         break;
     case STYLE_FLAGS_JOIN_MITER: {
         float hyp = flen(F2(cr, d));
@@ -479,19 +573,19 @@ __device__ void draw_join(Flat<EMIT> &f, uint32_t path_ix, uint32_t style_flags,
             fv2 v = fp_this - fp_last;
             float h = (tan_prev.x * v.y - tan_prev.y * v.x) / cr;
             fv2 miter_pt = fp_this - tan_next * h;
-            f.line_xf(path_ix, p, miter_pt, t);
+            f.line_xf(p, miter_pt, t);
             if (is_backside) back0 = miter_pt; else front0 = miter_pt;
         }
-        f.line_xf(path_ix, front0, front1, t);
-        f.line_xf(path_ix, back0, back1, t);
+        f.line_xf(front0, front1, t);
+        f.line_xf(back0, back1, t);
         break;
     }
     case STYLE_FLAGS_JOIN_ROUND: {
         fv2 arc0, arc1, other0, other1;
         if (cr > 0.f) { arc0 = back0; arc1 = back1; other0 = front0; other1 = front1; }
         else { arc0 = front0; arc1 = front1; other0 = back0; other1 = back1; }
-        flatten_arc<EMIT>(f, path_ix, arc0, arc1, p0, fabsf(vb_atan2f(cr, d)), t);
-        f.line_xf(path_ix, other0, other1, t);
+        flatten_arc(f, arc0, arc1, p0, fabsf(vb_atan2f(cr, d)), t);
+        f.line_xf(other0, other1, t);
         break;
     }
     default: break;
@@ -584,13 +678,11 @@ __device__ CubicPoints read_path_segment(const VbConfig &cfg, const uint32_t *__
     return r;
 }
 
-// Everything one tag byte produces. EMIT=false only counts lines.
-template <int EMIT>
-__device__ void flatten_tag(Flat<EMIT> &f, const VbConfig &cfg, const uint32_t *__restrict__ scene,
+// Everything one tag byte produces.
+__device__ void flatten_tag(Flat &f, const VbConfig &cfg, const uint32_t *__restrict__ scene,
                             const VbTagMonoid *__restrict__ tag_monoids, const PathTagData &tag, uint32_t ix, uint32_t style_flags) {
     uint32_t seg_type = tag.tag_byte & 3u;
     if (seg_type == 0u) return;
-    const uint32_t path_ix = tag.path_ix;
     bool is_stroke = (style_flags & STYLE_FLAGS_STYLE) != 0u;
     FXform transform;
     {
@@ -613,7 +705,7 @@ __device__ void flatten_tag(Flat<EMIT> &f, const VbConfig &cfg, const uint32_t *
                 fv2 tangent = pts.p3 - pts.p0;
                 fv2 offset_tangent = fnorm(tangent) * offset;
                 fv2 n = F2(-offset_tangent.y, offset_tangent.x);
-                draw_cap<EMIT>(f, path_ix, (style_flags & STYLE_FLAGS_START_CAP_MASK) >> 2, pts.p0, pts.p0 - n, pts.p0 + n,
+                draw_cap(f, (style_flags & STYLE_FLAGS_START_CAP_MASK) >> 2, pts.p0, pts.p0 - n, pts.p0 + n,
                                F2(-offset_tangent.x, -offset_tangent.y), transform);
             }
         } else {
@@ -635,12 +727,16 @@ __device__ void flatten_tag(Flat<EMIT> &f, const VbConfig &cfg, const uint32_t *
             fv2 n_prev = F2(-offset_tangent.y, offset_tangent.x);
             fv2 tnn = fnorm(tan_next) * offset;
             fv2 n_next = F2(-tnn.y, tnn.x);
-            flatten_euler<EMIT>(f, pts, path_ix, transform, offset, pts.p0 + n_start, pts.p3 + n_prev);
-            flatten_euler<EMIT>(f, pts, path_ix, transform, -offset, pts.p0 - n_start, pts.p3 - n_prev);
+#pragma unroll 1
+            for (int side = 0; side < 2; side++) { // one copy of the Euler machinery in the instruction stream
+                const bool fwd = side == 0;
+                flatten_euler(f, pts, transform, fwd ? offset : -offset, fwd ? pts.p0 + n_start : pts.p0 - n_start,
+                              fwd ? pts.p3 + n_prev : pts.p3 - n_prev);
+            }
             if (do_join) {
-                draw_join<EMIT>(f, path_ix, style_flags, pts.p3, tan_prev, tan_next, n_prev, n_next, transform);
+                draw_join(f, style_flags, pts.p3, tan_prev, tan_next, n_prev, n_next, transform);
             } else {
-                draw_cap<EMIT>(f, path_ix, style_flags & STYLE_FLAGS_END_CAP_MASK, pts.p3, pts.p3 + n_prev, pts.p3 - n_prev,
+                draw_cap(f, style_flags & STYLE_FLAGS_END_CAP_MASK, pts.p3, pts.p3 + n_prev, pts.p3 - n_prev,
                                offset_tangent, transform);
             }
         }
@@ -660,12 +756,11 @@ __device__ void flatten_tag(Flat<EMIT> &f, const VbConfig &cfg, const uint32_t *
             if (fabsf(q0.x) < lim && fabsf(q0.y) < lim && fabsf(q3.x) < lim && fabsf(q3.y) < lim && fabsf(q1.x) < lim && fabsf(q1.y) < lim &&
                 fabsf(q2.x) < lim && fabsf(q2.y) < lim) {
                 if (feq(q0, q1) && feq(q0, q2) && feq(q0, q3)) return;
-                if (EMIT != 0) f.write_line(path_ix, q0, q3);
-                else f.ix++;
+                f.write_line(q0, q3);
                 return;
             }
         }
-        flatten_euler<EMIT>(f, pts, path_ix, transform, 0.f, pts.p0, pts.p3);
+        flatten_euler(f, pts, transform, 0.f, pts.p0, pts.p3);
     }
 }
 
@@ -680,20 +775,13 @@ __global__ void k_bbox_clear(uint32_t n_paths, VbPathBbox *path_bboxes) {
     }
 }
 
-// Three small kernels instead of one look-back pass. flatten's per-thread work varies by 10-100x (a fill line vs a
-// stroked curve with round joins); with a single-pass look-back every warp that has finished counting sits on its
-// registers until ALL earlier partitions have published, so the slowest tag in flight gates the whole machine
-// (ncu r1: 18 % issue utilisation, stalls = barrier / look-back spin). Instead:
-//   A  k_flatten        : each thread flattens its tag ONCE, lines go to a scratch arena at an offset taken with one
-//                         atomicAdd per warp (lane order inside the warp = tag order); per-warp {count, scratch offset}
-//   B  k_flatten_scan   : exclusive scan of the per-warp counts (one CTA; ~50k values)
-//   C  k_flatten_reorder: per warp, block-copy scratch[src .. src+count) -> lines[dst ..): final order = tag order,
-//                         deterministic and identical to the serial CPU shader, independent of the atomics' order.
-#define FL_MAX_CACHE 12 // lines a thread keeps in registers/local before it learns its offset; beyond that: 2nd pass
+// A: thread per tag. Outputs: per-warp line count, per-tag offset inside its warp's block, literal records, jobs,
+// and the bbox contribution of the literal lines. (History: a single-pass look-back kernel was gated by the slowest
+// tag in flight, ncu r1: 18 % issue utilisation; a count+emit kernel computed long tags twice and its 200 KB of code
+// thrashed the instruction cache, ncu r1_f: no_instruction = top stall.)
 __global__ void __launch_bounds__(FL_THREADS)
 k_flatten(VbConfig cfg, const uint32_t *__restrict__ scene, const VbTagMonoid *__restrict__ tag_monoids,
-          VbPathBbox *path_bboxes, VbBump *bump, VbLineSoup *scratch, uint32_t *part_count, uint32_t *part_src, uint32_t *scratch_ctr,
-          uint32_t n_parts) {
+          VbPathBbox *path_bboxes, FlCtx ctx, uint32_t *part_count, uint32_t *tag_off, uint32_t n_parts) {
     const uint32_t lane = vb_lane();
     const uint32_t part = blockIdx.x * (FL_THREADS / 32) + (threadIdx.x >> 5);
     if (part >= n_parts) return;
@@ -711,52 +799,41 @@ k_flatten(VbConfig cfg, const uint32_t *__restrict__ scene, const VbTagMonoid *_
             path_bboxes[tag.path_ix].trans_ix = tag.trans_ix;
         }
     }
-    // pass 1: count (cheap for the common tags: the geometry of the first FL_CACHE lines is kept in shared memory)
     __shared__ float4 sh_cache[FL_CACHE][FL_THREADS];
-    Flat<1> fc;
-    fc.lines = nullptr; fc.lines_size = 0; fc.ix = 0;
-    fc.bx0 = 1e31f; fc.by0 = 1e31f; fc.bx1 = -1e31f; fc.by1 = -1e31f;
-    fc.cache = &sh_cache[0][threadIdx.x];
-    flatten_tag<1>(fc, cfg, scene, tag_monoids, tag, ix, style_flags);
+    __shared__ uint32_t sh_rel[FL_CACHE][FL_THREADS];
+    Flat f;
+    f.c = ctx;
+    f.tag_ix = ix; f.path_ix = tag.path_ix; f.trans_ix = tag.trans_ix;
+    f.ix = 0u; f.nlit = 0u; f.force = false;
+    f.bx0 = 1e31f; f.by0 = 1e31f; f.bx1 = -1e31f; f.by1 = -1e31f;
+    f.cache = &sh_cache[0][threadIdx.x];
+    f.cache_rel = &sh_rel[0][threadIdx.x];
+    flatten_tag(f, cfg, scene, tag_monoids, tag, ix, style_flags);
     __syncwarp();
-    const uint32_t incl = vb_warp_incl_scan(fc.ix);
-    const uint32_t total = __shfl_sync(VB_FULL, incl, 31);
-    uint32_t base = 0u;
-    if (lane == 31u && total != 0u) base = atomicAdd(scratch_ctr, total);
-    base = __shfl_sync(VB_FULL, base, 31);
-    if (lane == 0u) {
-        part_count[part] = total;
-        part_src[part] = base;
+    const uint32_t incl = vb_warp_incl_scan(f.ix);
+    if (lane == 31u) part_count[part] = incl;
+    tag_off[ix] = incl - f.ix;
+    const uint32_t ncache = min(f.nlit, (uint32_t)FL_CACHE);
+    const uint32_t lincl = vb_warp_incl_scan(ncache);
+    const uint32_t ltotal = __shfl_sync(VB_FULL, lincl, 31);
+    uint32_t lbase = 0u;
+    if (lane == 31u && ltotal != 0u) lbase = atomicAdd(ctx.ctrs, ltotal);
+    lbase = __shfl_sync(VB_FULL, lbase, 31) + lincl - ncache;
+    for (uint32_t k = 0; k < ncache; k++) {
+        const uint32_t slot = lbase + k;
+        if (slot < ctx.lits_cap) {
+            const float4 l = sh_cache[k][threadIdx.x];
+            uint4 *dst = reinterpret_cast<uint4 *>(ctx.lits + slot);
+            dst[0] = make_uint4(ix, sh_rel[k][threadIdx.x], tag.path_ix, 0u);
+            dst[1] = make_uint4(__float_as_uint(l.x), __float_as_uint(l.y), __float_as_uint(l.z), __float_as_uint(l.w));
+        }
     }
-    if (fc.ix != 0u) {
-        const uint32_t out0 = base + incl - fc.ix;
-        float bx0 = fc.bx0, by0 = fc.by0, bx1 = fc.bx1, by1 = fc.by1;
-        if (fc.ix <= FL_CACHE) {
-            for (uint32_t k = 0; k < fc.ix; k++) {
-                const uint32_t o = out0 + k;
-                if (o < cfg.lines_size) {
-                    const float4 l = sh_cache[k][threadIdx.x];
-                    uint2 *dst = reinterpret_cast<uint2 *>(scratch + o);
-                    dst[0] = make_uint2(tag.path_ix, 0u);
-                    dst[1] = make_uint2(__float_as_uint(l.x), __float_as_uint(l.y));
-                    dst[2] = make_uint2(__float_as_uint(l.z), __float_as_uint(l.w));
-                }
-            }
-        } else {
-            Flat<2> fe;
-            fe.lines = scratch; fe.lines_size = cfg.lines_size; fe.ix = out0;
-            fe.bx0 = 1e31f; fe.by0 = 1e31f; fe.bx1 = -1e31f; fe.by1 = -1e31f;
-            fe.cache = nullptr;
-            flatten_tag<2>(fe, cfg, scene, tag_monoids, tag, ix, style_flags);
-            bx0 = fe.bx0; by0 = fe.by0; bx1 = fe.bx1; by1 = fe.by1;
-        }
-        if ((bx1 > bx0 || by1 > by0) && tag.path_ix < n_paths) {
-            VbPathBbox *o = path_bboxes + tag.path_ix;
-            atomicMin(&o->x0, vb_f2i_sat(floorf(bx0)));
-            atomicMin(&o->y0, vb_f2i_sat(floorf(by0)));
-            atomicMax(&o->x1, vb_f2i_sat(ceilf(bx1)));
-            atomicMax(&o->y1, vb_f2i_sat(ceilf(by1)));
-        }
+    if (f.nlit != 0u && (f.force || f.bx1 > f.bx0 || f.by1 > f.by0) && tag.path_ix < n_paths) {
+        VbPathBbox *o = path_bboxes + tag.path_ix;
+        atomicMin(&o->x0, vb_f2i_sat(floorf(f.bx0)));
+        atomicMin(&o->y0, vb_f2i_sat(floorf(f.by0)));
+        atomicMax(&o->x1, vb_f2i_sat(ceilf(f.bx1)));
+        atomicMax(&o->y1, vb_f2i_sat(ceilf(f.by1)));
     }
 }
 
@@ -790,38 +867,148 @@ k_flatten_scan(VbConfig cfg, uint32_t n_parts, const uint32_t *__restrict__ part
     }
 }
 
-// C: per partition, copy its block of lines from the scratch arena to its final position (8-byte words, coalesced).
-#define FR_THREADS 256
-__global__ void __launch_bounds__(FR_THREADS)
-k_flatten_reorder(VbConfig cfg, uint32_t n_parts, const uint32_t *__restrict__ part_count, const uint32_t *__restrict__ part_src,
-                  const uint32_t *__restrict__ part_dst, const VbLineSoup *__restrict__ scratch, VbLineSoup *lines) {
-    const uint32_t lane = vb_lane();
-    const uint32_t warps = gridDim.x * (FR_THREADS / 32);
-    for (uint32_t part = blockIdx.x * (FR_THREADS / 32) + (threadIdx.x >> 5); part < n_parts; part += warps) {
-        const uint32_t n = part_count[part];
-        if (n == 0u) continue;
-        const uint32_t src = part_src[part], dst = part_dst[part];
-        if (src + n > cfg.lines_size || dst + n > cfg.lines_size) continue; // overflowed frame: will be re-run
-        const uint2 *s = reinterpret_cast<const uint2 *>(scratch + src);
-        uint2 *d = reinterpret_cast<uint2 *>(lines + dst);
-        for (uint32_t k = lane; k < n * 3u; k += 32u) d[k] = __ldg(s + k);
+// C: thread per LINE. Phase 1 scatters the literal records; phase 2 expands the jobs, 32 per warp: the warp scans the
+// jobs' line counts and walks the concatenated line range 32 lines at a time, so lanes stay busy whatever the mix of
+// job sizes. A line's start point is its predecessor's end point: taken from the neighbouring lane when that lane
+// holds the predecessor, recomputed otherwise (same function, same bits).
+#define FP_THREADS 256
+#define FP_WARPS (FP_THREADS / 32)
+__device__ __forceinline__ int fl_floor_i(float v) { return v != v ? 0x7fffffff : vb_f2i_sat(floorf(v)); }
+__device__ __forceinline__ int fl_ceil_i(float v) { return v != v ? (int)0x80000000 : vb_f2i_sat(ceilf(v)); }
+
+__global__ void __launch_bounds__(FP_THREADS)
+k_flatten_place(VbConfig cfg, const uint32_t *__restrict__ scene, FlCtx ctx, const uint32_t *__restrict__ part_dst,
+                const uint32_t *__restrict__ tag_off, VbPathBbox *path_bboxes, VbLineSoup *lines) {
+    const uint32_t n_lit = min(ctx.ctrs[0], ctx.lits_cap);
+    const uint32_t n_job = min(ctx.ctrs[1], ctx.jobs_cap);
+    const uint32_t n_paths = cfg.layout.n_paths;
+    for (uint32_t i = blockIdx.x * FP_THREADS + threadIdx.x; i < n_lit; i += gridDim.x * FP_THREADS) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(ctx.lits + i);
+        const uint4 h = src[0], l = src[1];
+        const uint32_t dst = part_dst[h.x >> 5] + tag_off[h.x] + h.y;
+        if (dst < cfg.lines_size) {
+            uint2 *d = reinterpret_cast<uint2 *>(lines + dst);
+            d[0] = make_uint2(h.z, 0u);
+            d[1] = make_uint2(l.x, l.y);
+            d[2] = make_uint2(l.z, l.w);
+        }
+    }
+    __shared__ float4 sh_job[FP_WARPS][6][32];
+    __shared__ uint32_t sh_excl[FP_WARPS][32];
+    __shared__ uint32_t sh_dst[FP_WARPS][32];
+    const uint32_t lane = vb_lane(), w = threadIdx.x >> 5;
+    const uint32_t n_batches = (n_job + 31u) / 32u;
+    for (uint32_t batch = blockIdx.x * FP_WARPS + w; batch < n_batches; batch += gridDim.x * FP_WARPS) {
+        const uint32_t jix = batch * 32u + lane;
+        uint32_t n_l = 0u;
+        if (jix < n_job) {
+            const float4 *src = reinterpret_cast<const float4 *>(ctx.jobs + jix);
+            float4 r4 = src[4], r5 = src[5];
+#pragma unroll
+            for (int k = 0; k < 4; k++) sh_job[w][k][lane] = src[k];
+            sh_job[w][4][lane] = r4;
+            sh_job[w][5][lane] = r5;
+            n_l = FJ_N(__float_as_uint(r5.z));
+            const uint32_t tix = __float_as_uint(r4.z);
+            sh_dst[w][lane] = part_dst[tix >> 5] + tag_off[tix] + __float_as_uint(r4.w);
+        }
+        const uint32_t incl = vb_warp_incl_scan(n_l);
+        const uint32_t total = __shfl_sync(VB_FULL, incl, 31);
+        sh_excl[w][lane] = jix < n_job ? incl - n_l : 0xffffffffu;
+        __syncwarp();
+        for (uint32_t base = 0u; base < total; base += 32u) {
+            const uint32_t l = base + lane;
+            const bool act = l < total;
+            const uint32_t actmask = __ballot_sync(VB_FULL, act);
+            uint32_t k = 0u, i = 0u, meta = 0u, path_ix = 0u;
+            fv2 q1 = F2(0.f, 0.f);
+            FlJob j;
+            FXform t;
+            if (act) {
+#pragma unroll
+                for (uint32_t step = 16u; step > 0u; step >>= 1)
+                    if (sh_excl[w][k + step] <= l) k += step;
+                i = l - sh_excl[w][k];
+                const float4 a0 = sh_job[w][0][k], a1 = sh_job[w][1][k], a2 = sh_job[w][2][k], a3 = sh_job[w][3][k], a4 = sh_job[w][4][k],
+                             a5 = sh_job[w][5][k];
+                j.p0x = a0.x; j.p0y = a0.y; j.p1x = a0.z; j.p1y = a0.w;
+                j.th0 = a1.x; j.k0 = a1.y; j.k1 = a1.z; j.ch = a1.w;
+                j.noff = a2.x; j.n = a2.y; j.integral = a2.z; j.int0 = a2.w;
+                j.a = a3.x; j.b = a3.y; j.lp0x = a3.z; j.lp0y = a3.w;
+                j.tex = a4.x; j.tey = a4.y;
+                path_ix = __float_as_uint(a5.x);
+                j.trans_ix = __float_as_uint(a5.y);
+                meta = j.meta = __float_as_uint(a5.z);
+                if (meta & FJ_IDENT) {
+                    t.m0 = 1.f; t.m1 = 0.f; t.m2 = 0.f; t.m3 = 1.f; t.tx = 0.f; t.ty = 0.f;
+                } else {
+                    const uint32_t b = cfg.layout.transform_base + j.trans_ix * 6u;
+                    t.m0 = __uint_as_float(vb_scene(scene, cfg, b));
+                    t.m1 = __uint_as_float(vb_scene(scene, cfg, b + 1));
+                    t.m2 = __uint_as_float(vb_scene(scene, cfg, b + 2));
+                    t.m3 = __uint_as_float(vb_scene(scene, cfg, b + 3));
+                    t.tx = __uint_as_float(vb_scene(scene, cfg, b + 4));
+                    t.ty = __uint_as_float(vb_scene(scene, cfg, b + 5));
+                }
+                q1 = (meta & FJ_ARC) ? fl_arc_point(j, i, t) : fx_apply(t, fl_euler_point(j, i));
+            }
+            fv2 q0;
+            q0.x = __shfl_up_sync(VB_FULL, q1.x, 1);
+            q0.y = __shfl_up_sync(VB_FULL, q1.y, 1);
+            if (act) {
+                if (i == 0u) q0 = F2(j.lp0x, j.lp0y);
+                else if (lane == 0u) q0 = (meta & FJ_ARC) ? fl_arc_point(j, i - 1u, t) : fx_apply(t, fl_euler_point(j, i - 1u));
+                const fv2 l0 = (meta & FJ_NEG) ? q1 : q0, l1 = (meta & FJ_NEG) ? q0 : q1;
+                const uint32_t dst = sh_dst[w][k] + i;
+                if (dst < cfg.lines_size) {
+                    uint2 *d = reinterpret_cast<uint2 *>(lines + dst);
+                    d[0] = make_uint2(path_ix, 0u);
+                    d[1] = make_uint2(__float_as_uint(l0.x), __float_as_uint(l0.y));
+                    d[2] = make_uint2(__float_as_uint(l1.x), __float_as_uint(l1.y));
+                }
+                // bbox: floor / ceil commute with min / max, so reduce the integers across the lanes of a path
+                int x0 = fl_floor_i(fminf(q0.x, q1.x)), y0 = fl_floor_i(fminf(q0.y, q1.y));
+                int x1 = fl_ceil_i(fmaxf(q0.x, q1.x)), y1 = fl_ceil_i(fmaxf(q0.y, q1.y));
+                const uint32_t peers = __match_any_sync(actmask, path_ix);
+                x0 = __reduce_min_sync(peers, x0);
+                y0 = __reduce_min_sync(peers, y0);
+                x1 = __reduce_max_sync(peers, x1);
+                y1 = __reduce_max_sync(peers, y1);
+                if (lane == (uint32_t)(__ffs((int)peers) - 1) && path_ix < n_paths) {
+                    VbPathBbox *o = path_bboxes + path_ix;
+                    atomicMin(&o->x0, x0);
+                    atomicMin(&o->y0, y0);
+                    atomicMax(&o->x1, x1);
+                    atomicMax(&o->y1, y1);
+                }
+            }
+        }
+        __syncwarp();
     }
 }
 
 extern "C" void vb_launch_flatten(const VbConfig *cfg, const uint32_t *scene, const VbTagMonoid *tag_monoids,
-                                  VbPathBbox *path_bboxes, VbBump *bump, VbLineSoup *lines, VbLineSoup *scratch, uint32_t *part_mem /* 3*n_parts */,
-                                  uint32_t *scratch_ctr, uint32_t n_parts, cudaStream_t st) {
+                                  VbPathBbox *path_bboxes, VbBump *bump, VbLineSoup *lines, void *lit_arena, void *job_arena,
+                                  uint32_t *part_mem /* 34 * n_parts */, uint32_t *ctrs, uint32_t n_parts, cudaStream_t st) {
     uint32_t n_paths = cfg->layout.n_paths;
     if (n_paths) k_bbox_clear<<<(n_paths + 255) / 256, 256, 0, st>>>(n_paths, path_bboxes);
     if (n_parts) {
-        uint32_t *part_count = part_mem, *part_src = part_mem + n_parts, *part_dst = part_mem + 2 * (size_t)n_parts;
+        uint32_t *part_count = part_mem, *part_dst = part_mem + n_parts, *tag_off = part_mem + 2 * (size_t)n_parts;
+        FlCtx ctx;
+        ctx.lits = (FlLit *)lit_arena;
+        ctx.jobs = (FlJob *)job_arena;
+        ctx.lits_cap = cfg->lines_size;
+        ctx.jobs_cap = cfg->lines_size / FL_DEFER_MIN + 1u;
+        ctx.ctrs = ctrs;
         const uint32_t warps_per_cta = FL_THREADS / 32;
-        k_flatten<<<(n_parts + warps_per_cta - 1) / warps_per_cta, FL_THREADS, 0, st>>>(*cfg, scene, tag_monoids, path_bboxes, bump, scratch,
-                                                                                       part_count, part_src, scratch_ctr, n_parts);
+        k_flatten<<<(n_parts + warps_per_cta - 1) / warps_per_cta, FL_THREADS, 0, st>>>(*cfg, scene, tag_monoids, path_bboxes, ctx, part_count,
+                                                                                       tag_off, n_parts);
         k_flatten_scan<<<1, FS_THREADS, 0, st>>>(*cfg, n_parts, part_count, part_dst, bump);
-        uint32_t blocks = (n_parts + (FR_THREADS / 32) - 1) / (FR_THREADS / 32);
-        if (blocks > 148u * 8u) blocks = 148u * 8u;
-        k_flatten_reorder<<<blocks, FR_THREADS, 0, st>>>(*cfg, n_parts, part_count, part_src, part_dst, scratch, lines);
+        k_flatten_place<<<148 * 4, FP_THREADS, 0, st>>>(*cfg, scene, ctx, part_dst, tag_off, path_bboxes, lines);
     }
 }
 extern "C" uint32_t vb_flatten_parts(uint32_t n_tag_words) { return (n_tag_words * 4u + 31u) / 32u; }
+extern "C" void vb_flatten_arena_bytes(uint32_t cap_lines, size_t *lit_bytes, size_t *job_bytes) {
+    *lit_bytes = (size_t)cap_lines * sizeof(FlLit);
+    *job_bytes = ((size_t)cap_lines / FL_DEFER_MIN + 1u) * sizeof(FlJob);
+}

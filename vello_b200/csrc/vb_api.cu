@@ -20,9 +20,10 @@
 extern "C" {
 void vb_launch_pathtag(const VbConfig *, const uint32_t *, VbTagMonoid *, uint32_t *, uint32_t, cudaStream_t);
 uint32_t vb_pathtag_parts(uint32_t);
-void vb_launch_flatten(const VbConfig *, const uint32_t *, const VbTagMonoid *, VbPathBbox *, VbBump *, VbLineSoup *, VbLineSoup *, uint32_t *,
+void vb_launch_flatten(const VbConfig *, const uint32_t *, const VbTagMonoid *, VbPathBbox *, VbBump *, VbLineSoup *, void *, void *, uint32_t *,
                        uint32_t *, uint32_t, cudaStream_t);
 uint32_t vb_flatten_parts(uint32_t);
+void vb_flatten_arena_bytes(uint32_t, size_t *, size_t *);
 void vb_launch_draw(const VbConfig *, const uint32_t *, const VbPathBbox *, VbDrawMonoid *, uint32_t *, VbClipInp *, uint32_t *, uint32_t,
                     cudaStream_t);
 uint32_t vb_draw_parts(uint32_t);
@@ -100,7 +101,7 @@ struct vb_renderer {
     DevBuf tag_monoids, path_bboxes, draw_monoids, info_bin_data, clip_inp, clip_bboxes, clip_scratch, draw_bboxes, bin_headers, paths,
         ctl, target;
     // bump arenas (capacities in elements live in cap_*)
-    DevBuf lines, line_scratch, flatten_parts, tiles, seg_counts, segments, ptcl, blend_spill;
+    DevBuf lines, line_scratch, flatten_jobs, flatten_parts, tiles, seg_counts, segments, ptcl, blend_spill;
     uint32_t cap_lines = 0, cap_binning = 0, cap_tiles = 0, cap_seg_counts = 0, cap_segments = 0, cap_blend = 0, cap_ptcl = 0;
 
     // per-frame
@@ -144,7 +145,7 @@ static int ensure(vb_renderer *r, DevBuf &b, size_t bytes) {
 static size_t arena_bytes(const vb_renderer *r) {
     const DevBuf *all[] = {&r->scene, &r->ramps, &r->atlas, &r->mask8, &r->mask16, &r->tag_monoids, &r->path_bboxes, &r->draw_monoids,
                            &r->info_bin_data, &r->clip_inp, &r->clip_bboxes, &r->clip_scratch, &r->draw_bboxes, &r->bin_headers, &r->paths,
-                           &r->ctl, &r->target, &r->lines, &r->line_scratch, &r->flatten_parts, &r->tiles, &r->seg_counts, &r->segments, &r->ptcl, &r->blend_spill};
+                           &r->ctl, &r->target, &r->lines, &r->line_scratch, &r->flatten_jobs, &r->flatten_parts, &r->tiles, &r->seg_counts, &r->segments, &r->ptcl, &r->blend_spill};
     size_t s = 0;
     for (auto b : all) s += b->cap;
     return s;
@@ -226,7 +227,7 @@ extern "C" void vb_renderer_free(vb_renderer *r) {
     if (r->stream) cudaStreamSynchronize(r->stream);
     DevBuf *all[] = {&r->scene, &r->ramps, &r->atlas, &r->mask8, &r->mask16, &r->tag_monoids, &r->path_bboxes, &r->draw_monoids,
                      &r->info_bin_data, &r->clip_inp, &r->clip_bboxes, &r->clip_scratch, &r->draw_bboxes, &r->bin_headers, &r->paths,
-                     &r->ctl, &r->target, &r->lines, &r->line_scratch, &r->flatten_parts, &r->tiles, &r->seg_counts, &r->segments, &r->ptcl, &r->blend_spill};
+                     &r->ctl, &r->target, &r->lines, &r->line_scratch, &r->flatten_jobs, &r->flatten_parts, &r->tiles, &r->seg_counts, &r->segments, &r->ptcl, &r->blend_spill};
     for (auto b : all)
         if (b->p) cudaFree(b->p);
     if (r->h_bump) cudaFreeHost(r->h_bump);
@@ -351,7 +352,12 @@ static int prepare(vb_renderer *r, const vb_params *p) {
     if (r->cap_ptcl < n_tiles * VB_PTCL_INITIAL_ALLOC + VB_PTCL_INCREMENT)
         r->cap_ptcl = n_tiles * VB_PTCL_INITIAL_ALLOC + VB_PTCL_INCREMENT;
     if ((rc = ensure(r, r->lines, (size_t)r->cap_lines * sizeof(VbLineSoup)))) return rc;
-    if ((rc = ensure(r, r->line_scratch, (size_t)r->cap_lines * sizeof(VbLineSoup)))) return rc;
+    {
+        size_t lit_bytes, job_bytes;
+        vb_flatten_arena_bytes(r->cap_lines, &lit_bytes, &job_bytes);
+        if ((rc = ensure(r, r->line_scratch, lit_bytes))) return rc;
+        if ((rc = ensure(r, r->flatten_jobs, job_bytes))) return rc;
+    }
     if ((rc = ensure(r, r->info_bin_data, ((size_t)L.bin_data_start + r->cap_binning) * 4))) return rc;
     if ((rc = ensure(r, r->tiles, (size_t)r->cap_tiles * sizeof(VbTile)))) return rc;
     if ((rc = ensure(r, r->seg_counts, (size_t)r->cap_seg_counts * sizeof(VbSegmentCount)))) return rc;
@@ -373,12 +379,12 @@ static int prepare(vb_renderer *r, const vb_params *p) {
     r->parts_tile = vb_tile_alloc_parts(n_draw);
     size_t off = 16;
     r->off_lb_pathtag = off; off += vb_lookback_words(r->parts_pathtag, 5);
-    r->off_lb_flatten = off; off += 4; // [0] = scratch line counter of flatten
+    r->off_lb_flatten = off; off += 4; // flatten: [0] literal-record counter, [1] job counter
     r->off_lb_draw = off; off += vb_lookback_words(r->parts_draw, 4);
     r->off_lb_tile = off; off += vb_lookback_words(r->parts_tile, 1);
     r->ctl_words = off;
     if ((rc = ensure(r, r->ctl, off * 4))) return rc;
-    if ((rc = ensure(r, r->flatten_parts, (size_t)r->parts_flatten * 3 * 4))) return rc;
+    if ((rc = ensure(r, r->flatten_parts, (size_t)r->parts_flatten * 34 * 4))) return rc;
     return VB_OK;
 }
 
@@ -407,7 +413,7 @@ static int enqueue(vb_renderer *r, int first, int last, void *out_dev) {
             break;
         case VB_STAGE_ID_FLATTEN:
             vb_launch_flatten(&c, (const uint32_t *)r->scene.p, (const VbTagMonoid *)r->tag_monoids.p, (VbPathBbox *)r->path_bboxes.p, bump,
-                              (VbLineSoup *)r->lines.p, (VbLineSoup *)r->line_scratch.p, (uint32_t *)r->flatten_parts.p,
+                              (VbLineSoup *)r->lines.p, r->line_scratch.p, r->flatten_jobs.p, (uint32_t *)r->flatten_parts.p,
                               ctl + r->off_lb_flatten, r->parts_flatten, st);
             launches += (c.layout.n_paths ? 1 : 0) + (r->parts_flatten ? 3 : 0);
             break;
