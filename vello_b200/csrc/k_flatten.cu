@@ -83,6 +83,15 @@ __device__ __forceinline__ uint32_t fl_alloc(uint32_t *ctr) { // one atomic per 
     return g.shfl(base, 0) + g.thread_rank();
 }
 
+__device__ __noinline__ void fl_spill_line(const FlCtx c, uint32_t tag_ix, uint32_t rel, uint32_t path_ix, fv2 p0, fv2 p1) {
+    const uint32_t slot = fl_alloc(c.ctrs); // literal beyond the shared-memory cache: rare
+    if (slot < c.lits_cap) {
+        uint4 *dst = reinterpret_cast<uint4 *>(c.lits + slot);
+        dst[0] = make_uint4(tag_ix, rel, path_ix, 0u);
+        dst[1] = make_uint4(__float_as_uint(p0.x), __float_as_uint(p0.y), __float_as_uint(p1.x), __float_as_uint(p1.y));
+    }
+}
+
 struct Flat {
     FlCtx c;
     uint32_t tag_ix, path_ix, trans_ix;
@@ -101,12 +110,7 @@ struct Flat {
             cache[nlit * FL_THREADS] = make_float4(p0.x, p0.y, p1.x, p1.y);
             cache_rel[nlit * FL_THREADS] = ix;
         } else {
-            const uint32_t slot = fl_alloc(c.ctrs);
-            if (slot < c.lits_cap) {
-                uint4 *dst = reinterpret_cast<uint4 *>(c.lits + slot);
-                dst[0] = make_uint4(tag_ix, ix, path_ix, 0u);
-                dst[1] = make_uint4(__float_as_uint(p0.x), __float_as_uint(p0.y), __float_as_uint(p1.x), __float_as_uint(p1.y));
-            }
+            fl_spill_line(c, tag_ix, ix, path_ix, p0, p1);
         }
         nlit++;
         ix++;
@@ -528,10 +532,31 @@ __device__ void flatten_arc(Flat &f, fv2 begin, fv2 end, fv2 center, float angle
 #define STYLE_FLAGS_JOIN_MITER 0x10000000u
 #define STYLE_FLAGS_JOIN_ROUND 0x20000000u
 
-__device__ void draw_cap(Flat &f, uint32_t cap_style, fv2 point, fv2 cap0, fv2 cap1, fv2 offset_tangent,
-                         const FXform &t) { // flatten.wgsl:521-545 (slot order of the WGSL)
+// What a cap or join adds after the offset curves: at most one arc, then at most three straight lines (the slot
+// order of the WGSL). Caps and joins only DESCRIBE their output here; flatten_tag emits it at a single site, so the
+// instruction stream holds one copy of the arc / line writers (the fully inlined kernel was 133 KB of code and
+// stalled on instruction fetch).
+struct TailOps {
+    bool have_arc;
+    fv2 arc_begin, arc_end, arc_center;
+    float arc_angle;
+    uint32_t n_lines;
+    fv2 a0, b0, a1, b1, a2, b2;
+    __device__ __forceinline__ void line(fv2 a, fv2 b) {
+        if (n_lines == 0u) { a0 = a; b0 = b; }
+        else if (n_lines == 1u) { a1 = a; b1 = b; }
+        else { a2 = a; b2 = b; }
+        n_lines++;
+    }
+    __device__ __forceinline__ void arc(fv2 begin, fv2 end, fv2 center, float angle) {
+        have_arc = true; arc_begin = begin; arc_end = end; arc_center = center; arc_angle = angle;
+    }
+};
+
+__device__ __forceinline__ void draw_cap(TailOps &o, uint32_t cap_style, fv2 point, fv2 cap0, fv2 cap1, fv2 offset_tangent) {
+    // flatten.wgsl:521-545
     if (cap_style == STYLE_FLAGS_CAP_ROUND) {
-        flatten_arc(f, cap0, cap1, point, 3.1415927f, t);
+        o.arc(cap0, cap1, point, 3.1415927f);
         return;
     }
     fv2 start = cap0, end = cap1;
@@ -539,18 +564,18 @@ __device__ void draw_cap(Flat &f, uint32_t cap_style, fv2 point, fv2 cap0, fv2 c
         fv2 v = offset_tangent;
         fv2 p0 = start + v;
         fv2 p1 = end + v;
-        f.line_xf(p0, p1, t);
-        f.line_xf(start, p0, t);
-        f.line_xf(p1, end, t);
+        o.line(p0, p1);
+        o.line(start, p0);
+        o.line(p1, end);
         return;
     }
-    f.line_xf(start, end, t);
+    o.line(start, end);
 }
 
 __device__ __forceinline__ float f16_bits_to_f32(uint32_t h) { return __half2float(__ushort_as_half((unsigned short)(h & 0xffffu))); }
 
-__device__ void draw_join(Flat &f, uint32_t style_flags, fv2 p0, fv2 tan_prev, fv2 tan_next, fv2 n_prev,
-                          fv2 n_next, const FXform &t) { // flatten.wgsl:547-631
+__device__ __forceinline__ void draw_join(TailOps &o, uint32_t style_flags, fv2 p0, fv2 tan_prev, fv2 tan_next, fv2 n_prev, fv2 n_next) {
+    // flatten.wgsl:547-631
     fv2 front0 = p0 + n_prev;
     fv2 front1 = p0 + n_next;
     fv2 back0 = p0 - n_next;
@@ -559,8 +584,8 @@ __device__ void draw_join(Flat &f, uint32_t style_flags, fv2 p0, fv2 tan_prev, f
     float d = fdot(tan_prev, tan_next);
     switch (style_flags & STYLE_FLAGS_JOIN_MASK) {
     case STYLE_FLAGS_JOIN_BEVEL:
-        f.line_xf(front0, front1, t);
-        f.line_xf(back0, back1, t);
+        o.line(front0, front1);
+        o.line(back0, back1);
         break;
     case STYLE_FLAGS_JOIN_MITER: {
         float hyp = flen(F2(cr, d));
@@ -573,19 +598,19 @@ __device__ void draw_join(Flat &f, uint32_t style_flags, fv2 p0, fv2 tan_prev, f
             fv2 v = fp_this - fp_last;
             float h = (tan_prev.x * v.y - tan_prev.y * v.x) / cr;
             fv2 miter_pt = fp_this - tan_next * h;
-            f.line_xf(p, miter_pt, t);
+            o.line(p, miter_pt);
             if (is_backside) back0 = miter_pt; else front0 = miter_pt;
         }
-        f.line_xf(front0, front1, t);
-        f.line_xf(back0, back1, t);
+        o.line(front0, front1);
+        o.line(back0, back1);
         break;
     }
     case STYLE_FLAGS_JOIN_ROUND: {
         fv2 arc0, arc1, other0, other1;
         if (cr > 0.f) { arc0 = back0; arc1 = back1; other0 = front0; other1 = front1; }
         else { arc0 = front0; arc1 = front1; other0 = back0; other1 = back1; }
-        flatten_arc(f, arc0, arc1, p0, fabsf(vb_atan2f(cr, d)), t);
-        f.line_xf(other0, other1, t);
+        o.arc(arc0, arc1, p0, fabsf(vb_atan2f(cr, d)));
+        o.line(other0, other1);
         break;
     }
     default: break;
@@ -695,9 +720,17 @@ __device__ void flatten_tag(Flat &f, const VbConfig &cfg, const uint32_t *__rest
         transform.ty = __uint_as_float(vb_scene(scene, cfg, b + 5));
     }
     CubicPoints pts = read_path_segment(cfg, scene, tag, is_stroke);
+    // the offset curves to flatten (0, 1 or 2 of them) and what follows them
+    int n_sides = 0;
+    float offset = 0.f;
+    fv2 n_start = F2(0.f, 0.f), n_prev = F2(0.f, 0.f);
+    TailOps tail;
+    tail.have_arc = false; tail.n_lines = 0u; tail.arc_angle = 0.f;
+    tail.arc_begin = tail.arc_end = tail.arc_center = F2(0.f, 0.f);
+    tail.a0 = tail.b0 = tail.a1 = tail.b1 = tail.a2 = tail.b2 = F2(0.f, 0.f);
     if (is_stroke) {
         float linewidth = __uint_as_float(vb_scene(scene, cfg, cfg.layout.style_base + tag.style_ix + 1u));
-        float offset = 0.5f * linewidth;
+        offset = 0.5f * linewidth;
         bool is_open = seg_type != 1u;
         bool is_stroke_cap_marker = (tag.tag_byte & 4u) != 0u;
         if (is_stroke_cap_marker) {
@@ -705,8 +738,8 @@ __device__ void flatten_tag(Flat &f, const VbConfig &cfg, const uint32_t *__rest
                 fv2 tangent = pts.p3 - pts.p0;
                 fv2 offset_tangent = fnorm(tangent) * offset;
                 fv2 n = F2(-offset_tangent.y, offset_tangent.x);
-                draw_cap(f, (style_flags & STYLE_FLAGS_START_CAP_MASK) >> 2, pts.p0, pts.p0 - n, pts.p0 + n,
-                               F2(-offset_tangent.x, -offset_tangent.y), transform);
+                draw_cap(tail, (style_flags & STYLE_FLAGS_START_CAP_MASK) >> 2, pts.p0, pts.p0 - n, pts.p0 + n,
+                         F2(-offset_tangent.x, -offset_tangent.y));
             }
         } else {
             PathTagData ntag = compute_tag_monoid(cfg, scene, tag_monoids, ix + 1u);
@@ -722,23 +755,14 @@ __device__ void flatten_tag(Flat &f, const VbConfig &cfg, const uint32_t *__rest
             if (fdot(tan_prev, tan_prev) < TANGENT_THRESH * TANGENT_THRESH) tan_prev = F2(TANGENT_THRESH, 0.f);
             fv2 tan_next = n_tangent;
             if (fdot(tan_next, tan_next) < TANGENT_THRESH * TANGENT_THRESH) tan_next = F2(TANGENT_THRESH, 0.f);
-            fv2 n_start = fnorm(F2(-tan_start.y, tan_start.x)) * offset;
+            n_start = fnorm(F2(-tan_start.y, tan_start.x)) * offset;
             fv2 offset_tangent = fnorm(tan_prev) * offset;
-            fv2 n_prev = F2(-offset_tangent.y, offset_tangent.x);
+            n_prev = F2(-offset_tangent.y, offset_tangent.x);
             fv2 tnn = fnorm(tan_next) * offset;
             fv2 n_next = F2(-tnn.y, tnn.x);
-#pragma unroll 1
-            for (int side = 0; side < 2; side++) { // one copy of the Euler machinery in the instruction stream
-                const bool fwd = side == 0;
-                flatten_euler(f, pts, transform, fwd ? offset : -offset, fwd ? pts.p0 + n_start : pts.p0 - n_start,
-                              fwd ? pts.p3 + n_prev : pts.p3 - n_prev);
-            }
-            if (do_join) {
-                draw_join(f, style_flags, pts.p3, tan_prev, tan_next, n_prev, n_next, transform);
-            } else {
-                draw_cap(f, style_flags & STYLE_FLAGS_END_CAP_MASK, pts.p3, pts.p3 + n_prev, pts.p3 - n_prev,
-                               offset_tangent, transform);
-            }
+            n_sides = 2;
+            if (do_join) draw_join(tail, style_flags, pts.p3, tan_prev, tan_next, n_prev, n_next);
+            else draw_cap(tail, style_flags & STYLE_FLAGS_END_CAP_MASK, pts.p3, pts.p3 + n_prev, pts.p3 - n_prev, offset_tangent);
         }
     } else {
         // Fast path for a line-to in a fill (the bulk of map-like scenes). For a degree-raised line the general
@@ -749,19 +773,29 @@ __device__ void flatten_tag(Flat &f, const VbConfig &cfg, const uint32_t *__rest
         //  * the single line runs from t_start = p0' to t_end = p3' (t1 == 1 exactly).
         // The bounds need ulp(coord) <= 2^-8, hence the |coord| < 65536 guard; anything else takes the general path.
         // tests/test_gpu_parity.py compares `lines` bit-for-bit with the oracle, which has no such shortcut.
+        n_sides = 1;
         if (seg_type == 1u) {
             const fv2 q0 = fx_apply(transform, pts.p0), q1 = fx_apply(transform, pts.p1);
             const fv2 q2 = fx_apply(transform, pts.p2), q3 = fx_apply(transform, pts.p3);
             const float lim = 65536.0f;
             if (fabsf(q0.x) < lim && fabsf(q0.y) < lim && fabsf(q3.x) < lim && fabsf(q3.y) < lim && fabsf(q1.x) < lim && fabsf(q1.y) < lim &&
                 fabsf(q2.x) < lim && fabsf(q2.y) < lim) {
-                if (feq(q0, q1) && feq(q0, q2) && feq(q0, q3)) return;
-                f.write_line(q0, q3);
-                return;
+                n_sides = 0;
+                if (!(feq(q0, q1) && feq(q0, q2) && feq(q0, q3))) tail.line(q0, q3); // device space
             }
         }
-        flatten_euler(f, pts, transform, 0.f, pts.p0, pts.p3);
     }
+#pragma unroll 1
+    for (int side = 0; side < n_sides; side++) { // one copy of the Euler machinery in the instruction stream
+        const bool fwd = side == 0;
+        flatten_euler(f, pts, transform, fwd ? offset : -offset, fwd ? pts.p0 + n_start : pts.p0 - n_start,
+                      fwd ? pts.p3 + n_prev : pts.p3 - n_prev);
+    }
+    if (tail.have_arc) flatten_arc(f, tail.arc_begin, tail.arc_end, tail.arc_center, tail.arc_angle, transform);
+    // the fast-path line of a fill is in device space already; cap / join lines are in local space
+    if (tail.n_lines > 0u) f.write_line(is_stroke ? fx_apply(transform, tail.a0) : tail.a0, is_stroke ? fx_apply(transform, tail.b0) : tail.b0);
+    if (tail.n_lines > 1u) f.line_xf(tail.a1, tail.b1, transform);
+    if (tail.n_lines > 2u) f.line_xf(tail.a2, tail.b2, transform);
 }
 
 // bbox_clear.wgsl: path bboxes start at (+INT_MAX, -INT_MAX)

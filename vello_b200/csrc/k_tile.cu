@@ -61,9 +61,16 @@ k_tile_alloc(VbConfig cfg, const uint32_t *__restrict__ scene, const VbBbox4 *__
         p._pad[0] = p._pad[1] = p._pad[2] = 0;
         paths[drawobj_ix] = p;
     }
-    const uint32_t end = min(base + total, cfg.tiles_size);
-    uint2 *t2 = reinterpret_cast<uint2 *>(tiles);
-    for (uint32_t i = base + threadIdx.x; i < end; i += TA_THREADS) t2[i] = make_uint2(0u, 0u);
+}
+
+// Tiles start zeroed (tile_alloc.wgsl:100-107 does this per workgroup). A grid-wide pass instead: a scene with a few
+// huge paths (one CTA of tile_alloc owning 500k tiles) is zeroed at full bandwidth.
+__global__ void __launch_bounds__(256) k_tile_zero(VbConfig cfg, const VbBump *__restrict__ bump, VbTile *tiles) {
+    const uint32_t end = min(bump->tile, cfg.tiles_size);
+    uint4 *t4 = reinterpret_cast<uint4 *>(tiles);
+    const uint32_t n4 = end / 2u;
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n4; i += gridDim.x * 256u) t4[i] = make_uint4(0u, 0u, 0u, 0u);
+    if ((end & 1u) != 0u && blockIdx.x == 0 && threadIdx.x == 0) reinterpret_cast<uint2 *>(tiles)[end - 1u] = make_uint2(0u, 0u);
 }
 
 // backdrop: per (path, tile row) inclusive prefix sum along x (backdrop_dyn.wgsl:66-84).
@@ -102,7 +109,8 @@ k_backdrop(VbConfig cfg, const VbBump *__restrict__ bump, const VbPath *__restri
     sh_chunks[threadIdx.x] = ex + n_chunks;
     __syncthreads();
     const uint32_t lane = vb_lane();
-    for (uint32_t c = threadIdx.x >> 5; c < total; c += BD_THREADS / 32) {
+    // gridDim.y CTAs share one group of paths (few-but-huge paths would otherwise leave most SMs idle)
+    for (uint32_t c = (threadIdx.x >> 5) + blockIdx.y * (BD_THREADS / 32); c < total; c += gridDim.y * (BD_THREADS / 32)) {
         uint32_t el = 0u;
 #pragma unroll
         for (uint32_t i = 0u; i < 8u; i++) {
@@ -139,10 +147,14 @@ extern "C" void vb_launch_tile_alloc(const VbConfig *cfg, const uint32_t *scene,
                                      VbPath *paths, VbTile *tiles, uint32_t *lb_mem, uint32_t n_parts, cudaStream_t st) {
     if (n_parts == 0) return;
     k_tile_alloc<<<n_parts, TA_THREADS, 0, st>>>(*cfg, scene, draw_bboxes, bump, paths, tiles, lb_mem, n_parts);
+    k_tile_zero<<<148 * 4, 256, 0, st>>>(*cfg, bump, tiles);
 }
 extern "C" uint32_t vb_tile_alloc_parts(uint32_t n_draw) { return (n_draw + TA_THREADS - 1) / TA_THREADS; }
 extern "C" void vb_launch_backdrop(const VbConfig *cfg, const VbBump *bump, const VbPath *paths, VbTile *tiles, cudaStream_t st) {
     uint32_t n = cfg->layout.n_draw_objects;
     if (n == 0) return;
-    k_backdrop<<<(n + BD_PATHS - 1) / BD_PATHS, BD_THREADS, 0, st>>>(*cfg, bump, paths, tiles);
+    const uint32_t groups = (n + BD_PATHS - 1) / BD_PATHS;
+    uint32_t split = (148u * 4u + groups - 1u) / groups;
+    if (split > 64u) split = 64u;
+    k_backdrop<<<dim3(groups, split), BD_THREADS, 0, st>>>(*cfg, bump, paths, tiles);
 }

@@ -436,7 +436,7 @@ static int enqueue(vb_renderer *r, int first, int last, void *out_dev) {
         case VB_STAGE_ID_TILE_ALLOC:
             vb_launch_tile_alloc(&c, (const uint32_t *)r->scene.p, (const VbBbox4 *)r->draw_bboxes.p, bump, (VbPath *)r->paths.p,
                                  (VbTile *)r->tiles.p, ctl + r->off_lb_tile, r->parts_tile, st);
-            launches += r->parts_tile ? 1 : 0;
+            launches += r->parts_tile ? 2 : 0;
             break;
         case VB_STAGE_ID_PATH_COUNT: {
             // grid from the arena capacity; the kernel strides over bump.lines read on the device
