@@ -127,6 +127,11 @@ int vb_debug_upload(vb_renderer *, const char *name, const void *src, size_t byt
 
 /* Traffic statistics of the last frame's `fine` (for the roofline): PTCL words its interpreters read,
  * segments referenced by CMD_FILL, number of CMD_FILL commands. */
+/* fine starts every tile at its last opaque full-tile cover (CMD_SOLID + CMD_COLOR with alpha 255 outside any clip);
+ * commands before it cannot reach the output, so pixels are identical. On by default; 0 executes every command, as
+ * vello_shaders/shader/fine.wgsl:1064-1398 does. No counterpart in the reference (an addition, like early-z). */
+int vb_set_occlusion_cull(vb_renderer *, int on);
+
 int vb_debug_fine_traffic(vb_renderer *, uint64_t *ptcl_words, uint64_t *segment_refs, uint64_t *fill_cmds);
 
 #ifdef __cplusplus

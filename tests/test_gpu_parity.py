@@ -229,3 +229,49 @@ def test_flatten_fill_line_fast_path_extremes(renderer, oracle):
     g, c = renderer.download("lines", DTYPES["lines"]), oracle.buffer("lines")
     assert g.shape == c.shape and g.tobytes() == c.tobytes()
     assert renderer.download("path_bboxes", DTYPES["path_bboxes"]).tobytes() == oracle.buffer("path_bboxes").tobytes()
+
+
+def test_occlusion_cull_is_invisible(renderer, oracle):
+    """fine's occlusion pre-scan (start at the last opaque full-tile cover) must not change a single pixel: opaque
+    covers at depth 0, inside clip layers (must NOT be used), translucent covers, covers followed by more content,
+    and a command list long enough to need PTCL chunk links between the covers."""
+    from vello_b200.encoding import FILL_NON_ZERO
+    from vello_b200.shapes import Affine, Rect, Circle
+    rng = np.random.default_rng(5)
+    s = Scene()
+    w = h = 256
+    full = Rect(-10, -10, 300, 300)
+
+    def clutter(n):
+        for _ in range(n):
+            x, y = rng.uniform(0, 256, 2)
+            s.fill(FILL_NON_ZERO, Affine.IDENTITY, Color.from_rgba8(*[int(v) for v in rng.integers(0, 256, 3)], int(rng.choice([255, 255, 120]))),
+                   None, Circle(float(x), float(y), float(rng.uniform(3, 40))))
+    clutter(150)
+    s.fill(FILL_NON_ZERO, Affine.IDENTITY, Color.from_rgba8(10, 200, 30, 255), None, full)          # opaque cover
+    clutter(30)
+    s.fill(FILL_NON_ZERO, Affine.IDENTITY, Color.from_rgba8(200, 20, 30, 128), None, full)          # translucent cover
+    s.push_clip_layer(FILL_NON_ZERO, Affine.IDENTITY, Circle(128.0, 128.0, 100.0))
+    s.fill(FILL_NON_ZERO, Affine.IDENTITY, Color.from_rgba8(0, 0, 250, 255), None, full)            # opaque, but clipped
+    clutter(10)
+    s.pop_layer()
+    clutter(20)
+    s.fill(FILL_NON_ZERO, Affine.IDENTITY, Color.from_rgba8(90, 90, 90, 255), None, Rect(0, 0, 128, 300))  # covers half the tiles
+    clutter(15)
+    packed = resolve(s.encoding)
+    for aa in (AA_AREA, AA_MSAA8, AA_MSAA16):
+        p = RenderParams(Color.from_rgba8(7, 7, 7, 255), w, h, aa)
+        ref = oracle.render(packed, w, h, p.base_color.premul_rgba8_u32(), aa)
+        renderer.set_occlusion_cull(False)
+        off = renderer.render_to_texture(packed, p)
+        renderer.set_occlusion_cull(True)
+        on = renderer.render_to_texture(packed, p)
+        assert np.array_equal(on, off)
+        assert_pixels(on, ref, aa)
+    # and on the map-like workload, where most tiles have an opaque cover somewhere in their list
+    packed = resolve(scenes.paris_like(3000, 1024, seed=11).encoding)
+    p = RenderParams(BLACK, 1024, 1024, AA_MSAA16)
+    renderer.set_occlusion_cull(False)
+    off = renderer.render_to_texture(packed, p)
+    renderer.set_occlusion_cull(True)
+    assert np.array_equal(renderer.render_to_texture(packed, p), off)

@@ -19,7 +19,12 @@
 #include "vb_detmath.h"
 #include "vb_device.cuh"
 
+#ifndef FL_THREADS
 #define FL_THREADS 256
+#endif
+#ifndef FL_MINB
+#define FL_MINB 1
+#endif
 
 namespace cg = cooperative_groups;
 
@@ -813,7 +818,7 @@ __global__ void k_bbox_clear(uint32_t n_paths, VbPathBbox *path_bboxes) {
 // and the bbox contribution of the literal lines. (History: a single-pass look-back kernel was gated by the slowest
 // tag in flight, ncu r1: 18 % issue utilisation; a count+emit kernel computed long tags twice and its 200 KB of code
 // thrashed the instruction cache, ncu r1_f: no_instruction = top stall.)
-__global__ void __launch_bounds__(FL_THREADS)
+__global__ void __launch_bounds__(FL_THREADS, FL_MINB)
 k_flatten(VbConfig cfg, const uint32_t *__restrict__ scene, const VbTagMonoid *__restrict__ tag_monoids,
           VbPathBbox *path_bboxes, FlCtx ctx, uint32_t *part_count, uint32_t *tag_off, uint32_t n_parts) {
     const uint32_t lane = vb_lane();

@@ -42,7 +42,7 @@ void vb_launch_coarse(const VbConfig *, const uint32_t *, const VbDrawMonoid *, 
 void vb_launch_path_tiling(const VbConfig *, const VbBump *, const VbSegmentCount *, const VbLineSoup *, const VbPath *, const VbTile *,
                            VbSegment *, uint32_t, cudaStream_t);
 void vb_launch_fine(const VbConfig *, int, const VbSegment *, const uint32_t *, const uint32_t *, uint32_t *, uint32_t *, const uint32_t *,
-                    const uint8_t *, const uint32_t *, const uint32_t *, cudaStream_t);
+                    const uint8_t *, const uint32_t *, const uint32_t *, uint32_t, cudaStream_t);
 }
 
 extern "C" int vb_fine_init_constants(void);
@@ -111,6 +111,7 @@ struct vb_renderer {
     VbBump *h_bump = nullptr; // pinned
     uint32_t retries = 0, launches = 0;
     size_t ctl_words = 0;
+    uint32_t occlusion_cull = 1; // fine starts each tile at its last opaque full-tile cover
     uint32_t parts_pathtag = 0, parts_flatten = 0, parts_draw = 0, parts_tile = 0;
     size_t off_lb_pathtag = 0, off_lb_flatten = 0, off_lb_draw = 0, off_lb_tile = 0;
     cudaEvent_t ev[VB_N_STAGE_IDS + 1]{};
@@ -481,7 +482,7 @@ static int enqueue(vb_renderer *r, int first, int last, void *out_dev) {
                 vb_launch_fine(&cb, (int)r->params.aa, (const VbSegment *)r->segments.p, (const uint32_t *)r->ptcl.p,
                                (const uint32_t *)r->info_bin_data.p, (uint32_t *)r->blend_spill.p, (uint32_t *)out_dev,
                                (const uint32_t *)r->ramps.p, (const uint8_t *)r->atlas.p, (const uint32_t *)r->mask8.p,
-                               (const uint32_t *)r->mask16.p, st);
+                               (const uint32_t *)r->mask16.p, r->occlusion_cull, st);
                 launches += 1;
                 if (r->host_out) {
                     size_t y0 = (size_t)cb.win_ty0 * 16u, y1 = (size_t)cb.win_ty1 * 16u;
@@ -683,6 +684,12 @@ extern "C" int vb_debug_download(vb_renderer *r, const char *name, void *dst, si
             return VB_OK;
         }
     return VB_E_UNKNOWN_BUFFER;
+}
+
+extern "C" int vb_set_occlusion_cull(vb_renderer *r, int on) {
+    if (!r) return VB_E_INVALID;
+    r->occlusion_cull = on ? 1u : 0u;
+    return VB_OK;
 }
 
 extern "C" int vb_debug_fine_traffic(vb_renderer *r, uint64_t *ptcl_words, uint64_t *segment_refs, uint64_t *fill_cmds) {

@@ -63,10 +63,11 @@ def load_library() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise VelloB200Error(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+    path = os.environ.get("VELLO_B200_LIB", LIB_PATH)  # development knob: A/B a differently tuned build
+    if not os.path.exists(path):
+        raise VelloB200Error(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                              "(nvcc, sm_100a). vello_b200 has no CPU fallback.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp = C.c_void_p
     lib.vb_renderer_new.argtypes = [C.POINTER(_Options), C.POINTER(vp)]
     lib.vb_renderer_free.argtypes = [vp]
@@ -87,6 +88,7 @@ def load_library() -> C.CDLL:
     lib.vb_run_stages.argtypes = [vp, C.POINTER(_Params), C.c_int, C.c_int, vp]
     lib.vb_debug_download.argtypes = [vp, C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.vb_debug_upload.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
+    lib.vb_set_occlusion_cull.argtypes = [vp, C.c_int]
     lib.vb_debug_fine_traffic.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     _lib = lib
     return lib
@@ -94,7 +96,7 @@ def load_library() -> C.CDLL:
 
 EXPORTED_SYMBOLS = ["vb_renderer_new", "vb_renderer_free", "vb_strerror", "vb_last_error", "vb_scene_upload",
                     "vb_render_resident", "vb_render_enqueue", "vb_frame_finish", "vb_render", "vb_target", "vb_copy_to_host", "vb_stream",
-                    "vb_run_stages", "vb_debug_download", "vb_debug_upload", "vb_debug_fine_traffic"]
+                    "vb_run_stages", "vb_debug_download", "vb_debug_upload", "vb_debug_fine_traffic", "vb_set_occlusion_cull"]
 
 
 @dataclass
@@ -225,6 +227,10 @@ class Renderer:
     def upload_buffer(self, name: str, arr: np.ndarray):
         a = np.ascontiguousarray(arr)
         self._check(self.lib.vb_debug_upload(self.handle, name.encode(), a.ctypes.data, a.nbytes), f"upload {name}")
+
+    def set_occlusion_cull(self, on: bool):
+        """fine skips the commands under a tile's last opaque full-tile cover (identical pixels). Default on."""
+        self._check(self.lib.vb_set_occlusion_cull(self.handle, 1 if on else 0), "vb_set_occlusion_cull")
 
     def fine_traffic(self):
         """(ptcl_words, segment_refs, fill_cmds) of the last frame -- inputs of the fine roofline."""
