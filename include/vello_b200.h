@@ -108,6 +108,16 @@ int vb_render(vb_renderer *, const uint8_t *scene, size_t scene_len, const vb_la
               uint32_t ramp_h, const uint8_t *atlas_rgba8, uint32_t atlas_w, uint32_t atlas_h, const vb_params *, void *out,
               uint32_t out_is_device, vb_frame_stats *);
 
+/* Streaming form of vb_render for back-to-back frames with HOST buffers (a viewer / exporter reading every frame back,
+ * as vello's headless examples do with a mapped read-back buffer, examples/headless/src/main.rs:188-210). Returns once
+ * the frame is rasterised; the tail of its device->host copy may still be in flight and overlaps the next call's upload
+ * and geometry stages. On return every EARLIER frame's out_host is complete; vb_readback_wait completes the last one.
+ * Consecutive frames must use different out_host buffers. */
+int vb_render_begin(vb_renderer *, const uint8_t *scene, size_t scene_len, const vb_layout *, const uint32_t *ramps, uint32_t ramp_w,
+                    uint32_t ramp_h, const uint8_t *atlas_rgba8, uint32_t atlas_w, uint32_t atlas_h, const vb_params *, void *out_host,
+                    vb_frame_stats *);
+int vb_readback_wait(vb_renderer *);
+
 /* The renderer-owned target of the last frame (device pointer) and its size in bytes. */
 void *vb_target(vb_renderer *, size_t *bytes);
 /* Copy `bytes` from a device pointer to a host pointer on the renderer's stream, then synchronise. */

@@ -275,3 +275,15 @@ def test_occlusion_cull_is_invisible(renderer, oracle):
     off = renderer.render_to_texture(packed, p)
     renderer.set_occlusion_cull(True)
     assert np.array_equal(renderer.render_to_texture(packed, p), off)
+
+
+def test_streaming_readback_matches_blocking(renderer):
+    """vb_render_begin / vb_readback_wait (read-back of frame n overlapping frame n+1, alternating targets) deliver
+    exactly the frames the blocking vb_render does, in order."""
+    p = RenderParams(BLACK, 1024, 1024, AA_MSAA16)
+    seq = [resolve(scenes.paris_like(400 + 150 * k, 1024, seed=20 + k).encoding) for k in range(5)]
+    want = [renderer.render_to_texture(s, p) for s in seq]
+    got = list(renderer.render_stream(seq, p))
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)

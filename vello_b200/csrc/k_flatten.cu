@@ -23,7 +23,7 @@
 #define FL_THREADS 256
 #endif
 #ifndef FL_MINB
-#define FL_MINB 1
+#define FL_MINB 2
 #endif
 
 namespace cg = cooperative_groups;

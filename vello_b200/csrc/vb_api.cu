@@ -99,7 +99,7 @@ struct vb_renderer {
 
     // fixed-size intermediates
     DevBuf tag_monoids, path_bboxes, draw_monoids, info_bin_data, clip_inp, clip_bboxes, clip_scratch, draw_bboxes, bin_headers, paths,
-        ctl, target;
+        ctl, target, target_alt;
     // bump arenas (capacities in elements live in cap_*)
     DevBuf lines, line_scratch, flatten_jobs, flatten_parts, tiles, seg_counts, segments, ptcl, blend_spill;
     uint32_t cap_lines = 0, cap_binning = 0, cap_tiles = 0, cap_seg_counts = 0, cap_segments = 0, cap_blend = 0, cap_ptcl = 0;
@@ -120,6 +120,11 @@ struct vb_renderer {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t band_ev[8]{};
     void *host_out = nullptr; // set by vb_render for the duration of one frame
+    // streaming read-back (vb_render_begin): frames alternate between two targets so that the copy of frame n can
+    // still be draining while frame n+1 is rasterised
+    bool use_alt = false, stream_pending = false;
+    uint32_t stream_parity = 0;
+    cudaEvent_t copy_done[2]{};
     bool frame_pending = false;
 };
 
@@ -146,7 +151,7 @@ static int ensure(vb_renderer *r, DevBuf &b, size_t bytes) {
 static size_t arena_bytes(const vb_renderer *r) {
     const DevBuf *all[] = {&r->scene, &r->ramps, &r->atlas, &r->mask8, &r->mask16, &r->tag_monoids, &r->path_bboxes, &r->draw_monoids,
                            &r->info_bin_data, &r->clip_inp, &r->clip_bboxes, &r->clip_scratch, &r->draw_bboxes, &r->bin_headers, &r->paths,
-                           &r->ctl, &r->target, &r->lines, &r->line_scratch, &r->flatten_jobs, &r->flatten_parts, &r->tiles, &r->seg_counts, &r->segments, &r->ptcl, &r->blend_spill};
+                           &r->ctl, &r->target, &r->target_alt, &r->lines, &r->line_scratch, &r->flatten_jobs, &r->flatten_parts, &r->tiles, &r->seg_counts, &r->segments, &r->ptcl, &r->blend_spill};
     size_t s = 0;
     for (auto b : all) s += b->cap;
     return s;
@@ -201,6 +206,7 @@ extern "C" int vb_renderer_new(const vb_options *opt, vb_renderer **out) {
     memset(r->h_bump, 0, sizeof(VbBump));
     for (auto &ev : r->ev) cudaEventCreate(&ev);
     for (auto &ev : r->band_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    for (auto &ev : r->copy_done) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     if (cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete r;
         return VB_E_CUDA;
@@ -228,13 +234,14 @@ extern "C" void vb_renderer_free(vb_renderer *r) {
     if (r->stream) cudaStreamSynchronize(r->stream);
     DevBuf *all[] = {&r->scene, &r->ramps, &r->atlas, &r->mask8, &r->mask16, &r->tag_monoids, &r->path_bboxes, &r->draw_monoids,
                      &r->info_bin_data, &r->clip_inp, &r->clip_bboxes, &r->clip_scratch, &r->draw_bboxes, &r->bin_headers, &r->paths,
-                     &r->ctl, &r->target, &r->lines, &r->line_scratch, &r->flatten_jobs, &r->flatten_parts, &r->tiles, &r->seg_counts, &r->segments, &r->ptcl, &r->blend_spill};
+                     &r->ctl, &r->target, &r->target_alt, &r->lines, &r->line_scratch, &r->flatten_jobs, &r->flatten_parts, &r->tiles, &r->seg_counts, &r->segments, &r->ptcl, &r->blend_spill};
     for (auto b : all)
         if (b->p) cudaFree(b->p);
     if (r->h_bump) cudaFreeHost(r->h_bump);
     if (r->ev_ok) {
         for (auto &ev : r->ev) cudaEventDestroy(ev);
         for (auto &ev : r->band_ev) cudaEventDestroy(ev);
+        for (auto &ev : r->copy_done) cudaEventDestroy(ev);
     }
     if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
     if (r->stream) cudaStreamDestroy(r->stream);
@@ -514,8 +521,9 @@ static int pick_out(vb_renderer *r, void *out_device, void **out) {
     }
     const VbConfig &c = r->cfg;
     size_t rows = (size_t)(c.win_ty1 - c.win_ty0) * 16u;
-    int rc = ensure(r, r->target, (size_t)c.out_pitch_px * 4u * rows);
-    *out = r->target.p;
+    DevBuf &t = r->use_alt ? r->target_alt : r->target;
+    int rc = ensure(r, t, (size_t)c.out_pitch_px * 4u * rows);
+    *out = t.p;
     return rc;
 }
 
@@ -611,6 +619,37 @@ extern "C" int vb_render(vb_renderer *r, const uint8_t *scene, size_t scene_len,
         }
     }
     return rc;
+}
+
+// Streaming variant of vb_render for back-to-back frames with HOST buffers. Returns as soon as the frame has been
+// rasterised (arena overflows handled as usual); the tail of ITS read-back may still be in flight on the copy stream,
+// overlapping the next call's upload and geometry stages. On return every EARLIER frame's `out_host` is complete;
+// vb_readback_wait() completes the last one. Use a different out_host for consecutive frames.
+extern "C" int vb_render_begin(vb_renderer *r, const uint8_t *scene, size_t scene_len, const vb_layout *layout, const uint32_t *ramps,
+                               uint32_t ramp_w, uint32_t ramp_h, const uint8_t *atlas, uint32_t atlas_w, uint32_t atlas_h,
+                               const vb_params *p, void *out_host, vb_frame_stats *stats) {
+    if (!r || !p || !out_host) return VB_E_INVALID;
+    int rc = vb_scene_upload(r, scene, scene_len, layout, ramps, ramp_w, ramp_h, atlas, atlas_w, atlas_h);
+    if (rc) return rc;
+    const uint32_t par = r->stream_parity;
+    r->host_out = out_host;
+    r->use_alt = par != 0u;
+    rc = vb_render_resident(r, p, nullptr, stats);
+    r->host_out = nullptr;
+    r->use_alt = false;
+    CK(cudaEventRecord(r->copy_done[par], r->copy_stream));
+    if (r->stream_pending) CK(cudaEventSynchronize(r->copy_done[par ^ 1u])); // the previous frame's pixels are on the host
+    r->stream_pending = true;
+    r->stream_parity = par ^ 1u;
+    return rc;
+}
+
+extern "C" int vb_readback_wait(vb_renderer *r) {
+    if (!r) return VB_E_INVALID;
+    CK(cudaSetDevice(r->device));
+    CK(cudaStreamSynchronize(r->copy_stream));
+    r->stream_pending = false;
+    return VB_OK;
 }
 
 extern "C" int vb_run_stages(vb_renderer *r, const vb_params *p, int first, int last, void *out_device) {

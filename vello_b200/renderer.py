@@ -80,6 +80,9 @@ def load_library() -> C.CDLL:
     lib.vb_frame_finish.argtypes = [vp, C.POINTER(FrameStats)]
     lib.vb_render.argtypes = [vp, vp, C.c_size_t, C.POINTER(_Layout), vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, C.c_uint32,
                               C.POINTER(_Params), vp, C.c_uint32, C.POINTER(FrameStats)]
+    lib.vb_render_begin.argtypes = [vp, vp, C.c_size_t, C.POINTER(_Layout), vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, C.c_uint32,
+                                    C.POINTER(_Params), vp, C.POINTER(FrameStats)]
+    lib.vb_readback_wait.argtypes = [vp]
     lib.vb_target.restype = vp
     lib.vb_target.argtypes = [vp, C.POINTER(C.c_size_t)]
     lib.vb_copy_to_host.argtypes = [vp, vp, vp, C.c_size_t]
@@ -96,7 +99,7 @@ def load_library() -> C.CDLL:
 
 EXPORTED_SYMBOLS = ["vb_renderer_new", "vb_renderer_free", "vb_strerror", "vb_last_error", "vb_scene_upload",
                     "vb_render_resident", "vb_render_enqueue", "vb_frame_finish", "vb_render", "vb_target", "vb_copy_to_host", "vb_stream",
-                    "vb_run_stages", "vb_debug_download", "vb_debug_upload", "vb_debug_fine_traffic", "vb_set_occlusion_cull"]
+                    "vb_run_stages", "vb_debug_download", "vb_debug_upload", "vb_debug_fine_traffic", "vb_set_occlusion_cull", "vb_render_begin", "vb_readback_wait"]
 
 
 @dataclass
@@ -175,6 +178,32 @@ class Renderer:
         self.last_stats = st
         self._check(rc, "vb_render")
         return out
+
+    def render_stream(self, scenes, params: RenderParams):
+        """Render a sequence of scenes through the streaming entry points (vb_render_begin / vb_readback_wait):
+        a generator of RGBA8 images, each complete when yielded."""
+        bufs, prev = [None, None], None
+        for k, scene in enumerate(scenes):
+            packed = scene if isinstance(scene, Packed) else resolve(scene.encoding)
+            scene_w = np.ascontiguousarray(packed.scene, dtype=np.uint32)
+            ramps = np.ascontiguousarray(packed.ramps, dtype=np.uint32)
+            atlas = np.ascontiguousarray(packed.atlas, dtype=np.uint8)
+            lay = _Layout(*[int(v) for v in packed.layout.as_array()])
+            ps = _params_struct(params, (0, 0))
+            out = np.zeros((params.height, params.width, 4), dtype=np.uint8)
+            bufs[k & 1] = out
+            st = FrameStats()
+            rc = self.lib.vb_render_begin(self.handle, scene_w.ctypes.data, scene_w.nbytes, C.byref(lay),
+                                          ramps.ctypes.data if ramps.size else None, 512, ramps.shape[0],
+                                          atlas.ctypes.data, atlas.shape[1], atlas.shape[0], C.byref(ps), out.ctypes.data, C.byref(st))
+            self.last_stats = st
+            self._check(rc, "vb_render_begin")
+            if prev is not None:
+                yield prev  # complete: vb_render_begin returned for a later frame
+            prev = out
+        if prev is not None:
+            self._check(self.lib.vb_readback_wait(self.handle), "vb_readback_wait")
+            yield prev
 
     @staticmethod
     def stripe_rows(params: RenderParams, bin_rows=(0, 0)):
