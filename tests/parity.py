@@ -70,8 +70,11 @@ def compare_all(r, o, layout, width, height, check_ptcl_tiles=None):
     c = {n: o.buffer(n) for n in g}
     gb, cb = g["bump"][0], c["bump"][0]
     assert int(gb["failed"]) == 0
+    # coarse reserves segment slices per 256-draw chunk; slots of fills it then skips (zero-coverage clips) stay unused
+    holes = int(r.download("seg_holes", np.uint32)[0])
     for f in ("lines", "tile", "seg_counts", "segments", "blend", "binning"):
-        assert int(gb[f]) == int(cb[f]), (f, int(gb[f]), int(cb[f]))
+        have = int(gb[f]) - (holes if f == "segments" else 0)
+        assert have == int(cb[f]), (f, have, int(cb[f]))
     # exact, order included
     for n in ("tag_monoids", "path_bboxes", "lines", "draw_monoids", "clip_inp", "clip_bboxes", "draw_bboxes", "paths"):
         a, b = g[n], c[n][: g[n].shape[0]] if n == "paths" else c[n]

@@ -31,7 +31,9 @@ for i in range(n):
     a = agg.setdefault(k, [0.0, 0.0]); a[0] += sass[i][1]; a[1] += sass[i][2]
 ti = sum(v[0] for v in agg.values()); ts = sum(v[1] for v in agg.values())
 src = {}
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+import os
+key_ix = 1 if os.environ.get("BY_SAMPLES") else 0
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][key_ix])[:top]:
     f, ln = k if k else ("?", 0)
     if f not in src:
         try: src[f] = open("/root/repo/vello_b200/csrc/" + f).read().splitlines()

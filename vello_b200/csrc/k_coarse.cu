@@ -10,12 +10,13 @@
 // per-bin coverage loop is a chain of dependent global loads. Here every bin is split into four 8x8-tile QUADRANTS,
 // each handled by its own CTA (all 256 threads share the (draw, tile) coverage loop, threads 0..63 own a tile each for
 // emission), and the coverage loop keeps two independent tile loads in flight.
-#include <cooperative_groups.h>
-#include <cooperative_groups/scan.h>
-
+// Segment slices: the WGSL takes one global atomicAdd per CMD_FILL (coarse.wgsl:100), ~1.7 M same-address atomics on a
+// map-like frame, each sitting in the middle of a tile's serial emission chain (tile load -> atomic -> stores). Here
+// the coverage pass, which has every (draw, tile) record in registers anyway, sums the segment counts per tile in
+// shared memory; one atomicAdd per CTA and 256-draw chunk reserves the slices of all 64 tiles, and emission hands them
+// out with plain adds. Fills that emission then skips (inside a zero-coverage clip) leave their reserved slots unused;
+// those are counted in ctl[VB_CTL_SEG_HOLES] so that `bump.segments - holes` is the reference's number.
 #include "vb_device.cuh"
-
-namespace cg = cooperative_groups;
 
 #define CO_THREADS 256
 #define CO_N_SLICE 8
@@ -42,22 +43,18 @@ __device__ __forceinline__ void co_alloc_cmd(TileState &s, uint32_t size, const 
     }
 }
 
+__device__ __forceinline__ bool co_tag_writes_path(uint32_t tag) { // the draw tags whose emission calls co_write_path
+    return tag == VB_DRAWTAG_FILL_COLOR || tag == VB_DRAWTAG_BLURRED_ROUNDED_RECT || tag == VB_DRAWTAG_FILL_LIN_GRADIENT ||
+           tag == VB_DRAWTAG_FILL_RAD_GRADIENT || tag == VB_DRAWTAG_FILL_SWEEP_GRADIENT || tag == VB_DRAWTAG_FILL_IMAGE ||
+           tag == VB_DRAWTAG_END_CLIP;
+}
+
 __device__ __forceinline__ void co_write_path(TileState &s, const VbTile &tile, uint32_t tile_ix, uint32_t draw_flags, const VbConfig &cfg,
-                                              VbBump *bump, uint32_t *ptcl, VbTile *tiles) {
+                                              VbBump *bump, uint32_t *ptcl, VbTile *tiles, uint32_t &seg_next) {
     const uint32_t n_segs = tile.segment_count_or_ix;
     if (n_segs != 0u) {
-        // Every CMD_FILL of the frame allocates from ONE counter (about a million times on a map-like scene): as
-        // separate same-address atomics they serialise in L2 and dominated this kernel. Aggregate over the lanes
-        // that happen to be here together (opportunistic warp aggregation): one atomic per group.
-        uint32_t seg_ix;
-        {
-            cg::coalesced_group g = cg::coalesced_threads();
-            const uint32_t pre = cg::exclusive_scan(g, n_segs);
-            uint32_t base = 0u;
-            if (g.thread_rank() == g.size() - 1u) base = atomicAdd(&bump->segments, pre + n_segs);
-            base = g.shfl(base, g.size() - 1u);
-            seg_ix = base + pre;
-        }
+        const uint32_t seg_ix = seg_next; // reserved for this tile by the coverage pass
+        seg_next += n_segs;
         tiles[tile_ix].segment_count_or_ix = ~seg_ix;
         co_alloc_cmd(s, 4u, cfg, bump, ptcl);
         ptcl[s.cmd_offset] = VB_CMD_FILL;
@@ -92,6 +89,8 @@ k_coarse(VbConfig cfg, const uint32_t *__restrict__ scene, const VbDrawMonoid *_
     __shared__ uint32_t sh_di[CO_THREADS];     // info word offset
     __shared__ uint32_t sh_dflags[CO_THREADS]; // bit0 even-odd, bit1 non-trivial blend (clip objects)
     __shared__ uint32_t sh_scan[CO_THREADS / 32 + 2];
+    __shared__ uint32_t sh_tile_segs[64]; // per tile of the quadrant: segments its fills of this chunk need
+    __shared__ uint32_t sh_seg_base;
 
     const uint32_t lid = threadIdx.x;
     // Only PRIOR stages abort coarse (coarse.wgsl:164-179); read once per CTA so the decision is
@@ -123,6 +122,7 @@ k_coarse(VbConfig cfg, const uint32_t *__restrict__ scene, const VbDrawMonoid *_
 
     while (true) {
         for (int i = 0; i < CO_N_SLICE; i++) sh_bitmaps[i][lid] = 0u;
+        if (lid < 64u) sh_tile_segs[lid] = 0u;
         while (true) {
             if (ready_ix == wr_ix && partition_ix < n_partitions) {
                 part_start_ix = ready_ix;
@@ -232,39 +232,74 @@ k_coarse(VbConfig cfg, const uint32_t *__restrict__ scene, const VbDrawMonoid *_
                 const uint32_t n_segs = tl[u].segment_count_or_ix;
                 const bool backdrop_clear = (even_odd ? (abs(tl[u].backdrop) & 1) : tl[u].backdrop) == 0;
                 const bool include_tile = n_segs != 0u || (backdrop_clear == is_clip) || is_blend;
-                if (include_tile) atomicOr(&sh_bitmaps[el_ix / 32u][bit[u]], 1u << (el_ix & 31u));
+                if (include_tile) {
+                    atomicOr(&sh_bitmaps[el_ix / 32u][bit[u]], 1u << (el_ix & 31u));
+                    if (n_segs != 0u && co_tag_writes_path(dtag)) atomicAdd(&sh_tile_segs[bit[u]], n_segs);
+                }
             }
         }
         __syncthreads();
+        // reserve the segment slices of this chunk: one global atomic for the CTA
+        uint32_t seg_next, seg_end;
+        {
+            const uint32_t mine = owns_tile ? sh_tile_segs[lid] : 0u; // the owners are warps 0 and 1
+            const uint32_t incl = vb_warp_incl_scan(mine);
+            if (lid == 31u || lid == 63u) sh_scan[lid >> 5] = incl;
+            __syncthreads();
+            if (lid == 0u) {
+                const uint32_t chunk_total = sh_scan[0] + sh_scan[1];
+                sh_seg_base = chunk_total != 0u ? atomicAdd(&bump->segments, chunk_total) : 0u;
+            }
+            __syncthreads();
+            seg_next = sh_seg_base + incl - mine + (lid >= 32u ? sh_scan[0] : 0u);
+            seg_end = seg_next + mine;
+        }
 
+        // emission: each owner walks the set bits of its tile in draw order. The tile record of the NEXT element is
+        // requested before the current one is emitted, so the walk is not a chain of exposed global-load latencies.
         uint32_t slice_ix = 0u;
         uint32_t bitmap = owns_tile ? sh_bitmaps[0][lid] : 0u;
-        while (owns_tile) {
-            if (bitmap == 0u) {
-                slice_ix += 1u;
-                if (slice_ix == CO_N_SLICE) break;
-                bitmap = sh_bitmaps[slice_ix][lid];
-                if (bitmap == 0u) continue;
+        uint32_t nx_el = 0u, nx_tile_ix = 0u;
+        VbTile nx_tile;
+        nx_tile.backdrop = 0; nx_tile.segment_count_or_ix = 0u;
+        bool nx_have = false;
+        auto advance = [&]() {
+            nx_have = false;
+            while (owns_tile) {
+                if (bitmap == 0u) {
+                    slice_ix += 1u;
+                    if (slice_ix >= CO_N_SLICE) break;
+                    bitmap = sh_bitmaps[slice_ix][lid];
+                    continue;
+                }
+                nx_el = slice_ix * 32u + (uint32_t)(__ffs((int)bitmap) - 1);
+                bitmap &= bitmap - 1u;
+                nx_tile_ix = sh_tile_base[nx_el] + sh_tile_stride[nx_el] * tile_y + tile_x;
+                nx_tile = tiles[nx_tile_ix];
+                nx_have = true;
+                break;
             }
-            const uint32_t el_ix = slice_ix * 32u + (uint32_t)(__ffs((int)bitmap) - 1);
-            bitmap &= bitmap - 1u;
+        };
+        advance();
+        while (nx_have) {
+            const uint32_t el_ix = nx_el, tile_ix = nx_tile_ix;
+            const VbTile tile = nx_tile;
+            advance();
             const uint32_t drawtag = sh_tag[el_ix];
             const uint32_t dd = sh_dd[el_ix];
             const uint32_t di = sh_di[el_ix];
             const uint32_t draw_flags = sh_dflags[el_ix] & 1u; // only the fill-rule bit is defined (drawtag.wgsl:42)
             if (clip_zero_depth == 0u) {
-                const uint32_t tile_ix = sh_tile_base[el_ix] + sh_tile_stride[el_ix] * tile_y + tile_x;
-                const VbTile tile = tiles[tile_ix];
                 switch (drawtag) {
                 case VB_DRAWTAG_FILL_COLOR:
-                    co_write_path(st, tile, tile_ix, draw_flags, cfg, bump, ptcl, tiles);
+                    co_write_path(st, tile, tile_ix, draw_flags, cfg, bump, ptcl, tiles, seg_next);
                     co_alloc_cmd(st, 2u, cfg, bump, ptcl);
                     ptcl[st.cmd_offset] = VB_CMD_COLOR;
                     ptcl[st.cmd_offset + 1u] = vb_scene(scene, cfg, dd);
                     st.cmd_offset += 2u;
                     break;
                 case VB_DRAWTAG_BLURRED_ROUNDED_RECT:
-                    co_write_path(st, tile, tile_ix, draw_flags, cfg, bump, ptcl, tiles);
+                    co_write_path(st, tile, tile_ix, draw_flags, cfg, bump, ptcl, tiles, seg_next);
                     co_alloc_cmd(st, 3u, cfg, bump, ptcl);
                     ptcl[st.cmd_offset] = VB_CMD_BLUR_RECT;
                     ptcl[st.cmd_offset + 1u] = di + 1u;
@@ -276,7 +311,7 @@ k_coarse(VbConfig cfg, const uint32_t *__restrict__ scene, const VbDrawMonoid *_
                 case VB_DRAWTAG_FILL_SWEEP_GRADIENT: {
                     const uint32_t ty = drawtag == VB_DRAWTAG_FILL_LIN_GRADIENT ? VB_CMD_LIN_GRAD
                                         : drawtag == VB_DRAWTAG_FILL_RAD_GRADIENT ? VB_CMD_RAD_GRAD : VB_CMD_SWEEP_GRAD;
-                    co_write_path(st, tile, tile_ix, draw_flags, cfg, bump, ptcl, tiles);
+                    co_write_path(st, tile, tile_ix, draw_flags, cfg, bump, ptcl, tiles, seg_next);
                     co_alloc_cmd(st, 3u, cfg, bump, ptcl);
                     ptcl[st.cmd_offset] = ty;
                     ptcl[st.cmd_offset + 1u] = vb_scene(scene, cfg, dd);
@@ -285,7 +320,7 @@ k_coarse(VbConfig cfg, const uint32_t *__restrict__ scene, const VbDrawMonoid *_
                     break;
                 }
                 case VB_DRAWTAG_FILL_IMAGE:
-                    co_write_path(st, tile, tile_ix, draw_flags, cfg, bump, ptcl, tiles);
+                    co_write_path(st, tile, tile_ix, draw_flags, cfg, bump, ptcl, tiles, seg_next);
                     co_alloc_cmd(st, 2u, cfg, bump, ptcl);
                     ptcl[st.cmd_offset] = VB_CMD_IMAGE;
                     ptcl[st.cmd_offset + 1u] = di + 1u;
@@ -308,7 +343,7 @@ k_coarse(VbConfig cfg, const uint32_t *__restrict__ scene, const VbDrawMonoid *_
                 }
                 case VB_DRAWTAG_END_CLIP:
                     clip_depth -= 1u;
-                    co_write_path(st, tile, tile_ix, draw_flags, cfg, bump, ptcl, tiles);
+                    co_write_path(st, tile, tile_ix, draw_flags, cfg, bump, ptcl, tiles, seg_next);
                     co_alloc_cmd(st, 3u, cfg, bump, ptcl);
                     ptcl[st.cmd_offset] = VB_CMD_END_CLIP;
                     ptcl[st.cmd_offset + 1u] = vb_scene(scene, cfg, dd);
@@ -327,6 +362,7 @@ k_coarse(VbConfig cfg, const uint32_t *__restrict__ scene, const VbDrawMonoid *_
                 }
             }
         }
+        if (seg_next != seg_end) atomicAdd(reinterpret_cast<uint32_t *>(bump) + VB_CTL_SEG_HOLES, seg_end - seg_next);
         rd_ix += VB_N_TILE;
         if (rd_ix >= ready_ix && partition_ix >= n_partitions) break;
         __syncthreads();

@@ -710,6 +710,11 @@ extern "C" int vb_debug_download(vb_renderer *r, const char *name, void *dst, si
         if (dst && cap >= sizeof(VbBump)) CK(cudaMemcpy(dst, r->ctl.p, sizeof(VbBump), cudaMemcpyDeviceToHost));
         return VB_OK;
     }
+    if (!strcmp(name, "seg_holes")) { // reserved-but-unused segment slots of the last frame (k_coarse.cu)
+        if (bytes) *bytes = 4;
+        if (dst && cap >= 4) CK(cudaMemcpy(dst, (const uint32_t *)r->ctl.p + VB_CTL_SEG_HOLES, 4, cudaMemcpyDeviceToHost));
+        return VB_OK;
+    }
     if (!strcmp(name, "config")) {
         if (bytes) *bytes = sizeof(VbConfig);
         if (dst && cap >= sizeof(VbConfig)) memcpy(dst, &r->cfg, sizeof(VbConfig));

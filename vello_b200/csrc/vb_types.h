@@ -22,6 +22,9 @@ typedef struct { int32_t backdrop; uint32_t segment_count_or_ix; } VbTile;
 typedef struct { uint32_t line_ix, counts; } VbSegmentCount;
 typedef struct { float p0[2], p1[2]; float y_edge; uint32_t _pad; } VbSegment;
 typedef struct { uint32_t failed, binning, ptcl, tile, seg_counts, segments, blend, lines; } VbBump;
+/* The control block starts with VbBump (8 words) padded to 16; word 8 counts segment slots that coarse reserved but did
+ * not hand out (fills skipped inside a zero-coverage clip): bump.segments - holes = the reference's bump.segments. */
+#define VB_CTL_SEG_HOLES 8
 
 typedef struct {
     uint32_t n_draw_objects, n_paths, n_clips, bin_data_start;
