@@ -814,6 +814,9 @@ __global__ void k_bbox_clear(uint32_t n_paths, VbPathBbox *path_bboxes) {
     }
 }
 
+__device__ __forceinline__ int fl_floor_i(float v) { return v != v ? 0x7fffffff : vb_f2i_sat(floorf(v)); }
+__device__ __forceinline__ int fl_ceil_i(float v) { return v != v ? (int)0x80000000 : vb_f2i_sat(ceilf(v)); }
+
 // A: thread per tag. Outputs: per-warp line count, per-tag offset inside its warp's block, literal records, jobs,
 // and the bbox contribution of the literal lines. (History: a single-pass look-back kernel was gated by the slowest
 // tag in flight, ncu r1: 18 % issue utilisation; a count+emit kernel computed long tags twice and its 200 KB of code
@@ -867,12 +870,24 @@ k_flatten(VbConfig cfg, const uint32_t *__restrict__ scene, const VbTagMonoid *_
             dst[1] = make_uint4(__float_as_uint(l.x), __float_as_uint(l.y), __float_as_uint(l.z), __float_as_uint(l.w));
         }
     }
-    if (f.nlit != 0u && (f.force || f.bx1 > f.bx0 || f.by1 > f.by0) && tag.path_ix < n_paths) {
-        VbPathBbox *o = path_bboxes + tag.path_ix;
-        atomicMin(&o->x0, vb_f2i_sat(floorf(f.bx0)));
-        atomicMin(&o->y0, vb_f2i_sat(floorf(f.by0)));
-        atomicMax(&o->x1, vb_f2i_sat(ceilf(f.bx1)));
-        atomicMax(&o->y1, vb_f2i_sat(ceilf(f.by1)));
+    // bbox: consecutive tags mostly belong to the same path, so reduce across the lanes of a path first (floor / ceil
+    // commute with min / max) and issue one set of atomics per (warp, path) instead of one per tag
+    const bool pub = f.nlit != 0u && (f.force || f.bx1 > f.bx0 || f.by1 > f.by0) && tag.path_ix < n_paths;
+    const uint32_t pubmask = __ballot_sync(VB_FULL, pub);
+    if (pub) {
+        int x0 = fl_floor_i(f.bx0), y0 = fl_floor_i(f.by0), x1 = fl_ceil_i(f.bx1), y1 = fl_ceil_i(f.by1);
+        const uint32_t peers = __match_any_sync(pubmask, tag.path_ix);
+        x0 = __reduce_min_sync(peers, x0);
+        y0 = __reduce_min_sync(peers, y0);
+        x1 = __reduce_max_sync(peers, x1);
+        y1 = __reduce_max_sync(peers, y1);
+        if (lane == (uint32_t)(__ffs((int)peers) - 1)) {
+            VbPathBbox *o = path_bboxes + tag.path_ix;
+            atomicMin(&o->x0, x0);
+            atomicMin(&o->y0, y0);
+            atomicMax(&o->x1, x1);
+            atomicMax(&o->y1, y1);
+        }
     }
 }
 
@@ -912,8 +927,6 @@ k_flatten_scan(VbConfig cfg, uint32_t n_parts, const uint32_t *__restrict__ part
 // holds the predecessor, recomputed otherwise (same function, same bits).
 #define FP_THREADS 256
 #define FP_WARPS (FP_THREADS / 32)
-__device__ __forceinline__ int fl_floor_i(float v) { return v != v ? 0x7fffffff : vb_f2i_sat(floorf(v)); }
-__device__ __forceinline__ int fl_ceil_i(float v) { return v != v ? (int)0x80000000 : vb_f2i_sat(ceilf(v)); }
 
 __global__ void __launch_bounds__(FP_THREADS)
 k_flatten_place(VbConfig cfg, const uint32_t *__restrict__ scene, FlCtx ctx, const uint32_t *__restrict__ part_dst,
