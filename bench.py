@@ -301,7 +301,10 @@ def main():
         sd = rt.render_resident(params, out.data_ptr(), bin_rows).as_dict()
         for k, v in sd["stage_ms"].items():
             stage_ms[k] = stage_ms.get(k, 0.0) + v / n_t
-    ptcl_words, seg_refs, fill_cmds = rt.fine_traffic()
+    ptcl_words, seg_refs, fill_cmds = rt.fine_traffic()  # what the interpreter reads, from each tile's occlusion start
+    rt.set_occlusion_cull(False)
+    full_words, full_segs, full_fills = rt.fine_traffic()  # the whole command lists, as the reference executes them
+    rt.set_occlusion_cull(True)
     px = (h1 - h0) * args.size
     seg_bytes = 24 * seg_refs * (2 if args.aa else 1)  # MSAA reads each segment twice (count + rasterise), fine.wgsl:177,225
     alg_bytes = 4 * px + 4 * ptcl_words + 24 * seg_refs  # each datum once
@@ -311,8 +314,12 @@ def main():
     roofline = {"kernel": f"k_fine<{args.aa}>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes": alg_bytes, "bytes_breakdown": {"pixels": 4 * px, "ptcl": 4 * ptcl_words, "segments": 24 * seg_refs},
-                "fine_ms": stage_ms["fine"], "note": "MSAA16 fine is shared-memory-atomic / ALU bound (SURVEY.md 8d caveat); "
-                "segments re-read from L2 by the second MSAA pass are not counted"}
+                "fine_ms": stage_ms["fine"], "fill_cmds_executed": fill_cmds,
+                "whole_list": {"bytes": 4 * px + 4 * full_words + 24 * full_segs, "fill_cmds": full_fills},
+                "note": "bytes = pixels + the PTCL words and segments fine reads from each tile's occlusion start (last opaque "
+                "full-tile cover, noted by coarse); whole_list = the same count over the complete lists the reference executes. "
+                "MSAA16 fine is shared-memory-atomic / ALU bound (SURVEY.md 8d caveat); segments re-read from L2 by the second "
+                "MSAA pass are not counted"}
     tp = os.path.join(ROOT, "profiles", "fine_traffic.json")
     if os.path.exists(tp):
         try:

@@ -49,8 +49,9 @@ __device__ __forceinline__ bool co_tag_writes_path(uint32_t tag) { // the draw t
            tag == VB_DRAWTAG_END_CLIP;
 }
 
-__device__ __forceinline__ void co_write_path(TileState &s, const VbTile &tile, uint32_t tile_ix, uint32_t draw_flags, const VbConfig &cfg,
-                                              VbBump *bump, uint32_t *ptcl, VbTile *tiles, uint32_t &seg_next) {
+// Returns the PTCL offset of the CMD_SOLID it wrote, or 0 when it wrote a CMD_FILL.
+__device__ __forceinline__ uint32_t co_write_path(TileState &s, const VbTile &tile, uint32_t tile_ix, uint32_t draw_flags, const VbConfig &cfg,
+                                                  VbBump *bump, uint32_t *ptcl, VbTile *tiles, uint32_t &seg_next) {
     const uint32_t n_segs = tile.segment_count_or_ix;
     if (n_segs != 0u) {
         const uint32_t seg_ix = seg_next; // reserved for this tile by the coverage pass
@@ -62,17 +63,18 @@ __device__ __forceinline__ void co_write_path(TileState &s, const VbTile &tile, 
         ptcl[s.cmd_offset + 2u] = seg_ix;
         ptcl[s.cmd_offset + 3u] = (uint32_t)tile.backdrop;
         s.cmd_offset += 4u;
-    } else {
-        co_alloc_cmd(s, 1u, cfg, bump, ptcl);
-        ptcl[s.cmd_offset] = VB_CMD_SOLID;
-        s.cmd_offset += 1u;
+        return 0u;
     }
+    co_alloc_cmd(s, 1u, cfg, bump, ptcl);
+    ptcl[s.cmd_offset] = VB_CMD_SOLID;
+    s.cmd_offset += 1u;
+    return s.cmd_offset - 1u;
 }
 
 __global__ void __launch_bounds__(CO_THREADS)
 k_coarse(VbConfig cfg, const uint32_t *__restrict__ scene, const VbDrawMonoid *__restrict__ draw_monoids,
          const VbBinHeader *__restrict__ bin_headers, const uint32_t *__restrict__ info_bin_data, const VbPath *__restrict__ paths,
-         VbTile *tiles, VbBump *bump, uint32_t *ptcl) {
+         VbTile *tiles, VbBump *bump, uint32_t *ptcl, uint32_t *tile_start) {
     __shared__ uint32_t sh_bitmaps[CO_N_SLICE][VB_N_TILE];
     __shared__ uint32_t sh_part_count[CO_THREADS];
     __shared__ uint32_t sh_part_offsets[CO_THREADS];
@@ -117,6 +119,7 @@ k_coarse(VbConfig cfg, const uint32_t *__restrict__ scene, const VbDrawMonoid *_
     uint32_t clip_zero_depth = 0u, clip_depth = 0u;
     uint32_t partition_ix = 0u, rd_ix = 0u, wr_ix = 0u, part_start_ix = 0u, ready_ix = 0u;
     uint32_t render_blend_depth = 0u, max_blend_depth = 0u;
+    uint32_t cull_start = 0u; // PTCL offset of the CMD_SOLID of this tile's last opaque full-tile cover (0: none)
     const uint32_t blend_offset = st.cmd_offset;
     st.cmd_offset += 1u;
 
@@ -291,13 +294,17 @@ k_coarse(VbConfig cfg, const uint32_t *__restrict__ scene, const VbDrawMonoid *_
             const uint32_t draw_flags = sh_dflags[el_ix] & 1u; // only the fill-rule bit is defined (drawtag.wgsl:42)
             if (clip_zero_depth == 0u) {
                 switch (drawtag) {
-                case VB_DRAWTAG_FILL_COLOR:
-                    co_write_path(st, tile, tile_ix, draw_flags, cfg, bump, ptcl, tiles, seg_next);
+                case VB_DRAWTAG_FILL_COLOR: {
+                    const uint32_t solid_at = co_write_path(st, tile, tile_ix, draw_flags, cfg, bump, ptcl, tiles, seg_next);
+                    const uint32_t rgba = vb_scene(scene, cfg, dd);
                     co_alloc_cmd(st, 2u, cfg, bump, ptcl);
                     ptcl[st.cmd_offset] = VB_CMD_COLOR;
-                    ptcl[st.cmd_offset + 1u] = vb_scene(scene, cfg, dd);
+                    ptcl[st.cmd_offset + 1u] = rgba;
                     st.cmd_offset += 2u;
+                    // an opaque colour over the whole tile, outside any clip: nothing emitted so far can show through
+                    if (solid_at != 0u && (rgba >> 24) == 0xffu && render_blend_depth == 0u) cull_start = solid_at;
                     break;
+                }
                 case VB_DRAWTAG_BLURRED_ROUNDED_RECT:
                     co_write_path(st, tile, tile_ix, draw_flags, cfg, bump, ptcl, tiles, seg_next);
                     co_alloc_cmd(st, 3u, cfg, bump, ptcl);
@@ -376,6 +383,7 @@ k_coarse(VbConfig cfg, const uint32_t *__restrict__ scene, const VbDrawMonoid *_
             if (blend_ix + scratch_size > cfg.blend_size) atomicOr(&bump->failed, VB_STAGE_COARSE);
         }
         ptcl[blend_offset] = blend_ix;
+        tile_start[this_tile_ix] = cull_start;
     }
 }
 
@@ -387,11 +395,11 @@ __global__ void k_coarse_check(VbConfig cfg, VbBump *bump) {
 
 extern "C" void vb_launch_coarse(const VbConfig *cfg, const uint32_t *scene, const VbDrawMonoid *draw_monoids,
                                  const VbBinHeader *bin_headers, const uint32_t *info_bin_data, const VbPath *paths, VbTile *tiles,
-                                 VbBump *bump, uint32_t *ptcl, cudaStream_t st) {
+                                 VbBump *bump, uint32_t *ptcl, uint32_t *tile_start, cudaStream_t st) {
     uint32_t width_in_bins = (cfg->width_in_tiles + 15u) / 16u;
     uint32_t rows = cfg->win_by1 - cfg->win_by0;
     if (width_in_bins == 0 || rows == 0) return;
     dim3 grid(width_in_bins * 2u, rows * 2u); // four quadrant CTAs per bin
-    k_coarse<<<grid, CO_THREADS, 0, st>>>(*cfg, scene, draw_monoids, bin_headers, info_bin_data, paths, tiles, bump, ptcl);
+    k_coarse<<<grid, CO_THREADS, 0, st>>>(*cfg, scene, draw_monoids, bin_headers, info_bin_data, paths, tiles, bump, ptcl, tile_start);
     k_coarse_check<<<1, 1, 0, st>>>(*cfg, bump);
 }

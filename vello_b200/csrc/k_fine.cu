@@ -64,7 +64,8 @@ struct FineArgs {
     const uint32_t *ramps;
     const uint8_t *atlas;
     const uint32_t *mask_lut;
-    uint32_t cull; // 1: start each tile at its last opaque full-tile cover (see fine_cull_start)
+    const uint32_t *tile_start; // per tile: PTCL offset of its last opaque full-tile cover, or 0 (written by coarse)
+    uint32_t cull;              // 1: start each tile there
 };
 
 __device__ __forceinline__ VbSegment ld_segment(const VbSegment *__restrict__ segs, uint32_t ix) {
@@ -636,38 +637,12 @@ __device__ rgba_t bicubic_sample(const FineArgs &A, const VbConfig &cfg, float c
     return RG(vb_clampf(r.r, 0.0f, a), vb_clampf(r.g, 0.0f, a), vb_clampf(r.b, 0.0f, a), a);
 }
 
-// Occlusion pre-scan. A tile's command list is painted back to front; `CMD_SOLID, CMD_COLOR` with alpha 255 outside
-// any clip replaces every pixel of the tile (over(bg, fg) = fg + bg * (1 - 1) = fg exactly), so nothing before the LAST
-// such pair can reach the output. Walk the list once (command words only, warp-uniform) and start there: identical
-// pixels, and on map-like scenes with opaque area fills most of a tile's commands are never executed.
-// The reference executes the whole list (fine.wgsl:1064); the PTCL itself is unchanged.
-__device__ __noinline__ uint32_t fine_cull_start(const uint32_t *__restrict__ ptcl, uint32_t cmd_ix) {
-    uint32_t start = cmd_ix, p = cmd_ix, depth = 0u, solid_pos = 0u;
-    bool solid = false;
-    for (;;) {
-        const uint32_t tag = __ldg(ptcl + p);
-        if (tag == VB_CMD_END) break;
-        switch (tag) {
-        case VB_CMD_FILL: p += 4u; solid = false; break;
-        case VB_CMD_SOLID: solid_pos = p; solid = true; p += 1u; break;
-        case VB_CMD_COLOR:
-            if (solid && depth == 0u && (__ldg(ptcl + p + 1u) >> 24) == 0xffu) start = solid_pos;
-            solid = false;
-            p += 2u;
-            break;
-        case VB_CMD_BEGIN_CLIP: depth += 1u; p += 1u; break; // (area survives BEGIN_CLIP, but depth > 0 disables the test)
-        case VB_CMD_END_CLIP: depth -= 1u; p += 3u; solid = false; break;
-        case VB_CMD_JUMP: p = __ldg(ptcl + p + 1u); break;    // chunk link: area state carries over
-        case VB_CMD_IMAGE: p += 2u; solid = false; break;
-        case VB_CMD_BLUR_RECT:
-        case VB_CMD_LIN_GRAD:
-        case VB_CMD_RAD_GRAD:
-        case VB_CMD_SWEEP_GRAD: p += 3u; solid = false; break;
-        default: p += 1u; break;
-        }
-    }
-    return start;
-}
+// Occlusion start. A tile's command list is painted back to front; `CMD_SOLID, CMD_COLOR` with alpha 255 outside any
+// clip replaces every pixel of the tile (over(bg, fg) = fg + bg * (1 - 1) = fg exactly), so nothing before the LAST such
+// pair can reach the output. coarse notes the offset of that CMD_SOLID per tile while it writes the list
+// (k_coarse.cu, tile_start) and fine starts there: identical pixels, and on map-like scenes with opaque area fills most
+// of a tile's commands are never executed. The reference executes the whole list (fine.wgsl:1064); the PTCL is unchanged.
+// (A first version found the start by walking the list in fine: a chain of dependent loads, 25 % of the kernel.)
 
 // ---------------- the interpreter: fine.wgsl:1064-1398 ----------------
 template <int AA>
@@ -709,7 +684,10 @@ k_fine(VbConfig cfg, FineArgs A) {
     uint32_t cmd_ix = tile_ix * VB_PTCL_INITIAL_ALLOC;
     const uint32_t blend_offset = __ldg(ptcl + cmd_ix);
     cmd_ix += 1u;
-    if (A.cull != 0u) cmd_ix = fine_cull_start(ptcl, cmd_ix);
+    if (A.cull != 0u) {
+        const uint32_t s0 = __ldg(A.tile_start + tile_ix);
+        if (s0 != 0u) cmd_ix = s0;
+    }
     if (AA != 0) ms_init(reinterpret_cast<WarpMs<AA == 0 ? 1 : AA> *>(&SH)[warp], lane);
 #define PXX(i) ((((i) < 4) ? xyx0 : xyx1) + (float)((i) & 3))
     for (;;) {
@@ -993,7 +971,7 @@ k_fine(VbConfig cfg, FineArgs A) {
 
 extern "C" void vb_launch_fine(const VbConfig *cfg, int aa, const VbSegment *segments, const uint32_t *ptcl, const uint32_t *info,
                                uint32_t *blend_spill, uint32_t *out, const uint32_t *ramps, const uint8_t *atlas,
-                               const uint32_t *mask_lut8, const uint32_t *mask_lut16, uint32_t cull, cudaStream_t st) {
+                               const uint32_t *mask_lut8, const uint32_t *mask_lut16, const uint32_t *tile_start, uint32_t cull, cudaStream_t st) {
     uint32_t rows = cfg->win_ty1 - cfg->win_ty0;
     uint32_t n = cfg->width_in_tiles * rows;
     if (n == 0) return;
@@ -1002,6 +980,7 @@ extern "C" void vb_launch_fine(const VbConfig *cfg, int aa, const VbSegment *seg
     A.segments = segments; A.ptcl = ptcl; A.info = info; A.blend_spill = blend_spill; A.out = out; A.ramps = ramps; A.atlas = atlas;
     A.mask_lut = aa == 2 ? mask_lut16 : mask_lut8;
     A.cull = cull;
+    A.tile_start = tile_start;
     if (aa == 0) k_fine<0><<<grid, FI_THREADS, 0, st>>>(*cfg, A);
     else if (aa == 1) k_fine<1><<<grid, FI_THREADS, 0, st>>>(*cfg, A);
     else k_fine<2><<<grid, FI_THREADS, 0, st>>>(*cfg, A);

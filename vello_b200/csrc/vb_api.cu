@@ -38,11 +38,11 @@ void vb_launch_backdrop(const VbConfig *, const VbBump *, const VbPath *, VbTile
 void vb_launch_path_count(const VbConfig *, VbBump *, const VbLineSoup *, const VbPath *, VbTile *, VbSegmentCount *, uint32_t,
                           cudaStream_t);
 void vb_launch_coarse(const VbConfig *, const uint32_t *, const VbDrawMonoid *, const VbBinHeader *, const uint32_t *, const VbPath *,
-                      VbTile *, VbBump *, uint32_t *, cudaStream_t);
+                      VbTile *, VbBump *, uint32_t *, uint32_t *, cudaStream_t);
 void vb_launch_path_tiling(const VbConfig *, const VbBump *, const VbSegmentCount *, const VbLineSoup *, const VbPath *, const VbTile *,
                            VbSegment *, uint32_t, cudaStream_t);
 void vb_launch_fine(const VbConfig *, int, const VbSegment *, const uint32_t *, const uint32_t *, uint32_t *, uint32_t *, const uint32_t *,
-                    const uint8_t *, const uint32_t *, const uint32_t *, uint32_t, cudaStream_t);
+                    const uint8_t *, const uint32_t *, const uint32_t *, const uint32_t *, uint32_t, cudaStream_t);
 }
 
 extern "C" int vb_fine_init_constants(void);
@@ -54,13 +54,18 @@ __global__ void k_flag_failure(const VbBump *bump, uint32_t *ptcl) {
 
 // Statistics for the roofline of `fine`: PTCL words each tile's interpreter reads and segments it
 // references (one thread per tile walks its command stream, as fine does).
-__global__ void k_ptcl_stats(VbConfig cfg, const uint32_t *__restrict__ ptcl, unsigned long long *out) {
+__global__ void k_ptcl_stats(VbConfig cfg, const uint32_t *__restrict__ ptcl, const uint32_t *__restrict__ tile_start,
+                             unsigned long long *out) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t wt = cfg.width_in_tiles, rows = cfg.win_ty1 - cfg.win_ty0;
     if (t >= wt * rows) return;
     uint32_t tile_ix = (cfg.win_ty0 + t / wt) * wt + t % wt;
     uint32_t ix = tile_ix * VB_PTCL_INITIAL_ALLOC + 1u;
     unsigned long long words = 1, segs = 0, fills = 0;
+    if (tile_start && tile_start[tile_ix]) { // occlusion start: the interpreter begins at the tile's last opaque cover
+        ix = tile_start[tile_ix];
+        words += 1;
+    }
     for (uint32_t guard = 0; guard < (1u << 24); guard++) {
         uint32_t tag = ptcl[ix];
         uint32_t size = 1;
@@ -99,7 +104,7 @@ struct vb_renderer {
 
     // fixed-size intermediates
     DevBuf tag_monoids, path_bboxes, draw_monoids, info_bin_data, clip_inp, clip_bboxes, clip_scratch, draw_bboxes, bin_headers, paths,
-        ctl, target, target_alt;
+        ctl, target, target_alt, tile_start;
     // bump arenas (capacities in elements live in cap_*)
     DevBuf lines, line_scratch, flatten_jobs, flatten_parts, tiles, seg_counts, segments, ptcl, blend_spill;
     uint32_t cap_lines = 0, cap_binning = 0, cap_tiles = 0, cap_seg_counts = 0, cap_segments = 0, cap_blend = 0, cap_ptcl = 0;
@@ -151,7 +156,7 @@ static int ensure(vb_renderer *r, DevBuf &b, size_t bytes) {
 static size_t arena_bytes(const vb_renderer *r) {
     const DevBuf *all[] = {&r->scene, &r->ramps, &r->atlas, &r->mask8, &r->mask16, &r->tag_monoids, &r->path_bboxes, &r->draw_monoids,
                            &r->info_bin_data, &r->clip_inp, &r->clip_bboxes, &r->clip_scratch, &r->draw_bboxes, &r->bin_headers, &r->paths,
-                           &r->ctl, &r->target, &r->target_alt, &r->lines, &r->line_scratch, &r->flatten_jobs, &r->flatten_parts, &r->tiles, &r->seg_counts, &r->segments, &r->ptcl, &r->blend_spill};
+                           &r->ctl, &r->target, &r->target_alt, &r->tile_start, &r->lines, &r->line_scratch, &r->flatten_jobs, &r->flatten_parts, &r->tiles, &r->seg_counts, &r->segments, &r->ptcl, &r->blend_spill};
     size_t s = 0;
     for (auto b : all) s += b->cap;
     return s;
@@ -234,7 +239,7 @@ extern "C" void vb_renderer_free(vb_renderer *r) {
     if (r->stream) cudaStreamSynchronize(r->stream);
     DevBuf *all[] = {&r->scene, &r->ramps, &r->atlas, &r->mask8, &r->mask16, &r->tag_monoids, &r->path_bboxes, &r->draw_monoids,
                      &r->info_bin_data, &r->clip_inp, &r->clip_bboxes, &r->clip_scratch, &r->draw_bboxes, &r->bin_headers, &r->paths,
-                     &r->ctl, &r->target, &r->target_alt, &r->lines, &r->line_scratch, &r->flatten_jobs, &r->flatten_parts, &r->tiles, &r->seg_counts, &r->segments, &r->ptcl, &r->blend_spill};
+                     &r->ctl, &r->target, &r->target_alt, &r->tile_start, &r->lines, &r->line_scratch, &r->flatten_jobs, &r->flatten_parts, &r->tiles, &r->seg_counts, &r->segments, &r->ptcl, &r->blend_spill};
     for (auto b : all)
         if (b->p) cudaFree(b->p);
     if (r->h_bump) cudaFreeHost(r->h_bump);
@@ -343,6 +348,7 @@ static int prepare(vb_renderer *r, const vb_params *p) {
     if ((rc = ensure(r, r->draw_bboxes, (size_t)n_draw * sizeof(VbBbox4)))) return rc;
     if ((rc = ensure(r, r->bin_headers, (size_t)((n_draw + 255u) / 256u) * aligned_n_bins * sizeof(VbBinHeader)))) return rc;
     if ((rc = ensure(r, r->paths, (size_t)((n_draw + 255u) & ~255u) * sizeof(VbPath)))) return rc;
+    if ((rc = ensure(r, r->tile_start, ((size_t)n_tiles + 256) * 4))) return rc;
 
     // first-guess arena capacities (elements); they only ever grow
     const uint32_t n_tags = c.n_tag_words * 4u;
@@ -462,7 +468,7 @@ static int enqueue(vb_renderer *r, int first, int last, void *out_dev) {
         case VB_STAGE_ID_COARSE:
             vb_launch_coarse(&c, (const uint32_t *)r->scene.p, (const VbDrawMonoid *)r->draw_monoids.p, (const VbBinHeader *)r->bin_headers.p,
                              (const uint32_t *)r->info_bin_data.p, (const VbPath *)r->paths.p, (VbTile *)r->tiles.p, bump,
-                             (uint32_t *)r->ptcl.p, st);
+                             (uint32_t *)r->ptcl.p, (uint32_t *)r->tile_start.p, st);
             launches += 2;
             break;
         case VB_STAGE_ID_PATH_TILING: {
@@ -489,7 +495,7 @@ static int enqueue(vb_renderer *r, int first, int last, void *out_dev) {
                 vb_launch_fine(&cb, (int)r->params.aa, (const VbSegment *)r->segments.p, (const uint32_t *)r->ptcl.p,
                                (const uint32_t *)r->info_bin_data.p, (uint32_t *)r->blend_spill.p, (uint32_t *)out_dev,
                                (const uint32_t *)r->ramps.p, (const uint8_t *)r->atlas.p, (const uint32_t *)r->mask8.p,
-                               (const uint32_t *)r->mask16.p, r->occlusion_cull, st);
+                               (const uint32_t *)r->mask16.p, (const uint32_t *)r->tile_start.p, r->occlusion_cull, st);
                 launches += 1;
                 if (r->host_out) {
                     size_t y0 = (size_t)cb.win_ty0 * 16u, y1 = (size_t)cb.win_ty1 * 16u;
@@ -744,7 +750,8 @@ extern "C" int vb_debug_fine_traffic(vb_renderer *r, uint64_t *ptcl_words, uint6
     CK(cudaMalloc(&d, sizeof h));
     CK(cudaMemset(d, 0, sizeof h));
     uint32_t n = r->cfg.width_in_tiles * (r->cfg.win_ty1 - r->cfg.win_ty0);
-    if (n) k_ptcl_stats<<<(n + 127) / 128, 128, 0, r->stream>>>(r->cfg, (const uint32_t *)r->ptcl.p, d);
+    if (n) k_ptcl_stats<<<(n + 127) / 128, 128, 0, r->stream>>>(r->cfg, (const uint32_t *)r->ptcl.p,
+                                                                r->occlusion_cull ? (const uint32_t *)r->tile_start.p : nullptr, d);
     CK(cudaStreamSynchronize(r->stream));
     CK(cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost));
     cudaFree(d);
