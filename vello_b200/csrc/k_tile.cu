@@ -74,71 +74,86 @@ __global__ void __launch_bounds__(256) k_tile_zero(VbConfig cfg, const VbBump *_
 }
 
 // backdrop: per (path, tile row) inclusive prefix sum along x (backdrop_dyn.wgsl:66-84).
-// B200 design: the WGSL assigns one thread per row, walking 8-byte tiles at a stride of the row width
-// (uncoalesced). Here a CTA takes 32 consecutive paths, cuts every path's row-major tile rectangle into chunks of
-// whole rows (<= ~1024 tiles), and its warps take chunks round-robin (binary search over the CTA's chunk prefix, the
-// same balancing idea as backdrop_dyn.wgsl:52-84). A warp sweeps its chunk 32 consecutive tiles at a time
-// (coalesced) with a segmented warp-shuffle scan whose segments are the rows. Integer sums: identical results.
+// B200 design: the WGSL assigns one thread per row, walking 8-byte tiles at a stride of the row width (uncoalesced).
+// tile_alloc hands out tiles in draw order, so the tiles of 32 consecutive paths are ONE contiguous range of the arena,
+// made of rows laid end to end. A CTA owns that range; it is cut into 8 x gridDim.y pieces of equal size, each piece
+// moved to whole-row boundaries, and one warp streams its piece 128 consecutive tiles at a time (four independent
+// coalesced loads per lane in flight) through a segmented warp-shuffle scan whose segments are the rows. Groups whose
+// deltas are all zero -- most of the arena -- are skipped after the load. Integer sums: identical results.
 #define BD_THREADS 256
-#define BD_PATHS 32u      // paths per CTA: small, so that the grid has enough CTAs to fill the machine
-#define BD_CHUNK_TILES 512u
+#define BD_WARPS (BD_THREADS / 32)
+#define BD_PATHS 32u // paths per CTA
 __global__ void __launch_bounds__(BD_THREADS)
 k_backdrop(VbConfig cfg, const VbBump *__restrict__ bump, const VbPath *__restrict__ paths, VbTile *tiles) {
-    __shared__ uint32_t sh_chunks[BD_THREADS];   // inclusive prefix of chunk counts
-    __shared__ uint32_t sh_width[BD_THREADS];
-    __shared__ uint32_t sh_height[BD_THREADS];
-    __shared__ uint32_t sh_offset[BD_THREADS];
-    __shared__ uint32_t sh_scan[BD_THREADS / 32 + 2];
+    __shared__ uint32_t sh_start[BD_PATHS + 1]; // first tile of each path, then the end of the range
+    __shared__ uint32_t sh_width[BD_PATHS];
     if (bump->failed != 0u) return;
-    const uint32_t p = blockIdx.x * BD_PATHS + threadIdx.x;
-    uint32_t width = 0u, height = 0u, n_chunks = 0u;
-    if (threadIdx.x < BD_PATHS && p < cfg.layout.n_draw_objects) {
-        const VbPath path = paths[p];
-        width = path.bbox[2] - path.bbox[0];
-        height = path.bbox[3] - path.bbox[1];
-        sh_offset[threadIdx.x] = path.tiles;
-        if (width > 1u && height > 0u) {
-            const uint32_t rows_per_chunk = max(1u, BD_CHUNK_TILES / width);
-            n_chunks = (height + rows_per_chunk - 1u) / rows_per_chunk;
+    const uint32_t n_draw = cfg.layout.n_draw_objects;
+    const uint32_t p0 = blockIdx.x * BD_PATHS;
+    const uint32_t arena_end = min(bump->tile, cfg.tiles_size);
+    if (threadIdx.x <= BD_PATHS) {
+        const uint32_t p = p0 + threadIdx.x;
+        uint32_t start = arena_end, width = 0u;
+        if (p < n_draw) {
+            const VbPath path = paths[p];
+            start = min(path.tiles, arena_end);
+            width = path.bbox[2] - path.bbox[0];
         }
+        sh_start[threadIdx.x] = start;
+        if (threadIdx.x < BD_PATHS) sh_width[threadIdx.x] = width;
     }
-    sh_width[threadIdx.x] = width;
-    sh_height[threadIdx.x] = height;
-    uint32_t total;
-    const uint32_t ex = vb_block_excl_scan(n_chunks, sh_scan, &total);
-    sh_chunks[threadIdx.x] = ex + n_chunks;
     __syncthreads();
     const uint32_t lane = vb_lane();
-    // gridDim.y CTAs share one group of paths (few-but-huge paths would otherwise leave most SMs idle)
-    for (uint32_t c = (threadIdx.x >> 5) + blockIdx.y * (BD_THREADS / 32); c < total; c += gridDim.y * (BD_THREADS / 32)) {
-        uint32_t el = 0u;
+    const uint32_t r0 = sh_start[0], r1 = sh_start[BD_PATHS];
+    if (r1 <= r0) return;
+    // the path owning tile t (the last path starting at or before t; empty paths share their successor's start) and
+    // t's column inside its row
+    auto column = [&](uint32_t t, uint32_t &w) -> uint32_t {
+        uint32_t p = 0u;
 #pragma unroll
-        for (uint32_t i = 0u; i < 8u; i++) {
-            const uint32_t probe = el + (128u >> i);
-            if (c >= sh_chunks[probe - 1u]) el = probe;
+        for (uint32_t step = 16u; step > 0u; step >>= 1)
+            if (sh_start[p + step] <= t) p += step;
+        w = max(sh_width[p], 1u);
+        return (t - sh_start[p]) % w;
+    };
+    auto row_align = [&](uint32_t t) -> uint32_t { // first row start at or after t
+        if (t >= r1) return r1;
+        uint32_t w;
+        const uint32_t x = column(t, w);
+        return x == 0u ? t : min(t + (w - x), r1);
+    };
+    const uint32_t pieces = BD_WARPS * gridDim.y;
+    const uint32_t piece = blockIdx.y * BD_WARPS + (threadIdx.x >> 5);
+    const uint32_t len = (r1 - r0 + pieces - 1u) / pieces;
+    const uint64_t na = (uint64_t)r0 + (uint64_t)piece * len;
+    if (na >= r1) return;
+    const uint32_t A = row_align((uint32_t)na);
+    const uint32_t B = row_align((uint32_t)min((uint64_t)r1, na + len));
+    int32_t carry = 0;
+    for (uint32_t base = A; base < B; base += 128u) {
+        int32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t idx = base + (uint32_t)k * 32u + lane;
+            v[k] = idx < B ? tiles[idx].backdrop : 0;
         }
-        const uint32_t w = sh_width[el];
-        const uint32_t rows_per_chunk = max(1u, BD_CHUNK_TILES / w);
-        const uint32_t chunk_in_path = c - (el > 0u ? sh_chunks[el - 1u] : 0u);
-        const uint32_t r0 = chunk_in_path * rows_per_chunk;
-        const uint32_t r1 = min(r0 + rows_per_chunk, sh_height[el]);
-        const uint32_t base = sh_offset[el] + r0 * w;
-        const uint32_t n = (r1 - r0) * w;
-        int32_t carry = 0;
-        for (uint32_t off = 0u; off < n; off += 32u) {
-            const uint32_t idx = off + lane;
-            const bool valid = idx < n;
-            int32_t v = valid ? tiles[base + idx].backdrop : 0;
-            const uint32_t x = idx % w;             // column inside the row
-            const uint32_t reach = min(x, lane);    // elements of my row to my left inside this 32-tile group
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t idx = base + (uint32_t)k * 32u + lane;
+            if (!__any_sync(VB_FULL, v[k] != 0) && carry == 0) continue; // nothing to propagate in these 32 tiles
+            const bool valid = idx < B;
+            uint32_t w;
+            const uint32_t x = valid ? column(idx, w) : 0u;
+            const uint32_t reach = min(x, lane); // elements of my row to my left inside this 32-tile group
+            int32_t s = v[k];
 #pragma unroll
             for (uint32_t o = 1u; o < 32u; o <<= 1) {
-                const int32_t t = __shfl_up_sync(VB_FULL, v, o);
-                if (o <= reach) v += t;
+                const int32_t t = __shfl_up_sync(VB_FULL, s, o);
+                if (o <= reach) s += t;
             }
-            if (x > lane) v += carry;               // my row started in an earlier group
-            if (valid && x != 0u) tiles[base + idx].backdrop = v;
-            carry = __shfl_sync(VB_FULL, v, 31);
+            if (x > lane) s += carry; // my row started in an earlier group
+            if (valid && x != 0u && s != v[k]) tiles[idx].backdrop = s;
+            carry = __shfl_sync(VB_FULL, s, 31);
         }
     }
 }
