@@ -161,6 +161,17 @@ def test_stripes_equal_full_frame(renderer):
     assert np.array_equal(np.concatenate(parts, axis=0), full)
     parts = [renderer.render_to_texture(packed, p, bin_rows=br) for br in ((0, 3), (3, 4))]
     assert np.array_equal(np.concatenate(parts, axis=0), full)
+    # curves, strokes with round / miter joins and caps, rotated transforms: flatten skips the segments that cannot
+    # reach a stripe's rows (k_flatten.cu, win_cull), which must not move a pixel
+    from vello_b200.shapes import Affine
+    for scene, (sw, sh) in ((scenes.tiger(1024, 1024), (1024, 1024)), (scenes.stroke_styles(Affine.translate(180.0, -40.0) * Affine.rotate(0.31) * Affine.scale(1.7, 1.5))[0], (1024, 768))):
+        pk = resolve(scene.encoding)
+        for aa in (AA_MSAA16, AA_MSAA8):
+            pp = RenderParams(BLACK, sw, sh, aa)
+            whole = renderer.render_to_texture(pk, pp)
+            rows = (sh + 255) // 256
+            stripes = [renderer.render_to_texture(pk, pp, bin_rows=(b, b + 1)) for b in range(rows)]
+            assert np.array_equal(np.concatenate(stripes, axis=0), whole)
 
 
 def test_arena_growth_and_retry(oracle):

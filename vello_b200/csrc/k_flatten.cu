@@ -725,6 +725,25 @@ __device__ void flatten_tag(Flat &f, const VbConfig &cfg, const uint32_t *__rest
         transform.ty = __uint_as_float(vb_scene(scene, cfg, b + 5));
     }
     CubicPoints pts = read_path_segment(cfg, scene, tag, is_stroke);
+    if (cfg.win_cull != 0u) {
+        // Stripe rendering (one bin-row window per GPU): everything this tag emits lies within R of the convex hull of
+        // its control points (R = half width x max(miter limit, sqrt 2) for strokes), so a tag whose hull, grown by R
+        // and one pixel, misses the window's rows cannot contribute a line, a backdrop or a bbox extent to them.
+        // Rows are independent in this algorithm (backdrop runs left to right inside a tile row), so the rows of the
+        // window still see every line that touches them: pixels are unchanged (test_stripes_equal_full_frame).
+        const float y_0 = fmaf(transform.m1, pts.p0.x, fmaf(transform.m3, pts.p0.y, transform.ty));
+        const float y_1 = fmaf(transform.m1, pts.p1.x, fmaf(transform.m3, pts.p1.y, transform.ty));
+        const float y_2 = fmaf(transform.m1, pts.p2.x, fmaf(transform.m3, pts.p2.y, transform.ty));
+        const float y_3 = fmaf(transform.m1, pts.p3.x, fmaf(transform.m3, pts.p3.y, transform.ty));
+        float grow = 1.0f;
+        if (is_stroke) {
+            const float lw = __uint_as_float(vb_scene(scene, cfg, cfg.layout.style_base + tag.style_ix + 1u));
+            const float lim = fmaxf(f16_bits_to_f32(style_flags & STYLE_MITER_LIMIT_MASK), 1.5f);
+            grow += 0.5f * fabsf(lw) * lim * (fabsf(transform.m0) + fabsf(transform.m1) + fabsf(transform.m2) + fabsf(transform.m3));
+        }
+        const float lo = fminf(fminf(y_0, y_1), fminf(y_2, y_3)) - grow, hi = fmaxf(fmaxf(y_0, y_1), fmaxf(y_2, y_3)) + grow;
+        if (hi < (float)(cfg.win_ty0 * VB_TILE_HEIGHT) || lo > (float)(cfg.win_ty1 * VB_TILE_HEIGHT)) return; // NaN: kept
+    }
     // the offset curves to flatten (0, 1 or 2 of them) and what follows them
     int n_sides = 0;
     float offset = 0.f;

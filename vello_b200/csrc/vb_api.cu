@@ -325,6 +325,7 @@ static int prepare(vb_renderer *r, const vb_params *p) {
     }
     c.win_ty0 = c.win_by0 * 16u;
     c.win_ty1 = c.win_by1 * 16u < c.height_in_tiles ? c.win_by1 * 16u : c.height_in_tiles;
+    c.win_cull = (c.win_by0 > 0u || c.win_by1 < hb) ? 1u : 0u;
     c.n_tag_words = r->layout.path_data_base - r->layout.path_tag_base;
     c.scene_words = (uint32_t)r->scene_words;
     c.n_ramps = r->n_ramps;

@@ -45,7 +45,7 @@ typedef struct {
     uint32_t n_ramps, atlas_w, atlas_h;
     uint32_t out_pitch_px;     /* output row pitch in pixels */
     uint32_t out_row0;         /* first pixel row stored at out[0] (stripe outputs) */
-    uint32_t _pad0;
+    uint32_t win_cull;         /* 1: a stripe window is set -- flatten skips segments that cannot reach its rows */
 } VbConfig;
 
 #define VB_STAGE_BINNING 0x1u
