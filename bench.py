@@ -145,7 +145,26 @@ def run_cpu_arm(args, packed, as_reference):
         1000.0 * sum(times) / len(times), len(times)
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # Libraries print to fd 1 behind Python's back (NCCL's version banner, for one). Everything that is not the JSON
+    # line is sent to stderr: fd 1 is re-pointed at fd 2 for the run and the line is written to the saved descriptor.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -174,11 +193,11 @@ def main():
             return
         packed, _ = build_scene(args)
         fps, cb, ms, n = run_cpu_arm(args, packed, True)
-        print(json.dumps({"impl": "reference", "metric": "frames/sec paris-30k@4K", "value": fps, "unit": "frames/s",
+        emit({"impl": "reference", "metric": "frames/sec paris-30k@4K", "value": fps, "unit": "frames/s",
                           "n_gpus": args.gpus, "steps": n, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                           "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                           "cpu_baseline": cb, "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                          "gpu_launches": 0}))
+                          "gpu_launches": 0})
         return
 
     rank, world, local, dist = dist_setup(args.gpus)
@@ -341,7 +360,7 @@ def main():
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "stage_ms": stage_ms, "bump": {k: int(getattr(st, k)) for k in ("lines", "tile", "seg_counts", "segments", "ptcl", "binning")},
             "scene_bytes": int(packed.scene.nbytes), "wall_s_timed_region": wall, "scene_build_s": gen_s}
-    print(json.dumps(line))
+    emit(line)
     r.close()
     if dist is not None:
         dist.destroy_process_group()
