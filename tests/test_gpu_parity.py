@@ -298,3 +298,59 @@ def test_streaming_readback_matches_blocking(renderer):
     assert len(got) == len(want)
     for a, b in zip(got, want):
         assert np.array_equal(a, b)
+
+
+def test_flatten_stroke_line_fast_path_extremes(renderer, oracle):
+    """k_flatten short-cuts stroked line-to segments (one line per side instead of the Euler machinery) behind a guard
+    on chord / coordinate magnitude / width / transform scale. The oracle has no shortcut: bit-identical `lines` and
+    path bboxes on strokes built to sit on both sides of that guard proves the equivalence where it is taken."""
+    from vello_b200.encoding import Stroke, STYLE_JOIN_BEVEL, STYLE_JOIN_MITER, STYLE_JOIN_ROUND, STYLE_CAP_BUTT, STYLE_CAP_ROUND, STYLE_CAP_SQUARE
+    from vello_b200.shapes import Affine, BezPath
+    from oracle.vbo import DTYPES
+    rng = np.random.default_rng(321)
+    s = Scene()
+    joins, caps = (STYLE_JOIN_BEVEL, STYLE_JOIN_MITER, STYLE_JOIN_ROUND), (STYLE_CAP_BUTT, STYLE_CAP_ROUND, STYLE_CAP_SQUARE)
+    for k in range(1500):
+        p = BezPath()
+        mag = [0.0, 1.0, 100.0, 4000.0, 16000.0, 60000.0, 3.0e5][k % 7]
+        step = [1e-6, 1e-5, 1e-4, 1e-3, 1e-2, 0.05, 0.3, 5.0, 300.0, 5e4][k % 10]
+        width = [1e-3, 0.05, 1.0, 6.0, 40.0, 500.0, 1e4][(k // 3) % 7]
+        x, y = rng.uniform(-mag, mag, 2) if mag else (0.0, 0.0)
+        p.move_to(x, y)
+        for _ in range(int(rng.integers(1, 7))):
+            x += rng.normal(0, step)
+            y += rng.normal(0, step)
+            p.line_to(x, y)
+        if k % 4 == 0:
+            p.close_path()
+        if k % 5 == 0:
+            t = Affine((rng.normal(0, 2), rng.normal(0, 2), rng.normal(0, 2), rng.normal(0, 2), rng.normal(0, 50), rng.normal(0, 50)))
+        elif k % 5 == 1:
+            t = Affine.scale(float(rng.choice([1e-3, 0.1, 0.999, 1.0, 3.7, 50.0, 2000.0])))
+        else:
+            t = Affine.translate(*rng.uniform(-10, 10, 2))
+        # keep round joins / caps to a few hundred lines each (an arc of radius r px takes ~ pi / (2 acos(1 - 0.25 / r)) lines)
+        norm = float(np.abs(np.array(t.coeffs[:4])).sum())
+        width = min(width, 8000.0 / max(norm, 1e-6))
+        st = Stroke(width, join=joins[k % 3], start_cap=caps[(k // 2) % 3], end_cap=caps[(k // 5) % 3], miter_limit=float(rng.choice([1.0, 4.0, 20.0])))
+        s.stroke(st, t, Color.from_rgba8(50, 200, 50, 200), None, p)
+    packed = resolve(s.encoding)
+    p = RenderParams(BLACK, 256, 256, AA_AREA)
+    renderer.render_to_texture(packed, p)  # sizes the arenas (grow-and-retry); run_stages below is a single attempt
+    renderer.upload(packed)
+    renderer.run_stages(p, "pathtag", "flatten")
+    oracle.bind(packed, 256, 256)
+    oracle.run("pathtag", "flatten")
+    g, c = renderer.download("lines", DTYPES["lines"]), oracle.buffer("lines")
+    assert g.shape == c.shape, (g.shape, c.shape)
+    # degenerate strokes (zero-length tangents) yield NaN points on both sides; NaN payload bits differ between x86 and
+    # the GPU (0xffc00000 vs 0x7fffffff), so NaNs are matched by position and everything else by bits
+    gf = np.concatenate([g["p0"], g["p1"]], axis=1)
+    cf = np.concatenate([c["p0"], c["p1"]], axis=1)
+    assert np.array_equal(g["path_ix"], c["path_ix"])
+    assert np.array_equal(np.isnan(gf), np.isnan(cf))
+    same = (gf.view(np.uint32) == cf.view(np.uint32)) | np.isnan(gf)
+    bad = np.nonzero(~same.all(axis=1))[0]
+    assert len(bad) == 0, f"{len(bad)} of {len(g)} lines differ; first: {[(int(i), g[i], c[i]) for i in bad[:3]]}"
+    assert int(np.isnan(gf).any(axis=1).sum()) < len(g) // 50
+    assert renderer.download("path_bboxes", DTYPES["path_bboxes"]).tobytes() == oracle.buffer("path_bboxes").tobytes()

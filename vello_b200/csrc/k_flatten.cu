@@ -746,6 +746,7 @@ __device__ void flatten_tag(Flat &f, const VbConfig &cfg, const uint32_t *__rest
     }
     // the offset curves to flatten (0, 1 or 2 of them) and what follows them
     int n_sides = 0;
+    bool fast_stroke = false;
     float offset = 0.f;
     fv2 n_start = F2(0.f, 0.f), n_prev = F2(0.f, 0.f);
     TailOps tail;
@@ -785,6 +786,24 @@ __device__ void flatten_tag(Flat &f, const VbConfig &cfg, const uint32_t *__rest
             fv2 tnn = fnorm(tan_next) * offset;
             fv2 n_next = F2(-tnn.y, tnn.x);
             n_sides = 2;
+            // Fast path for a stroked line-to. The offset curves of a (degree-raised) line are the two parallel lines;
+            // the general algorithm accepts the whole range at its first step and emits exactly one line per side,
+            // (p0 + n_start, p3 + n_prev) and, end points swapped for the negative offset, (p3 - n_prev, p0 - n_start),
+            // provided the rounding noise in the raised control points stays small against the chord:
+            //   with u = ulp of the local coordinates, c = chord, s = scale: tangent-angle noise is ~3u/c, the error
+            //   estimate O((3u/c)^2) c s and the line count ceil(sqrt(|k (k d + 1)| c s / 2)), |k| <~ 6u/c,
+            //   d = offset / c; both stay below their thresholds when  u s <= 2^-8,  c >= 16 u  and  c^2 >= u * offset.
+            // (u is taken as 2^-22 max|coord|, s as |m0|+|m1|+|m2|+|m3| -- both over-estimates.) Anything else, and any
+            // NaN, takes the general path. tests/test_gpu_parity.py compares `lines` bit-for-bit with the oracle, which has
+            // no such shortcut, on adversarial strokes (tiny segments, huge widths, large coordinates, odd transforms).
+            if (seg_type == 1u && offset > 0.f) {
+                const fv2 chord = pts.p3 - pts.p0;
+                const float c2 = fdot(chord, chord);
+                const float mag = fmaxf(fmaxf(fabsf(pts.p0.x), fabsf(pts.p0.y)), fmaxf(fabsf(pts.p3.x), fabsf(pts.p3.y)));
+                const float s1 = fabsf(transform.m0) + fabsf(transform.m1) + fabsf(transform.m2) + fabsf(transform.m3);
+                const float u = mag * 2.3841858e-07f; // 2^-22
+                if (mag * s1 < 16384.0f && c2 >= 256.0f * u * u && c2 >= u * offset && c2 >= 1e-10f && c2 < 1e30f) fast_stroke = true;
+            }
             if (do_join) draw_join(tail, style_flags, pts.p3, tan_prev, tan_next, n_prev, n_next);
             else draw_cap(tail, style_flags & STYLE_FLAGS_END_CAP_MASK, pts.p3, pts.p3 + n_prev, pts.p3 - n_prev, offset_tangent);
         }
@@ -808,6 +827,11 @@ __device__ void flatten_tag(Flat &f, const VbConfig &cfg, const uint32_t *__rest
                 if (!(feq(q0, q1) && feq(q0, q2) && feq(q0, q3))) tail.line(q0, q3); // device space
             }
         }
+    }
+    if (fast_stroke) {
+        f.line_xf(pts.p0 + n_start, pts.p3 + n_prev, transform);
+        f.line_xf(pts.p3 - n_prev, pts.p0 - n_start, transform);
+        n_sides = 0;
     }
 #pragma unroll 1
     for (int side = 0; side < n_sides; side++) { // one copy of the Euler machinery in the instruction stream
