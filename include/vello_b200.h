@@ -117,6 +117,9 @@ int vb_render_begin(vb_renderer *, const uint8_t *scene, size_t scene_len, const
                     uint32_t ramp_h, const uint8_t *atlas_rgba8, uint32_t atlas_w, uint32_t atlas_h, const vb_params *, void *out_host,
                     vb_frame_stats *);
 int vb_readback_wait(vb_renderer *);
+/* vb_render with a host destination launches fine in `n` bands of tile rows (1..8, default 8) and copies each band back
+ * while the next one rasterises. Tuning knob; vb_render_begin always uses one band. */
+int vb_set_readback_bands(vb_renderer *, uint32_t n);
 
 /* The renderer-owned target of the last frame (device pointer) and its size in bytes. */
 void *vb_target(vb_renderer *, size_t *bytes);

@@ -83,6 +83,7 @@ def load_library() -> C.CDLL:
     lib.vb_render_begin.argtypes = [vp, vp, C.c_size_t, C.POINTER(_Layout), vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, C.c_uint32,
                                     C.POINTER(_Params), vp, C.POINTER(FrameStats)]
     lib.vb_readback_wait.argtypes = [vp]
+    lib.vb_set_readback_bands.argtypes = [vp, C.c_uint32]
     lib.vb_target.restype = vp
     lib.vb_target.argtypes = [vp, C.POINTER(C.c_size_t)]
     lib.vb_copy_to_host.argtypes = [vp, vp, vp, C.c_size_t]
@@ -99,7 +100,7 @@ def load_library() -> C.CDLL:
 
 EXPORTED_SYMBOLS = ["vb_renderer_new", "vb_renderer_free", "vb_strerror", "vb_last_error", "vb_scene_upload",
                     "vb_render_resident", "vb_render_enqueue", "vb_frame_finish", "vb_render", "vb_target", "vb_copy_to_host", "vb_stream",
-                    "vb_run_stages", "vb_debug_download", "vb_debug_upload", "vb_debug_fine_traffic", "vb_set_occlusion_cull", "vb_render_begin", "vb_readback_wait"]
+                    "vb_run_stages", "vb_debug_download", "vb_debug_upload", "vb_debug_fine_traffic", "vb_set_occlusion_cull", "vb_render_begin", "vb_readback_wait", "vb_set_readback_bands"]
 
 
 @dataclass
