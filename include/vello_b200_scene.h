@@ -1,0 +1,119 @@
+/* vello_b200_scene.h -- C ABI of the scene-building front end.
+ *
+ * Above the drop-in boundary the reference has `vello::Scene` (vello/src/scene.rs:52-470), the stream encoder
+ * `vello_encoding::Encoding` / `PathEncoder` (vello_encoding/src/encoding.rs:26-530, path.rs:425-838) and
+ * `Resolver::resolve` (vello_encoding/src/resolve.rs:107-399, gradient ramps ramp_cache.rs:119-155). A Rust caller keeps
+ * using those and hands the packed bytes to vb_render (include/vello_b200.h). This header is the same thing for callers
+ * WITHOUT a Rust toolchain: a native (C++) implementation producing byte-identical packed scenes, so a C / C++ / Python
+ * program can go from shapes to pixels through libvello_b200.so alone. Glyph runs are not covered (they need a font
+ * stack); everything else `Scene` offers is.
+ *
+ * Conventions: transforms are kurbo `Affine` coefficient order [a, b, c, d, e, f] (x' = a x + c y + e), doubles like kurbo;
+ * paths are kurbo `PathEl` sequences; colours are straight-alpha sRGB floats like peniko `Color`.
+ * All functions return VB_OK (0) or a negative vb_status; none of them touches the GPU.
+ */
+#ifndef VELLO_B200_SCENE_H
+#define VELLO_B200_SCENE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "vello_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vb_scene vb_scene;
+
+/* kurbo::PathEl stream: verbs[i] in {'M','L','Q','C','Z'} consuming 2,2,4,6,0 doubles of `coords` (kurbo/bezpath.rs). */
+typedef struct {
+    const uint8_t *verbs;
+    uint32_t n_verbs;
+    const double *coords;
+} vb_path;
+
+typedef struct { float r, g, b, a; } vb_color; /* peniko::Color, straight alpha */
+typedef struct { float offset; vb_color color; } vb_color_stop; /* peniko::ColorStop */
+
+/* peniko::ImageBrush (image data + sampler). format: 0 RGBA8, 1 BGRA8; alpha_type: 0 straight, 1 premultiplied;
+ * quality: 0 low, 1 medium, 2 high; extend: 0 pad, 1 repeat, 2 reflect. */
+typedef struct {
+    const uint8_t *pixels; /* height x width x 4 */
+    uint32_t width, height;
+    uint32_t format, alpha_type, quality, x_extend, y_extend;
+    float alpha;
+} vb_image;
+
+enum { VB_BRUSH_SOLID = 0, VB_BRUSH_LINEAR = 1, VB_BRUSH_RADIAL = 2, VB_BRUSH_SWEEP = 3, VB_BRUSH_IMAGE = 4 };
+
+/* peniko::Brush. geom: linear {x0,y0,x1,y1}; radial {cx0,cy0,cx1,cy1,r0,r1}; sweep {cx,cy,start_angle,end_angle}. */
+typedef struct {
+    uint32_t kind;
+    vb_color color;             /* VB_BRUSH_SOLID */
+    double geom[6];             /* gradients */
+    const vb_color_stop *stops; /* gradients */
+    uint32_t n_stops;
+    uint32_t extend;            /* gradients: 0 pad, 1 repeat, 2 reflect */
+    uint32_t premul_interp;     /* gradients: interpolate in premultiplied space (peniko default: 1) */
+    const vb_image *image;      /* VB_BRUSH_IMAGE */
+} vb_brush;
+
+/* kurbo::Stroke restricted to what the encoding carries (path.rs:70-120): no dashes (vello expands them on the CPU). */
+enum { VB_JOIN_BEVEL = 0, VB_JOIN_MITER = 0x10000000, VB_JOIN_ROUND = 0x20000000 };
+enum { VB_CAP_BUTT = 0, VB_CAP_SQUARE = 0x01000000, VB_CAP_ROUND = 0x02000000 };
+typedef struct {
+    double width;
+    uint32_t join, start_cap, end_cap;
+    double miter_limit;
+} vb_stroke;
+
+enum { VB_FILL_NON_ZERO = 0, VB_FILL_EVEN_ODD = 1 };
+
+vb_scene *vb_scene_new(void);        /* Scene::new, scene.rs:54 */
+void vb_scene_free(vb_scene *);
+void vb_scene_reset(vb_scene *);     /* Scene::reset, scene.rs:59 */
+
+/* Scene::fill, scene.rs:316-345. brush_transform may be NULL. */
+int vb_scene_fill(vb_scene *, uint32_t fill_rule, const double transform[6], const vb_brush *, const double *brush_transform,
+                  const vb_path *);
+/* Scene::stroke, scene.rs:347-441 (solid strokes; a zero width draws nothing). */
+int vb_scene_stroke(vb_scene *, const vb_stroke *, const double transform[6], const vb_brush *, const double *brush_transform,
+                    const vb_path *);
+/* Scene::push_layer / push_luminance_mask_layer / push_clip_layer, scene.rs:105-249. The clip is filled with
+ * `clip_fill_rule`, or stroked when clip_stroke is not NULL. mix / compose: peniko numeric values (0..15, 128 = clip;
+ * 0..13). */
+int vb_scene_push_layer(vb_scene *, uint32_t clip_fill_rule, const vb_stroke *clip_stroke, uint32_t mix, uint32_t compose, float alpha,
+                        const double transform[6], const vb_path *clip);
+int vb_scene_push_luminance_mask_layer(vb_scene *, uint32_t clip_fill_rule, const vb_stroke *clip_stroke, float alpha,
+                                       const double transform[6], const vb_path *clip);
+int vb_scene_push_clip_layer(vb_scene *, uint32_t clip_fill_rule, const vb_stroke *clip_stroke, const double transform[6],
+                             const vb_path *clip);
+int vb_scene_pop_layer(vb_scene *);  /* scene.rs:251-254 */
+/* Scene::draw_image, scene.rs:443-452. */
+int vb_scene_draw_image(vb_scene *, const vb_image *, const double transform[6]);
+/* Scene::draw_blurred_rounded_rect, scene.rs:256-314. rect = {x0, y0, x1, y1}. */
+int vb_scene_draw_blurred_rounded_rect(vb_scene *, const double transform[6], const double rect[4], vb_color color, double radius,
+                                       double std_dev);
+
+/* Resolver::resolve (resolve.rs:183-399) without glyph runs: late-bound gradient ramps (512 premultiplied RGBA8 samples
+ * each) and the image atlas are built, their indices patched into the draw data, and the six streams packed. The
+ * pointers stay owned by the scene and valid until it is changed, resolved again or freed. */
+typedef struct {
+    const uint8_t *scene;
+    size_t scene_len;
+    vb_layout layout;
+    const uint32_t *ramps;
+    uint32_t ramp_w, ramp_h;
+    const uint8_t *atlas;
+    uint32_t atlas_w, atlas_h;
+} vb_packed;
+int vb_scene_resolve(vb_scene *, vb_packed *out);
+
+/* Renderer::render_to_texture (vello/src/lib.rs:474-515) for a vb_scene: resolve + vb_render. */
+int vb_render_scene(vb_renderer *, vb_scene *, const vb_params *, void *out, uint32_t out_is_device, vb_frame_stats *);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

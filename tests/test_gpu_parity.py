@@ -354,3 +354,33 @@ def test_flatten_stroke_line_fast_path_extremes(renderer, oracle):
     assert len(bad) == 0, f"{len(bad)} of {len(g)} lines differ; first: {[(int(i), g[i], c[i]) for i in bad[:3]]}"
     assert int(np.isnan(gf).any(axis=1).sum()) < len(g) // 50
     assert renderer.download("path_bboxes", DTYPES["path_bboxes"]).tobytes() == oracle.buffer("path_bboxes").tobytes()
+
+
+def test_native_scene_to_pixels(renderer, oracle):
+    """Shapes -> pixels through the C ABI alone: a scene built with the native front end (vb_scene_*) and rendered with
+    vb_render_scene gives the image the Python-encoded scene gives, which in turn matches the oracle."""
+    import ctypes as C
+    from vello_b200.renderer import FrameStats, _params_struct
+    from vello_b200.scene_native import NativeScene
+    from vello_b200.shapes import Affine, Circle, Rect
+    from vello_b200.encoding import FILL_NON_ZERO, Gradient, Stroke, EXTEND_REFLECT, MIX_MULTIPLY, COMPOSE_SRC_OVER
+    stops = [(0.0, Color.from_rgba8(255, 40, 0)), (0.6, Color.from_rgba8(0, 200, 90, 160)), (1.0, Color.from_rgba8(20, 0, 255))]
+    py, nat = Scene(), NativeScene()
+    for s in (py, nat):
+        s.fill(FILL_NON_ZERO, Affine.IDENTITY, Gradient.linear((0, 0), (300, 200), stops, EXTEND_REFLECT), None, Rect(10, 10, 290, 190))
+        s.push_layer(FILL_NON_ZERO, MIX_MULTIPLY, COMPOSE_SRC_OVER, 0.8, Affine.rotate(0.2), Circle(150.0, 90.0, 80.0))
+        s.stroke(Stroke(7.5), Affine.translate(20.0, 15.0), Color.from_rgba8(250, 250, 30, 220), None, Circle(120.0, 80.0, 60.0))
+        s.fill(FILL_NON_ZERO, Affine.scale(1.5), Gradient.sweep((80, 60), 0.0, 6.0, stops), None, Rect(30, 20, 150, 110))
+        s.pop_layer()
+        s.draw_blurred_rounded_rect(Affine.translate(200.0, 150.0), Rect(-40, -20, 40, 20), Color.from_rgba8(255, 255, 255, 200), 6.0, 4.0)
+    w, h = 300, 200
+    for aa in (AA_AREA, AA_MSAA16):
+        p = RenderParams(Color.from_rgba8(12, 12, 12), w, h, aa)
+        packed = resolve(py.encoding)
+        want = renderer.render_to_texture(packed, p)
+        got = np.zeros((h, w, 4), dtype=np.uint8)
+        ps, st = _params_struct(p, (0, 0)), FrameStats()
+        rc = renderer.lib.vb_render_scene(renderer.handle, nat.handle, C.byref(ps), C.c_void_p(got.ctypes.data), 0, C.byref(st))
+        assert rc == 0
+        assert np.array_equal(got, want)
+        assert_pixels(got, oracle.render(packed, w, h, p.base_color.premul_rgba8_u32(), aa), aa)

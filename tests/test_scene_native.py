@@ -1,0 +1,140 @@
+"""The native scene front end (include/vello_b200_scene.h, vb_scene.cpp) against the Python statement of the encoder
+(vello_b200/encoding.py, which the reference's golden images pin through the renderer): every `Scene` call of every
+test recipe is issued to both, and the resolved packed scene, layout, gradient ramps and image atlas must be identical
+byte for byte. CPU only (no GPU call is made)."""
+import numpy as np
+import pytest
+
+from vello_b200 import encoding, scenes
+from vello_b200.encoding import resolve
+from vello_b200.scene_native import NativeScene, SCENE_SYMBOLS
+
+
+class MirrorScene(encoding.Scene):
+    """A Scene that repeats every high-level call on a NativeScene."""
+
+    def __init__(self):
+        super().__init__()
+        self.native = NativeScene()
+
+    def fill(self, *a):
+        super().fill(*a)
+        self.native.fill(*a)
+
+    def stroke(self, *a):
+        super().stroke(*a)
+        self.native.stroke(*a)
+
+    def push_layer(self, *a):
+        super().push_layer(*a)
+        self.native.push_layer(*a)
+
+    def push_luminance_mask_layer(self, *a):
+        super().push_luminance_mask_layer(*a)
+        self.native.push_luminance_mask_layer(*a)
+
+    def push_clip_layer(self, *a):
+        super().push_clip_layer(*a)
+        self.native.push_clip_layer(*a)
+
+    def pop_layer(self):
+        super().pop_layer()
+        self.native.pop_layer()
+
+    def draw_image(self, image, transform):
+        # Scene.draw_image is fill() with an image brush in both implementations; call the dedicated native entry point
+        encoding.Scene.fill(self, encoding.FILL_NON_ZERO, transform, image, None,
+                            scenes._shapes.Rect(0.0, 0.0, float(image.width), float(image.height)) if hasattr(scenes, "_shapes") else
+                            __import__("vello_b200.shapes", fromlist=["Rect"]).Rect(0.0, 0.0, float(image.width), float(image.height)))
+        self.native.draw_image(image, transform)
+
+    def draw_blurred_rounded_rect(self, *a):
+        encoding.Scene.draw_blurred_rounded_rect(self, *a)
+        self.native.draw_blurred_rounded_rect(*a)
+
+
+@pytest.fixture()
+def mirror(monkeypatch):
+    monkeypatch.setattr(scenes, "Scene", MirrorScene)
+    return None
+
+
+def assert_same(scene: MirrorScene):
+    a = resolve(scene.encoding)
+    b = scene.native.resolve()
+    assert a.layout == b.layout, (a.layout, b.layout)
+    assert a.scene.shape == b.scene.shape
+    assert a.scene.tobytes() == b.scene.tobytes(), f"packed scene differs at words {np.nonzero(a.scene != b.scene)[0][:8]}"
+    assert a.ramps.shape == b.ramps.shape and a.ramps.tobytes() == b.ramps.tobytes()
+    assert a.atlas.shape == b.atlas.shape and a.atlas.tobytes() == b.atlas.tobytes()
+
+
+def test_symbols_exported():
+    import ctypes
+    from vello_b200.renderer import load_library
+    lib = load_library()
+    for s in SCENE_SYMBOLS:
+        assert hasattr(lib, s) and isinstance(getattr(lib, s), ctypes._CFuncPtr), s
+
+
+RECIPES = ["filled_square", "filled_circle", "simple_square", "layer_size", "robust_paths", "funky_paths", "fill_types", "stroke_styles",
+           "many_clips", "deep_blend", "brushes"]
+
+
+@pytest.mark.parametrize("name", RECIPES)
+def test_recipe_bytes_identical(mirror, name):
+    s = getattr(scenes, name)()[0]
+    assert isinstance(s, MirrorScene)
+    assert_same(s)
+
+
+@pytest.mark.parametrize("premul", [True, False])
+def test_gradient_recipes(mirror, premul):
+    assert_same(scenes.gradient_color_alpha(premul)[0])
+
+
+@pytest.mark.parametrize("extend", [encoding.EXTEND_PAD, encoding.EXTEND_REPEAT, encoding.EXTEND_REFLECT])
+def test_image_recipe(mirror, extend):
+    img = (np.arange(16 * 12 * 4, dtype=np.uint32) * 37 % 256).astype(np.uint8).reshape(12, 16, 4)
+    assert_same(scenes.image_roundtrip(img, extend)[0])
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_scenes(mirror, seed):
+    assert_same(scenes.random_small(seed)[0])
+
+
+def test_tiger(mirror):
+    assert_same(scenes.tiger(512, 512))
+
+
+def test_open_clips_and_empty_scene(mirror):
+    from vello_b200.shapes import Affine, Rect, Circle
+    s = MirrorScene()
+    assert_same(s)  # empty
+    s.push_clip_layer(encoding.FILL_NON_ZERO, Affine.IDENTITY, Rect(0, 0, 50, 50))
+    s.push_layer(encoding.Stroke(3.0), encoding.MIX_MULTIPLY, encoding.COMPOSE_SRC_OVER, 0.5, Affine.scale(2.0), Circle(10.0, 10.0, 8.0))
+    s.fill(encoding.FILL_EVEN_ODD, Affine.IDENTITY, encoding.Color(0.2, 0.4, 0.6, 0.8), Affine.rotate(0.3), Circle(5.0, 5.0, 4.0))
+    s.push_luminance_mask_layer(encoding.FILL_NON_ZERO, 0.25, Affine.IDENTITY, Rect(1, 2, 3, 4))
+    assert_same(s)  # three layers left open: trailing PATH tags / END_CLIP draw tags
+    s.pop_layer()
+    s.pop_layer()
+    s.pop_layer()
+    s.pop_layer()  # one too many: ignored
+    s.stroke(encoding.Stroke(0.0), Affine.IDENTITY, encoding.RED, None, Rect(0, 0, 1, 1))  # zero width: nothing
+    s.draw_blurred_rounded_rect(Affine.translate(3.0, 4.0), Rect(10, 10, 60, 40), encoding.Color(0.9, 0.1, 0.1, 0.7), 6.0, 3.5)
+    assert_same(s)
+
+
+def test_c_example_builds(tmp_path):
+    """examples/native_demo.c uses nothing but the two C headers and libvello_b200.so."""
+    import os, shutil, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    exe = tmp_path / "native_demo"
+    subprocess.run([cc, "-O1", "-Wall", "-Werror", "-I" + os.path.join(root, "include"), os.path.join(root, "examples", "native_demo.c"),
+                    "-L" + os.path.join(root, "vello_b200"), "-lvello_b200", "-Wl,-rpath," + os.path.join(root, "vello_b200"), "-lm",
+                    "-o", str(exe)], check=True)
+    assert exe.exists()

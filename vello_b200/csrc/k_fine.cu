@@ -20,7 +20,13 @@
 #include "vb_detmath.h"
 #include "vb_device.cuh"
 
-#define FI_WARPS 2                 // tiles per CTA (independent warps)
+#ifndef FI_WARPS
+#define FI_WARPS 2
+#endif
+#ifndef FI_MINB
+#define FI_MINB 16
+#endif
+//                 // tiles per CTA (independent warps)
 #define FI_THREADS (32 * FI_WARPS)
 #define PX 8                       // pixels per lane
 #define ONE_MINUS_ULP 0.99999994f
@@ -651,7 +657,7 @@ template <>
 struct FineShared<0> { uint32_t unused; };
 
 template <int AA>
-__global__ void __launch_bounds__(FI_THREADS, 16)
+__global__ void __launch_bounds__(FI_THREADS, FI_MINB)
 k_fine(VbConfig cfg, FineArgs A) {
     __shared__ FineShared<AA> SH;
     const uint32_t *__restrict__ ptcl = A.ptcl;

@@ -1,0 +1,717 @@
+// vb_scene.cpp -- native scene front end: Scene builder, stream encoder, path encoder, resolve / pack.
+//
+// What it stands in for (for callers without a Rust toolchain; see include/vello_b200_scene.h):
+//   vello::Scene                       vello/src/scene.rs:52-470
+//   vello_encoding::Encoding           vello_encoding/src/encoding.rs:26-530
+//   vello_encoding::PathEncoder        vello_encoding/src/path.rs:425-838   (state machine, stroke cap markers)
+//   Style bit layout                   vello_encoding/src/path.rs:11-120
+//   draw tags / draw data              vello_encoding/src/draw.rs:17-236
+//   f32 -> f16                         vello_encoding/src/math.rs:93-127
+//   Resolver::resolve, Layout          vello_encoding/src/resolve.rs:16-39,107-399
+//   gradient ramps                     vello_encoding/src/ramp_cache.rs:119-155
+// Written from the behaviour of those (and kept byte-identical to vello_b200/encoding.py, the Python statement of the
+// same behaviour that the reference's golden images pin): tests/test_scene_native.py compares the packed bytes, layout,
+// ramps and atlas of both on every test scene. Plain C++17, no CUDA; all arithmetic that reaches the output is done in
+// float exactly where the reference uses f32 (no contraction: this file is compiled with -ffp-contract=off).
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/vello_b200_scene.h"
+
+namespace {
+
+constexpr uint8_t TAG_LINE_TO_F32 = 0x9, TAG_QUAD_TO_F32 = 0xA, TAG_CUBIC_TO_F32 = 0xB;
+constexpr uint8_t TAG_TRANSFORM = 0x20, TAG_PATH = 0x10, TAG_STYLE = 0x40, TAG_SUBPATH_END_BIT = 0x4;
+constexpr uint32_t DRAWTAG_COLOR = 0x44, DRAWTAG_LINEAR_GRADIENT = 0x114, DRAWTAG_RADIAL_GRADIENT = 0x29C, DRAWTAG_SWEEP_GRADIENT = 0x254,
+                   DRAWTAG_IMAGE = 0x28C, DRAWTAG_BLUR_RECT = 0x2D4, DRAWTAG_BEGIN_CLIP = 0x49, DRAWTAG_END_CLIP = 0x21;
+constexpr uint32_t STYLE_FLAGS_STYLE_BIT = 0x80000000u, STYLE_FLAGS_FILL_BIT = 0x40000000u;
+constexpr uint32_t CLIP_BLEND_MODE = 0x8003u, LUMINANCE_MASK_BLEND_MODE = 0x10000u; // draw.rs:215-216
+constexpr uint32_t PATH_REDUCE_WG = 256;                                            // config.rs
+constexpr uint32_t N_RAMP_SAMPLES = 512;
+constexpr float EPS = 1e-12f; // path.rs:841
+
+inline uint32_t f32_bits(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+inline float bits_f32(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+
+uint32_t f32_to_f16(float val) { // math.rs:93-127 (float_to_half_fast3)
+    const uint32_t INF_32 = 255u << 23, INF_16 = 31u << 23, MAGIC = 15u << 23, ROUND_MASK = ~0xFFFu;
+    uint32_t u = f32_bits(val);
+    const uint32_t sign = u & 0x80000000u;
+    u ^= sign;
+    uint32_t out;
+    if (u >= INF_32) {
+        out = u > INF_32 ? 0x7E00u : 0x7C00u;
+    } else {
+        u &= ROUND_MASK;
+        u = f32_bits(bits_f32(u) * bits_f32(MAGIC));
+        u -= ROUND_MASK;
+        if (u > INF_16) u = INF_16;
+        out = (u >> 13) & 0xFFFFu;
+    }
+    return out | (sign >> 16);
+}
+
+struct Color { float r, g, b, a; };
+inline bool operator==(const Color &x, const Color &y) { return x.r == y.r && x.g == y.g && x.b == y.b && x.a == y.a; }
+inline Color multiply_alpha(Color c, float m) { return Color{c.r, c.g, c.b, c.a * m}; }
+uint32_t premul_rgba8(Color c) { // premultiply().to_rgba8().to_u32(), draw.rs:76-84; r is the low byte
+    const float comps[4] = {c.r * c.a, c.g * c.a, c.b * c.a, c.a};
+    uint32_t out = 0;
+    for (int i = 0; i < 4; i++) {
+        double v = std::floor((double)(comps[i] * 255.0f + 0.5f));
+        if (!(v > 0.0)) v = 0.0; // also NaN
+        if (v > 255.0) v = 255.0;
+        out |= (uint32_t)v << (8 * i);
+    }
+    return out;
+}
+const Color TRANSPARENT{0.f, 0.f, 0.f, 0.f};
+
+struct Affine {
+    double c[6];
+};
+inline Affine mul(const Affine &a, const Affine &b) { // kurbo Affine * Affine
+    Affine r;
+    r.c[0] = a.c[0] * b.c[0] + a.c[2] * b.c[1];
+    r.c[1] = a.c[1] * b.c[0] + a.c[3] * b.c[1];
+    r.c[2] = a.c[0] * b.c[2] + a.c[2] * b.c[3];
+    r.c[3] = a.c[1] * b.c[2] + a.c[3] * b.c[3];
+    r.c[4] = a.c[0] * b.c[4] + a.c[2] * b.c[5] + a.c[4];
+    r.c[5] = a.c[1] * b.c[4] + a.c[3] * b.c[5] + a.c[5];
+    return r;
+}
+
+struct Stop { float offset; Color color; };
+struct RampPatch { uint32_t draw_data_offset; std::vector<Stop> stops; uint32_t extend; bool premul; };
+struct ImagePatch { uint32_t draw_data_offset; vb_image image; };
+struct Style { uint32_t flags; float width; };
+struct Xform { float c[6]; };
+
+struct Encoding {
+    std::vector<uint8_t> path_tags;
+    std::vector<float> path_data;
+    std::vector<uint32_t> draw_tags, draw_data;
+    std::vector<Xform> transforms;
+    std::vector<Style> styles;
+    uint32_t n_paths = 0, n_path_segments = 0, n_clips = 0, n_open_clips = 0;
+    std::vector<RampPatch> ramp_patches;
+    std::vector<ImagePatch> image_patches;
+
+    void encode_style(Style s) { // encoding.rs: only emitted when it changes
+        if (styles.empty() || styles.back().flags != s.flags || !(styles.back().width == s.width)) {
+            path_tags.push_back(TAG_STYLE);
+            styles.push_back(s);
+        }
+    }
+    void encode_fill_style(uint32_t fill) { encode_style(Style{fill == VB_FILL_EVEN_ODD ? STYLE_FLAGS_FILL_BIT : 0u, 0.0f}); }
+    bool encode_stroke_style(const vb_stroke &s) { // path.rs:70-120
+        if (s.width == 0.0) return false;
+        const uint32_t flags = STYLE_FLAGS_STYLE_BIT | s.join | (s.start_cap << 2) | s.end_cap | f32_to_f16((float)s.miter_limit);
+        encode_style(Style{flags, (float)s.width});
+        return true;
+    }
+    bool encode_transform(const Affine &t) {
+        Xform x;
+        for (int i = 0; i < 6; i++) x.c[i] = (float)t.c[i];
+        bool same = !transforms.empty();
+        if (same)
+            for (int i = 0; i < 6; i++) same = same && transforms.back().c[i] == x.c[i];
+        if (!same) {
+            path_tags.push_back(TAG_TRANSFORM);
+            transforms.push_back(x);
+            return true;
+        }
+        return false;
+    }
+    void swap_last_path_tags() {
+        const size_t n = path_tags.size();
+        const uint8_t t = path_tags[n - 1];
+        path_tags[n - 1] = path_tags[n - 2];
+        path_tags[n - 2] = t;
+    }
+    void encode_color(Color c) {
+        draw_tags.push_back(DRAWTAG_COLOR);
+        draw_data.push_back(premul_rgba8(c));
+    }
+    void encode_begin_clip(uint32_t blend_mode, float alpha) {
+        draw_tags.push_back(DRAWTAG_BEGIN_CLIP);
+        draw_data.push_back(blend_mode);
+        draw_data.push_back(f32_bits(alpha));
+        n_clips += 1;
+        n_open_clips += 1;
+    }
+    void encode_end_clip() {
+        if (n_open_clips > 0) {
+            draw_tags.push_back(DRAWTAG_END_CLIP);
+            path_tags.push_back(TAG_PATH);
+            n_paths += 1;
+            n_clips += 1;
+            n_open_clips -= 1;
+        }
+    }
+};
+
+// path.rs:425-838. Coordinates are rounded to f32 on entry.
+class PathEncoder {
+public:
+    PathEncoder(Encoding &e, bool fill) : enc(e), tags(e.path_tags), data(e.path_data), is_fill(fill) {}
+    void move_to(float x, float y) {
+        if (is_fill) close();
+        if (state == MOVETO) {
+            data.resize(data.size() - 2);
+        } else if (state == NONEMPTY) {
+            if (!is_fill) insert_stroke_cap_marker(false);
+            if (!tags.empty()) tags.back() |= TAG_SUBPATH_END_BIT;
+        }
+        first_x = x; first_y = y;
+        data.push_back(x); data.push_back(y);
+        state = MOVETO;
+    }
+    void line_to(float x, float y) {
+        if (state == START) {
+            if (n_encoded_segments == 0) { move_to(x, y); return; }
+            move_to(first_x, first_y);
+        }
+        if (state == MOVETO) {
+            if (!neq(x, y, first_x, first_y)) return;
+            const float third = 1.0f / 3.0f;
+            tan_x = first_x + third * (x - first_x);
+            tan_y = first_y + third * (y - first_y);
+        }
+        if (zero_len(x, y, x, y, x, y)) return;
+        data.push_back(x); data.push_back(y);
+        tags.push_back(TAG_LINE_TO_F32);
+        state = NONEMPTY;
+        n_encoded_segments += 1;
+    }
+    void quad_to(float x1, float y1, float x2, float y2) {
+        if (state == START) {
+            if (n_encoded_segments == 0) { move_to(x2, y2); return; }
+            move_to(first_x, first_y);
+        }
+        if (state == MOVETO) {
+            const float third = 1.0f / 3.0f;
+            if (neq(x1, y1, first_x, first_y)) {
+                tan_x = x1 + third * (first_x - x1);
+                tan_y = y1 + third * (first_y - y1);
+            } else if (neq(x2, y2, first_x, first_y)) {
+                tan_x = x1 + third * (x2 - x1);
+                tan_y = y1 + third * (y2 - y1);
+            } else {
+                return;
+            }
+        }
+        if (zero_len(x1, y1, x2, y2, x2, y2)) return; // (p3 defaults to p1 in the Python statement; see zero_len)
+        data.push_back(x1); data.push_back(y1); data.push_back(x2); data.push_back(y2);
+        tags.push_back(TAG_QUAD_TO_F32);
+        state = NONEMPTY;
+        n_encoded_segments += 1;
+    }
+    void cubic_to(float x1, float y1, float x2, float y2, float x3, float y3) {
+        if (state == START) {
+            if (n_encoded_segments == 0) { move_to(x3, y3); return; }
+            move_to(first_x, first_y);
+        }
+        if (state == MOVETO) {
+            if (neq(x1, y1, first_x, first_y)) { tan_x = x1; tan_y = y1; }
+            else if (neq(x2, y2, first_x, first_y)) { tan_x = x2; tan_y = y2; }
+            else if (neq(x3, y3, first_x, first_y)) { tan_x = x3; tan_y = y3; }
+            else return;
+        }
+        if (zero_len(x1, y1, x2, y2, x3, y3)) return;
+        data.push_back(x1); data.push_back(y1); data.push_back(x2); data.push_back(y2); data.push_back(x3); data.push_back(y3);
+        tags.push_back(TAG_CUBIC_TO_F32);
+        state = NONEMPTY;
+        n_encoded_segments += 1;
+    }
+    void empty_path() {
+        for (int i = 0; i < 4; i++) data.push_back(0.0f);
+        tags.push_back(TAG_LINE_TO_F32);
+        n_encoded_segments += 1;
+    }
+    void close() {
+        if (state == START) return;
+        if (state == MOVETO) {
+            data.resize(data.size() - 2);
+            state = START;
+            return;
+        }
+        if (data.size() < 2) return;
+        const float lx = data[data.size() - 2], ly = data[data.size() - 1];
+        if (f32_bits(lx) != f32_bits(first_x) || f32_bits(ly) != f32_bits(first_y)) { // bitwise, path.rs:661-662
+            data.push_back(first_x); data.push_back(first_y);
+            tags.push_back(TAG_LINE_TO_F32);
+            n_encoded_segments += 1;
+        }
+        if (!is_fill) insert_stroke_cap_marker(true);
+        if (!tags.empty()) tags.back() |= TAG_SUBPATH_END_BIT;
+        state = START;
+    }
+    uint32_t finish(bool insert_path_marker) {
+        if (is_fill) close();
+        if (state == MOVETO) data.resize(data.size() - 2);
+        if (n_encoded_segments != 0) {
+            if (!is_fill && state == NONEMPTY) insert_stroke_cap_marker(false);
+            if (!tags.empty()) tags.back() |= TAG_SUBPATH_END_BIT;
+            enc.n_path_segments += n_encoded_segments;
+            if (insert_path_marker) {
+                tags.push_back(TAG_PATH);
+                enc.n_paths += 1;
+            }
+        }
+        return n_encoded_segments;
+    }
+    int path_elements(const vb_path &p) {
+        const double *c = p.coords;
+        for (uint32_t i = 0; i < p.n_verbs; i++) {
+            switch (p.verbs[i]) {
+            case 'M': move_to((float)c[0], (float)c[1]); c += 2; break;
+            case 'L': line_to((float)c[0], (float)c[1]); c += 2; break;
+            case 'Q': quad_to((float)c[0], (float)c[1], (float)c[2], (float)c[3]); c += 4; break;
+            case 'C': cubic_to((float)c[0], (float)c[1], (float)c[2], (float)c[3], (float)c[4], (float)c[5]); c += 6; break;
+            case 'Z': close(); break;
+            default: return VB_E_INVALID;
+            }
+        }
+        return VB_OK;
+    }
+
+private:
+    enum State { START, MOVETO, NONEMPTY };
+    Encoding &enc;
+    std::vector<uint8_t> &tags;
+    std::vector<float> &data;
+    float first_x = 0.f, first_y = 0.f, tan_x = 0.f, tan_y = 0.f;
+    State state = START;
+    uint32_t n_encoded_segments = 0;
+    bool is_fill;
+
+    static bool neq(float ax, float ay, float bx, float by) { return std::fabs(ax - bx) > EPS || std::fabs(ay - by) > EPS; }
+    // all of (last point, p1, p2, p3) within EPS of each other in both axes
+    bool zero_len(float x1, float y1, float x2, float y2, float x3, float y3) const {
+        const float x0 = data[data.size() - 2], y0 = data[data.size() - 1];
+        const float xmax = std::fmax(std::fmax(x0, x1), std::fmax(x2, x3)), xmin = std::fmin(std::fmin(x0, x1), std::fmin(x2, x3));
+        const float ymax = std::fmax(std::fmax(y0, y1), std::fmax(y2, y3)), ymin = std::fmin(std::fmin(y0, y1), std::fmin(y2, y3));
+        return !((xmax - xmin) > EPS || (ymax - ymin) > EPS);
+    }
+    void insert_stroke_cap_marker(bool is_closed) { // path.rs:711-730: carries the start tangent
+        if (is_closed) line_to(tan_x, tan_y);
+        else quad_to(first_x, first_y, tan_x, tan_y);
+    }
+};
+
+// ramp_cache.rs:119-155: 512 premultiplied RGBA8 samples
+void make_ramp(const std::vector<Stop> &stops, bool premul, uint32_t *out) {
+    float last_u = 0.0f, this_u = 0.0f;
+    Color last_c = stops[0].color, this_c = last_c;
+    size_t j = 0;
+    for (uint32_t i = 0; i < N_RAMP_SAMPLES; i++) {
+        const float u = (float)i / (float)(N_RAMP_SAMPLES - 1);
+        while (u > this_u) {
+            last_u = this_u;
+            last_c = this_c;
+            if (j + 1 < stops.size()) {
+                this_u = stops[j + 1].offset;
+                this_c = stops[j + 1].color;
+                j += 1;
+            } else {
+                break;
+            }
+        }
+        const float du = this_u - last_u;
+        Color c;
+        if (du < 1e-9f) {
+            c = this_c;
+        } else {
+            const float t = (u - last_u) / du;
+            const Color a = last_c, b = this_c;
+            if (premul) { // AlphaColor::lerp: premultiply, lerp_rect, un-premultiply (color crate)
+                const float pa[4] = {a.r * a.a, a.g * a.a, a.b * a.a, a.a};
+                const float pb[4] = {b.r * b.a, b.g * b.a, b.b * b.a, b.a};
+                float pc[4];
+                for (int k = 0; k < 4; k++) pc[k] = pa[k] + (pb[k] - pa[k]) * t;
+                if (pc[3] == 0.0f || pc[3] == 1.0f) {
+                    c = Color{pc[0], pc[1], pc[2], pc[3]};
+                } else {
+                    const float inv = 1.0f / pc[3];
+                    c = Color{pc[0] * inv, pc[1] * inv, pc[2] * inv, pc[3]};
+                }
+            } else {
+                c = Color{a.r + (b.r - a.r) * t, a.g + (b.g - a.g) * t, a.b + (b.b - a.b) * t, a.a + (b.a - a.a) * t};
+            }
+        }
+        out[i] = premul_rgba8(c);
+    }
+}
+
+} // namespace
+
+struct vb_scene {
+    Encoding e;
+    // outputs of the last resolve
+    std::vector<uint32_t> packed;
+    std::vector<uint32_t> ramps;
+    std::vector<uint8_t> atlas;
+};
+
+namespace {
+
+inline Affine to_affine(const double t[6]) {
+    Affine a;
+    for (int i = 0; i < 6; i++) a.c[i] = t[i];
+    return a;
+}
+inline Color to_color(vb_color c) { return Color{c.r, c.g, c.b, c.a}; }
+
+bool encode_path(Encoding &e, const vb_path &p, bool is_fill, int *rc) {
+    PathEncoder pe(e, is_fill);
+    *rc = pe.path_elements(p);
+    return pe.finish(true) != 0;
+}
+void encode_empty_shape(Encoding &e) {
+    PathEncoder pe(e, true);
+    pe.empty_path();
+    pe.finish(true);
+}
+bool encode_rect(Encoding &e, double x0, double y0, double x1, double y1) { // kurbo Rect::path_elements
+    PathEncoder pe(e, true);
+    pe.move_to((float)x0, (float)y0);
+    pe.line_to((float)x1, (float)y0);
+    pe.line_to((float)x1, (float)y1);
+    pe.line_to((float)x0, (float)y1);
+    pe.close();
+    return pe.finish(true) != 0;
+}
+
+// encoding.rs:300-470 (encode_brush and the gradient special cases)
+int encode_brush(Encoding &e, const vb_brush &b, float alpha) {
+    switch (b.kind) {
+    case VB_BRUSH_SOLID: {
+        const Color c = to_color(b.color);
+        e.encode_color(alpha == 1.0f ? c : multiply_alpha(c, alpha));
+        return VB_OK;
+    }
+    case VB_BRUSH_LINEAR:
+    case VB_BRUSH_RADIAL:
+    case VB_BRUSH_SWEEP: {
+        float p[6];
+        for (int i = 0; i < 6; i++) p[i] = (float)b.geom[i];
+        float t0 = 0.f, t1 = 0.f;
+        if (b.kind == VB_BRUSH_RADIAL) {
+            if (p[0] == p[2] && p[1] == p[3] && std::fabs((double)p[4] - (double)p[5]) < 1.0 / (1 << 12)) {
+                e.encode_color(TRANSPARENT);
+                return VB_OK;
+            }
+        }
+        if (b.kind == VB_BRUSH_SWEEP) {
+            const float tau = (float)(2.0 * 3.141592653589793);
+            t0 = p[2] / tau;
+            t1 = p[3] / tau;
+            if (std::fabs((double)t0 - (double)t1) < 1.0 / (1 << 15)) {
+                e.encode_color(TRANSPARENT);
+                return VB_OK;
+            }
+        }
+        if (b.n_stops && !b.stops) return VB_E_INVALID;
+        std::vector<Stop> stops(b.n_stops);
+        for (uint32_t i = 0; i < b.n_stops; i++) {
+            stops[i].offset = b.stops[i].offset;
+            stops[i].color = to_color(b.stops[i].color);
+            if (alpha != 1.0f) stops[i].color = multiply_alpha(stops[i].color, alpha);
+        }
+        if (stops.empty()) {
+            e.encode_color(TRANSPARENT);
+            return VB_OK;
+        }
+        if (stops.size() == 1) {
+            e.encode_color(stops[0].color);
+            return VB_OK;
+        }
+        RampPatch rp;
+        rp.draw_data_offset = (uint32_t)e.draw_data.size();
+        rp.stops = std::move(stops);
+        rp.extend = b.extend;
+        rp.premul = b.premul_interp != 0;
+        e.ramp_patches.push_back(std::move(rp));
+        if (b.kind == VB_BRUSH_LINEAR) {
+            e.draw_tags.push_back(DRAWTAG_LINEAR_GRADIENT);
+            e.draw_data.push_back(0);
+            for (int i = 0; i < 4; i++) e.draw_data.push_back(f32_bits(p[i]));
+        } else if (b.kind == VB_BRUSH_RADIAL) {
+            e.draw_tags.push_back(DRAWTAG_RADIAL_GRADIENT);
+            e.draw_data.push_back(0);
+            for (int i = 0; i < 6; i++) e.draw_data.push_back(f32_bits(p[i]));
+        } else {
+            e.draw_tags.push_back(DRAWTAG_SWEEP_GRADIENT);
+            e.draw_data.push_back(0);
+            e.draw_data.push_back(f32_bits(p[0]));
+            e.draw_data.push_back(f32_bits(p[1]));
+            e.draw_data.push_back(f32_bits(t0));
+            e.draw_data.push_back(f32_bits(t1));
+        }
+        return VB_OK;
+    }
+    case VB_BRUSH_IMAGE: {
+        if (!b.image) return VB_E_INVALID;
+        const vb_image &im = *b.image;
+        const uint32_t a8 = (uint32_t)(int)(im.alpha * alpha * 255.0f + 0.5f) & 0xFFu;
+        ImagePatch ip;
+        ip.draw_data_offset = (uint32_t)e.draw_data.size();
+        ip.image = im;
+        e.image_patches.push_back(ip);
+        e.draw_tags.push_back(DRAWTAG_IMAGE);
+        e.draw_data.push_back(0);
+        e.draw_data.push_back((im.width << 16) | (im.height & 0xFFFFu));
+        e.draw_data.push_back((im.format << 15) | (im.alpha_type << 14) | (im.quality << 12) | (im.x_extend << 10) | (im.y_extend << 8) | a8);
+        return VB_OK;
+    }
+    default: return VB_E_INVALID;
+    }
+}
+
+bool stroke_inner(Encoding &e, const vb_stroke &st, const Affine &t, const vb_path &p, int *rc) {
+    e.encode_transform(t);
+    e.encode_stroke_style(st);
+    return encode_path(e, p, false, rc);
+}
+
+int push_layer_inner(vb_scene *s, uint32_t blend_mode, float alpha, uint32_t fill_rule, const vb_stroke *stroke, const double transform[6],
+                     const vb_path *clip) {
+    if (!s || !transform || !clip) return VB_E_INVALID;
+    Encoding &e = s->e;
+    const Affine t = to_affine(transform);
+    int rc = VB_OK;
+    bool ok;
+    if (stroke) {
+        if (stroke->width == 0.0) {
+            e.encode_fill_style(VB_FILL_NON_ZERO);
+            ok = false;
+        } else {
+            ok = stroke_inner(e, *stroke, t, *clip, &rc);
+        }
+    } else {
+        e.encode_transform(t);
+        e.encode_fill_style(fill_rule);
+        ok = encode_path(e, *clip, true, &rc);
+    }
+    if (!ok) encode_empty_shape(e);
+    e.encode_begin_clip(blend_mode, alpha);
+    return rc;
+}
+
+inline float clamp01(float a) { return a < 0.0f ? 0.0f : (a > 1.0f ? 1.0f : a); }
+inline uint32_t align_up(uint32_t n, uint32_t a) { return (n + a - 1) / a * a; }
+
+} // namespace
+
+extern "C" {
+
+vb_scene *vb_scene_new(void) { return new (std::nothrow) vb_scene(); }
+void vb_scene_free(vb_scene *s) { delete s; }
+void vb_scene_reset(vb_scene *s) {
+    if (s) *s = vb_scene();
+}
+
+int vb_scene_fill(vb_scene *s, uint32_t fill_rule, const double transform[6], const vb_brush *brush, const double *brush_transform,
+                  const vb_path *path) {
+    if (!s || !transform || !brush || !path) return VB_E_INVALID;
+    Encoding &e = s->e;
+    const Affine t = to_affine(transform);
+    e.encode_transform(t);
+    e.encode_fill_style(fill_rule);
+    int rc = VB_OK;
+    if (encode_path(e, *path, true, &rc)) {
+        if (brush_transform && e.encode_transform(mul(t, to_affine(brush_transform)))) e.swap_last_path_tags();
+        const int rb = encode_brush(e, *brush, 1.0f);
+        if (rb) return rb;
+    }
+    return rc;
+}
+
+int vb_scene_stroke(vb_scene *s, const vb_stroke *stroke, const double transform[6], const vb_brush *brush, const double *brush_transform,
+                    const vb_path *path) {
+    if (!s || !stroke || !transform || !brush || !path) return VB_E_INVALID;
+    if (stroke->width == 0.0) return VB_OK;
+    Encoding &e = s->e;
+    const Affine t = to_affine(transform);
+    int rc = VB_OK;
+    if (stroke_inner(e, *stroke, t, *path, &rc)) {
+        if (brush_transform && e.encode_transform(mul(t, to_affine(brush_transform)))) e.swap_last_path_tags();
+        const int rb = encode_brush(e, *brush, 1.0f);
+        if (rb) return rb;
+    }
+    return rc;
+}
+
+int vb_scene_push_layer(vb_scene *s, uint32_t clip_fill_rule, const vb_stroke *clip_stroke, uint32_t mix, uint32_t compose, float alpha,
+                        const double transform[6], const vb_path *clip) {
+    return push_layer_inner(s, (mix << 8) | compose, clamp01(alpha), clip_fill_rule, clip_stroke, transform, clip);
+}
+int vb_scene_push_luminance_mask_layer(vb_scene *s, uint32_t clip_fill_rule, const vb_stroke *clip_stroke, float alpha,
+                                       const double transform[6], const vb_path *clip) {
+    return push_layer_inner(s, LUMINANCE_MASK_BLEND_MODE, clamp01(alpha), clip_fill_rule, clip_stroke, transform, clip);
+}
+int vb_scene_push_clip_layer(vb_scene *s, uint32_t clip_fill_rule, const vb_stroke *clip_stroke, const double transform[6],
+                             const vb_path *clip) {
+    return push_layer_inner(s, CLIP_BLEND_MODE, 1.0f, clip_fill_rule, clip_stroke, transform, clip);
+}
+int vb_scene_pop_layer(vb_scene *s) {
+    if (!s) return VB_E_INVALID;
+    s->e.encode_end_clip();
+    return VB_OK;
+}
+
+int vb_scene_draw_image(vb_scene *s, const vb_image *image, const double transform[6]) {
+    if (!s || !image || !transform) return VB_E_INVALID;
+    Encoding &e = s->e;
+    e.encode_transform(to_affine(transform));
+    e.encode_fill_style(VB_FILL_NON_ZERO);
+    if (encode_rect(e, 0.0, 0.0, (double)image->width, (double)image->height)) {
+        vb_brush b;
+        std::memset(&b, 0, sizeof b);
+        b.kind = VB_BRUSH_IMAGE;
+        b.image = image;
+        return encode_brush(e, b, 1.0f);
+    }
+    return VB_OK;
+}
+
+int vb_scene_draw_blurred_rounded_rect(vb_scene *s, const double transform[6], const double rect[4], vb_color color, double radius,
+                                       double std_dev) {
+    if (!s || !transform || !rect) return VB_E_INVALID;
+    Encoding &e = s->e;
+    const Affine t = to_affine(transform);
+    const double k = 2.5 * std_dev; // the shape drawn is the rectangle inflated by 2.5 sigma (scene.rs:296-300)
+    e.encode_transform(t);
+    e.encode_fill_style(VB_FILL_NON_ZERO);
+    if (encode_rect(e, rect[0] - k, rect[1] - k, rect[2] + k, rect[3] + k)) {
+        const double cx = 0.5 * (rect[0] + rect[2]), cy = 0.5 * (rect[1] + rect[3]);
+        Affine tr{{1.0, 0.0, 0.0, 1.0, cx, cy}};
+        if (e.encode_transform(mul(t, tr))) e.swap_last_path_tags();
+        e.draw_tags.push_back(DRAWTAG_BLUR_RECT);
+        e.draw_data.push_back(premul_rgba8(to_color(color)));
+        e.draw_data.push_back(f32_bits((float)(rect[2] - rect[0])));
+        e.draw_data.push_back(f32_bits((float)(rect[3] - rect[1])));
+        e.draw_data.push_back(f32_bits((float)radius));
+        e.draw_data.push_back(f32_bits((float)std_dev));
+    }
+    return VB_OK;
+}
+
+int vb_scene_resolve(vb_scene *s, vb_packed *out) {
+    if (!s || !out) return VB_E_INVALID;
+    const Encoding &e = s->e;
+    std::vector<uint32_t> draw_data = e.draw_data;
+    // late-bound gradient ramps, de-duplicated by (stops, interpolation space) -- ramp_cache.rs
+    std::vector<const RampPatch *> ramp_of;
+    s->ramps.clear();
+    for (const RampPatch &p : e.ramp_patches) {
+        uint32_t rid = (uint32_t)ramp_of.size();
+        for (uint32_t k = 0; k < ramp_of.size(); k++) {
+            const RampPatch &q = *ramp_of[k];
+            bool same = q.premul == p.premul && q.stops.size() == p.stops.size();
+            for (size_t i = 0; same && i < p.stops.size(); i++) same = q.stops[i].offset == p.stops[i].offset && q.stops[i].color == p.stops[i].color;
+            if (same) { rid = k; break; }
+        }
+        if (rid == ramp_of.size()) {
+            ramp_of.push_back(&p);
+            s->ramps.resize(s->ramps.size() + N_RAMP_SAMPLES);
+            make_ramp(p.stops, p.premul, s->ramps.data() + (size_t)rid * N_RAMP_SAMPLES);
+        }
+        draw_data[p.draw_data_offset] = (rid << 2) | p.extend;
+    }
+    // late-bound images: shelf-packed atlas (placement is ours; only the (x, y) written into the draw data matters)
+    struct Placed { const uint8_t *key; uint32_t w, h, x, y; };
+    std::vector<Placed> placed;
+    uint32_t atlas_w = 1, x = 0, y = 0, shelf_h = 0;
+    const uint32_t MAXW = 2048;
+    for (const ImagePatch &p : e.image_patches) {
+        const vb_image &im = p.image;
+        const Placed *hit = nullptr;
+        for (const Placed &q : placed)
+            if (q.key == im.pixels && q.w == im.width && q.h == im.height) { hit = &q; break; }
+        uint32_t px, py;
+        if (!hit) {
+            if (x + im.width > MAXW) {
+                y += shelf_h;
+                x = 0;
+                shelf_h = 0;
+            }
+            placed.push_back(Placed{im.pixels, im.width, im.height, x, y});
+            px = x; py = y;
+            x += im.width;
+            if (im.height > shelf_h) shelf_h = im.height;
+            if (x > atlas_w) atlas_w = x;
+        } else {
+            px = hit->x; py = hit->y;
+        }
+        draw_data[p.draw_data_offset] = (px << 16) | py;
+    }
+    const uint32_t atlas_h = (y + shelf_h) > 1u ? (y + shelf_h) : 1u;
+    s->atlas.assign((size_t)atlas_w * atlas_h * 4, 0);
+    for (const Placed &q : placed)
+        for (uint32_t row = 0; row < q.h && q.key; row++)
+            std::memcpy(&s->atlas[((size_t)(q.y + row) * atlas_w + q.x) * 4], q.key + (size_t)row * q.w * 4, (size_t)q.w * 4);
+
+    // pack the six streams (resolve.rs:107-154); unclosed clips get a trailing PATH tag and END_CLIP draw tag each
+    vb_layout L;
+    std::memset(&L, 0, sizeof L);
+    L.n_paths = e.n_paths;
+    L.n_clips = e.n_clips;
+    const uint32_t n_tags = (uint32_t)e.path_tags.size() + e.n_open_clips;
+    const uint32_t padded = align_up(n_tags, 4 * PATH_REDUCE_WG);
+    const size_t total = (size_t)padded / 4 + e.path_data.size() + e.draw_tags.size() + e.n_open_clips + draw_data.size() + e.transforms.size() * 6 +
+                         e.styles.size() * 2;
+    s->packed.assign(total, 0u);
+    uint8_t *tag_bytes = reinterpret_cast<uint8_t *>(s->packed.data());
+    if (!e.path_tags.empty()) std::memcpy(tag_bytes, e.path_tags.data(), e.path_tags.size());
+    for (uint32_t i = 0; i < e.n_open_clips; i++) tag_bytes[e.path_tags.size() + i] = TAG_PATH;
+    uint32_t off = padded / 4;
+    L.path_tag_base = 0;
+    L.path_data_base = off;
+    if (!e.path_data.empty()) std::memcpy(&s->packed[off], e.path_data.data(), e.path_data.size() * 4);
+    off += (uint32_t)e.path_data.size();
+    L.draw_tag_base = off;
+    uint32_t info = 0;
+    for (uint32_t t : e.draw_tags) {
+        s->packed[off++] = t;
+        info += (t >> 6) & 0xFu;
+    }
+    for (uint32_t i = 0; i < e.n_open_clips; i++) s->packed[off++] = DRAWTAG_END_CLIP;
+    L.bin_data_start = info;
+    L.draw_data_base = off;
+    if (!draw_data.empty()) std::memcpy(&s->packed[off], draw_data.data(), draw_data.size() * 4);
+    off += (uint32_t)draw_data.size();
+    L.transform_base = off;
+    for (const Xform &t : e.transforms)
+        for (int i = 0; i < 6; i++) s->packed[off++] = f32_bits(t.c[i]);
+    L.style_base = off;
+    for (const Style &st : e.styles) {
+        s->packed[off++] = st.flags;
+        s->packed[off++] = f32_bits(st.width);
+    }
+    L.n_draw_objects = L.n_paths;
+    out->scene = reinterpret_cast<const uint8_t *>(s->packed.data());
+    out->scene_len = s->packed.size() * 4;
+    out->layout = L;
+    out->ramps = s->ramps.empty() ? nullptr : s->ramps.data();
+    out->ramp_w = N_RAMP_SAMPLES;
+    out->ramp_h = (uint32_t)(s->ramps.size() / N_RAMP_SAMPLES);
+    out->atlas = s->atlas.data();
+    out->atlas_w = atlas_w;
+    out->atlas_h = atlas_h;
+    return VB_OK;
+}
+
+int vb_render_scene(vb_renderer *r, vb_scene *s, const vb_params *p, void *out, uint32_t out_is_device, vb_frame_stats *stats) {
+    vb_packed pk;
+    const int rc = vb_scene_resolve(s, &pk);
+    if (rc) return rc;
+    return vb_render(r, pk.scene, pk.scene_len, &pk.layout, pk.ramps, pk.ramp_w, pk.ramp_h, pk.atlas, pk.atlas_w, pk.atlas_h, p, out,
+                     out_is_device, stats);
+}
+
+} // extern "C"

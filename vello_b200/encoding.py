@@ -768,7 +768,7 @@ def resolve(enc: Encoding) -> Packed:
     placed = {}
     for p in enc.image_patches:
         im = p["image"]
-        k = id(im)
+        k = id(im.data)  # the image cache is keyed by the pixel blob's identity (image_cache.rs:113-114), not by the brush
         if k not in placed:
             if x + im.width > MAXW:
                 y += shelf_h

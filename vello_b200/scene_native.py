@@ -1,0 +1,215 @@
+"""ctypes binding of the native scene front end (include/vello_b200_scene.h, vello_b200/csrc/vb_scene.cpp).
+
+`NativeScene` has the call surface of `vello_b200.encoding.Scene` (= `vello::Scene`, vello/src/scene.rs) and takes the same
+Python value objects; every call goes straight into libvello_b200.so. `resolve()` returns the same `Packed` the Python
+encoder produces -- byte for byte, which tests/test_scene_native.py asserts on every test scene."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import shapes as _shapes
+from .encoding import Color, Gradient, Image, Layout, Packed, Stroke
+from .renderer import _Layout, load_library
+from .shapes import Affine
+
+
+class _Path(C.Structure):
+    _fields_ = [("verbs", C.c_void_p), ("n_verbs", C.c_uint32), ("coords", C.c_void_p)]
+
+
+class _Color(C.Structure):
+    _fields_ = [("r", C.c_float), ("g", C.c_float), ("b", C.c_float), ("a", C.c_float)]
+
+
+class _Stop(C.Structure):
+    _fields_ = [("offset", C.c_float), ("color", _Color)]
+
+
+class _Image(C.Structure):
+    _fields_ = [("pixels", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32), ("format", C.c_uint32), ("alpha_type", C.c_uint32),
+                ("quality", C.c_uint32), ("x_extend", C.c_uint32), ("y_extend", C.c_uint32), ("alpha", C.c_float)]
+
+
+class _Brush(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("color", _Color), ("geom", C.c_double * 6), ("stops", C.c_void_p), ("n_stops", C.c_uint32),
+                ("extend", C.c_uint32), ("premul_interp", C.c_uint32), ("image", C.c_void_p)]
+
+
+class _Stroke(C.Structure):
+    _fields_ = [("width", C.c_double), ("join", C.c_uint32), ("start_cap", C.c_uint32), ("end_cap", C.c_uint32), ("miter_limit", C.c_double)]
+
+
+class _Packed(C.Structure):
+    _fields_ = [("scene", C.c_void_p), ("scene_len", C.c_size_t), ("layout", _Layout), ("ramps", C.c_void_p), ("ramp_w", C.c_uint32),
+                ("ramp_h", C.c_uint32), ("atlas", C.c_void_p), ("atlas_w", C.c_uint32), ("atlas_h", C.c_uint32)]
+
+
+SCENE_SYMBOLS = ["vb_scene_new", "vb_scene_free", "vb_scene_reset", "vb_scene_fill", "vb_scene_stroke", "vb_scene_push_layer",
+                 "vb_scene_push_luminance_mask_layer", "vb_scene_push_clip_layer", "vb_scene_pop_layer", "vb_scene_draw_image",
+                 "vb_scene_draw_blurred_rounded_rect", "vb_scene_resolve", "vb_render_scene"]
+
+_bound = False
+
+
+def _lib():
+    global _bound
+    lib = load_library()
+    if not _bound:
+        vp = C.c_void_p
+        lib.vb_scene_new.restype = vp
+        lib.vb_scene_free.argtypes = [vp]
+        lib.vb_scene_reset.argtypes = [vp]
+        lib.vb_scene_fill.argtypes = [vp, C.c_uint32, vp, vp, vp, vp]
+        lib.vb_scene_stroke.argtypes = [vp, vp, vp, vp, vp, vp]
+        lib.vb_scene_push_layer.argtypes = [vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, C.c_float, vp, vp]
+        lib.vb_scene_push_luminance_mask_layer.argtypes = [vp, C.c_uint32, vp, C.c_float, vp, vp]
+        lib.vb_scene_push_clip_layer.argtypes = [vp, C.c_uint32, vp, vp, vp]
+        lib.vb_scene_pop_layer.argtypes = [vp]
+        lib.vb_scene_draw_image.argtypes = [vp, vp, vp]
+        lib.vb_scene_draw_blurred_rounded_rect.argtypes = [vp, vp, vp, _Color, C.c_double, C.c_double]
+        lib.vb_scene_resolve.argtypes = [vp, vp]
+        lib.vb_render_scene.argtypes = [vp, vp, vp, vp, C.c_uint32, vp]
+        _bound = True
+    return lib
+
+
+def _affine(t: Affine):
+    return (C.c_double * 6)(*[float(v) for v in t.coeffs])
+
+
+_VERB = {"M": ord("M"), "L": ord("L"), "Q": ord("Q"), "C": ord("C"), "Z": ord("Z")}
+
+
+class NativeScene:
+    def __init__(self):
+        self.lib = _lib()
+        self.handle = C.c_void_p(self.lib.vb_scene_new())
+        self._keep = []  # buffers the C side refers to until resolve (image pixels)
+        self._images = {}
+        self._pixels = {}
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            self.lib.vb_scene_free(self.handle)
+            self.handle = None
+
+    # -- marshalling ---------------------------------------------------------------------------------
+    def _path(self, shape, tolerance: float):
+        els = list(_shapes.path_elements(shape, tolerance))
+        verbs = np.array([_VERB[e[0]] for e in els], dtype=np.uint8)
+        coords = np.array([v for e in els for v in e[1:]], dtype=np.float64)
+        p = _Path(verbs.ctypes.data, len(verbs), coords.ctypes.data)
+        return p, (verbs, coords)
+
+    @staticmethod
+    def _color(c: Color) -> _Color:
+        return _Color(c.r, c.g, c.b, c.a)
+
+    def _image(self, im: Image) -> _Image:
+        k = id(im)
+        if k not in self._images:
+            dk = id(im.data)  # one pixel buffer per blob: the atlas is keyed by it (image_cache.rs:113-114)
+            if dk not in self._pixels:
+                self._pixels[dk] = np.ascontiguousarray(im.data, dtype=np.uint8).copy()
+            px = self._pixels[dk]
+            self._images[k] = _Image(px.ctypes.data, im.width, im.height, im.format, im.alpha_type, im.quality, im.x_extend, im.y_extend, im.alpha)
+        return self._images[k]
+
+    def _brush(self, brush):
+        b = _Brush()
+        hold = []
+        if isinstance(brush, Color):
+            b.kind = 0
+            b.color = self._color(brush)
+        elif isinstance(brush, Gradient):
+            b.kind = {"linear": 1, "radial": 2, "sweep": 3}[brush.kind]
+            for i, v in enumerate(brush.params):
+                b.geom[i] = float(v)
+            stops = (_Stop * max(len(brush.stops), 1))()
+            for i, (o, c) in enumerate(brush.stops):
+                stops[i] = _Stop(o, self._color(c))
+            hold.append(stops)
+            b.stops = C.cast(stops, C.c_void_p)
+            b.n_stops = len(brush.stops)
+            b.extend = brush.extend
+            b.premul_interp = 1 if brush.premul_interp else 0
+        elif isinstance(brush, Image):
+            b.kind = 4
+            img = self._image(brush)
+            hold.append(img)
+            b.image = C.cast(C.pointer(img), C.c_void_p)
+        else:
+            raise TypeError(type(brush))
+        return b, hold
+
+    @staticmethod
+    def _stroke(s: Stroke) -> _Stroke:
+        return _Stroke(float(s.width), s.join, s.start_cap, s.end_cap, float(s.miter_limit))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise ValueError(f"vb_scene call failed: {rc}")
+
+    # -- vello::Scene surface ------------------------------------------------------------------------
+    def fill(self, style: int, transform: Affine, brush, brush_transform: Optional[Affine], shape):
+        p, hold = self._path(shape, 0.1)
+        b, hb = self._brush(brush)
+        bt = _affine(brush_transform) if brush_transform is not None else None
+        self._check(self.lib.vb_scene_fill(self.handle, style, _affine(transform), C.byref(b), bt, C.byref(p)))
+
+    def stroke(self, stroke: Stroke, transform: Affine, brush, brush_transform: Optional[Affine], shape):
+        p, hold = self._path(shape, 0.01)
+        b, hb = self._brush(brush)
+        st = self._stroke(stroke)
+        bt = _affine(brush_transform) if brush_transform is not None else None
+        self._check(self.lib.vb_scene_stroke(self.handle, C.byref(st), _affine(transform), C.byref(b), bt, C.byref(p)))
+
+    def _clip_args(self, clip_style, clip):
+        if isinstance(clip_style, Stroke):
+            st = self._stroke(clip_style)
+            p, hold = self._path(clip, 0.01)
+            return 0, C.byref(st), p, (st, hold)
+        p, hold = self._path(clip, 0.1)
+        return int(clip_style), None, p, hold
+
+    def push_layer(self, clip_style, mix: int, compose: int, alpha: float, transform: Affine, clip):
+        rule, st, p, hold = self._clip_args(clip_style, clip)
+        self._check(self.lib.vb_scene_push_layer(self.handle, rule, st, mix, compose, alpha, _affine(transform), C.byref(p)))
+
+    def push_luminance_mask_layer(self, clip_style, alpha: float, transform: Affine, clip):
+        rule, st, p, hold = self._clip_args(clip_style, clip)
+        self._check(self.lib.vb_scene_push_luminance_mask_layer(self.handle, rule, st, alpha, _affine(transform), C.byref(p)))
+
+    def push_clip_layer(self, clip_style, transform: Affine, clip):
+        rule, st, p, hold = self._clip_args(clip_style, clip)
+        self._check(self.lib.vb_scene_push_clip_layer(self.handle, rule, st, _affine(transform), C.byref(p)))
+
+    def pop_layer(self):
+        self._check(self.lib.vb_scene_pop_layer(self.handle))
+
+    def draw_image(self, image: Image, transform: Affine):
+        img = self._image(image)
+        self._check(self.lib.vb_scene_draw_image(self.handle, C.byref(img), _affine(transform)))
+
+    def draw_blurred_rounded_rect(self, transform: Affine, rect, color: Color, radius: float, std_dev: float):
+        r = (C.c_double * 4)(rect.x0, rect.y0, rect.x1, rect.y1)
+        self._check(self.lib.vb_scene_draw_blurred_rounded_rect(self.handle, _affine(transform), r, self._color(color), float(radius), float(std_dev)))
+
+    # -- Resolver::resolve ---------------------------------------------------------------------------
+    def resolve(self) -> Packed:
+        pk = _Packed()
+        self._check(self.lib.vb_scene_resolve(self.handle, C.byref(pk)))
+        n_words = pk.scene_len // 4
+        scene = np.ctypeslib.as_array(C.cast(pk.scene, C.POINTER(C.c_uint32)), shape=(n_words,)).copy() if n_words else np.zeros(0, np.uint32)
+        if pk.ramp_h:
+            ramps = np.ctypeslib.as_array(C.cast(pk.ramps, C.POINTER(C.c_uint32)), shape=(pk.ramp_h, pk.ramp_w)).copy()
+        else:
+            ramps = np.zeros((0, 512), dtype=np.uint32)
+        atlas = np.ctypeslib.as_array(C.cast(pk.atlas, C.POINTER(C.c_uint8)), shape=(pk.atlas_h, pk.atlas_w, 4)).copy()
+        L = pk.layout
+        layout = Layout(L.n_draw_objects, L.n_paths, L.n_clips, L.bin_data_start, L.path_tag_base, L.path_data_base, L.draw_tag_base,
+                        L.draw_data_base, L.transform_base, L.style_base)
+        return Packed(scene=scene, layout=layout, ramps=ramps, atlas=atlas)
