@@ -12,7 +12,9 @@
 // Per-tile slot order (seg_within_slice) is atomic-order dependent exactly as in the reference.
 #include "vb_device.cuh"
 
+#ifndef PC_THREADS
 #define PC_THREADS 256
+#endif
 #define ONE_MINUS_ULP 0.99999994f
 #define ROBUST_EPSILON 2e-7f
 #define TILE_SCALE 0.0625f
