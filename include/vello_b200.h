@@ -120,6 +120,10 @@ int vb_readback_wait(vb_renderer *);
 /* vb_render with a host destination launches fine in `n` bands of tile rows (1..8, default 8) and copies each band back
  * while the next one rasterises. Tuning knob; vb_render_begin always uses one band. */
 int vb_set_readback_bands(vb_renderer *, uint32_t n);
+/* Whole frames are replayed as CUDA graphs (one submission instead of ~20 launches; captured again whenever an arena,
+ * the scene layout, the frame size or the window changes). On by default; 0 launches every kernel individually.
+ * Environment: VELLO_B200_NO_GRAPH=1 disables it at renderer creation. */
+int vb_set_cuda_graph(vb_renderer *, int on);
 
 /* The renderer-owned target of the last frame (device pointer) and its size in bytes. */
 void *vb_target(vb_renderer *, size_t *bytes);

@@ -384,3 +384,30 @@ def test_native_scene_to_pixels(renderer, oracle):
         assert rc == 0
         assert np.array_equal(got, want)
         assert_pixels(got, oracle.render(packed, w, h, p.base_color.premul_rgba8_u32(), aa), aa)
+
+
+def test_cuda_graph_replay_is_invisible(oracle):
+    """Whole frames are replayed as CUDA graphs, re-captured when anything a launch depends on changes. Alternating
+    scenes, frame sizes, AA modes, stripes and host/device destinations must give the frames plain launches give."""
+    from vello_b200.renderer import Renderer
+    rg, rd = Renderer(), Renderer()
+    rd.set_cuda_graph(False)
+    a = resolve(scenes.paris_like(800, 512, seed=5).encoding)
+    b = resolve(scenes.stroke_styles()[0].encoding)
+    plan = [(a, 512, 512, AA_MSAA16, (0, 0)), (a, 512, 512, AA_MSAA16, (0, 0)), (b, 560, 480, AA_AREA, (0, 0)), (a, 512, 512, AA_MSAA16, (0, 0)),
+            (a, 512, 512, AA_MSAA8, (0, 0)), (a, 512, 512, AA_MSAA16, (1, 2)), (b, 300, 200, AA_MSAA16, (0, 0)), (a, 512, 512, AA_MSAA16, (0, 0))]
+    for packed, w, h, aa, rows in plan:
+        p = RenderParams(BLACK, w, h, aa)
+        g = rg.render_to_texture(packed, p, bin_rows=rows)
+        d = rd.render_to_texture(packed, p, bin_rows=rows)
+        assert np.array_equal(g, d)
+        rg.upload(packed)
+        rd.upload(packed)
+        for _ in range(3):  # resident replays of the cached graph
+            rg.render_resident(p, 0, rows)
+        rd.render_resident(p, 0, rows)
+        assert np.array_equal(rg.download_target(p, rows), rd.download_target(p, rows))
+    full = oracle.render(a, 512, 512, BLACK.premul_rgba8_u32(), AA_MSAA16)
+    assert np.array_equal(rg.render_to_texture(a, RenderParams(BLACK, 512, 512, AA_MSAA16)), full)
+    rg.close()
+    rd.close()

@@ -46,8 +46,11 @@ print("upload (H2D %.1f MB)      %.3f ms" % (scene_h.numel() * 4 / 1e6, T(upload
 print("render_resident           %.3f ms" % T(resident), " device total_ms %.3f" % fs.total_ms)
 print("read-back 64 MiB          %.3f ms" % T(readback))
 print("vb_render (blocking)      %.3f ms" % T(blocking), " device total_ms %.3f" % fs.total_ms, {k2: round(v, 3) for k2, v in fs.as_dict()["stage_ms"].items() if k2 in ("fine", "flatten")})
-for nb in (1, 2, 4, 8):
+for nb in (8,):
     r.lib.vb_set_readback_bands(r.handle, nb)
     print("vb_render, %d band(s)      %.3f ms" % (nb, T(blocking)), " device total_ms %.3f fine %.3f" % (fs.total_ms, fs.as_dict()["stage_ms"]["fine"]))
 print("vb_render_begin (stream)  %.3f ms" % T(streaming), " device total_ms %.3f" % fs.total_ms)
+print("   streamed stage_ms", {k2: round(v, 3) for k2, v in fs.as_dict()["stage_ms"].items()})
+resident()
+print("   resident stage_ms", {k2: round(v, 3) for k2, v in fs.as_dict()["stage_ms"].items()})
 r.lib.vb_readback_wait(r.handle)

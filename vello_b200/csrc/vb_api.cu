@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -97,6 +98,19 @@ struct DevBuf {
     size_t cap = 0; // bytes
 };
 
+// key of a captured frame: everything a launch argument is derived from (see enqueue)
+struct GraphKey {
+    VbConfig cfg;
+    const void *ptrs[32];
+    uint64_t ctl_words;
+    uint32_t aa, cull, last;
+};
+struct GraphSlot {
+    GraphKey key;
+    cudaGraphExec_t exec = nullptr;
+    uint32_t launches = 0;
+};
+
 struct vb_renderer {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -127,6 +141,9 @@ struct vb_renderer {
     VbBump *h_bump_dev = nullptr; // device-side address of h_bump
     uint32_t retries = 0, launches = 0;
     size_t ctl_words = 0;
+    bool use_graph = true;        // replay whole frames as CUDA graphs (see enqueue)
+    GraphSlot graphs[4];
+    uint32_t graph_next = 0;
     uint32_t readback_bands = 8; // fine launches per frame when the pixels go to the host (vb_render); 1 while streaming
     uint32_t occlusion_cull = 1; // fine starts each tile at its last opaque full-tile cover
     uint32_t parts_pathtag = 0, parts_flatten = 0, parts_draw = 0, parts_tile = 0;
@@ -225,6 +242,7 @@ extern "C" int vb_renderer_new(const vb_options *opt, vb_renderer **out) {
     for (auto &ev : r->ev) cudaEventCreate(&ev);
     for (auto &ev : r->band_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (auto &ev : r->copy_done) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (getenv("VELLO_B200_NO_GRAPH")) r->use_graph = false;
     if (cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete r;
         return VB_E_CUDA;
@@ -260,6 +278,8 @@ extern "C" void vb_renderer_free(vb_renderer *r) {
         for (auto &ev : r->ev) cudaEventDestroy(ev);
         for (auto &ev : r->band_ev) cudaEventDestroy(ev);
         for (auto &ev : r->copy_done) cudaEventDestroy(ev);
+        for (auto &gs : r->graphs)
+            if (gs.exec) cudaGraphExecDestroy(gs.exec);
     }
     if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
     if (r->stream) cudaStreamDestroy(r->stream);
@@ -421,7 +441,7 @@ static void rec(vb_renderer *r, int i) {
 }
 
 // Enqueue stages first..last. Does not synchronise.
-static int enqueue(vb_renderer *r, int first, int last, void *out_dev) {
+static int enqueue_direct(vb_renderer *r, int first, int last, void *out_dev) {
     const VbConfig &c = r->cfg;
     cudaStream_t st = r->stream;
     uint32_t *ctl = (uint32_t *)r->ctl.p;
@@ -534,6 +554,92 @@ static int enqueue(vb_renderer *r, int first, int last, void *out_dev) {
     launches++;
     CK(cudaGetLastError());
     r->launches = launches;
+    return VB_OK;
+}
+
+// ---- whole-frame CUDA graphs ---------------------------------------------------------------------------------------------
+// A frame is ~20 kernel launches. Each launch makes the GPU fetch a command buffer from host memory over PCIe; while a
+// 64 MiB read-back of the previous frame is streaming the other way that fetch queues behind it (measured with
+// tools/e2e_probe.py: every stage of a streamed frame started ~10 us late per launch, +0.3 ms per frame). In steady state
+// the launches of a frame are identical -- same kernels, grids, arena pointers, config -- so they are captured once into a
+// graph and replayed with ONE submission. The key is everything a launch argument is derived from; growing an arena or
+// changing the scene layout / frame size / window simply misses the cache and re-captures.
+static void graph_key(const vb_renderer *r, int last, const void *out_dev, GraphKey *k) {
+    memset(k, 0, sizeof *k);
+    k->cfg = r->cfg;
+    const DevBuf *bufs[] = {&r->scene, &r->ramps, &r->atlas, &r->mask8, &r->mask16, &r->tag_monoids, &r->path_bboxes, &r->draw_monoids,
+                            &r->info_bin_data, &r->clip_inp, &r->clip_bboxes, &r->clip_scratch, &r->draw_bboxes, &r->bin_headers, &r->paths,
+                            &r->ctl, &r->tile_start, &r->lines, &r->line_scratch, &r->flatten_jobs, &r->flatten_parts, &r->tiles,
+                            &r->seg_counts, &r->segments, &r->ptcl, &r->blend_spill};
+    size_t n = 0;
+    for (const DevBuf *b : bufs) k->ptrs[n++] = b->p;
+    k->ptrs[n++] = out_dev;
+    k->ptrs[n++] = r->h_bump_dev;
+    k->ctl_words = r->ctl_words;
+    k->aa = r->params.aa;
+    k->cull = r->occlusion_cull;
+    k->last = (uint32_t)last;
+}
+
+static void queue_readback(vb_renderer *r, const VbConfig &c, uint32_t ty0, uint32_t ty1, void *out_dev, uint32_t band) {
+    size_t y0 = (size_t)ty0 * 16u, y1 = (size_t)ty1 * 16u;
+    if (y1 > c.target_height) y1 = c.target_height;
+    if (y1 <= y0) return;
+    const size_t off = (y0 - c.out_row0) * c.out_pitch_px * 4u, bytes = (y1 - y0) * c.out_pitch_px * 4u;
+    cudaEventRecord(r->band_ev[band], r->stream);
+    cudaStreamWaitEvent(r->copy_stream, r->band_ev[band], 0);
+    cudaMemcpyAsync((char *)r->host_out + off, (const char *)out_dev + off, bytes, cudaMemcpyDeviceToHost, r->copy_stream);
+}
+
+// Enqueue stages first..last: through a cached graph for whole frames, directly otherwise.
+static int enqueue(vb_renderer *r, int first, int last, void *out_dev) {
+    const VbConfig &c = r->cfg;
+    if (!r->use_graph || r->timing || first != 0 || last != VB_N_STAGE_IDS - 1) return enqueue_direct(r, first, last, out_dev);
+    // with a host destination split into bands, fine and its interleaved copies stay outside the graph
+    const uint32_t rows = c.win_ty1 - c.win_ty0;
+    const bool banded = r->host_out && rows >= 64u && r->readback_bands > 1u;
+    const int g_last = banded ? VB_STAGE_ID_FINE - 1 : last;
+    GraphKey key;
+    graph_key(r, g_last, out_dev, &key);
+    GraphSlot *slot = nullptr;
+    for (GraphSlot &gs : r->graphs)
+        if (gs.exec && memcmp(&gs.key, &key, sizeof key) == 0) slot = &gs;
+    void *host_out = r->host_out;
+    if (!slot) {
+        slot = &r->graphs[r->graph_next++ % (sizeof r->graphs / sizeof r->graphs[0])];
+        if (slot->exec) {
+            cudaGraphExecDestroy(slot->exec);
+            slot->exec = nullptr;
+        }
+        r->host_out = nullptr; // the captured fine is one launch; its read-back is queued after the graph, below
+        CK(cudaStreamBeginCapture(r->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue_direct(r, 0, g_last, out_dev);
+        cudaGraph_t g = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(r->stream, &g);
+        r->host_out = host_out;
+        if (rc != VB_OK || e != cudaSuccess) {
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            return enqueue_direct(r, first, last, out_dev); // capture refused (e.g. a profiler): plain launches
+        }
+        const cudaError_t ei = cudaGraphInstantiate(&slot->exec, g, 0);
+        cudaGraphDestroy(g);
+        if (ei != cudaSuccess) {
+            slot->exec = nullptr;
+            cudaGetLastError();
+            return enqueue_direct(r, first, last, out_dev);
+        }
+        slot->key = key;
+        slot->launches = r->launches;
+    }
+    CK(cudaGraphLaunch(slot->exec, r->stream));
+    r->launches = slot->launches;
+    if (banded) {
+        const int rc = enqueue_direct(r, VB_STAGE_ID_FINE, VB_STAGE_ID_FINE, out_dev);
+        r->launches += slot->launches;
+        return rc;
+    }
+    if (host_out) queue_readback(r, c, c.win_ty0, c.win_ty1, out_dev, 0);
     return VB_OK;
 }
 
@@ -754,6 +860,12 @@ extern "C" int vb_debug_download(vb_renderer *r, const char *name, void *dst, si
             return VB_OK;
         }
     return VB_E_UNKNOWN_BUFFER;
+}
+
+extern "C" int vb_set_cuda_graph(vb_renderer *r, int on) {
+    if (!r) return VB_E_INVALID;
+    r->use_graph = on != 0;
+    return VB_OK;
 }
 
 extern "C" int vb_set_readback_bands(vb_renderer *r, uint32_t n) {

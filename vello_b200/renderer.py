@@ -84,6 +84,7 @@ def load_library() -> C.CDLL:
                                     C.POINTER(_Params), vp, C.POINTER(FrameStats)]
     lib.vb_readback_wait.argtypes = [vp]
     lib.vb_set_readback_bands.argtypes = [vp, C.c_uint32]
+    lib.vb_set_cuda_graph.argtypes = [vp, C.c_int]
     lib.vb_target.restype = vp
     lib.vb_target.argtypes = [vp, C.POINTER(C.c_size_t)]
     lib.vb_copy_to_host.argtypes = [vp, vp, vp, C.c_size_t]
@@ -100,7 +101,7 @@ def load_library() -> C.CDLL:
 
 EXPORTED_SYMBOLS = ["vb_renderer_new", "vb_renderer_free", "vb_strerror", "vb_last_error", "vb_scene_upload",
                     "vb_render_resident", "vb_render_enqueue", "vb_frame_finish", "vb_render", "vb_target", "vb_copy_to_host", "vb_stream",
-                    "vb_run_stages", "vb_debug_download", "vb_debug_upload", "vb_debug_fine_traffic", "vb_set_occlusion_cull", "vb_render_begin", "vb_readback_wait", "vb_set_readback_bands"]
+                    "vb_run_stages", "vb_debug_download", "vb_debug_upload", "vb_debug_fine_traffic", "vb_set_occlusion_cull", "vb_render_begin", "vb_readback_wait", "vb_set_readback_bands", "vb_set_cuda_graph"]
 
 
 @dataclass
@@ -257,6 +258,10 @@ class Renderer:
     def upload_buffer(self, name: str, arr: np.ndarray):
         a = np.ascontiguousarray(arr)
         self._check(self.lib.vb_debug_upload(self.handle, name.encode(), a.ctypes.data, a.nbytes), f"upload {name}")
+
+    def set_cuda_graph(self, on: bool):
+        """Replay whole frames as CUDA graphs (default on)."""
+        self._check(self.lib.vb_set_cuda_graph(self.handle, 1 if on else 0), "vb_set_cuda_graph")
 
     def set_occlusion_cull(self, on: bool):
         """fine skips the commands under a tile's last opaque full-tile cover (identical pixels). Default on."""
