@@ -937,6 +937,7 @@ k_flatten(VbConfig cfg, const uint32_t *__restrict__ scene, const VbTagMonoid *_
 // B: exclusive scan of part_count -> destination offsets; publishes bump.lines. One CTA, 8 values per thread per pass.
 #define FS_THREADS 1024
 #define FS_PER_THREAD 8
+static_assert(FS_PER_THREAD == 8, "k_flatten_scan is written for 8 values per thread");
 __global__ void __launch_bounds__(FS_THREADS)
 k_flatten_scan(VbConfig cfg, uint32_t n_parts, const uint32_t *__restrict__ part_count, uint32_t *part_dst, VbBump *bump) {
     __shared__ uint32_t sh_scan[FS_THREADS / 32 + 2];
@@ -944,17 +945,30 @@ k_flatten_scan(VbConfig cfg, uint32_t n_parts, const uint32_t *__restrict__ part
     for (uint32_t base = 0u; base < n_parts; base += FS_THREADS * FS_PER_THREAD) {
         const uint32_t i0 = base + threadIdx.x * FS_PER_THREAD;
         uint32_t v[FS_PER_THREAD], sum = 0u;
+        if (i0 + FS_PER_THREAD <= n_parts) { // two 128-bit loads (the arrays are 16-byte aligned, i0 is a multiple of 8):
+            const uint4 a = *reinterpret_cast<const uint4 *>(part_count + i0); // one CTA issuing 8 scalar loads per thread
+            const uint4 b = *reinterpret_cast<const uint4 *>(part_count + i0 + 4); // stalls on its own LSU queue (lg_throttle)
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
 #pragma unroll
-        for (int k = 0; k < FS_PER_THREAD; k++) {
-            v[k] = i0 + k < n_parts ? part_count[i0 + k] : 0u;
-            sum += v[k];
+            for (int k = 0; k < FS_PER_THREAD; k++) v[k] = i0 + k < n_parts ? part_count[i0 + k] : 0u;
         }
+#pragma unroll
+        for (int k = 0; k < FS_PER_THREAD; k++) sum += v[k];
         uint32_t total;
         uint32_t run = carry + vb_block_excl_scan(sum, sh_scan, &total);
+        if (i0 + FS_PER_THREAD <= n_parts) {
+            uint4 a, b;
+            a.x = run; a.y = a.x + v[0]; a.z = a.y + v[1]; a.w = a.z + v[2];
+            b.x = a.w + v[3]; b.y = b.x + v[4]; b.z = b.y + v[5]; b.w = b.z + v[6];
+            *reinterpret_cast<uint4 *>(part_dst + i0) = a;
+            *reinterpret_cast<uint4 *>(part_dst + i0 + 4) = b;
+        } else {
 #pragma unroll
-        for (int k = 0; k < FS_PER_THREAD; k++) {
-            if (i0 + k < n_parts) part_dst[i0 + k] = run;
-            run += v[k];
+            for (int k = 0; k < FS_PER_THREAD; k++) {
+                if (i0 + k < n_parts) part_dst[i0 + k] = run;
+                run += v[k];
+            }
         }
         carry += total;
     }
@@ -1084,11 +1098,12 @@ k_flatten_place(VbConfig cfg, const uint32_t *__restrict__ scene, FlCtx ctx, con
 
 extern "C" void vb_launch_flatten(const VbConfig *cfg, const uint32_t *scene, const VbTagMonoid *tag_monoids,
                                   VbPathBbox *path_bboxes, VbBump *bump, VbLineSoup *lines, void *lit_arena, void *job_arena,
-                                  uint32_t *part_mem /* 34 * n_parts */, uint32_t *ctrs, uint32_t n_parts, cudaStream_t st) {
+                                  uint32_t *part_mem /* 34 * n_parts + 8 words */, uint32_t *ctrs, uint32_t n_parts, cudaStream_t st) {
     uint32_t n_paths = cfg->layout.n_paths;
     if (n_paths) k_bbox_clear<<<(n_paths + 255) / 256, 256, 0, st>>>(n_paths, path_bboxes);
     if (n_parts) {
-        uint32_t *part_count = part_mem, *part_dst = part_mem + n_parts, *tag_off = part_mem + 2 * (size_t)n_parts;
+        const size_t np4 = ((size_t)n_parts + 3u) & ~(size_t)3u; // 16-byte aligned sub-arrays (k_flatten_scan uses 128-bit accesses)
+        uint32_t *part_count = part_mem, *part_dst = part_mem + np4, *tag_off = part_mem + 2 * np4;
         FlCtx ctx;
         ctx.lits = (FlLit *)lit_arena;
         ctx.jobs = (FlJob *)job_arena;

@@ -432,7 +432,7 @@ static int prepare(vb_renderer *r, const vb_params *p) {
     r->off_lb_tile = off; off += vb_lookback_words(r->parts_tile, 1);
     r->ctl_words = off;
     if ((rc = ensure(r, r->ctl, off * 4))) return rc;
-    if ((rc = ensure(r, r->flatten_parts, (size_t)r->parts_flatten * 34 * 4))) return rc;
+    if ((rc = ensure(r, r->flatten_parts, ((size_t)r->parts_flatten * 34 + 8) * 4))) return rc;
     return VB_OK;
 }
 
