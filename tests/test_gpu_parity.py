@@ -411,3 +411,27 @@ def test_cuda_graph_replay_is_invisible(oracle):
     assert np.array_equal(rg.render_to_texture(a, RenderParams(BLACK, 512, 512, AA_MSAA16)), full)
     rg.close()
     rd.close()
+
+
+@pytest.mark.parametrize("workload", ["paris-30k", "beziers-100k-clips-1k"])
+def test_full_size_properties(workload):
+    """BASELINE.json configs 2 and 4 at their full size (4096x4096 MSAA16; the oracle would need minutes per frame):
+    size-independent properties instead -- bin-row stripes reproduce the rows of the full frame bit for bit (so does a
+    second run), the occlusion start and graph replay are invisible, no arena failure is left behind."""
+    from vello_b200.renderer import Renderer
+    if workload == "paris-30k":
+        packed = resolve(scenes.paris_like(30000, 4096, seed=30000).encoding)
+    else:
+        packed = resolve(scenes.beziers_clips(100000, 1000, 4096, seed=100000).encoding)
+    p = RenderParams(BLACK, 4096, 4096, AA_MSAA16)
+    r = Renderer()
+    full = r.render_to_texture(packed, p)
+    assert r.last_stats.as_dict()["failed"] == 0
+    assert np.array_equal(r.render_to_texture(packed, p), full)  # run-to-run: integer sample counts, no order dependence
+    for b in (0, 7, 15):
+        assert np.array_equal(r.render_to_texture(packed, p, bin_rows=(b, b + 1)), full[b * 256:(b + 1) * 256]), b
+    r.set_occlusion_cull(False)
+    r.set_cuda_graph(False)
+    assert np.array_equal(r.render_to_texture(packed, p, bin_rows=(4, 8)), full[1024:2048])
+    assert full[..., 3].min() == 255 and len(np.unique(np.ascontiguousarray(full).view(np.uint32))) > 1000
+    r.close()
