@@ -13,6 +13,7 @@
 // CLEAN between fills: a 256-bit `touched` bitmap records which pixels received sample masks, the
 // resolve reads and re-clears only those, and untouched pixels resolve to 0 or 1 from the winding
 // words alone. The integer arithmetic per touched pixel is the WGSL's, word for word.
+// Each tile starts at its occlusion start (the last opaque full-tile cover, noted by coarse): see "Occlusion start" below.
 // Conventions fixed where WGSL leaves latitude: see oracle/vbo_fine.c.
 // Algorithmic bytes: 4 B/pixel stored + 4 B per PTCL word + 24 B per segment referenced.
 #include <cuda_fp16.h>

@@ -4,12 +4,14 @@
 // caps :521-545, joins :547-631, segment decode :683-766, main :831-923) and its CPU twin
 // vello_shaders/src/cpu/{flatten,euler}.rs. Also folds in bbox_clear.wgsl.
 //
-// B200 design (differs from the WGSL on purpose):
-//  * The WGSL bump-allocates every line with a global atomicAdd, so the line order is a race.
-//    Here each thread first COUNTS the lines of its tag, the CTA scans the counts with warp
-//    shuffles, resolves its base by decoupled look-back over CTAs, and then EMITS: line order is
-//    deterministic (tag order, then emission order), identical to the serial CPU shader, and there
-//    is no per-line atomic. Consecutive threads write consecutive 24 B records.
+// B200 design (differs from the WGSL on purpose; the pieces are described where they are defined below):
+//  * The WGSL bump-allocates every line with a global atomicAdd, so the line order is a race. Here line order is
+//    deterministic -- tag order, then emission order, i.e. the serial CPU shader's -- and independent of any atomic:
+//    k_flatten (thread per TAG) emits literal-line and job records plus per-warp counts, k_flatten_scan turns the counts
+//    into offsets, k_flatten_place (thread per LINE) writes every line at its final position.
+//  * Fast paths for line-tos (filled: one line; stroked: one line per side) behind guards that are derived in place,
+//    property-tested on the CPU against the oracle and compared bit for bit on the GPU.
+//  * With a stripe window set (multi-GPU), tags that cannot reach the window's rows are skipped.
 //  * Transcendentals come from vb_detmath.h (IEEE-only) and the TU is compiled with -fmad=false,
 //    so `lines` is bit-identical to the oracle's, and so is everything downstream.
 // Algorithmic bytes: 1 B tag + 20/4 B monoid + <= 32 B coords per segment, 24 B per line out.

@@ -7,7 +7,8 @@
 //
 // B200 design: one thread per line as in the WGSL, but (i) no indirect dispatch -- the grid is
 // sized from the arena capacity and reads bump.lines on the device, (ii) the seg_counts
-// allocation is warp-aggregated (one atomicAdd per warp instead of one per line),
+// allocation is aggregated per CTA: one atomicAdd per 256 lines instead of one per line (same-address atomics cost
+// ~2 ns each on this part: per-warp aggregation, 133 k atomics a frame, measured 0.26 ms against 0.14 ms),
 // (iii) backdrop / count updates are fire-and-forget RED operations except the slot fetch.
 // Per-tile slot order (seg_within_slice) is atomic-order dependent exactly as in the reference.
 #include "vb_device.cuh"

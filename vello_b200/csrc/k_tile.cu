@@ -5,7 +5,8 @@
 //
 // B200 design: tile_alloc's per-workgroup atomicAdd(bump.tile) becomes a decoupled look-back scan,
 // so `Path.tiles` offsets are deterministic and equal to the serial CPU shader's -- `tiles[]` can be
-// compared byte for byte. Each CTA zeroes the tile range it allocated with coalesced 8 B stores.
+// compared byte for byte. The allocated range is zeroed by a grid-wide pass (k_tile_zero). backdrop streams the
+// arena as contiguous per-CTA ranges (see k_backdrop).
 // Extension: tile rows are clamped to the stripe window [win_ty0, win_ty1).
 #include "vb_device.cuh"
 
