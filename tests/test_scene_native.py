@@ -138,3 +138,57 @@ def test_c_example_builds(tmp_path):
                     "-L" + os.path.join(root, "vello_b200"), "-lvello_b200", "-Wl,-rpath," + os.path.join(root, "vello_b200"), "-lm",
                     "-o", str(exe)], check=True)
     assert exe.exists()
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_path_encoder_state_machine_fuzz(seed):
+    """Degenerate element sequences -- repeated move-tos, closes with nothing to close, zero-length and near-zero
+    segments, paths that start with a curve, empty paths, several subpaths -- drive every branch of the PathEncoder state
+    machine (path.rs:425-838), for fills and for strokes (cap markers), in both implementations."""
+    from vello_b200.shapes import Affine, BezPath
+    rng = np.random.default_rng(1000 + seed)
+    s = MirrorScene()
+    for k in range(120):
+        p = BezPath()
+        last = [float(v) for v in rng.integers(0, 50, 2)]
+        for _ in range(int(rng.integers(0, 9))):
+            op = int(rng.integers(0, 8))
+            def pt(repeat_prob=0.35):
+                nonlocal last
+                if rng.random() < repeat_prob:
+                    return list(last)
+                if rng.random() < 0.2:  # within float noise of the last point
+                    return [last[0] + float(rng.choice([0.0, 1e-13, 1e-7])), last[1]]
+                last = [float(v) for v in rng.uniform(-20, 80, 2)]
+                return list(last)
+            if op == 0:
+                p.move_to(*pt())
+            elif op in (1, 2):
+                p.line_to(*pt())
+            elif op == 3:
+                p.quad_to(*pt(), *pt())
+            elif op == 4:
+                p.curve_to(*pt(), *pt(), *pt())
+            elif op == 5:
+                p.close_path()
+            elif op == 6:
+                p.move_to(*pt())
+                p.move_to(*pt())
+            else:
+                p.close_path()
+                p.line_to(*pt())
+        t = Affine.translate(float(k % 5), 0.0) if k % 3 else Affine.IDENTITY
+        col = encoding.Color.from_rgba8(*[int(v) for v in rng.integers(0, 256, 4)])
+        if k % 2:
+            s.fill(encoding.FILL_NON_ZERO if k % 4 == 1 else encoding.FILL_EVEN_ODD, t, col, None, p)
+        else:
+            st = encoding.Stroke(float(rng.choice([0.0, 0.5, 3.0])), join=(encoding.STYLE_JOIN_BEVEL, encoding.STYLE_JOIN_MITER, encoding.STYLE_JOIN_ROUND)[k % 3],
+                                 start_cap=(encoding.STYLE_CAP_BUTT, encoding.STYLE_CAP_SQUARE, encoding.STYLE_CAP_ROUND)[(k // 2) % 3],
+                                 end_cap=(encoding.STYLE_CAP_BUTT, encoding.STYLE_CAP_SQUARE, encoding.STYLE_CAP_ROUND)[(k // 3) % 3],
+                                 miter_limit=float(rng.choice([1.0, 4.0, 1e4])))
+            s.stroke(st, t, col, None, p)
+        if k % 17 == 0:
+            s.push_clip_layer(encoding.FILL_NON_ZERO, t, p)  # clip with a possibly empty shape -> the empty-path sentinel
+        if k % 17 == 9:
+            s.pop_layer()
+    assert_same(s)
