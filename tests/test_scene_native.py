@@ -192,3 +192,35 @@ def test_path_encoder_state_machine_fuzz(seed):
         if k % 17 == 9:
             s.pop_layer()
     assert_same(s)
+
+
+def test_append(mirror, oracle):
+    """Scene::append: fragments (with gradients and images, i.e. late-bound patches) appended with and without a
+    transform; native == Python, and a translated fragment renders like the same content drawn at the translated place."""
+    from vello_b200.shapes import Affine, Rect, Circle
+    frag = scenes.brushes()[0]
+    frag2 = scenes.stroke_styles()[0]
+    s = MirrorScene()
+    s.fill(encoding.FILL_NON_ZERO, Affine.IDENTITY, encoding.Color(0.1, 0.1, 0.1, 1.0), None, Rect(0, 0, 900, 900))
+    for sc in (s,):
+        encoding.Scene.append(sc, frag, None)
+        sc.native.append(frag.native, None)
+        encoding.Scene.append(sc, frag2, Affine.translate(450.0, 20.0) * Affine.scale(0.5))
+        sc.native.append(frag2.native, Affine.translate(450.0, 20.0) * Affine.scale(0.5))
+        encoding.Scene.append(sc, frag, Affine((0.5, 0.1, -0.1, 0.5, 30.0, 470.0)))
+        sc.native.append(frag.native, Affine((0.5, 0.1, -0.1, 0.5, 30.0, 470.0)))
+    s.fill(encoding.FILL_NON_ZERO, Affine.IDENTITY, encoding.Color(1.0, 1.0, 1.0, 0.5), None, Circle(400.0, 400.0, 50.0))
+    assert_same(s)
+    # semantics: appending with an integral translation == drawing the same shapes translated (all f32 products exact)
+    part = encoding.Scene()
+    part.fill(encoding.FILL_NON_ZERO, Affine.IDENTITY, encoding.Color(0.9, 0.2, 0.1, 0.8), None, Circle(40.0, 40.0, 30.0))
+    part.stroke(encoding.Stroke(4.0), Affine.translate(3.0, 5.0), encoding.Color(0.1, 0.9, 0.3, 1.0), None, Rect(10, 10, 90, 60))
+    whole = encoding.Scene()
+    whole.append(part, Affine.translate(64.0, 32.0))
+    direct = encoding.Scene()
+    direct.fill(encoding.FILL_NON_ZERO, Affine.translate(64.0, 32.0), encoding.Color(0.9, 0.2, 0.1, 0.8), None, Circle(40.0, 40.0, 30.0))
+    direct.stroke(encoding.Stroke(4.0), Affine.translate(67.0, 37.0), encoding.Color(0.1, 0.9, 0.3, 1.0), None, Rect(10, 10, 90, 60))
+    from vello_b200.config import AA_MSAA16
+    a = oracle.render(resolve(whole.encoding), 200, 128, encoding.BLACK.premul_rgba8_u32(), AA_MSAA16)
+    b = oracle.render(resolve(direct.encoding), 200, 128, encoding.BLACK.premul_rgba8_u32(), AA_MSAA16)
+    assert np.array_equal(a, b) and a[..., :3].max() > 100

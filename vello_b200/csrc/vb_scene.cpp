@@ -601,6 +601,49 @@ int vb_scene_draw_blurred_rounded_rect(vb_scene *s, const double transform[6], c
     return VB_OK;
 }
 
+// Scene::append (scene.rs:464-469) = Encoding::append (encoding.rs:94-174) without glyph runs
+int vb_scene_append(vb_scene *dst, const vb_scene *src, const double *transform) {
+    if (!dst || !src || dst == src) return VB_E_INVALID;
+    Encoding &e = dst->e;
+    const Encoding &o = src->e;
+    const uint32_t dd = (uint32_t)e.draw_data.size();
+    for (RampPatch p : o.ramp_patches) {
+        p.draw_data_offset += dd;
+        e.ramp_patches.push_back(std::move(p));
+    }
+    for (ImagePatch p : o.image_patches) {
+        p.draw_data_offset += dd;
+        e.image_patches.push_back(p);
+    }
+    e.path_tags.insert(e.path_tags.end(), o.path_tags.begin(), o.path_tags.end());
+    e.path_data.insert(e.path_data.end(), o.path_data.begin(), o.path_data.end());
+    e.draw_tags.insert(e.draw_tags.end(), o.draw_tags.begin(), o.draw_tags.end());
+    e.draw_data.insert(e.draw_data.end(), o.draw_data.begin(), o.draw_data.end());
+    e.n_paths += o.n_paths;
+    e.n_path_segments += o.n_path_segments;
+    e.n_clips += o.n_clips;
+    e.n_open_clips += o.n_open_clips;
+    if (transform) { // Transform * Transform in f32 (math.rs:51-73)
+        float a[6];
+        for (int i = 0; i < 6; i++) a[i] = (float)transform[i];
+        for (const Xform &x : o.transforms) {
+            const float *b = x.c;
+            Xform r;
+            r.c[0] = a[0] * b[0] + a[2] * b[1];
+            r.c[1] = a[1] * b[0] + a[3] * b[1];
+            r.c[2] = a[0] * b[2] + a[2] * b[3];
+            r.c[3] = a[1] * b[2] + a[3] * b[3];
+            r.c[4] = a[0] * b[4] + a[2] * b[5] + a[4];
+            r.c[5] = a[1] * b[4] + a[3] * b[5] + a[5];
+            e.transforms.push_back(r);
+        }
+    } else {
+        e.transforms.insert(e.transforms.end(), o.transforms.begin(), o.transforms.end());
+    }
+    e.styles.insert(e.styles.end(), o.styles.begin(), o.styles.end());
+    return VB_OK;
+}
+
 int vb_scene_resolve(vb_scene *s, vb_packed *out) {
     if (!s || !out) return VB_E_INVALID;
     const Encoding &e = s->e;

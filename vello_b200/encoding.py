@@ -594,6 +594,33 @@ class Encoding:
         self.n_clips += 1
         self.n_open_clips += 1
 
+    def append(self, other: "Encoding", transform: Optional[Affine] = None):
+        """`Encoding::append` (encoding.rs:94-174) without glyph runs: concatenate `other`'s streams; its transforms are
+        pre-multiplied by `transform` in f32 (`Transform * Transform`, math.rs:51-73); late-bound patches move with the
+        draw data."""
+        dd = len(self.draw_data)
+        self.ramp_patches.extend(dict(p, draw_data_offset=p["draw_data_offset"] + dd) for p in other.ramp_patches)
+        self.image_patches.extend(dict(p, draw_data_offset=p["draw_data_offset"] + dd) for p in other.image_patches)
+        self.path_tags.extend(other.path_tags)
+        self.path_data.extend(other.path_data)
+        self.draw_tags.extend(other.draw_tags)
+        self.draw_data.extend(other.draw_data)
+        self.n_paths += other.n_paths
+        self.n_path_segments += other.n_path_segments
+        self.n_clips += other.n_clips
+        self.n_open_clips += other.n_open_clips
+        if transform is not None:
+            f = np.float32
+            a = [f(v) for v in transform.coeffs]
+            for x in other.transforms:
+                b = [f(v) for v in x]
+                self.transforms.append(tuple(float(v) for v in (
+                    a[0] * b[0] + a[2] * b[1], a[1] * b[0] + a[3] * b[1], a[0] * b[2] + a[2] * b[3], a[1] * b[2] + a[3] * b[3],
+                    a[0] * b[4] + a[2] * b[5] + a[4], a[1] * b[4] + a[3] * b[5] + a[5])))
+        else:
+            self.transforms.extend(other.transforms)
+        self.styles.extend(other.styles)
+
     def encode_end_clip(self):
         if self.n_open_clips > 0:
             self.draw_tags.append(DRAWTAG_END_CLIP)
@@ -662,6 +689,10 @@ class Scene:
 
     def pop_layer(self):
         self.encoding.encode_end_clip()
+
+    def append(self, other: "Scene", transform: Optional[Affine] = None):
+        """`Scene::append` (vello/src/scene.rs:464-469)."""
+        self.encoding.append(other.encoding, transform)
 
     def draw_image(self, image: Image, transform: Affine):
         self.fill(FILL_NON_ZERO, transform, image, None, _shapes.Rect(0.0, 0.0, float(image.width), float(image.height)))
