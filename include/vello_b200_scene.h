@@ -96,6 +96,10 @@ int vb_scene_draw_image(vb_scene *, const vb_image *, const double transform[6])
 int vb_scene_draw_blurred_rounded_rect(vb_scene *, const double transform[6], const double rect[4], vb_color color, double radius,
                                        double std_dev);
 
+/* Scene::draw_blurred_rounded_rect_in, scene.rs:282-314: the same, clipped to `shape` instead of the inflated rectangle. */
+int vb_scene_draw_blurred_rounded_rect_in(vb_scene *, const vb_path *shape, const double transform[6], const double rect[4],
+                                          vb_color color, double radius, double std_dev);
+
 /* Scene::append, scene.rs:464-469: add everything `src` holds to `dst`, with `transform` (may be NULL) applied in front of
  * src's transforms. Images referenced by src must stay alive like dst's own. */
 int vb_scene_append(vb_scene *dst, const vb_scene *src, const double *transform);

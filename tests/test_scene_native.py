@@ -49,8 +49,17 @@ class MirrorScene(encoding.Scene):
         self.native.draw_image(image, transform)
 
     def draw_blurred_rounded_rect(self, *a):
-        encoding.Scene.draw_blurred_rounded_rect(self, *a)
+        self._quiet = True  # the Python method is a wrapper around ..._in; the native side has its own entry point
+        try:
+            encoding.Scene.draw_blurred_rounded_rect(self, *a)
+        finally:
+            self._quiet = False
         self.native.draw_blurred_rounded_rect(*a)
+
+    def draw_blurred_rounded_rect_in(self, *a):
+        encoding.Scene.draw_blurred_rounded_rect_in(self, *a)
+        if not getattr(self, "_quiet", False):
+            self.native.draw_blurred_rounded_rect_in(*a)
 
 
 @pytest.fixture()
@@ -123,6 +132,7 @@ def test_open_clips_and_empty_scene(mirror):
     s.pop_layer()  # one too many: ignored
     s.stroke(encoding.Stroke(0.0), Affine.IDENTITY, encoding.RED, None, Rect(0, 0, 1, 1))  # zero width: nothing
     s.draw_blurred_rounded_rect(Affine.translate(3.0, 4.0), Rect(10, 10, 60, 40), encoding.Color(0.9, 0.1, 0.1, 0.7), 6.0, 3.5)
+    s.draw_blurred_rounded_rect_in(Circle(40.0, 30.0, 25.0), Affine.rotate(0.2), Rect(10, 10, 60, 40), encoding.Color(0.2, 0.1, 0.9, 1.0), 3.0, 2.0)
     assert_same(s)
 
 

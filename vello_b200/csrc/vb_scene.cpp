@@ -579,26 +579,41 @@ int vb_scene_draw_image(vb_scene *s, const vb_image *image, const double transfo
     return VB_OK;
 }
 
+static int blurred_rect_tail(Encoding &e, const Affine &t, const double rect[4], vb_color color, double radius, double std_dev) {
+    const double cx = 0.5 * (rect[0] + rect[2]), cy = 0.5 * (rect[1] + rect[3]);
+    Affine tr{{1.0, 0.0, 0.0, 1.0, cx, cy}};
+    if (e.encode_transform(mul(t, tr))) e.swap_last_path_tags();
+    e.draw_tags.push_back(DRAWTAG_BLUR_RECT);
+    e.draw_data.push_back(premul_rgba8(to_color(color)));
+    e.draw_data.push_back(f32_bits((float)(rect[2] - rect[0])));
+    e.draw_data.push_back(f32_bits((float)(rect[3] - rect[1])));
+    e.draw_data.push_back(f32_bits((float)radius));
+    e.draw_data.push_back(f32_bits((float)std_dev));
+    return VB_OK;
+}
+
 int vb_scene_draw_blurred_rounded_rect(vb_scene *s, const double transform[6], const double rect[4], vb_color color, double radius,
                                        double std_dev) {
     if (!s || !transform || !rect) return VB_E_INVALID;
     Encoding &e = s->e;
     const Affine t = to_affine(transform);
-    const double k = 2.5 * std_dev; // the shape drawn is the rectangle inflated by 2.5 sigma (scene.rs:296-300)
+    const double k = 2.5 * std_dev; // the shape drawn is the rectangle inflated by 2.5 sigma (scene.rs:266-269)
     e.encode_transform(t);
     e.encode_fill_style(VB_FILL_NON_ZERO);
-    if (encode_rect(e, rect[0] - k, rect[1] - k, rect[2] + k, rect[3] + k)) {
-        const double cx = 0.5 * (rect[0] + rect[2]), cy = 0.5 * (rect[1] + rect[3]);
-        Affine tr{{1.0, 0.0, 0.0, 1.0, cx, cy}};
-        if (e.encode_transform(mul(t, tr))) e.swap_last_path_tags();
-        e.draw_tags.push_back(DRAWTAG_BLUR_RECT);
-        e.draw_data.push_back(premul_rgba8(to_color(color)));
-        e.draw_data.push_back(f32_bits((float)(rect[2] - rect[0])));
-        e.draw_data.push_back(f32_bits((float)(rect[3] - rect[1])));
-        e.draw_data.push_back(f32_bits((float)radius));
-        e.draw_data.push_back(f32_bits((float)std_dev));
-    }
+    if (encode_rect(e, rect[0] - k, rect[1] - k, rect[2] + k, rect[3] + k)) return blurred_rect_tail(e, t, rect, color, radius, std_dev);
     return VB_OK;
+}
+
+int vb_scene_draw_blurred_rounded_rect_in(vb_scene *s, const vb_path *shape, const double transform[6], const double rect[4],
+                                          vb_color color, double radius, double std_dev) {
+    if (!s || !shape || !transform || !rect) return VB_E_INVALID;
+    Encoding &e = s->e;
+    const Affine t = to_affine(transform);
+    e.encode_transform(t);
+    e.encode_fill_style(VB_FILL_NON_ZERO);
+    int rc = VB_OK;
+    if (encode_path(e, *shape, true, &rc)) return blurred_rect_tail(e, t, rect, color, radius, std_dev);
+    return rc;
 }
 
 // Scene::append (scene.rs:464-469) = Encoding::append (encoding.rs:94-174) without glyph runs

@@ -698,8 +698,13 @@ class Scene:
         self.fill(FILL_NON_ZERO, transform, image, None, _shapes.Rect(0.0, 0.0, float(image.width), float(image.height)))
 
     def draw_blurred_rounded_rect(self, transform: Affine, rect: "_shapes.Rect", color: Color, radius: float, std_dev: float):
+        """scene.rs:256-270: the blurred rectangle drawn in the rectangle inflated by 2.5 sigma."""
         k = 2.5 * std_dev
         shape = _shapes.Rect(rect.x0 - k, rect.y0 - k, rect.x1 + k, rect.y1 + k)
+        self.draw_blurred_rounded_rect_in(shape, transform, rect, color, radius, std_dev)
+
+    def draw_blurred_rounded_rect_in(self, shape, transform: Affine, rect: "_shapes.Rect", color: Color, radius: float, std_dev: float):
+        """scene.rs:282-314: the blurred rounded rectangle clipped to `shape`."""
         e = self.encoding
         e.encode_transform(transform)
         e.encode_fill_style(FILL_NON_ZERO)

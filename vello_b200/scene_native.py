@@ -49,7 +49,7 @@ class _Packed(C.Structure):
 
 SCENE_SYMBOLS = ["vb_scene_new", "vb_scene_free", "vb_scene_reset", "vb_scene_fill", "vb_scene_stroke", "vb_scene_push_layer",
                  "vb_scene_push_luminance_mask_layer", "vb_scene_push_clip_layer", "vb_scene_pop_layer", "vb_scene_draw_image",
-                 "vb_scene_draw_blurred_rounded_rect", "vb_scene_append", "vb_scene_resolve", "vb_render_scene"]
+                 "vb_scene_draw_blurred_rounded_rect", "vb_scene_draw_blurred_rounded_rect_in", "vb_scene_append", "vb_scene_resolve", "vb_render_scene"]
 
 _bound = False
 
@@ -70,6 +70,7 @@ def _lib():
         lib.vb_scene_pop_layer.argtypes = [vp]
         lib.vb_scene_draw_image.argtypes = [vp, vp, vp]
         lib.vb_scene_draw_blurred_rounded_rect.argtypes = [vp, vp, vp, _Color, C.c_double, C.c_double]
+        lib.vb_scene_draw_blurred_rounded_rect_in.argtypes = [vp, vp, vp, vp, _Color, C.c_double, C.c_double]
         lib.vb_scene_append.argtypes = [vp, vp, vp]
         lib.vb_scene_resolve.argtypes = [vp, vp]
         lib.vb_render_scene.argtypes = [vp, vp, vp, vp, C.c_uint32, vp]
@@ -198,6 +199,12 @@ class NativeScene:
     def draw_blurred_rounded_rect(self, transform: Affine, rect, color: Color, radius: float, std_dev: float):
         r = (C.c_double * 4)(rect.x0, rect.y0, rect.x1, rect.y1)
         self._check(self.lib.vb_scene_draw_blurred_rounded_rect(self.handle, _affine(transform), r, self._color(color), float(radius), float(std_dev)))
+
+    def draw_blurred_rounded_rect_in(self, shape, transform: Affine, rect, color: Color, radius: float, std_dev: float):
+        p, hold = self._path(shape, 0.1)
+        r = (C.c_double * 4)(rect.x0, rect.y0, rect.x1, rect.y1)
+        self._check(self.lib.vb_scene_draw_blurred_rounded_rect_in(self.handle, C.byref(p), _affine(transform), r, self._color(color),
+                                                                    float(radius), float(std_dev)))
 
     def append(self, other: "NativeScene", transform: Optional[Affine] = None):
         self._keep.append(other)  # its image buffers must outlive this scene's resolve
