@@ -37,7 +37,9 @@ typedef struct { float r, g, b, a; } vb_color; /* peniko::Color, straight alpha 
 typedef struct { float offset; vb_color color; } vb_color_stop; /* peniko::ColorStop */
 
 /* peniko::ImageBrush (image data + sampler). format: 0 RGBA8, 1 BGRA8; alpha_type: 0 straight, 1 premultiplied;
- * quality: 0 low, 1 medium, 2 high; extend: 0 pad, 1 repeat, 2 reflect. */
+ * quality: 0 low, 1 medium, 2 high; extend: 0 pad, 1 repeat, 2 reflect.
+ * `pixels` is referenced, not copied: it must stay valid until the scene is resolved for the last time. Images are placed
+ * in the atlas once per distinct pixel buffer (the reference keys its image cache by blob id, image_cache.rs:113). */
 typedef struct {
     const uint8_t *pixels; /* height x width x 4 */
     uint32_t width, height;
