@@ -860,9 +860,12 @@ void vbo_fine(vbo_ctx *c, uint8_t *out) {
         fine_worker(&j);
         return;
     }
-    pthread_t th[64];
-    Job jobs[64];
-    if (nt > 64) nt = 64;
+    enum { MAX_THREADS = 1024 };
+    static pthread_t th[MAX_THREADS]; /* vbo_fine is not re-entrant (one context renders at a time) */
+    static Job jobs[MAX_THREADS];
+    if (nt > MAX_THREADS) nt = MAX_THREADS;
+    if ((uint32_t)nt > c->win_ty1 - c->win_ty0) nt = (int)(c->win_ty1 - c->win_ty0); /* a thread per tile row at most */
+    if (nt < 1) nt = 1;
     for (int t = 0; t < nt; t++) {
         Job j = {&in, lut, out, c->win_ty0, c->win_ty1, c->cfg.width_in_tiles, t, nt};
         jobs[t] = j;
