@@ -48,6 +48,20 @@ int main(int argc, char **argv) {
     white.color.r = white.color.g = white.color.b = white.color.a = 1.0f;
     if (vb_scene_stroke(scene, &pen, IDENTITY, &white, NULL, &zig)) return 2;
 
+    /* shapes through the path builder (kurbo's Shape::path_elements, tolerance 0.1 like vello's fills) */
+    vb_pathbuf *pb = vb_pathbuf_new();
+    vb_pathbuf_circle(pb, 410.0, 90.0, 42.0, 0.1);
+    vb_brush sun = white;
+    sun.color.r = 1.0f; sun.color.g = 0.85f; sun.color.b = 0.3f; sun.color.a = 0.9f;
+    vb_path shape = vb_pathbuf_view(pb);
+    if (vb_scene_fill(scene, VB_FILL_NON_ZERO, IDENTITY, &sun, NULL, &shape)) return 2;
+    vb_pathbuf_clear(pb);
+    vb_pathbuf_rounded_rect(pb, 30.0, 30.0, 190.0, 110.0, 18.0, 0.1);
+    shape = vb_pathbuf_view(pb);
+    const vb_stroke thin = {3.0, VB_JOIN_MITER, VB_CAP_BUTT, VB_CAP_BUTT, 4.0};
+    if (vb_scene_stroke(scene, &thin, IDENTITY, &white, NULL, &shape)) return 2;
+    vb_pathbuf_free(pb);
+
     vb_renderer *r = NULL;
     vb_options opt;
     memset(&opt, 0, sizeof opt);

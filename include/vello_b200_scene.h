@@ -33,6 +33,24 @@ typedef struct {
     const double *coords;
 } vb_path;
 
+/* A growable path: kurbo::BezPath plus the `Shape::path_elements(tolerance)` conversions of the kurbo shapes vello's callers
+ * use most (kurbo 0.13: rect.rs, line.rs, circle.rs, rounded_rect.rs / arc.rs). vb_pathbuf_view() stays valid until the
+ * buffer is changed or freed. vello uses tolerance 0.1 for fills and clips (scene.rs:316-345). */
+typedef struct vb_pathbuf vb_pathbuf;
+vb_pathbuf *vb_pathbuf_new(void);
+void vb_pathbuf_free(vb_pathbuf *);
+void vb_pathbuf_clear(vb_pathbuf *);
+int vb_pathbuf_move_to(vb_pathbuf *, double x, double y);
+int vb_pathbuf_line_to(vb_pathbuf *, double x, double y);
+int vb_pathbuf_quad_to(vb_pathbuf *, double x1, double y1, double x, double y);
+int vb_pathbuf_curve_to(vb_pathbuf *, double x1, double y1, double x2, double y2, double x, double y);
+int vb_pathbuf_close(vb_pathbuf *);
+int vb_pathbuf_rect(vb_pathbuf *, double x0, double y0, double x1, double y1);
+int vb_pathbuf_line(vb_pathbuf *, double x0, double y0, double x1, double y1);
+int vb_pathbuf_circle(vb_pathbuf *, double cx, double cy, double r, double tolerance);
+int vb_pathbuf_rounded_rect(vb_pathbuf *, double x0, double y0, double x1, double y1, double radius, double tolerance);
+vb_path vb_pathbuf_view(const vb_pathbuf *);
+
 typedef struct { float r, g, b, a; } vb_color; /* peniko::Color, straight alpha */
 typedef struct { float offset; vb_color color; } vb_color_stop; /* peniko::ColorStop */
 

@@ -234,3 +234,30 @@ def test_append(mirror, oracle):
     a = oracle.render(resolve(whole.encoding), 200, 128, encoding.BLACK.premul_rgba8_u32(), AA_MSAA16)
     b = oracle.render(resolve(direct.encoding), 200, 128, encoding.BLACK.premul_rgba8_u32(), AA_MSAA16)
     assert np.array_equal(a, b) and a[..., :3].max() > 100
+
+
+def test_native_shapes_equal_python_statement_of_kurbo():
+    """vb_pathbuf's Rect / Line / Circle / RoundedRect -> Bezier conversions (kurbo `Shape::path_elements`) produce exactly
+    the doubles vello_b200.shapes does, over radii that take every branch of the subdivision-count formulas."""
+    from vello_b200.scene_native import NativePath, PATHBUF_SYMBOLS
+    from vello_b200.renderer import load_library
+    from vello_b200.shapes import Circle, Line, Rect, RoundedRect, BezPath, path_elements
+    lib = load_library()
+    for s in PATHBUF_SYMBOLS:
+        assert hasattr(lib, s), s
+    rng = np.random.default_rng(9)
+    shapes = [Rect(1.5, -2.0, 30.25, 17.0), Line(0.0, 1.0, -5.0, 9.5), RoundedRect(0, 0, 10, 10, 0.0), RoundedRect(0, 0, 10, 4, 50.0)]
+    for _ in range(200):
+        r = float(10 ** rng.uniform(-2, 6))
+        shapes.append(Circle(float(rng.normal(0, 100)), float(rng.normal(0, 100)), r * float(rng.choice([1.0, -1.0]))))
+        x0, y0 = (float(v) for v in rng.normal(0, 50, 2))
+        w, h = (float(v) for v in 10 ** rng.uniform(-1, 5, 2))
+        shapes.append(RoundedRect(x0, y0, x0 + w, y0 + h, float(10 ** rng.uniform(-2, 5))))
+    for tol in (0.1, 0.01, 3.0):
+        for sh in shapes:
+            want = [tuple(float(v) if not isinstance(v, str) else v for v in e) for e in path_elements(sh, tol)]
+            got = NativePath().add(sh, tol).elements()
+            assert got == want, (sh, tol)
+    p = BezPath()
+    p.move_to(1, 2); p.quad_to(3, 4, 5, 6); p.curve_to(7, 8, 9, 10, 11, 12); p.line_to(0, 0); p.close_path()
+    assert NativePath().add(p).elements() == [tuple(float(v) if not isinstance(v, str) else v for v in e) for e in p.els]

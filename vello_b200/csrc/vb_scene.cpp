@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <initializer_list>
 #include <new>
 #include <vector>
 
@@ -507,7 +508,141 @@ inline uint32_t align_up(uint32_t n, uint32_t a) { return (n + a - 1) / a * a; }
 
 } // namespace
 
+struct vb_pathbuf {
+    std::vector<uint8_t> verbs;
+    std::vector<double> coords;
+    void el(uint8_t v, std::initializer_list<double> c) {
+        verbs.push_back(v);
+        coords.insert(coords.end(), c.begin(), c.end());
+    }
+};
+
+namespace {
+const double PI = 3.141592653589793;
+// kurbo Arc::append_iter: n cubic pieces (n from the tolerance), arm = 4/3 tan(sweep / 4n)
+void arc_elements(vb_pathbuf &pb, double cx, double cy, double rx, double ry, double start, double sweep, double x_rot, double tolerance) {
+    const double sign = sweep >= 0 ? 1.0 : -1.0;
+    const double scaled_err = std::fmax(rx, ry) / tolerance;
+    const double n_err = std::fmax(std::pow(1.1163 * scaled_err, 1.0 / 6.0), 3.999999);
+    long n = (long)std::ceil(n_err * std::fabs(sweep) * (1.0 / (2.0 * PI)));
+    if (n < 1) n = 1;
+    const double angle_step = sweep / (double)n;
+    const double arm_len = (4.0 / 3.0) * std::fabs(std::tan(0.25 * angle_step)) * sign;
+    const double cr = std::cos(x_rot), sr = std::sin(x_rot);
+    auto sample = [&](double a, double &ox, double &oy) {
+        const double x = rx * std::cos(a), y = ry * std::sin(a);
+        ox = cr * x - sr * y;
+        oy = sr * x + cr * y;
+    };
+    auto rot_d = [&](double a, double &ox, double &oy) { // rotated (rx sin a, -ry cos a)
+        const double x = rx * std::sin(a), y = -ry * std::cos(a);
+        ox = cr * x - sr * y;
+        oy = sr * x + cr * y;
+    };
+    double angle0 = start, p0x, p0y;
+    sample(angle0, p0x, p0y);
+    for (long i = 0; i < n; i++) {
+        const double angle1 = angle0 + angle_step;
+        double d0x, d0y, d1x, d1y, p3x, p3y;
+        rot_d(angle0, d0x, d0y);
+        const double p1x = p0x - arm_len * d0x, p1y = p0y - arm_len * d0y;
+        sample(angle1, p3x, p3y);
+        rot_d(angle1, d1x, d1y);
+        const double p2x = p3x + arm_len * d1x, p2y = p3y + arm_len * d1y;
+        pb.el('C', {cx + p1x, cy + p1y, cx + p2x, cy + p2y, cx + p3x, cy + p3y});
+        angle0 = angle1;
+        p0x = p3x;
+        p0y = p3y;
+    }
+}
+} // namespace
+
 extern "C" {
+
+vb_pathbuf *vb_pathbuf_new(void) { return new (std::nothrow) vb_pathbuf(); }
+void vb_pathbuf_free(vb_pathbuf *p) { delete p; }
+void vb_pathbuf_clear(vb_pathbuf *p) {
+    if (p) {
+        p->verbs.clear();
+        p->coords.clear();
+    }
+}
+int vb_pathbuf_move_to(vb_pathbuf *p, double x, double y) { if (!p) return VB_E_INVALID; p->el('M', {x, y}); return VB_OK; }
+int vb_pathbuf_line_to(vb_pathbuf *p, double x, double y) { if (!p) return VB_E_INVALID; p->el('L', {x, y}); return VB_OK; }
+int vb_pathbuf_quad_to(vb_pathbuf *p, double x1, double y1, double x, double y) { if (!p) return VB_E_INVALID; p->el('Q', {x1, y1, x, y}); return VB_OK; }
+int vb_pathbuf_curve_to(vb_pathbuf *p, double x1, double y1, double x2, double y2, double x, double y) {
+    if (!p) return VB_E_INVALID;
+    p->el('C', {x1, y1, x2, y2, x, y});
+    return VB_OK;
+}
+int vb_pathbuf_close(vb_pathbuf *p) { if (!p) return VB_E_INVALID; p->el('Z', {}); return VB_OK; }
+int vb_pathbuf_rect(vb_pathbuf *p, double x0, double y0, double x1, double y1) { // kurbo Rect::path_elements
+    if (!p) return VB_E_INVALID;
+    p->el('M', {x0, y0});
+    p->el('L', {x1, y0});
+    p->el('L', {x1, y1});
+    p->el('L', {x0, y1});
+    p->el('Z', {});
+    return VB_OK;
+}
+int vb_pathbuf_line(vb_pathbuf *p, double x0, double y0, double x1, double y1) {
+    if (!p) return VB_E_INVALID;
+    p->el('M', {x0, y0});
+    p->el('L', {x1, y1});
+    return VB_OK;
+}
+int vb_pathbuf_circle(vb_pathbuf *p, double cx, double cy, double radius, double tolerance) { // kurbo Circle::path_elements
+    if (!p || !(tolerance > 0.0)) return VB_E_INVALID;
+    const double r = std::fabs(radius);
+    const double scaled_err = r / tolerance;
+    long n;
+    double arm;
+    if (scaled_err < 1.0 / 1.9608e-4) {
+        n = 4;
+        arm = 0.551915024494;
+    } else {
+        n = (long)std::ceil(std::pow(1.1163 * scaled_err, 1.0 / 6.0));
+        arm = (4.0 / 3.0) * std::tan(PI / (2.0 * (double)n));
+    }
+    p->el('M', {cx + r, cy});
+    const double dth = 2.0 * PI / (double)n;
+    for (long ix = 1; ix <= n; ix++) {
+        const double th1 = dth * (double)ix, th0 = th1 - dth;
+        const double s0 = std::sin(th0), c0 = std::cos(th0);
+        double s1 = 0.0, c1 = 1.0;
+        if (ix != n) {
+            s1 = std::sin(th1);
+            c1 = std::cos(th1);
+        }
+        const double a = arm * r;
+        p->el('C', {cx + r * c0 - a * s0, cy + r * s0 + a * c0, cx + r * c1 + a * s1, cy + r * s1 - a * c1, cx + r * c1, cy + r * s1});
+    }
+    p->el('Z', {});
+    return VB_OK;
+}
+int vb_pathbuf_rounded_rect(vb_pathbuf *p, double x0, double y0, double x1, double y1, double radius, double tolerance) {
+    if (!p || !(tolerance > 0.0)) return VB_E_INVALID;
+    const double rad = std::fmin(std::fabs(radius), std::fmin(0.5 * std::fabs(x1 - x0), 0.5 * std::fabs(y1 - y0)));
+    if (rad <= 0.0) return vb_pathbuf_rect(p, x0, y0, x1, y1);
+    const double hp = 0.5 * PI;
+    p->el('M', {x0 + rad, y0}); // start on the top edge after the top-left corner, clockwise (y down)
+    const double corners[4][3] = {{x1 - rad, y0 + rad, -hp}, {x1 - rad, y1 - rad, 0.0}, {x0 + rad, y1 - rad, hp}, {x0 + rad, y0 + rad, 2 * hp}};
+    for (const auto &c : corners) {
+        p->el('L', {c[0] + rad * std::cos(c[2]), c[1] + rad * std::sin(c[2])});
+        arc_elements(*p, c[0], c[1], rad, rad, c[2], hp, 0.0, tolerance);
+    }
+    p->el('Z', {});
+    return VB_OK;
+}
+vb_path vb_pathbuf_view(const vb_pathbuf *p) {
+    vb_path v = {nullptr, 0, nullptr};
+    if (p) {
+        v.verbs = p->verbs.data();
+        v.n_verbs = (uint32_t)p->verbs.size();
+        v.coords = p->coords.data();
+    }
+    return v;
+}
 
 vb_scene *vb_scene_new(void) { return new (std::nothrow) vb_scene(); }
 void vb_scene_free(vb_scene *s) { delete s; }

@@ -47,6 +47,9 @@ class _Packed(C.Structure):
                 ("ramp_h", C.c_uint32), ("atlas", C.c_void_p), ("atlas_w", C.c_uint32), ("atlas_h", C.c_uint32)]
 
 
+PATHBUF_SYMBOLS = ["vb_pathbuf_new", "vb_pathbuf_free", "vb_pathbuf_clear", "vb_pathbuf_move_to", "vb_pathbuf_line_to", "vb_pathbuf_quad_to",
+                   "vb_pathbuf_curve_to", "vb_pathbuf_close", "vb_pathbuf_rect", "vb_pathbuf_line", "vb_pathbuf_circle", "vb_pathbuf_rounded_rect",
+                   "vb_pathbuf_view"]
 SCENE_SYMBOLS = ["vb_scene_new", "vb_scene_free", "vb_scene_reset", "vb_scene_fill", "vb_scene_stroke", "vb_scene_push_layer",
                  "vb_scene_push_luminance_mask_layer", "vb_scene_push_clip_layer", "vb_scene_pop_layer", "vb_scene_draw_image",
                  "vb_scene_draw_blurred_rounded_rect", "vb_scene_draw_blurred_rounded_rect_in", "vb_scene_append", "vb_scene_resolve", "vb_render_scene"]
@@ -74,6 +77,21 @@ def _lib():
         lib.vb_scene_append.argtypes = [vp, vp, vp]
         lib.vb_scene_resolve.argtypes = [vp, vp]
         lib.vb_render_scene.argtypes = [vp, vp, vp, vp, C.c_uint32, vp]
+        d = C.c_double
+        lib.vb_pathbuf_new.restype = vp
+        lib.vb_pathbuf_free.argtypes = [vp]
+        lib.vb_pathbuf_clear.argtypes = [vp]
+        lib.vb_pathbuf_move_to.argtypes = [vp, d, d]
+        lib.vb_pathbuf_line_to.argtypes = [vp, d, d]
+        lib.vb_pathbuf_quad_to.argtypes = [vp, d, d, d, d]
+        lib.vb_pathbuf_curve_to.argtypes = [vp, d, d, d, d, d, d]
+        lib.vb_pathbuf_close.argtypes = [vp]
+        lib.vb_pathbuf_rect.argtypes = [vp, d, d, d, d]
+        lib.vb_pathbuf_line.argtypes = [vp, d, d, d, d]
+        lib.vb_pathbuf_circle.argtypes = [vp, d, d, d, d]
+        lib.vb_pathbuf_rounded_rect.argtypes = [vp, d, d, d, d, d, d]
+        lib.vb_pathbuf_view.restype = _Path
+        lib.vb_pathbuf_view.argtypes = [vp]
         _bound = True
     return lib
 
@@ -225,3 +243,45 @@ class NativeScene:
         layout = Layout(L.n_draw_objects, L.n_paths, L.n_clips, L.bin_data_start, L.path_tag_base, L.path_data_base, L.draw_tag_base,
                         L.draw_data_base, L.transform_base, L.style_base)
         return Packed(scene=scene, layout=layout, ramps=ramps, atlas=atlas)
+
+
+class NativePath:
+    """vb_pathbuf: a growable kurbo-style path with the shape -> Bezier conversions done natively."""
+
+    def __init__(self):
+        self.lib = _lib()
+        self.handle = C.c_void_p(self.lib.vb_pathbuf_new())
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            self.lib.vb_pathbuf_free(self.handle)
+            self.handle = None
+
+    def add(self, shape, tolerance: float = 0.1) -> "NativePath":
+        L = self.lib
+        if isinstance(shape, _shapes.Rect):
+            L.vb_pathbuf_rect(self.handle, shape.x0, shape.y0, shape.x1, shape.y1)
+        elif isinstance(shape, _shapes.Line):
+            L.vb_pathbuf_line(self.handle, shape.x0, shape.y0, shape.x1, shape.y1)
+        elif isinstance(shape, _shapes.Circle):
+            L.vb_pathbuf_circle(self.handle, shape.cx, shape.cy, shape.r, tolerance)
+        elif isinstance(shape, _shapes.RoundedRect):
+            L.vb_pathbuf_rounded_rect(self.handle, shape.x0, shape.y0, shape.x1, shape.y1, shape.radius, tolerance)
+        else:
+            for e in _shapes.path_elements(shape, tolerance):
+                {"M": L.vb_pathbuf_move_to, "L": L.vb_pathbuf_line_to, "Q": L.vb_pathbuf_quad_to, "C": L.vb_pathbuf_curve_to}.get(
+                    e[0], lambda h: L.vb_pathbuf_close(h))(self.handle, *[float(v) for v in e[1:]])
+        return self
+
+    def elements(self):
+        """The path as ("M", x, y) ... tuples, like vello_b200.shapes.path_elements."""
+        v = self.lib.vb_pathbuf_view(self.handle)
+        verbs = bytes((C.c_uint8 * v.n_verbs).from_address(v.verbs)) if v.n_verbs else b""
+        n = sum({77: 2, 76: 2, 81: 4, 67: 6, 90: 0}[b] for b in verbs)
+        coords = list((C.c_double * n).from_address(v.coords)) if n else []
+        out, i = [], 0
+        for b in verbs:
+            k = {77: 2, 76: 2, 81: 4, 67: 6, 90: 0}[b]
+            out.append((chr(b),) + tuple(coords[i:i + k]))
+            i += k
+        return out
