@@ -49,6 +49,9 @@ int vb_pathbuf_rect(vb_pathbuf *, double x0, double y0, double x1, double y1);
 int vb_pathbuf_line(vb_pathbuf *, double x0, double y0, double x1, double y1);
 int vb_pathbuf_circle(vb_pathbuf *, double cx, double cy, double r, double tolerance);
 int vb_pathbuf_rounded_rect(vb_pathbuf *, double x0, double y0, double x1, double y1, double radius, double tolerance);
+/* kurbo::BezPath::from_svg (kurbo svg.rs): SVG path data with the commands MmLlHhVvCcSsQqTtAaZz, appended to the buffer;
+ * elliptical arcs become cubics. VB_E_INVALID on a syntax error (elements parsed before it stay in the buffer). */
+int vb_pathbuf_svg(vb_pathbuf *, const char *path_data);
 vb_path vb_pathbuf_view(const vb_pathbuf *);
 
 typedef struct { float r, g, b, a; } vb_color; /* peniko::Color, straight alpha */

@@ -261,3 +261,33 @@ def test_native_shapes_equal_python_statement_of_kurbo():
     p = BezPath()
     p.move_to(1, 2); p.quad_to(3, 4, 5, 6); p.curve_to(7, 8, 9, 10, 11, 12); p.line_to(0, 0); p.close_path()
     assert NativePath().add(p).elements() == [tuple(float(v) if not isinstance(v, str) else v for v in e) for e in p.els]
+
+
+def test_native_svg_path_parser():
+    """vb_pathbuf_svg == vello_b200.shapes.parse_svg_path (kurbo BezPath::from_svg): every Ghostscript-tiger path string,
+    and synthetic data using every command, relative forms, implicit repeats, packed flags and numbers, arcs of all four
+    flag combinations, degenerate arcs; malformed data is rejected by both."""
+    import gzip, json, os
+    from vello_b200.scene_native import NativePath
+    from vello_b200.shapes import parse_svg_path
+    root = os.path.dirname(os.path.abspath(__file__))
+    tiger = json.load(gzip.open(os.path.join(root, "golden", "tiger_paths.json.gz")))
+    strings = [it["d"] for it in tiger["items"]]
+    strings += [
+        "M10 20L30 40H50V60h-5v-5l1 1z",
+        "m1,2 3,4 5,6 z m10 10 l1 1",
+        "M0 0C1 2 3 4 5 6S9 10 11 12s1 1 2 2Q1 1 2 2T5 5t1 1 2 2",
+        "M10-20.5.5-3e1,4E-1 1e+2.25.75",
+        "M0 0A10 20 30 0 1 50 60a5 5 0 1 0 10 10 5 5 0 0110 10A5 5 0 11 80 80A0 5 0 0 0 90 90A5 5 0 0 0 90 90 1000 1 45 1 0 95 300",
+        "M1 1S2 2 3 3T4 4",
+        "", "  \t\n", "Z", "M5 5zz",
+    ]
+    for d in strings:
+        want = [tuple(float(v) if not isinstance(v, str) else v for v in e) for e in parse_svg_path(d)]
+        got = NativePath().svg(d).elements()
+        assert got == want, d[:60]
+    for bad in ["10 10", "M10", "M1 1 L", "M0 0A1 1 0 2 0 5 5", "M0 0 X 1 1", "M 1 1 Z 5", "M1e"]:
+        with pytest.raises(ValueError):
+            parse_svg_path(bad)
+        with pytest.raises(ValueError):
+            NativePath().svg(bad)

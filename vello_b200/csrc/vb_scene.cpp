@@ -15,6 +15,7 @@
 // float exactly where the reference uses f32 (no contraction: this file is compiled with -ffp-contract=off).
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <initializer_list>
 #include <new>
@@ -634,6 +635,222 @@ int vb_pathbuf_rounded_rect(vb_pathbuf *p, double x0, double y0, double x1, doub
     p->el('Z', {});
     return VB_OK;
 }
+// SVG path data, the subset kurbo's BezPath::from_svg accepts (MmLlHhVvCcSsQqTtAaZz; kurbo svg.rs), arcs converted to
+// cubics per the SVG implementation notes F.6.5 (endpoint -> centre parametrisation) + Arc::append_iter.
+namespace {
+struct SvgLexer {
+    const char *s;
+    size_t i = 0, n;
+    explicit SvgLexer(const char *d) : s(d), n(std::strlen(d)) {}
+    static bool is_alpha(char c) { return (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z'); }
+    static bool is_digit(char c) { return c >= '0' && c <= '9'; }
+    void skip() {
+        while (i < n && (s[i] == ' ' || s[i] == '\t' || s[i] == '\r' || s[i] == '\n' || s[i] == ',')) i++;
+    }
+    char peek_cmd() {
+        skip();
+        return (i < n && is_alpha(s[i])) ? s[i] : 0;
+    }
+    bool more_numbers() {
+        skip();
+        return i < n && (s[i] == '+' || s[i] == '-' || s[i] == '.' || is_digit(s[i]));
+    }
+    bool num(double *out) { // [+-]?(\d+\.?\d*|\.\d+)([eE][+-]?\d+)?
+        skip();
+        size_t j = i;
+        if (j < n && (s[j] == '+' || s[j] == '-')) j++;
+        size_t d0 = j;
+        while (j < n && is_digit(s[j])) j++;
+        if (j > d0) {
+            if (j < n && s[j] == '.') {
+                j++;
+                while (j < n && is_digit(s[j])) j++;
+            }
+        } else {
+            if (!(j < n && s[j] == '.')) return false;
+            j++;
+            size_t f0 = j;
+            while (j < n && is_digit(s[j])) j++;
+            if (j == f0) return false;
+        }
+        if (j < n && (s[j] == 'e' || s[j] == 'E')) {
+            size_t k = j + 1;
+            if (k < n && (s[k] == '+' || s[k] == '-')) k++;
+            size_t e0 = k;
+            while (k < n && is_digit(s[k])) k++;
+            if (k > e0) j = k;
+        }
+        char buf[400];
+        const size_t len = j - i;
+        if (len == 0 || len >= sizeof buf) return false;
+        std::memcpy(buf, s + i, len);
+        buf[len] = 0;
+        *out = std::strtod(buf, nullptr);
+        i = j;
+        return true;
+    }
+    bool flag(bool *out) {
+        skip();
+        if (i >= n || (s[i] != '0' && s[i] != '1')) return false;
+        *out = s[i] == '1';
+        i++;
+        return true;
+    }
+};
+
+void svg_arc(vb_pathbuf &pb, double x0, double y0, double rx, double ry, double x_rot_deg, bool large, bool sweep, double x, double y) {
+    const double tolerance = 0.1;
+    if (rx == 0.0 || ry == 0.0 || (x0 == x && y0 == y)) {
+        if (!(x0 == x && y0 == y)) pb.el('L', {x, y});
+        return;
+    }
+    rx = std::fabs(rx);
+    ry = std::fabs(ry);
+    const double phi = x_rot_deg * (PI / 180.0);
+    const double cp = std::cos(phi), sp = std::sin(phi);
+    const double dx2 = 0.5 * (x0 - x), dy2 = 0.5 * (y0 - y);
+    const double x1p = cp * dx2 + sp * dy2, y1p = -sp * dx2 + cp * dy2;
+    const double lam = (x1p * x1p) / (rx * rx) + (y1p * y1p) / (ry * ry);
+    if (lam > 1.0) {
+        const double sc = std::sqrt(lam);
+        rx *= sc;
+        ry *= sc;
+    }
+    const double num = rx * rx * ry * ry - rx * rx * y1p * y1p - ry * ry * x1p * x1p;
+    const double den = rx * rx * y1p * y1p + ry * ry * x1p * x1p;
+    double coef = den != 0.0 ? std::sqrt(std::fmax(num / den, 0.0)) : 0.0;
+    if (large == sweep) coef = -coef;
+    const double cxp = coef * rx * y1p / ry, cyp = -coef * ry * x1p / rx;
+    const double cx = cp * cxp - sp * cyp + 0.5 * (x0 + x), cy = sp * cxp + cp * cyp + 0.5 * (y0 + y);
+    const double a0 = std::atan2((y1p - cyp) / ry, (x1p - cxp) / rx), a1 = std::atan2((-y1p - cyp) / ry, (-x1p - cxp) / rx);
+    double d = a1 - a0;
+    if (sweep && d < 0) d += 2 * PI;
+    else if (!sweep && d > 0) d -= 2 * PI;
+    const size_t before = pb.verbs.size();
+    arc_elements(pb, cx, cy, rx, ry, a0, d, phi, tolerance);
+    if (pb.verbs.size() > before) { // land exactly on the end point
+        pb.coords[pb.coords.size() - 2] = x;
+        pb.coords[pb.coords.size() - 1] = y;
+    }
+}
+} // namespace
+
+int vb_pathbuf_svg(vb_pathbuf *p, const char *d) {
+    if (!p || !d) return VB_E_INVALID;
+    SvgLexer lx(d);
+    double cx = 0.0, cy = 0.0, sx = 0.0, sy = 0.0, lcx = 0.0, lcy = 0.0;
+    bool have_ctrl = false;
+    char last_cmd = 0, cmd = 0;
+    for (;;) {
+        const char c = lx.peek_cmd();
+        if (c) {
+            cmd = c;
+            lx.i++;
+        } else if (!lx.more_numbers()) {
+            break;
+        } else if (!cmd) {
+            return VB_E_INVALID; // path data must start with a command
+        } else if (cmd == 'M') {
+            cmd = 'L'; // implicit line-to after move-to
+        } else if (cmd == 'm') {
+            cmd = 'l';
+        }
+        const bool rel = cmd >= 'a' && cmd <= 'z';
+        const char u = rel ? (char)(cmd - 32) : cmd;
+        double v[7];
+        auto nums = [&](int k) {
+            for (int q = 0; q < k; q++)
+                if (!lx.num(&v[q])) return false;
+            return true;
+        };
+        switch (u) {
+        case 'Z':
+            p->el('Z', {});
+            cx = sx; cy = sy;
+            have_ctrl = false;
+            last_cmd = u;
+            if (lx.more_numbers()) return VB_E_INVALID;
+            continue;
+        case 'M':
+            if (!nums(2)) return VB_E_INVALID;
+            if (rel) { v[0] += cx; v[1] += cy; }
+            p->el('M', {v[0], v[1]});
+            cx = sx = v[0]; cy = sy = v[1];
+            have_ctrl = false;
+            break;
+        case 'L':
+            if (!nums(2)) return VB_E_INVALID;
+            if (rel) { v[0] += cx; v[1] += cy; }
+            p->el('L', {v[0], v[1]});
+            cx = v[0]; cy = v[1];
+            have_ctrl = false;
+            break;
+        case 'H':
+            if (!nums(1)) return VB_E_INVALID;
+            if (rel) v[0] += cx;
+            p->el('L', {v[0], cy});
+            cx = v[0];
+            have_ctrl = false;
+            break;
+        case 'V':
+            if (!nums(1)) return VB_E_INVALID;
+            if (rel) v[0] += cy;
+            p->el('L', {cx, v[0]});
+            cy = v[0];
+            have_ctrl = false;
+            break;
+        case 'C':
+            if (!nums(6)) return VB_E_INVALID;
+            if (rel) { v[0] += cx; v[1] += cy; v[2] += cx; v[3] += cy; v[4] += cx; v[5] += cy; }
+            p->el('C', {v[0], v[1], v[2], v[3], v[4], v[5]});
+            lcx = v[2]; lcy = v[3]; have_ctrl = true;
+            cx = v[4]; cy = v[5];
+            break;
+        case 'S': {
+            if (!nums(4)) return VB_E_INVALID;
+            if (rel) { v[0] += cx; v[1] += cy; v[2] += cx; v[3] += cy; }
+            double x1 = cx, y1 = cy;
+            if ((last_cmd == 'C' || last_cmd == 'S') && have_ctrl) { x1 = 2 * cx - lcx; y1 = 2 * cy - lcy; }
+            p->el('C', {x1, y1, v[0], v[1], v[2], v[3]});
+            lcx = v[0]; lcy = v[1]; have_ctrl = true;
+            cx = v[2]; cy = v[3];
+            break;
+        }
+        case 'Q':
+            if (!nums(4)) return VB_E_INVALID;
+            if (rel) { v[0] += cx; v[1] += cy; v[2] += cx; v[3] += cy; }
+            p->el('Q', {v[0], v[1], v[2], v[3]});
+            lcx = v[0]; lcy = v[1]; have_ctrl = true;
+            cx = v[2]; cy = v[3];
+            break;
+        case 'T': {
+            if (!nums(2)) return VB_E_INVALID;
+            if (rel) { v[0] += cx; v[1] += cy; }
+            double x1 = cx, y1 = cy;
+            if ((last_cmd == 'Q' || last_cmd == 'T') && have_ctrl) { x1 = 2 * cx - lcx; y1 = 2 * cy - lcy; }
+            p->el('Q', {x1, y1, v[0], v[1]});
+            lcx = x1; lcy = y1; have_ctrl = true;
+            cx = v[0]; cy = v[1];
+            break;
+        }
+        case 'A': {
+            bool large, sweep;
+            if (!nums(3) || !lx.flag(&large) || !lx.flag(&sweep)) return VB_E_INVALID;
+            const double rx = v[0], ry = v[1], rot = v[2];
+            if (!nums(2)) return VB_E_INVALID;
+            if (rel) { v[0] += cx; v[1] += cy; }
+            svg_arc(*p, cx, cy, rx, ry, rot, large, sweep, v[0], v[1]);
+            cx = v[0]; cy = v[1];
+            have_ctrl = false;
+            break;
+        }
+        default: return VB_E_INVALID;
+        }
+        last_cmd = u;
+    }
+    return VB_OK;
+}
+
 vb_path vb_pathbuf_view(const vb_pathbuf *p) {
     vb_path v = {nullptr, 0, nullptr};
     if (p) {

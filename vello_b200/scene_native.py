@@ -49,7 +49,7 @@ class _Packed(C.Structure):
 
 PATHBUF_SYMBOLS = ["vb_pathbuf_new", "vb_pathbuf_free", "vb_pathbuf_clear", "vb_pathbuf_move_to", "vb_pathbuf_line_to", "vb_pathbuf_quad_to",
                    "vb_pathbuf_curve_to", "vb_pathbuf_close", "vb_pathbuf_rect", "vb_pathbuf_line", "vb_pathbuf_circle", "vb_pathbuf_rounded_rect",
-                   "vb_pathbuf_view"]
+                   "vb_pathbuf_svg", "vb_pathbuf_view"]
 SCENE_SYMBOLS = ["vb_scene_new", "vb_scene_free", "vb_scene_reset", "vb_scene_fill", "vb_scene_stroke", "vb_scene_push_layer",
                  "vb_scene_push_luminance_mask_layer", "vb_scene_push_clip_layer", "vb_scene_pop_layer", "vb_scene_draw_image",
                  "vb_scene_draw_blurred_rounded_rect", "vb_scene_draw_blurred_rounded_rect_in", "vb_scene_append", "vb_scene_resolve", "vb_render_scene"]
@@ -90,6 +90,7 @@ def _lib():
         lib.vb_pathbuf_line.argtypes = [vp, d, d, d, d]
         lib.vb_pathbuf_circle.argtypes = [vp, d, d, d, d]
         lib.vb_pathbuf_rounded_rect.argtypes = [vp, d, d, d, d, d, d]
+        lib.vb_pathbuf_svg.argtypes = [vp, C.c_char_p]
         lib.vb_pathbuf_view.restype = _Path
         lib.vb_pathbuf_view.argtypes = [vp]
         _bound = True
@@ -271,6 +272,11 @@ class NativePath:
             for e in _shapes.path_elements(shape, tolerance):
                 {"M": L.vb_pathbuf_move_to, "L": L.vb_pathbuf_line_to, "Q": L.vb_pathbuf_quad_to, "C": L.vb_pathbuf_curve_to}.get(
                     e[0], lambda h: L.vb_pathbuf_close(h))(self.handle, *[float(v) for v in e[1:]])
+        return self
+
+    def svg(self, d: str) -> "NativePath":
+        if self.lib.vb_pathbuf_svg(self.handle, d.encode()) != 0:
+            raise ValueError("bad SVG path data")
         return self
 
     def elements(self):
