@@ -291,3 +291,49 @@ def test_native_svg_path_parser():
             parse_svg_path(bad)
         with pytest.raises(ValueError):
             NativePath().svg(bad)
+
+
+def test_invalid_arguments_are_rejected_not_crashed():
+    """NULL handles / pointers and malformed inputs come back as VB_E_INVALID."""
+    import ctypes as C
+    from vello_b200.scene_native import _lib, _Brush, _Path, _Stroke, _Packed
+    lib = _lib()
+    ident = (C.c_double * 6)(1, 0, 0, 1, 0, 0)
+    s = C.c_void_p(lib.vb_scene_new())
+    verbs = (C.c_uint8 * 2)(ord("M"), ord("X"))  # unknown verb
+    coords = (C.c_double * 4)(0, 0, 1, 1)
+    bad_path = _Path(C.cast(verbs, C.c_void_p), 2, C.cast(coords, C.c_void_p))
+    brush = _Brush()
+    assert lib.vb_scene_fill(None, 0, ident, C.byref(brush), None, C.byref(bad_path)) == -1
+    assert lib.vb_scene_fill(s, 0, None, C.byref(brush), None, C.byref(bad_path)) == -1
+    assert lib.vb_scene_fill(s, 0, ident, None, None, C.byref(bad_path)) == -1
+    assert lib.vb_scene_fill(s, 0, ident, C.byref(brush), None, None) == -1
+    assert lib.vb_scene_fill(s, 0, ident, C.byref(brush), None, C.byref(bad_path)) == -1  # the verb
+    brush.kind = 99
+    ok_verbs = (C.c_uint8 * 3)(ord("M"), ord("L"), ord("L"))
+    ok_coords = (C.c_double * 6)(0, 0, 5, 0, 5, 5)
+    ok_path = _Path(C.cast(ok_verbs, C.c_void_p), 3, C.cast(ok_coords, C.c_void_p))
+    assert lib.vb_scene_fill(s, 0, ident, C.byref(brush), None, C.byref(ok_path)) == -1  # unknown brush kind
+    brush.kind = 4  # image brush without an image
+    assert lib.vb_scene_fill(s, 0, ident, C.byref(brush), None, C.byref(ok_path)) == -1
+    brush.kind = 1  # gradient claiming stops it does not have
+    brush.n_stops = 3
+    assert lib.vb_scene_fill(s, 0, ident, C.byref(brush), None, C.byref(ok_path)) == -1
+    st = _Stroke(2.0, 0, 0, 0, 4.0)
+    assert lib.vb_scene_stroke(s, None, ident, C.byref(brush), None, C.byref(ok_path)) == -1
+    assert lib.vb_scene_stroke(None, C.byref(st), ident, C.byref(brush), None, C.byref(ok_path)) == -1
+    assert lib.vb_scene_push_clip_layer(s, 0, None, None, C.byref(ok_path)) == -1
+    assert lib.vb_scene_pop_layer(None) == -1
+    assert lib.vb_scene_append(s, s, None) == -1  # a scene cannot be appended to itself
+    assert lib.vb_scene_resolve(s, None) == -1
+    pk = _Packed()
+    assert lib.vb_scene_resolve(s, C.byref(pk)) == 0  # still a valid (if odd) scene
+    assert lib.vb_pathbuf_circle(None, 0.0, 0.0, 1.0, 0.1) == -1
+    pb = C.c_void_p(lib.vb_pathbuf_new())
+    assert lib.vb_pathbuf_circle(pb, 0.0, 0.0, 1.0, 0.0) == -1  # tolerance must be positive
+    assert lib.vb_pathbuf_rounded_rect(pb, 0.0, 0.0, 1.0, 1.0, 0.2, float("nan")) == -1
+    assert lib.vb_pathbuf_svg(pb, None) == -1
+    lib.vb_pathbuf_free(pb)
+    lib.vb_scene_free(s)
+    lib.vb_scene_free(None)
+    lib.vb_pathbuf_free(None)
