@@ -611,28 +611,42 @@ static int enqueue(vb_renderer *r, int first, int last, void *out_dev) {
             cudaGraphExecDestroy(slot->exec);
             slot->exec = nullptr;
         }
+        // Any refusal along the way (a tool or driver that does not allow capture here) turns graph replay off for this
+        // renderer and the frame is launched kernel by kernel: graphs are an optimisation, never a requirement.
+        if (cudaStreamBeginCapture(r->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            r->use_graph = false;
+            return enqueue_direct(r, first, last, out_dev);
+        }
         r->host_out = nullptr; // the captured fine is one launch; its read-back is queued after the graph, below
-        CK(cudaStreamBeginCapture(r->stream, cudaStreamCaptureModeThreadLocal));
         const int rc = enqueue_direct(r, 0, g_last, out_dev);
         cudaGraph_t g = nullptr;
         const cudaError_t e = cudaStreamEndCapture(r->stream, &g);
         r->host_out = host_out;
-        if (rc != VB_OK || e != cudaSuccess) {
+        if (rc != VB_OK || e != cudaSuccess || !g) {
             if (g) cudaGraphDestroy(g);
             cudaGetLastError();
-            return enqueue_direct(r, first, last, out_dev); // capture refused (e.g. a profiler): plain launches
+            r->use_graph = false;
+            return enqueue_direct(r, first, last, out_dev);
         }
         const cudaError_t ei = cudaGraphInstantiate(&slot->exec, g, 0);
         cudaGraphDestroy(g);
         if (ei != cudaSuccess) {
             slot->exec = nullptr;
             cudaGetLastError();
+            r->use_graph = false;
             return enqueue_direct(r, first, last, out_dev);
         }
         slot->key = key;
         slot->launches = r->launches;
     }
-    CK(cudaGraphLaunch(slot->exec, r->stream));
+    if (cudaGraphLaunch(slot->exec, r->stream) != cudaSuccess) {
+        cudaGetLastError();
+        cudaGraphExecDestroy(slot->exec);
+        slot->exec = nullptr;
+        r->use_graph = false;
+        return enqueue_direct(r, first, last, out_dev);
+    }
     r->launches = slot->launches;
     if (banded) {
         const int rc = enqueue_direct(r, VB_STAGE_ID_FINE, VB_STAGE_ID_FINE, out_dev);
