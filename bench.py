@@ -132,12 +132,13 @@ def run_cpu_arm(args, packed, as_reference):
     warm = min(args.warmup, 1) if as_reference else 0
     times, serial, fine = [], [], []
     w, h = args.size, args.height or args.size
+    frame = None
     for i in range(warm + steps):
         t = time.perf_counter()
         o.bind(packed, w, h, BLACK.premul_rgba8_u32(), args.aa)
         o.run("pathtag", "path_tiling")  # one host thread, like the reference's CPU shaders (RendererOptions::use_cpu)
         t1 = time.perf_counter()
-        o.run("fine", "fine")            # the reference has no CPU fine; ours runs one thread per tile row, all cores
+        frame = o.run("fine", "fine")    # the reference has no CPU fine; ours runs one thread per tile row, all cores
         t2 = time.perf_counter()
         if i >= warm:
             times.append(t2 - t)
@@ -150,7 +151,7 @@ def run_cpu_arm(args, packed, as_reference):
     return fps, dict(value=fps, unit="frames/s", cores=cores, kind="port",
                      sample=f"{len(times)} full frame(s) of the workload; pathtag..path_tiling on ONE thread as the reference's CPU shaders run "
                             f"({1000 * sum(serial) / len(serial):.0f} ms/frame), fine on {fine_threads} threads ({1000 * sum(fine) / len(fine):.0f} ms/frame)"), \
-        1000.0 * sum(times) / len(times), len(times)
+        1000.0 * sum(times) / len(times), len(times), frame
 
 
 _REAL_STDOUT = None
@@ -200,7 +201,7 @@ def main():
         if rank != 0:
             return
         packed, _ = build_scene(args)
-        fps, cb, ms, n = run_cpu_arm(args, packed, True)
+        fps, cb, ms, n, _ = run_cpu_arm(args, packed, True)
         emit({"impl": "reference", "metric": "frames/sec paris-30k@4K", "value": fps, "unit": "frames/s",
                           "n_gpus": args.gpus, "steps": n, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                           "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
@@ -355,9 +356,17 @@ def main():
             pass
     rt.close()
 
-    cpu_baseline = None
+    cpu_baseline, parity = None, {"checked": False}
     if not args.no_cpu_baseline:
-        _, cpu_baseline, _, _ = run_cpu_arm(args, packed, False)
+        # the CPU arm renders this very frame: keep it and compare the GPU's pixels with it (the oracle is the checker here,
+        # after every timed region; it is never on the measured path)
+        _, cpu_baseline, _, _, cpu_frame = run_cpu_arm(args, packed, False)
+        r.render_resident(params, out.data_ptr(), bin_rows)
+        gpu_frame = out.cpu().numpy()
+        ref_rows = cpu_frame[h0:h1]
+        d = np.abs(gpu_frame.astype(np.int16) - ref_rows.astype(np.int16))
+        parity = {"checked": True, "against": "oracle (cpu_baseline frame)", "rows": [int(h0), int(h1)], "max_diff": int(d.max()) if d.size else 0,
+                  "differing_channel_values": int((d > 0).sum()), "tolerance": 0 if args.aa else 1}
 
     line = {"metric": "frames/sec paris-30k@4K", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -365,7 +374,7 @@ def main():
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "vb_render_begin x steps + vb_readback_wait (host scene in, host pixels out, every frame)",
                     "blocking_vb_render_value": e2e_fps_by_mode["sync"]},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
             "stage_ms": stage_ms, "bump": {k: int(getattr(st, k)) for k in ("lines", "tile", "seg_counts", "segments", "ptcl", "binning")},
             "scene_bytes": int(packed.scene.nbytes), "wall_s_timed_region": wall, "scene_build_s": gen_s}
     emit(line)

@@ -35,7 +35,9 @@ typedef struct {
 
 /* A growable path: kurbo::BezPath plus the `Shape::path_elements(tolerance)` conversions of the kurbo shapes vello's callers
  * use most (kurbo 0.13: rect.rs, line.rs, circle.rs, rounded_rect.rs / arc.rs). vb_pathbuf_view() stays valid until the
- * buffer is changed or freed. vello uses tolerance 0.1 for fills and clips (scene.rs:316-345). */
+ * buffer is changed or freed. vello uses tolerance 0.1 for fills, clips AND
+ * non-dashed strokes (Encoding::encode_shape -> PathEncoder::shape, vello_encoding/src/path.rs:655-657); only the CPU dash
+ * expansion flattens shapes at 0.01 (scene.rs:404,426). */
 typedef struct vb_pathbuf vb_pathbuf;
 vb_pathbuf *vb_pathbuf_new(void);
 void vb_pathbuf_free(vb_pathbuf *);

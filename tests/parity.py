@@ -61,6 +61,18 @@ def bins_canonical(headers: np.ndarray, info_bin_data: np.ndarray, bin_data_star
     return res
 
 
+def unpaired_endpoints(lines: np.ndarray) -> np.ndarray:
+    """vello/src/debug/validate.rs:47-64 (`validate_line_soup`): end points, compared as (path_ix, x bits, y bits), that occur
+    an odd number of times. Flatten's output is watertight iff none is left (every path's lines form closed loops)."""
+    if lines.size == 0:
+        return np.zeros((0, 3), np.uint32)
+    pts = np.concatenate([
+        np.stack([lines["path_ix"], np.ascontiguousarray(lines["p0"][:, 0]).view(np.uint32), np.ascontiguousarray(lines["p0"][:, 1]).view(np.uint32)], 1),
+        np.stack([lines["path_ix"], np.ascontiguousarray(lines["p1"][:, 0]).view(np.uint32), np.ascontiguousarray(lines["p1"][:, 1]).view(np.uint32)], 1)])
+    u, c = np.unique(pts, axis=0, return_counts=True)
+    return u[c % 2 == 1]
+
+
 def compare_all(r, o, layout, width, height, check_ptcl_tiles=None):
     """Assert stage-by-stage parity of the last GPU frame (renderer r) with the oracle context o.
     Returns a dict of counters for reporting."""
@@ -80,6 +92,7 @@ def compare_all(r, o, layout, width, height, check_ptcl_tiles=None):
         a, b = g[n], c[n][: g[n].shape[0]] if n == "paths" else c[n]
         assert a.shape == b.shape, (n, a.shape, b.shape)
         assert a.tobytes() == b.tobytes(), f"{n} differs"
+    assert len(unpaired_endpoints(g["lines"])) == 0, "flatten output is not watertight (debug/validate.rs)"
     bds = layout.bin_data_start
     assert g["info_bin_data"][:bds].tobytes() == c["info_bin_data"][:bds].tobytes(), "info differs"
     assert bins_canonical(g["bin_headers"], g["info_bin_data"], bds) == bins_canonical(c["bin_headers"], c["info_bin_data"], bds)

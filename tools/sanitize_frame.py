@@ -1,0 +1,31 @@
+"""Frames run under compute-sanitizer (tools/sanitize.sh): graph replay off (the sanitizer tools instrument plain launches),
+every kernel of the pipeline, all three AA modes, clips / blends / gradients / images / strokes, a stripe window and an arena
+overflow with grow-and-retry. Pixels are checked against the oracle so a 'clean' log is also a correct frame."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ["VELLO_B200_NO_GRAPH"] = "1"
+from vello_b200 import scenes  # noqa: E402
+from vello_b200.config import RenderParams  # noqa: E402
+from vello_b200.encoding import BLACK, resolve  # noqa: E402
+from vello_b200.renderer import Renderer  # noqa: E402
+from oracle.vbo import Oracle  # noqa: E402
+
+r, o = Renderer(), Oracle(threads=4)
+cases = [(scenes.tiger(256, 256), 256, 256), scenes.brushes(), scenes.deep_blend(), scenes.stroke_styles(), scenes.many_clips(),
+         (scenes.paris_like(300, 512, seed=1), 512, 512)]
+for s, w, h in cases:
+    packed = resolve(s.encoding)
+    for aa in (2, 1, 0):
+        img = r.render_to_texture(packed, RenderParams(BLACK, w, h, aa))
+        ref = o.render(packed, w, h, BLACK.premul_rgba8_u32(), aa)
+        d = int(np.abs(img.astype(int) - ref.astype(int)).max())
+        assert d <= (1 if aa == 0 else 0), (w, h, aa, d)
+packed = resolve(scenes.paris_like(300, 512, seed=1).encoding)
+ref = o.render(packed, 512, 512, BLACK.premul_rgba8_u32(), 2)
+assert np.array_equal(r.render_to_texture(packed, RenderParams(BLACK, 512, 512, 2), bin_rows=(1, 2)), ref[256:512])
+print("sanitize_frame: all frames match the oracle; launches of the last frame:", r.last_stats.as_dict()["kernel_launches"])
+r.close()

@@ -71,6 +71,7 @@ struct FineArgs {
     const uint32_t *ramps;
     const uint8_t *atlas;
     const uint32_t *mask_lut;
+    const VbBump *bump;         // bump.failed != 0: an upstream stage overflowed an arena, nothing to paint (fine.wgsl:1070)
     const uint32_t *tile_start; // per tile: PTCL offset of its last opaque full-tile cover, or 0 (written by coarse)
     uint32_t cull;              // 1: start each tile there
 };
@@ -663,7 +664,7 @@ k_fine(VbConfig cfg, FineArgs A) {
     __shared__ FineShared<AA> SH;
     const uint32_t *__restrict__ ptcl = A.ptcl;
     const uint32_t *__restrict__ info = A.info;
-    if (__ldg(ptcl) == ~0u) return; // upstream failure flag (path_tiling_setup.wgsl:25)
+    if (A.bump->failed != 0u) return; // upstream failure (the reference flags it through ptcl[0], path_tiling_setup.wgsl:25; see vb_api.cu)
     const uint32_t lane = vb_lane(), warp = threadIdx.x >> 5;
     const uint32_t n_win_tiles = cfg.width_in_tiles * (cfg.win_ty1 - cfg.win_ty0);
     const uint32_t t = blockIdx.x * FI_WARPS + warp;
@@ -976,7 +977,7 @@ k_fine(VbConfig cfg, FineArgs A) {
     }
 }
 
-extern "C" void vb_launch_fine(const VbConfig *cfg, int aa, const VbSegment *segments, const uint32_t *ptcl, const uint32_t *info,
+extern "C" void vb_launch_fine(const VbConfig *cfg, int aa, const VbBump *bump, const VbSegment *segments, const uint32_t *ptcl, const uint32_t *info,
                                uint32_t *blend_spill, uint32_t *out, const uint32_t *ramps, const uint8_t *atlas,
                                const uint32_t *mask_lut8, const uint32_t *mask_lut16, const uint32_t *tile_start, uint32_t cull, cudaStream_t st) {
     uint32_t rows = cfg->win_ty1 - cfg->win_ty0;
@@ -988,6 +989,7 @@ extern "C" void vb_launch_fine(const VbConfig *cfg, int aa, const VbSegment *seg
     A.mask_lut = aa == 2 ? mask_lut16 : mask_lut8;
     A.cull = cull;
     A.tile_start = tile_start;
+    A.bump = bump;
     if (aa == 0) k_fine<0><<<grid, FI_THREADS, 0, st>>>(*cfg, A);
     else if (aa == 1) k_fine<1><<<grid, FI_THREADS, 0, st>>>(*cfg, A);
     else k_fine<2><<<grid, FI_THREADS, 0, st>>>(*cfg, A);

@@ -42,16 +42,16 @@ void vb_launch_coarse(const VbConfig *, const uint32_t *, const VbDrawMonoid *, 
                       VbTile *, VbBump *, uint32_t *, uint32_t *, cudaStream_t);
 void vb_launch_path_tiling(const VbConfig *, const VbBump *, const VbSegmentCount *, const VbLineSoup *, const VbPath *, const VbTile *,
                            VbSegment *, uint32_t, cudaStream_t);
-void vb_launch_fine(const VbConfig *, int, const VbSegment *, const uint32_t *, const uint32_t *, uint32_t *, uint32_t *, const uint32_t *,
-                    const uint8_t *, const uint32_t *, const uint32_t *, const uint32_t *, uint32_t, cudaStream_t);
+void vb_launch_fine(const VbConfig *, int, const VbBump *, const VbSegment *, const uint32_t *, const uint32_t *, uint32_t *, uint32_t *,
+                    const uint32_t *, const uint8_t *, const uint32_t *, const uint32_t *, const uint32_t *, uint32_t, cudaStream_t);
 }
 
 extern "C" int vb_fine_init_constants(void);
 
-// path_tiling_setup.wgsl:21-26: a failed frame is flagged to fine through ptcl[0]
-__global__ void k_flag_failure(const VbBump *bump, uint32_t *ptcl) {
-    if (bump->failed != 0u) ptcl[0] = ~0u;
-}
+// path_tiling_setup.wgsl:21-26 flags a failed frame to fine through ptcl[0] = ~0. That word is also tile 0's blend offset
+// and is only rewritten when coarse visits tile 0 -- which a stripe window with bin_row0 > 0 never does, so the flag of a
+// failed attempt would outlive the successful re-run and every later frame of that renderer. fine therefore reads
+// bump.failed (zeroed with the control block at the start of every attempt) directly; ptcl[0] is not used as a flag.
 
 // Statistics for the roofline of `fine`: PTCL words each tile's interpreter reads and segments it
 // references (one thread per tile walks its command stream, as fine does).
@@ -341,6 +341,18 @@ static uint32_t grow(uint32_t need) {
 
 // Compute the config for these params, size the fixed buffers, and (first time / after growth) the arenas.
 static int prepare(vb_renderer *r, const vb_params *p) {
+    // RenderParams sanity (the reference panics / produces nothing on these; here they are argument errors)
+    if (p->width == 0u || p->height == 0u || p->aa > 2u || p->width > 65536u || p->height > 65536u) {
+        r->err = "vb_params: width/height must be 1..65536 and aa 0..2";
+        return VB_E_INVALID;
+    }
+    {
+        const uint64_t nt = (uint64_t)((p->width + 15u) / 16u) * ((p->height + 15u) / 16u);
+        if (nt * VB_PTCL_INITIAL_ALLOC + nt * (VB_PTCL_INCREMENT / 8u) + 65536u > 0xf0000000ull) {
+            r->err = "vb_params: tile count * PTCL allocation exceeds 32-bit word offsets";
+            return VB_E_INVALID;
+        }
+    }
     VbConfig &c = r->cfg;
     memset(&c, 0, sizeof c);
     c.width_in_tiles = (p->width + 15u) / 16u;
@@ -512,8 +524,7 @@ static int enqueue_direct(vb_renderer *r, int first, int last, void *out_dev) {
             uint32_t grid = (uint32_t)(blocks < (uint64_t)r->sm_count * 16 ? blocks : (uint64_t)r->sm_count * 16);
             vb_launch_path_tiling(&c, bump, (const VbSegmentCount *)r->seg_counts.p, (const VbLineSoup *)r->lines.p,
                                   (const VbPath *)r->paths.p, (const VbTile *)r->tiles.p, (VbSegment *)r->segments.p, grid, st);
-            k_flag_failure<<<1, 1, 0, st>>>(bump, (uint32_t *)r->ptcl.p);
-            launches += 2;
+            launches += 1;
             break;
         }
         case VB_STAGE_ID_FINE: {
@@ -528,7 +539,7 @@ static int enqueue_direct(vb_renderer *r, int first, int last, void *out_dev) {
                 cb.win_ty0 = c.win_ty0 + b * band_rows;
                 cb.win_ty1 = cb.win_ty0 + band_rows < c.win_ty1 ? cb.win_ty0 + band_rows : c.win_ty1;
                 if (cb.win_ty0 >= cb.win_ty1) break;
-                vb_launch_fine(&cb, (int)r->params.aa, (const VbSegment *)r->segments.p, (const uint32_t *)r->ptcl.p,
+                vb_launch_fine(&cb, (int)r->params.aa, bump, (const VbSegment *)r->segments.p, (const uint32_t *)r->ptcl.p,
                                (const uint32_t *)r->info_bin_data.p, (uint32_t *)r->blend_spill.p, (uint32_t *)out_dev,
                                (const uint32_t *)r->ramps.p, (const uint8_t *)r->atlas.p, (const uint32_t *)r->mask8.p,
                                (const uint32_t *)r->mask16.p, (const uint32_t *)r->tile_start.p, r->occlusion_cull, st);
@@ -581,14 +592,15 @@ static void graph_key(const vb_renderer *r, int last, const void *out_dev, Graph
     k->last = (uint32_t)last;
 }
 
-static void queue_readback(vb_renderer *r, const VbConfig &c, uint32_t ty0, uint32_t ty1, void *out_dev, uint32_t band) {
+static int queue_readback(vb_renderer *r, const VbConfig &c, uint32_t ty0, uint32_t ty1, void *out_dev, uint32_t band) {
     size_t y0 = (size_t)ty0 * 16u, y1 = (size_t)ty1 * 16u;
     if (y1 > c.target_height) y1 = c.target_height;
-    if (y1 <= y0) return;
+    if (y1 <= y0) return VB_OK;
     const size_t off = (y0 - c.out_row0) * c.out_pitch_px * 4u, bytes = (y1 - y0) * c.out_pitch_px * 4u;
-    cudaEventRecord(r->band_ev[band], r->stream);
-    cudaStreamWaitEvent(r->copy_stream, r->band_ev[band], 0);
-    cudaMemcpyAsync((char *)r->host_out + off, (const char *)out_dev + off, bytes, cudaMemcpyDeviceToHost, r->copy_stream);
+    CK(cudaEventRecord(r->band_ev[band], r->stream));
+    CK(cudaStreamWaitEvent(r->copy_stream, r->band_ev[band], 0));
+    CK(cudaMemcpyAsync((char *)r->host_out + off, (const char *)out_dev + off, bytes, cudaMemcpyDeviceToHost, r->copy_stream));
+    return VB_OK;
 }
 
 // Enqueue stages first..last: through a cached graph for whole frames, directly otherwise.
@@ -653,7 +665,7 @@ static int enqueue(vb_renderer *r, int first, int last, void *out_dev) {
         r->launches += slot->launches;
         return rc;
     }
-    if (host_out) queue_readback(r, c, c.win_ty0, c.win_ty1, out_dev, 0);
+    if (host_out) return queue_readback(r, c, c.win_ty0, c.win_ty1, out_dev, 0);
     return VB_OK;
 }
 

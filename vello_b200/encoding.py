@@ -651,7 +651,9 @@ class Scene:
         e.encode_transform(transform)
         ok = e.encode_stroke_style(stroke)
         assert ok
-        return e.encode_shape(shape, False, tolerance=0.01)
+        # non-dashed strokes go through Encoding::encode_shape -> PathEncoder::shape -> path_elements(0.1)
+        # (vello/src/scene.rs:417-421, vello_encoding/src/path.rs:655-657); only the dash expansion uses 0.01
+        return e.encode_shape(shape, False)
 
     def stroke(self, stroke: Stroke, transform: Affine, brush, brush_transform: Optional[Affine], shape):
         if stroke.width == 0.0:

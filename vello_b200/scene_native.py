@@ -182,7 +182,7 @@ class NativeScene:
         self._check(self.lib.vb_scene_fill(self.handle, style, _affine(transform), C.byref(b), bt, C.byref(p)))
 
     def stroke(self, stroke: Stroke, transform: Affine, brush, brush_transform: Optional[Affine], shape):
-        p, hold = self._path(shape, 0.01)
+        p, hold = self._path(shape, 0.1)  # scene.rs:417-421: encode_shape -> path_elements(0.1); 0.01 is the dash path only
         b, hb = self._brush(brush)
         st = self._stroke(stroke)
         bt = _affine(brush_transform) if brush_transform is not None else None
@@ -191,7 +191,7 @@ class NativeScene:
     def _clip_args(self, clip_style, clip):
         if isinstance(clip_style, Stroke):
             st = self._stroke(clip_style)
-            p, hold = self._path(clip, 0.01)
+            p, hold = self._path(clip, 0.1)
             return 0, C.byref(st), p, (st, hold)
         p, hold = self._path(clip, 0.1)
         return int(clip_style), None, p, hold

@@ -11,6 +11,10 @@
 * robust_paths, funky_paths, fill_types, stroke_styles, many_clips, deep_blend : recipes restated
   from examples/scenes/src/test_scenes.rs (:1610-1691, :293-333, :699-770, :335-560, :1278-1304,
   :1241-1276)
+* blend_grid (:1213-1239 + render_blend_square :1398-1436), tricky_strokes (:513-697), gradient_extend (:978-1043, the
+  text labels need fonts and are left out), two_point_radial (:1045-1211), many_draw_objects (:1928-1948),
+  conflation_artifacts (:1444-1531), image_extend_modes (:2168-2213), longpathdash (:779-819): the reference's recipes,
+  statement for statement; compose_grid is ours (the reference has no scene that walks the Compose operators)
 """
 from __future__ import annotations
 
@@ -24,13 +28,15 @@ import numpy as np
 
 from .encoding import (
     ALPHA_PREMULTIPLIED, ALPHA_STRAIGHT, BLACK, BLUE, COMPOSE_CLEAR, COMPOSE_SRC_OVER, COMPOSE_PLUS, COMPOSE_XOR,
+    COMPOSE_COPY, COMPOSE_DEST, COMPOSE_DEST_OVER, COMPOSE_SRC_IN, COMPOSE_DEST_IN, COMPOSE_SRC_OUT, COMPOSE_DEST_OUT,
+    COMPOSE_SRC_ATOP, COMPOSE_DEST_ATOP, COMPOSE_PLUS_LIGHTER,
     Color, EXTEND_PAD, EXTEND_REFLECT, EXTEND_REPEAT, Encoding, FILL_EVEN_ODD, FILL_NON_ZERO, FORMAT_BGRA8,
     FORMAT_RGBA8, Gradient, Image, LIME, MIX_MULTIPLY, MIX_NORMAL, MIX_SCREEN, MIX_HUE, MIX_DIFFERENCE, QUALITY_HIGH,
     QUALITY_LOW, QUALITY_MEDIUM, RED, STYLE_CAP_BUTT, STYLE_CAP_ROUND, STYLE_CAP_SQUARE, STYLE_JOIN_BEVEL,
     STYLE_JOIN_MITER, STYLE_JOIN_ROUND, Scene, Stroke, TAG_LINE_TO_F32, TAG_PATH, TAG_QUAD_TO_F32, TAG_CUBIC_TO_F32,
     TAG_SUBPATH_END_BIT, TRANSPARENT, WHITE, style_from_stroke, DRAWTAG_COLOR,
 )
-from .shapes import Affine, BezPath, Circle, Line, Rect, RoundedRect
+from .shapes import Affine, BezPath, Circle, Ellipse, Line, Rect, RoundedRect
 
 _REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TIGER_FIXTURE = os.path.join(_REPO, "tests", "golden", "tiger_paths.json.gz")
@@ -453,3 +459,270 @@ def random_small(seed: int, n: int = 40, size: int = 200) -> Tuple[Scene, int, i
             depth -= 1
     # leave some clips open on purpose: resolve closes them (resolve.rs:127-141)
     return s, size, size
+
+
+# ---------------------------------------------------------------------------------------------
+# more recipes of examples/scenes/src/test_scenes.rs, statement for statement
+# ---------------------------------------------------------------------------------------------
+YELLOW = Color.from_rgba8(255, 255, 0)
+CYAN = Color.from_rgba8(0, 255, 255)
+MAGENTA = Color.from_rgba8(255, 0, 255)
+
+
+def _even_stops(colors):
+    """`Gradient::with_stops([c0, c1, ..])`: evenly spaced offsets (peniko ColorStops from a colour slice)."""
+    n = len(colors)
+    return [(float(np.float32(i) / np.float32(n - 1)) if n > 1 else 0.0, c) for i, c in enumerate(colors)]
+
+
+def render_blend_square(s: Scene, mix: int, compose: int, transform: Affine):
+    """test_scenes.rs:1398-1436 (`blend` = BlendMode { mix, compose })."""
+    rect = Rect.from_origin_size((0.0, 0.0), (200.0, 200.0))
+    s.fill(FILL_NON_ZERO, transform, Gradient.linear((0.0, 0.0), (200.0, 0.0), _even_stops([BLACK, WHITE])), None, rect)
+    for (x, y, c) in ((150.0, 0.0, Color.from_rgba8(255, 240, 64)), (175.0, 100.0, Color.from_rgba8(255, 96, 240)),
+                      (125.0, 200.0, Color.from_rgba8(64, 192, 255))):
+        # Gradient::new_radial(center, r) = two-point radial with both centres equal, r0 = 0
+        s.fill(FILL_NON_ZERO, transform, Gradient.radial((x, y), 0.0, (x, y), 100.0, _even_stops([c, c.with_alpha(0.0)])), None, rect)
+    s.push_layer(FILL_NON_ZERO, MIX_NORMAL, COMPOSE_SRC_OVER, 1.0, transform, rect)
+    for i, c in enumerate((RED, LIME, BLUE)):
+        linear = Gradient.linear((0.0, 0.0), (0.0, 200.0), _even_stops([WHITE, c]))
+        s.push_layer(FILL_NON_ZERO, mix, compose, 1.0, transform, rect)
+        a = (transform * Affine.translate(100.0, 100.0) * Affine.rotate(math.pi / 3.0 * (i * 2 + 1))
+             * Affine.scale(1.0, 0.357) * Affine.translate(-100.0, -100.0))
+        s.fill(FILL_NON_ZERO, a, linear, None, Ellipse(100.0, 100.0, 90.0, 90.0, 0.0))
+        s.pop_layer()
+    s.pop_layer()
+
+
+def blend_grid() -> Tuple[Scene, int, int]:
+    """test_scenes.rs:1213-1239: the 16 Mix modes (in the reference's order), each as a fragment appended with a
+    translation (`Scene::append`)."""
+    from .encoding import (MIX_OVERLAY, MIX_DARKEN, MIX_LIGHTEN, MIX_COLOR_DODGE, MIX_COLOR_BURN, MIX_HARD_LIGHT, MIX_SOFT_LIGHT,
+                           MIX_EXCLUSION, MIX_SATURATION, MIX_COLOR, MIX_LUMINOSITY)
+    modes = [MIX_NORMAL, MIX_MULTIPLY, MIX_DARKEN, MIX_SCREEN, MIX_LIGHTEN, MIX_OVERLAY, MIX_COLOR_DODGE, MIX_COLOR_BURN,
+             MIX_HARD_LIGHT, MIX_SOFT_LIGHT, MIX_DIFFERENCE, MIX_EXCLUSION, MIX_HUE, MIX_SATURATION, MIX_COLOR, MIX_LUMINOSITY]
+    s = Scene()
+    for ix, mix in enumerate(modes):
+        frag = Scene()
+        render_blend_square(frag, mix, COMPOSE_SRC_OVER, Affine.IDENTITY)
+        s.append(frag, Affine.translate((ix % 4) * 225.0, (ix // 4) * 225.0))
+    return s, 900, 900
+
+
+def compose_grid() -> Tuple[Scene, int, int]:
+    """All 14 Compose operators (peniko `Compose`, blend.wgsl:255-331) on the blend square, each with Mix::Normal and with a
+    separable (Multiply) and a non-separable (Luminosity) mix in front of it."""
+    from .encoding import MIX_LUMINOSITY
+    composes = [COMPOSE_CLEAR, COMPOSE_COPY, COMPOSE_DEST, COMPOSE_SRC_OVER, COMPOSE_DEST_OVER, COMPOSE_SRC_IN, COMPOSE_DEST_IN,
+                COMPOSE_SRC_OUT, COMPOSE_DEST_OUT, COMPOSE_SRC_ATOP, COMPOSE_DEST_ATOP, COMPOSE_XOR, COMPOSE_PLUS, COMPOSE_PLUS_LIGHTER]
+    s = Scene()
+    for ix, comp in enumerate(composes):
+        for k, mix in enumerate((MIX_NORMAL, MIX_MULTIPLY, MIX_LUMINOSITY)):
+            render_blend_square(s, mix, comp, Affine.translate((ix % 7) * 210.0, (ix // 7) * 630.0 + k * 210.0) * Affine.scale(1.0))
+    return s, 7 * 210, 6 * 210
+
+
+def _cubic_bbox(p):
+    """kurbo `CubicBez::bounding_box`: end points + the interior extrema of each coordinate."""
+    lo = [min(p[0][k], p[3][k]) for k in (0, 1)]
+    hi = [max(p[0][k], p[3][k]) for k in (0, 1)]
+    for k in (0, 1):
+        p0, p1, p2, p3 = (q[k] for q in p)
+        a, b, c = 3.0 * (-p0 + 3.0 * p1 - 3.0 * p2 + p3), 6.0 * (p0 - 2.0 * p1 + p2), 3.0 * (p1 - p0)
+        ts = []
+        if abs(a) < 1e-12:
+            if abs(b) > 1e-12:
+                ts.append(-c / b)
+        else:
+            disc = b * b - 4.0 * a * c
+            if disc >= 0.0:
+                r = math.sqrt(disc)
+                ts += [(-b + r) / (2.0 * a), (-b - r) / (2.0 * a)]
+        for t in ts:
+            if 0.0 < t < 1.0:
+                mt = 1.0 - t
+                v = mt * mt * mt * p0 + 3.0 * mt * mt * t * p1 + 3.0 * mt * t * t * p2 + t * t * t * p3
+                lo[k], hi[k] = min(lo[k], v), max(hi[k], v)
+    return lo[0], lo[1], hi[0], hi[1]
+
+
+def _map_rect_to_rect(src, dst):
+    sw, sh, dw, dh = src[2] - src[0], src[3] - src[1], dst[2] - dst[0], dst[3] - dst[1]
+    sx, sy = dw / sw, dh / sh
+    scale, x_larger = min(sx, sy), sx > sy
+    tx, ty = dst[0] - src[0] * scale, dst[1] - src[1] * scale
+    if x_larger:
+        tx += 0.5 * (dw - sw * scale)
+    else:
+        ty += 0.5 * (dh - sh * scale)
+    return Affine((scale, 0.0, 0.0, scale, tx, ty)), scale
+
+
+def tricky_strokes() -> Tuple[Scene, int, int]:
+    """test_scenes.rs:513-697 (Skia's trickycubicstrokes): cusps, near-cusps, flat cubics with 180-degree turns, degenerate
+    circles, flat conics as quads; butt caps, miter joins, stroke width 30 in cell space."""
+    colors = [Color.from_rgba8(140, 181, 236), Color.from_rgba8(246, 236, 202), Color.from_rgba8(201, 147, 206), Color.from_rgba8(150, 195, 160)]
+    CELL, SW, NCOLS = 200.0, 30.0, 5
+    tricky = [
+        [(122., 737.), (348., 553.), (403., 761.), (400., 760.)], [(244., 520.), (244., 518.), (1141., 634.), (394., 688.)],
+        [(550., 194.), (138., 130.), (1035., 246.), (288., 300.)], [(226., 733.), (556., 779.), (-43., 471.), (348., 683.)],
+        [(268., 204.), (492., 304.), (352., 23.), (433., 412.)], [(172., 480.), (396., 580.), (256., 299.), (338., 677.)],
+        [(731., 340.), (318., 252.), (1026., -64.), (367., 265.)], [(475., 708.), (62., 620.), (770., 304.), (220., 659.)],
+        [(0., 0.), (128., 128.), (128., 0.), (0., 128.)], [(0., 0.01), (128., 127.999), (128., 0.01), (0., 127.99)],
+        [(0., -0.01), (128., 128.001), (128., -0.01), (0., 128.001)], [(0., 0.), (0., -10.), (0., -10.), (0., 10.)],
+        [(10., 0.), (0., 0.), (20., 0.), (10., 0.)], [(39., -39.), (40., -40.), (40., -40.), (0., 0.)],
+        [(40., 40.), (0., 0.), (200., 200.), (0., 0.)], [(0., 0.), (1e-2, 0.), (-1e-2, 0.), (0., 0.)],
+        [(400.75, 100.05), (400.75, 100.05), (100.05, 300.95), (100.05, 300.95)],
+        [(0.5, 0.), (0., 0.), (20., 0.), (10., 0.)], [(10., 0.), (0., 0.), (10., 0.), (10., 0.)],
+    ]
+    flat_quad = [[(2., 1.), (1., 1.)]]
+    flat_conic = [[(2.232486, 1.0), (3.471740, 1.0)], [(4.710995, 1.0), (5.949262, 1.0)], [(7.187530, 1.0), (8.417061, 1.0)],
+                  [(9.646591, 1.0), (10.859690, 1.0)], [(12.072789, 1.0), (13.261865, 1.0)], [(14.450940, 1.0), (15.608549, 1.0)],
+                  [(16.766161, 1.0), (17.885059, 1.0)], [(19.003958, 1.0), (20.077141, 1.0)], [(21.150328, 1.0), (22.171083, 1.0)],
+                  [(23.191839, 1.0), (24.153776, 1.0)], [(25.115715, 1.0), (26.012812, 1.0)], [(26.909912, 1.0), (27.736557, 1.0)],
+                  [(28.563202, 1.0), (29.314220, 1.0)], [(30.065239, 1.0), (30.735928, 1.0)], [(31.406620, 1.0), (31.992788, 1.0)],
+                  [(32.578957, 1.0), (33.076927, 1.0)], [(33.574905, 1.0), (33.981567, 1.0)], [(34.388233, 1.0), (34.701038, 1.0)],
+                  [(35.013851, 1.0), (35.230850, 1.0)], [(35.447845, 1.0), (35.567669, 1.0)], [(35.687500, 1.0), (35.709404, 1.0)],
+                  [(35.731312, 1.0), (35.655155, 1.0)], [(35.579006, 1.0), (35.405273, 1.0)], [(35.231541, 1.0), (34.961311, 1.0)],
+                  [(34.691086, 1.0), (34.326057, 1.0)], [(33.961029, 1.0), (33.503479, 1.0)], [(33.045937, 1.0), (32.498734, 1.0)],
+                  [(31.951530, 1.0), (31.318098, 1.0)], [(30.684669, 1.0), (29.968971, 1.0)], [(29.253277, 1.0), (28.459791, 1.0)],
+                  [(27.666309, 1.0), (26.800005, 1.0)], [(25.933704, 1.0), (25.000000, 1.0)]]
+    bigger_conic = [[(8.979845, 1.0), (15.795975, 1.0)], [(22.612104, 1.0), (28.363287, 1.0)], [(34.114471, 1.0), (38.884045, 1.0)],
+                    [(43.653618, 1.0), (47.510696, 1.0)], [(51.367767, 1.0), (54.368233, 1.0)], [(57.368698, 1.0), (59.556030, 1.0)],
+                    [(61.743366, 1.0), (63.149269, 1.0)], [(64.555168, 1.0), (65.200005, 1.0)], [(65.844841, 1.0), (65.737961, 1.0)],
+                    [(65.631073, 1.0), (64.770912, 1.0)], [(63.910763, 1.0), (62.284878, 1.0)], [(60.658997, 1.0), (58.243816, 1.0)],
+                    [(55.828640, 1.0), (52.589172, 1.0)], [(49.349705, 1.0), (45.239006, 1.0)], [(41.128315, 1.0), (36.086826, 1.0)],
+                    [(31.045338, 1.0), (25.000000, 1.0)]]
+    s = Scene()
+    idx = color_idx = 0
+
+    def cell_of(i):
+        x, y = (i % NCOLS) * CELL, (i // NCOLS) * CELL
+        return (x, y, x + CELL, y + CELL)
+
+    for i, cubic in enumerate(tricky):
+        idx += 1
+        b = _cubic_bbox(cubic)
+        t, sc = _map_rect_to_rect((b[0] - SW, b[1] - SW, b[2] + SW, b[3] + SW), cell_of(i))
+        st = Stroke(SW / sc, join=STYLE_JOIN_MITER, start_cap=STYLE_CAP_BUTT, end_cap=STYLE_CAP_BUTT)
+        s.stroke(st, t, colors[color_idx], None, BezPath([("M",) + cubic[0], ("C",) + cubic[1] + cubic[2] + cubic[3]]))
+        color_idx = (color_idx + 1) % len(colors)
+    for quads in (flat_quad, flat_conic, bigger_conic):
+        path = BezPath([("M", 1.0, 1.0)] + [("Q",) + q[0] + q[1] for q in quads])
+        xs = [1.0] + [q[k][0] for q in quads for k in (0, 1)]  # every control polygon is flat (y == 1): the bbox is the x range of
+        # the curve, which for these monotone-per-piece flat quads is reached at on-curve points or inside one piece
+        lo, hi = min(1.0, *[q[1][0] for q in quads]), max(1.0, *[q[1][0] for q in quads])
+        p0 = 1.0
+        for q in quads:  # interior extremum of a quadratic in x
+            c, p2 = q[0][0], q[1][0]
+            den = p0 - 2.0 * c + p2
+            if den != 0.0:
+                tt = (p0 - c) / den
+                if 0.0 < tt < 1.0:
+                    v = (1 - tt) * (1 - tt) * p0 + 2 * (1 - tt) * tt * c + tt * tt * p2
+                    lo, hi = min(lo, v), max(hi, v)
+            p0 = p2
+        t, sc = _map_rect_to_rect((lo - SW, 1.0 - SW, hi + SW, 1.0 + SW), cell_of(idx))
+        st = Stroke(SW / sc, join=STYLE_JOIN_MITER, start_cap=STYLE_CAP_BUTT, end_cap=STYLE_CAP_BUTT)
+        s.stroke(st, t, colors[color_idx], None, path)
+        color_idx = (color_idx + 1) % len(colors)
+        idx += 1
+    n = len(tricky) + 3
+    return s, int(CELL * NCOLS), int(CELL * (1 + n // NCOLS))
+
+
+def gradient_extend() -> Tuple[Scene, int, int]:
+    """test_scenes.rs:978-1043 without the three text labels (glyph runs are out of scope)."""
+    s = Scene()
+    colors = _even_stops([RED, LIME, BLUE])
+    w = h = 300.0
+    deg = float(np.float32(np.pi) / np.float32(180.0))
+    for x, ext in enumerate((EXTEND_PAD, EXTEND_REPEAT, EXTEND_REFLECT)):
+        for y, kind in enumerate(("linear", "radial", "sweep")):
+            t = Affine.translate(x * 350.0 + 50.0, y * 350.0 + 100.0)
+            if kind == "linear":
+                g = Gradient.linear((w * 0.35, h * 0.5), (w * 0.65, h * 0.5), colors, ext)
+            elif kind == "radial":
+                radius = float(np.float32(w * 0.25))
+                g = Gradient.radial((w * 0.5, h * 0.5), float(np.float32(radius) * np.float32(0.25)), (w * 0.5, h * 0.5), radius, colors, ext)
+            else:
+                g = Gradient.sweep((w * 0.5, h * 0.5), float(np.float32(30.0) * np.float32(deg)), float(np.float32(150.0) * np.float32(deg)), colors, ext)
+            s.fill(FILL_NON_ZERO, t, g, None, Rect(0.0, 0.0, w, h))
+    return s, 1200, 1200
+
+
+def two_point_radial() -> Tuple[Scene, int, int]:
+    """test_scenes.rs:1045-1211: the COLR radial-gradient cases (disjoint circles both ways, equal radii = strip, nested,
+    touching = focal on circle), each with the three extend modes."""
+    s = Scene()
+    stops = _even_stops([RED, YELLOW, Color.from_rgba8(6, 85, 186)])
+
+    def make(x0, y0, r0, x1, y1, r1, t, ext):
+        rect = Rect(0.0, 0.0, 400.0, 200.0)
+        s.fill(FILL_NON_ZERO, t, WHITE, None, rect)
+        s.fill(FILL_NON_ZERO, t, Gradient.radial((x0, y0), float(np.float32(r0)), (x1, y1), float(np.float32(r1)), stops, ext), None, rect)
+        ra, rb = float(np.float32(r0)) - 1.0, float(np.float32(r1)) - 1.0
+        s.stroke(Stroke(1.0), t, BLACK, None, Ellipse(x0, y0, ra, ra, 0.0))
+        s.stroke(Stroke(1.0), t, BLACK, None, Ellipse(x1, y1, rb, rb, 0.0))
+
+    exts = (EXTEND_PAD, EXTEND_REPEAT, EXTEND_REFLECT)
+    for i, m in enumerate(exts):
+        make(140.0, 100.0, 20.0, 280.0, 100.0, 50.0, Affine.translate(i * 420.0 + 20.0, 20.0), m)
+    for i, m in enumerate(exts):
+        make(280.0, 100.0, 50.0, 140.0, 100.0, 20.0, Affine.translate(i * 420.0 + 20.0, 240.0), m)
+    for i, m in enumerate(exts):
+        make(140.0, 100.0, 50.0, 280.0, 100.0, 50.0, Affine.translate(i * 420.0 + 20.0, 460.0), m)
+    for i, m in enumerate(exts):
+        make(140.0, 125.0, 20.0, 190.0, 100.0, 95.0, Affine.translate(i * 420.0 + 20.0, 680.0), m)
+    for i, m in enumerate(exts):
+        x0, y0, r0, x1, y1, r1 = 140.0, 125.0, 20.0, 190.0, 100.0, 96.0
+        dx, dy = x0 - x1, y0 - y1
+        n = math.hypot(dx, dy)
+        make(x1 + dx / n * (r1 - r0), y1 + dy / n * (r1 - r0), r0, x1, y1, r1, Affine.translate(i * 420.0 + 20.0, 900.0), m)
+    return s, 1280, 1120
+
+
+def many_draw_objects(n_wide: int = 300, n_high: int = 300) -> Tuple[Scene, int, int]:
+    """test_scenes.rs:1928-1948: 90,000 small circles (351 draw-object partitions, 90 k paths)."""
+    s = Scene()
+    W, H = 2000.0, 1500.0
+    for j in range(n_high):
+        y = (j + 0.5) * (H / n_high)
+        for i in range(n_wide):
+            s.fill(FILL_NON_ZERO, Affine.IDENTITY, YELLOW, None, Circle((i + 0.5) * (W / n_wide), y, 3.0))
+    return s, int(W), int(H)
+
+
+def conflation_artifacts() -> Tuple[Scene, int, int]:
+    """test_scenes.rs:1444-1531: shapes that abut with opposite / equal winding at a fractional pixel offset."""
+    s = Scene()
+    N, S = 50.0, 4.0
+    x, y = N + 0.5, N
+    bg, fg = Color.from_rgba8(255, 194, 19), Color.from_rgba8(12, 165, 255)
+    sc = Affine.scale(S)
+    s.fill(FILL_NON_ZERO, Affine.translate(x, y) * sc, fg, None,
+           BezPath([("M", 0.0, 0.0), ("L", N, N), ("L", 0.0, N), ("L", 0.0, 0.0), ("M", 0.0, 0.0), ("L", N, N), ("L", N, 0.0), ("L", 0.0, 0.0)]))
+    y += S * N + 10.0
+    s.fill(FILL_EVEN_ODD, Affine.translate(x, y) * sc, bg, None, Rect(0.0, 0.0, N, N))
+    s.fill(FILL_EVEN_ODD, Affine.translate(x, y) * sc, fg, None,
+           BezPath([("M", 0.0, 0.0), ("L", 0.0, N), ("L", N * 0.5, N), ("L", N * 0.5, 0.0),
+                    ("M", N * 0.5, 0.0), ("L", N, 0.0), ("L", N, N), ("L", N * 0.5, N)]))
+    y += S * N + 10.0
+    s.fill(FILL_EVEN_ODD, Affine.translate(x, y) * sc, bg, None, Rect(0.0, 0.0, N, N))
+    s.fill(FILL_EVEN_ODD, Affine.translate(x, y) * sc, fg, None,
+           BezPath([("M", 0.0, 0.0), ("L", 0.0, N), ("L", N * 0.5, N), ("L", N * 0.5, 0.0),
+                    ("M", N * 0.5, 0.0), ("L", N * 0.5, N), ("L", N, N), ("L", N, 0.0)]))
+    return s, 320, 720
+
+
+def image_extend_modes(quality: int = QUALITY_MEDIUM) -> Tuple[Scene, int, int]:
+    """test_scenes.rs:2168-2213: a 2x2 image (red, blue / cyan, magenta) drawn 100x with a (2, 2) brush offset under
+    pad / reflect / repeat / mixed extends. Base colour white in the reference (`params.base_color`)."""
+    px = np.array([[[255, 0, 0, 255], [0, 0, 255, 255]], [[0, 255, 255, 255], [255, 0, 255, 255]]], dtype=np.uint8)
+    s = Scene()
+    off = Affine.translate(2.0, 2.0)
+    for (tx, ty, xe, ye) in ((100.0, 100.0, EXTEND_PAD, EXTEND_PAD), (100.0, 800.0, EXTEND_REFLECT, EXTEND_REFLECT),
+                             (800.0, 100.0, EXTEND_REPEAT, EXTEND_REPEAT), (800.0, 800.0, EXTEND_REPEAT, EXTEND_REFLECT)):
+        im = Image(px, quality=quality, x_extend=xe, y_extend=ye)
+        s.fill(FILL_NON_ZERO, Affine.translate(tx, ty) * Affine.scale(100.0), im, off, Rect(0.0, 0.0, 6.0, 6.0))
+    return s, 1500, 1500

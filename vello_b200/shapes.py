@@ -87,6 +87,16 @@ class Circle:
 
 
 @dataclass(frozen=True)
+class Ellipse:
+    """kurbo `Ellipse::new(center, radii, x_rotation)` (ellipse.rs): path = MoveTo(start) + `Arc` over 2 pi + ClosePath."""
+    cx: float
+    cy: float
+    rx: float
+    ry: float
+    x_rotation: float = 0.0
+
+
+@dataclass(frozen=True)
 class RoundedRect:
     x0: float
     y0: float
@@ -202,6 +212,20 @@ def path_elements(shape, tolerance: float = 0.1) -> Iterator[tuple]:
                 x + r * c1 + a * s1, y + r * s1 - a * c1,
                 x + r * c1, y + r * s1,
             )
+        yield ("Z",)
+    elif isinstance(shape, Ellipse):
+        # Ellipse::path_elements: radii / rotation come back out of the affine through `svd` (kurbo affine.rs), then
+        # Arc { start 0, sweep 2 pi }.path_elements(tolerance) chained with ClosePath
+        a, b = shape.rx * math.cos(shape.x_rotation), shape.rx * math.sin(shape.x_rotation)
+        c, d = -shape.ry * math.sin(shape.x_rotation), shape.ry * math.cos(shape.x_rotation)
+        a2, b2, c2, d2 = a * a, b * b, c * c, d * d
+        rot = 0.5 * math.atan2(2.0 * (a * c + b * d), a2 - b2 + c2 - d2)
+        s1 = a2 + b2 + c2 + d2
+        s2 = math.sqrt((a2 - b2 + c2 - d2) ** 2 + 4.0 * (a * c + b * d) ** 2)
+        rx, ry = math.sqrt(0.5 * (s1 + s2)), math.sqrt(max(0.5 * (s1 - s2), 0.0))
+        cr, sr = math.cos(rot), math.sin(rot)
+        yield ("M", shape.cx + cr * rx, shape.cy + sr * rx)
+        yield from _arc_elements(shape.cx, shape.cy, rx, ry, 0.0, 2.0 * math.pi, rot, tolerance)
         yield ("Z",)
     elif isinstance(shape, RoundedRect):
         x0, y0, x1, y1 = shape.x0, shape.y0, shape.x1, shape.y1
