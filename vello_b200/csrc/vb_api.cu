@@ -43,7 +43,8 @@ void vb_launch_coarse(const VbConfig *, const uint32_t *, const VbDrawMonoid *, 
 void vb_launch_path_tiling(const VbConfig *, const VbBump *, const VbSegmentCount *, const VbLineSoup *, const VbPath *, const VbTile *,
                            VbSegment *, uint32_t, cudaStream_t);
 void vb_launch_fine(const VbConfig *, int, const VbBump *, const VbSegment *, const uint32_t *, const uint32_t *, uint32_t *, uint32_t *,
-                    const uint32_t *, const uint8_t *, const uint32_t *, const uint32_t *, const uint32_t *, uint32_t, cudaStream_t);
+                    const uint32_t *, const uint8_t *, const uint32_t *, const uint32_t *, const uint32_t *, uint32_t, uint32_t *, int,
+                    cudaStream_t);
 }
 
 extern "C" int vb_fine_init_constants(void);
@@ -160,6 +161,7 @@ struct vb_renderer {
     uint32_t stream_parity = 0;
     cudaEvent_t copy_done[2]{};
     bool frame_pending = false;
+    bool zero_fine_queue = false; // set by vb_run_stages (see enqueue_direct)
 };
 
 #define CK(call)                                                                                  \
@@ -423,7 +425,7 @@ static int prepare(vb_renderer *r, const vb_params *p) {
     if ((rc = ensure(r, r->seg_counts, (size_t)r->cap_seg_counts * sizeof(VbSegmentCount)))) return rc;
     if ((rc = ensure(r, r->segments, (size_t)r->cap_segments * sizeof(VbSegment)))) return rc;
     if ((rc = ensure(r, r->blend_spill, (size_t)r->cap_blend * 4))) return rc;
-    if ((rc = ensure(r, r->ptcl, (size_t)r->cap_ptcl * 4 + 64))) return rc; // + slack for fine's 4-word command fetch
+    if ((rc = ensure(r, r->ptcl, (size_t)r->cap_ptcl * 4 + 512))) return rc; // + slack for fine's 256-byte command windows
     c.lines_size = r->cap_lines;
     c.binning_size = r->cap_binning;
     c.tiles_size = r->cap_tiles;
@@ -437,7 +439,7 @@ static int prepare(vb_renderer *r, const vb_params *p) {
     r->parts_flatten = vb_flatten_parts(c.n_tag_words);
     r->parts_draw = vb_draw_parts(n_draw);
     r->parts_tile = vb_tile_alloc_parts(n_draw);
-    size_t off = 16;
+    size_t off = VB_CTL_HEADER_WORDS;
     r->off_lb_pathtag = off; off += vb_lookback_words(r->parts_pathtag, 5);
     r->off_lb_flatten = off; off += 4; // flatten: [0] literal-record counter, [1] job counter
     r->off_lb_draw = off; off += vb_lookback_words(r->parts_draw, 4);
@@ -465,6 +467,10 @@ static int enqueue_direct(vb_renderer *r, int first, int last, void *out_dev) {
         // 64 MiB read-back still draining from the previous frame (measured: +1.2 ms per streamed frame)
         k_ctl_zero<<<(unsigned)((r->ctl_words + 1023) / 1024), 256, 0, st>>>(ctl, (uint32_t)r->ctl_words);
         launches++;
+    }
+    else if (last >= VB_STAGE_ID_FINE && r->zero_fine_queue) {
+        // vb_run_stages starting after stage 0: the control block is not zeroed, but fine's tile queues must start at 0
+        CK(cudaMemsetAsync(ctl + VB_CTL_FINE_QUEUE, 0, 8 * sizeof(uint32_t), st));
     }
     rec(r, 0);
     for (int s = first; s <= last; s++) {
@@ -542,7 +548,8 @@ static int enqueue_direct(vb_renderer *r, int first, int last, void *out_dev) {
                 vb_launch_fine(&cb, (int)r->params.aa, bump, (const VbSegment *)r->segments.p, (const uint32_t *)r->ptcl.p,
                                (const uint32_t *)r->info_bin_data.p, (uint32_t *)r->blend_spill.p, (uint32_t *)out_dev,
                                (const uint32_t *)r->ramps.p, (const uint8_t *)r->atlas.p, (const uint32_t *)r->mask8.p,
-                               (const uint32_t *)r->mask16.p, (const uint32_t *)r->tile_start.p, r->occlusion_cull, st);
+                               (const uint32_t *)r->mask16.p, (const uint32_t *)r->tile_start.p, r->occlusion_cull,
+                               ctl + VB_CTL_FINE_QUEUE + b, r->sm_count, st);
                 launches += 1;
                 if (r->host_out) {
                     size_t y0 = (size_t)cb.win_ty0 * 16u, y1 = (size_t)cb.win_ty1 * 16u;
@@ -821,7 +828,9 @@ extern "C" int vb_run_stages(vb_renderer *r, const vb_params *p, int first, int 
         if ((rc = pick_out(r, out_device, &out))) return rc;
         r->out_dev = out;
     }
+    r->zero_fine_queue = true;
     rc = enqueue(r, first, last, out);
+    r->zero_fine_queue = false;
     if (rc) return rc;
     CK(cudaStreamSynchronize(r->stream));
     return VB_OK;

@@ -25,6 +25,9 @@ typedef struct { uint32_t failed, binning, ptcl, tile, seg_counts, segments, ble
 /* The control block starts with VbBump (8 words) padded to 16; word 8 counts segment slots that coarse reserved but did
  * not hand out (fills skipped inside a zero-coverage clip): bump.segments - holes = the reference's bump.segments. */
 #define VB_CTL_SEG_HOLES 8
+/* words 16..23: fine's tile queues, one per launch of a frame (up to 8 read-back bands); the header is 32 words */
+#define VB_CTL_FINE_QUEUE 16
+#define VB_CTL_HEADER_WORDS 32
 
 typedef struct {
     uint32_t n_draw_objects, n_paths, n_clips, bin_data_start;
