@@ -58,6 +58,9 @@ typedef struct {
     uint32_t aa;          /* AaConfig: 0 Area, 1 Msaa8, 2 Msaa16 (lib.rs:175-193) */
     uint32_t bin_row0, bin_row1; /* render only bin rows [bin_row0, bin_row1) (256 px each); 0,0 = all.
                                     The output buffer then holds rows bin_row0*256 .. min(bin_row1*256, height). */
+    uint32_t tile_row0, tile_row1; /* finer stripe window in TILE rows (16 px each), used when tile_row1 > tile_row0 (it then
+                                    takes precedence over bin_row*): the cost-balanced stripes of vb_group / the multi-GPU
+                                    bench. The output buffer holds rows tile_row0*16 .. min(tile_row1*16, height). */
 } vb_params;
 
 enum {
@@ -150,6 +153,46 @@ int vb_debug_upload(vb_renderer *, const char *name, const void *src, size_t byt
 int vb_set_occlusion_cull(vb_renderer *, int on);
 
 int vb_debug_fine_traffic(vb_renderer *, uint64_t *ptcl_words, uint64_t *segment_refs, uint64_t *fill_cmds);
+
+/* ---- one frame on several GPUs of one box (north_star: "a single frame shards across the GPUs by stripes") ----
+ * The frame is cut into horizontal stripes of tile rows, one per device; every device runs the element stages on the scene and
+ * the tile stages on its stripe (no winding seam exists between horizontal stripes), and `fine` on device k stores
+ * its pixels STRAIGHT INTO THE FRAME BUFFER ON DEVICE 0 through NVLink peer mapping (no gather pass, no staging copy); with a
+ * host destination every device reads its own stripe back over its own PCIe link instead. Stripe boundaries follow the measured
+ * per-device frame times of the previous frames (cost balancing). One host thread drives all devices.
+ *
+ * Single process: vb_group. One process per GPU (torchrun): each rank owns a plain vb_renderer, rank 0 exports its frame buffer
+ * with vb_ipc_export and the others map it with vb_ipc_open and pass `mapped + stripe offset` as out_device. */
+typedef struct vb_group vb_group;
+/* devices[]: CUDA ordinals, the first one owns the assembled frame (the same ordinal may be listed twice: two renderers share
+ * that GPU; used by the single-GPU tests). opt->device is ignored. */
+int vb_group_new(const int32_t *devices, uint32_t n_devices, const vb_options *opt, vb_group **out);
+void vb_group_free(vb_group *);
+uint32_t vb_group_size(const vb_group *);
+vb_renderer *vb_group_renderer(vb_group *, uint32_t i); /* the i-th device's renderer (statistics, debugging) */
+const char *vb_group_last_error(vb_group *);
+/* Same arguments as vb_render; p->bin_row* / tile_row* must be 0 (the group chooses the stripes). `out`: host pointer, or a
+ * device pointer ON devices[0] when out_is_device != 0, or NULL to leave the frame in the group's own buffer on devices[0]
+ * (vb_group_frame). stats: array of vb_group_size() entries or NULL. */
+int vb_group_render(vb_group *, const uint8_t *scene, size_t scene_len, const vb_layout *, const uint32_t *ramps, uint32_t ramp_w,
+                    uint32_t ramp_h, const uint8_t *atlas_rgba8, uint32_t atlas_w, uint32_t atlas_h, const vb_params *, void *out,
+                    uint32_t out_is_device, vb_frame_stats *stats);
+int vb_group_scene_upload(vb_group *, const uint8_t *scene, size_t scene_len, const vb_layout *, const uint32_t *ramps, uint32_t ramp_w,
+                          uint32_t ramp_h, const uint8_t *atlas_rgba8, uint32_t atlas_w, uint32_t atlas_h);
+int vb_group_render_resident(vb_group *, const vb_params *, void *out_device, vb_frame_stats *stats);
+void *vb_group_frame(vb_group *, size_t *bytes);
+/* tile-row boundaries in use (n_devices + 1 entries) and the device times (ms) of the last frame (n_devices entries) */
+int vb_group_stripes(vb_group *, uint32_t *boundaries, float *device_ms);
+int vb_group_set_balancing(vb_group *, int on); /* default on */
+
+/* CUDA IPC helpers for the one-process-per-GPU arrangement (64-byte handles, exchanged by the caller, e.g. over torch.distributed) */
+int vb_frame_alloc(vb_renderer *, size_t bytes, void **device_ptr);  /* cudaMalloc on the renderer's device */
+int vb_frame_free(vb_renderer *, void *device_ptr);
+int vb_ipc_export(vb_renderer *, void *device_ptr, uint8_t handle[64]);
+int vb_ipc_open(vb_renderer *, const uint8_t handle[64], void **device_ptr); /* enables peer access to the exporting device */
+int vb_ipc_close(vb_renderer *, void *device_ptr);
+/* device time of the last completed frame of this renderer in ms (events around the frame; 0 until a frame completed) */
+float vb_last_frame_ms(vb_renderer *);
 
 #ifdef __cplusplus
 }

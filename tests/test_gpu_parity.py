@@ -554,3 +554,51 @@ def test_gpu_against_libm_oracle(renderer, oracle_libm):
         gl = int(renderer.download("bump", np.uint32)[7])
         ol = int(oracle_libm.buffer("bump")["lines"][0])
         assert abs(gl - ol) <= max(4, ol // 2000)
+
+
+def test_tile_row_stripes_equal_full_frame(renderer, oracle):
+    """Stripes in TILE rows (vb_params.tile_row0/1, the granularity the cost-balanced multi-GPU split uses): any cut of the
+    frame reproduces the full frame's rows exactly, including cuts inside a bin row and one-tile-row stripes."""
+    w, h = 1024, 1000
+    packed = resolve(scenes.paris_like(1500, 1024, seed=7).encoding)
+    for aa in (AA_MSAA16, AA_AREA):
+        p = RenderParams(BLACK, w, h, aa)
+        full = renderer.render_to_texture(packed, p)
+        for cuts in ([0, 5, 23, 24, 40, 63], [0, 1, 17, 31, 32, 33, 62, 63], [0, 63]):
+            parts = [renderer.render_to_texture(packed, p, tile_rows=(a, b)) for a, b in zip(cuts, cuts[1:])]
+            assert np.array_equal(np.concatenate(parts, axis=0), full), (aa, cuts)
+    ref = oracle.render(packed, w, h, BLACK.premul_rgba8_u32(), AA_MSAA16)
+    assert np.array_equal(renderer.render_to_texture(packed, RenderParams(BLACK, w, h, AA_MSAA16), tile_rows=(10, 30)), ref[160:480])
+    s = scenes.tiger(512, 512)
+    pk = resolve(s.encoding)
+    pp = RenderParams(BLACK, 512, 512, AA_MSAA16)
+    whole = renderer.render_to_texture(pk, pp)
+    parts = [renderer.render_to_texture(pk, pp, tile_rows=(a, a + 3)) for a in range(0, 32, 3)]
+    assert np.array_equal(np.concatenate(parts, axis=0)[:512], whole)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_group_one_call_one_frame(oracle, n):
+    """vb_group: ONE call renders ONE frame on n renderers (here all on device 0 -- the multi-device path with every piece
+    but the NVLink hop; bench.py and tests/test_multi_gpu.py run it on real devices). Host destination and device frame,
+    with the cost balancing moving the stripe boundaries between frames: always the oracle's frame."""
+    from vello_b200.renderer import RendererGroup
+    packed = resolve(scenes.paris_like(2500, 1024, seed=4).encoding)
+    p = RenderParams(BLACK, 1024, 1024, AA_MSAA16)
+    ref = oracle.render(packed, 1024, 1024, BLACK.premul_rgba8_u32(), AA_MSAA16)
+    g = RendererGroup([0] * n)
+    assert np.array_equal(g.render_to_texture(packed, p), ref)
+    g.upload(packed)
+    seen = set()
+    for k in range(6):
+        st = g.render_resident(p)
+        assert all(int(s.failed) == 0 for s in st)
+        assert np.array_equal(g.frame_to_host(p), ref), k
+        b, ms = g.stripes()
+        assert b[0] == 0 and b[-1] == 64 and all(x < y for x, y in zip(b, b[1:]))
+        seen.add(tuple(b))
+    other = resolve(scenes.tiger(700, 500).encoding)
+    p2 = RenderParams(BLACK, 700, 500, AA_AREA)
+    got = g.render_to_texture(other, p2)
+    assert_pixels(got, oracle.render(other, 700, 500, BLACK.premul_rgba8_u32(), AA_AREA), AA_AREA)
+    g.close()

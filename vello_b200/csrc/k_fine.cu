@@ -31,7 +31,7 @@
 #include "vb_device.cuh"
 
 #ifndef FI_MAX_WARPS
-#define FI_MAX_WARPS 16 // warps (= tiles in flight) per CTA; the launcher picks 2..FI_MAX_WARPS by frame size
+#define FI_MAX_WARPS 12 // warps (= tiles in flight) per CTA; the launcher picks 2..FI_MAX_WARPS by frame size
 #endif
 #ifndef FI_MINB
 #define FI_MINB 2
@@ -811,9 +811,7 @@ k_fine(VbConfig cfg, FineArgs A) {
     }
     if (AA != 0) mbar_wait(lut_bar, 0u); // every thread of the CTA observes the LUT copy before its first use
 
-    const rgba_t base = unpack4x8unorm_uniform(cfg.base_color);
     const uint32_t ly = lane >> 1, h = lane & 1u;
-    const float local_x = (float)(h * 8u), local_y = (float)ly;
     while (t_cur < n_tiles) {
         // ---- pipeline bookkeeping for the tiles after this one
         const uint32_t start_nxt = START_OF(t_nxt, s0_nxt);
@@ -832,13 +830,17 @@ k_fine(VbConfig cfg, FineArgs A) {
         const uint32_t tile_x = t_cur % wt, tile_y = cfg.win_ty0 + t_cur / wt;
         const uint32_t tile_ix = tile_y * wt + tile_x;
         const uint32_t gx = tile_x * 16u + h * 8u, gy = tile_y * 16u + ly;
-        const float xyy = (float)gy;
-        // xy.x of the two WGSL thread groups this lane covers
-        const float xyx0 = (float)gx, xyx1 = (float)(gx + 4u);
+        // pixel coordinates are small integers: (float)(gx + i) is exactly the WGSL's xy.x + f32(i) of either 4-pixel group
+#define xyy ((float)gy)
+#define xyx0 ((float)gx)
+#define xyx1 ((float)(gx + 4u))
         rgba_t rgba[PX];
         float area[PX];
+        {
+            const rgba_t base = unpack4x8unorm_uniform(cfg.base_color);
 #pragma unroll
-        for (int i = 0; i < PX; i++) { rgba[i] = base; area[i] = 0.0f; }
+            for (int i = 0; i < PX; i++) { rgba[i] = base; area[i] = 0.0f; }
+        }
         // first BLEND_STACK_SPLIT levels of the blend stack: thread-private (local memory, L1 resident); deeper
         // levels spill to blend_spill exactly as in the reference
         // Dynamically indexed -> lives in local memory; every level is stored by BEGIN_CLIP before END_CLIP loads it.
@@ -874,7 +876,7 @@ k_fine(VbConfig cfg, FineArgs A) {
             case VB_CMD_FILL: {
                 const uint32_t sr = w1, sd = w2;
                 const int32_t bd = (int32_t)w3;
-                if (AA == 0) fill_path_area(A, sr, sd, bd, local_x, local_y, area);
+                if (AA == 0) fill_path_area(A, sr, sd, bd, (float)(h * 8u), (float)ly, area);
                 else fill_path_ms<AA == 0 ? 1 : AA>(A, S, lut, sr, sd, bd, lane, area);
                 cmd_ix += 4u;
                 break;
@@ -1124,6 +1126,9 @@ k_fine(VbConfig cfg, FineArgs A) {
             }
         }
 #undef PXX
+#undef xyy
+#undef xyx0
+#undef xyx1
         // ---- store: rgba8unorm with separated alpha (fine.wgsl:1386-1397). When every pixel of the warp is opaque
         // (the common case) a_inv is exactly 1 and the three multiplications are identities, so they are skipped.
         bool opaque = true;

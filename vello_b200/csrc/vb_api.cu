@@ -10,7 +10,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/vello_b200.h"
@@ -150,6 +152,8 @@ struct vb_renderer {
     uint32_t parts_pathtag = 0, parts_flatten = 0, parts_draw = 0, parts_tile = 0;
     size_t off_lb_pathtag = 0, off_lb_flatten = 0, off_lb_draw = 0, off_lb_tile = 0;
     cudaEvent_t ev[VB_N_STAGE_IDS + 1]{};
+    cudaEvent_t frame_ev[2]{}; // around every whole frame (vb_last_frame_ms: the signal stripe balancing uses)
+    bool frame_timed = false;
     bool ev_ok = false;
     // read-back pipeline of vb_render (host output): fine runs in row bands, each band's D2H copy overlaps the next band
     cudaStream_t copy_stream = nullptr;
@@ -162,7 +166,46 @@ struct vb_renderer {
     cudaEvent_t copy_done[2]{};
     bool frame_pending = false;
     bool zero_fine_queue = false; // set by vb_run_stages (see enqueue_direct)
+    bool in_stream_call = false;  // inside vb_render_begin / vb_readback_wait (their internal calls must not drain)
+
+    // Streaming (vb_render_begin) keeps TWO frames in flight: while frame k is rasterised, frame k+1's scene is uploaded
+    // into the other slot on its own stream and frame k-1's pixels drain to the host. The members above (scene, ramps,
+    // atlas, layout, ..., h_bump) are the CURRENT slot; `other` holds the parked one and swap_slot() exchanges them.
+    struct SceneSlot {
+        DevBuf scene, ramps, atlas;
+        VbLayout layout{};
+        size_t scene_words = 0;
+        uint32_t n_ramps = 0, atlas_w = 0, atlas_h = 0;
+        bool have_scene = false;
+        VbBump *h_bump = nullptr, *h_bump_dev = nullptr;
+    } other;
+    uint32_t cur_slot = 0;
+    cudaStream_t upload_stream = nullptr;
+    cudaEvent_t upload_done[2]{}, raster_done[2]{};
+    struct PendingFrame {
+        bool pending = false;
+        vb_params params{};
+        void *out_host = nullptr;
+    } inflight[2];
 };
+
+static void swap_slot(vb_renderer *r) {
+    std::swap(r->scene, r->other.scene);
+    std::swap(r->ramps, r->other.ramps);
+    std::swap(r->atlas, r->other.atlas);
+    std::swap(r->layout, r->other.layout);
+    std::swap(r->scene_words, r->other.scene_words);
+    std::swap(r->n_ramps, r->other.n_ramps);
+    std::swap(r->atlas_w, r->other.atlas_w);
+    std::swap(r->atlas_h, r->other.atlas_h);
+    std::swap(r->have_scene, r->other.have_scene);
+    std::swap(r->h_bump, r->other.h_bump);
+    std::swap(r->h_bump_dev, r->other.h_bump_dev);
+    r->cur_slot ^= 1u;
+}
+static void select_slot(vb_renderer *r, uint32_t slot) {
+    if (r->cur_slot != slot) swap_slot(r);
+}
 
 #define CK(call)                                                                                  \
     do {                                                                                          \
@@ -188,7 +231,7 @@ static size_t arena_bytes(const vb_renderer *r) {
     const DevBuf *all[] = {&r->scene, &r->ramps, &r->atlas, &r->mask8, &r->mask16, &r->tag_monoids, &r->path_bboxes, &r->draw_monoids,
                            &r->info_bin_data, &r->clip_inp, &r->clip_bboxes, &r->clip_scratch, &r->draw_bboxes, &r->bin_headers, &r->paths,
                            &r->ctl, &r->target, &r->target_alt, &r->tile_start, &r->lines, &r->line_scratch, &r->flatten_jobs, &r->flatten_parts, &r->tiles, &r->seg_counts, &r->segments, &r->ptcl, &r->blend_spill};
-    size_t s = 0;
+    size_t s = r->other.scene.cap + r->other.ramps.cap + r->other.atlas.cap;
     for (auto b : all) s += b->cap;
     return s;
 }
@@ -241,7 +284,17 @@ extern "C" int vb_renderer_new(const vb_options *opt, vb_renderer **out) {
         return VB_E_CUDA;
     }
     memset(r->h_bump, 0, sizeof(VbBump));
+    if (cudaHostAlloc((void **)&r->other.h_bump, sizeof(VbBump), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void **)&r->other.h_bump_dev, r->other.h_bump, 0) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&r->upload_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete r;
+        return VB_E_CUDA;
+    }
+    memset(r->other.h_bump, 0, sizeof(VbBump));
+    for (auto &ev : r->upload_done) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    for (auto &ev : r->raster_done) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (auto &ev : r->ev) cudaEventCreate(&ev);
+    for (auto &ev : r->frame_ev) cudaEventCreate(&ev);
     for (auto &ev : r->band_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     for (auto &ev : r->copy_done) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     if (getenv("VELLO_B200_NO_GRAPH")) r->use_graph = false;
@@ -275,15 +328,22 @@ extern "C" void vb_renderer_free(vb_renderer *r) {
                      &r->ctl, &r->target, &r->target_alt, &r->tile_start, &r->lines, &r->line_scratch, &r->flatten_jobs, &r->flatten_parts, &r->tiles, &r->seg_counts, &r->segments, &r->ptcl, &r->blend_spill};
     for (auto b : all)
         if (b->p) cudaFree(b->p);
+    for (DevBuf *b : {&r->other.scene, &r->other.ramps, &r->other.atlas})
+        if (b->p) cudaFree(b->p);
     if (r->h_bump) cudaFreeHost(r->h_bump);
+    if (r->other.h_bump) cudaFreeHost(r->other.h_bump);
     if (r->ev_ok) {
         for (auto &ev : r->ev) cudaEventDestroy(ev);
+        for (auto &ev : r->frame_ev) cudaEventDestroy(ev);
         for (auto &ev : r->band_ev) cudaEventDestroy(ev);
         for (auto &ev : r->copy_done) cudaEventDestroy(ev);
+        for (auto &ev : r->upload_done) cudaEventDestroy(ev);
+        for (auto &ev : r->raster_done) cudaEventDestroy(ev);
         for (auto &gs : r->graphs)
             if (gs.exec) cudaGraphExecDestroy(gs.exec);
     }
     if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
+    if (r->upload_stream) cudaStreamDestroy(r->upload_stream);
     if (r->stream) cudaStreamDestroy(r->stream);
     delete r;
 }
@@ -314,8 +374,8 @@ extern "C" int vb_copy_to_host(vb_renderer *r, const void *src_device, void *dst
     return VB_OK;
 }
 
-extern "C" int vb_scene_upload(vb_renderer *r, const uint8_t *scene, size_t scene_len, const vb_layout *layout, const uint32_t *ramps,
-                               uint32_t ramp_w, uint32_t ramp_h, const uint8_t *atlas, uint32_t atlas_w, uint32_t atlas_h) {
+static int upload_on(vb_renderer *r, cudaStream_t st, const uint8_t *scene, size_t scene_len, const vb_layout *layout, const uint32_t *ramps,
+                     uint32_t ramp_w, uint32_t ramp_h, const uint8_t *atlas, uint32_t atlas_w, uint32_t atlas_h) {
     if (!r || !layout || (scene_len && !scene) || (scene_len & 3)) return VB_E_INVALID;
     if (ramp_h && ramp_w != 512) return VB_E_INVALID;
     CK(cudaSetDevice(r->device));
@@ -323,17 +383,32 @@ extern "C" int vb_scene_upload(vb_renderer *r, const uint8_t *scene, size_t scen
     r->scene_words = scene_len / 4;
     int rc;
     if ((rc = ensure(r, r->scene, scene_len + 64))) return rc;
-    if (scene_len) CK(cudaMemcpyAsync(r->scene.p, scene, scene_len, cudaMemcpyHostToDevice, r->stream));
+    if (scene_len) CK(cudaMemcpyAsync(r->scene.p, scene, scene_len, cudaMemcpyHostToDevice, st));
     r->n_ramps = ramp_h;
     if ((rc = ensure(r, r->ramps, (size_t)ramp_h * 512 * 4))) return rc;
-    if (ramp_h) CK(cudaMemcpyAsync(r->ramps.p, ramps, (size_t)ramp_h * 512 * 4, cudaMemcpyHostToDevice, r->stream));
+    if (ramp_h) CK(cudaMemcpyAsync(r->ramps.p, ramps, (size_t)ramp_h * 512 * 4, cudaMemcpyHostToDevice, st));
     r->atlas_w = atlas ? atlas_w : 0;
     r->atlas_h = atlas ? atlas_h : 0;
     if ((rc = ensure(r, r->atlas, (size_t)r->atlas_w * r->atlas_h * 4))) return rc;
     if (r->atlas_w && r->atlas_h)
-        CK(cudaMemcpyAsync(r->atlas.p, atlas, (size_t)r->atlas_w * r->atlas_h * 4, cudaMemcpyHostToDevice, r->stream));
+        CK(cudaMemcpyAsync(r->atlas.p, atlas, (size_t)r->atlas_w * r->atlas_h * 4, cudaMemcpyHostToDevice, st));
     r->have_scene = true;
     return VB_OK;
+}
+
+extern "C" int vb_readback_wait(vb_renderer *r);
+// A non-streaming entry point used while streamed frames are still in flight completes them first.
+static int drain_stream(vb_renderer *r) {
+    if (r->stream_pending && !r->in_stream_call) return vb_readback_wait(r);
+    return VB_OK;
+}
+
+extern "C" int vb_scene_upload(vb_renderer *r, const uint8_t *scene, size_t scene_len, const vb_layout *layout, const uint32_t *ramps,
+                               uint32_t ramp_w, uint32_t ramp_h, const uint8_t *atlas, uint32_t atlas_w, uint32_t atlas_h) {
+    if (!r) return VB_E_INVALID;
+    int rc = drain_stream(r);
+    if (rc) return rc;
+    return upload_on(r, r->stream, scene, scene_len, layout, ramps, ramp_w, ramp_h, atlas, atlas_w, atlas_h);
 }
 
 static uint32_t grow(uint32_t need) {
@@ -372,7 +447,15 @@ static int prepare(vb_renderer *r, const vb_params *p) {
     }
     c.win_ty0 = c.win_by0 * 16u;
     c.win_ty1 = c.win_by1 * 16u < c.height_in_tiles ? c.win_by1 * 16u : c.height_in_tiles;
-    c.win_cull = (c.win_by0 > 0u || c.win_by1 < hb) ? 1u : 0u;
+    if (p->tile_row1 > p->tile_row0) {
+        // stripe in tile rows: binning / coarse cover the bins that contain it, tile_alloc clamps every path to its rows
+        // (so the extra tiles of a partly covered bin row hold empty command lists), fine paints exactly the stripe
+        c.win_ty0 = p->tile_row0 < c.height_in_tiles ? p->tile_row0 : c.height_in_tiles;
+        c.win_ty1 = p->tile_row1 < c.height_in_tiles ? p->tile_row1 : c.height_in_tiles;
+        c.win_by0 = c.win_ty0 / 16u;
+        c.win_by1 = (c.win_ty1 + 15u) / 16u;
+    }
+    c.win_cull = (c.win_ty0 > 0u || c.win_ty1 < c.height_in_tiles) ? 1u : 0u;
     c.n_tag_words = r->layout.path_data_base - r->layout.path_tag_base;
     c.scene_words = (uint32_t)r->scene_words;
     c.n_ramps = r->n_ramps;
@@ -698,7 +781,10 @@ extern "C" int vb_render_enqueue(vb_renderer *r, const vb_params *p, void *out_d
     void *out;
     if ((rc = pick_out(r, out_device, &out))) return rc;
     r->out_dev = out;
+    CK(cudaEventRecord(r->frame_ev[0], r->stream));
     rc = enqueue(r, 0, VB_N_STAGE_IDS - 1, out);
+    if (rc == VB_OK) CK(cudaEventRecord(r->frame_ev[1], r->stream));
+    r->frame_timed = rc == VB_OK;
     r->frame_pending = rc == VB_OK;
     return rc;
 }
@@ -743,6 +829,10 @@ extern "C" int vb_frame_finish(vb_renderer *r, vb_frame_stats *stats) {
 
 extern "C" int vb_render_resident(vb_renderer *r, const vb_params *p, void *out_device, vb_frame_stats *stats) {
     if (!r || !p) return VB_E_INVALID;
+    {
+        int rcd = drain_stream(r);
+        if (rcd) return rcd;
+    }
     if (!r->have_scene) return VB_E_NO_SCENE;
     r->retries = 0;
     for (uint32_t attempt = 0;; attempt++) {
@@ -783,38 +873,125 @@ extern "C" int vb_render(vb_renderer *r, const uint8_t *scene, size_t scene_len,
     return rc;
 }
 
-// Streaming variant of vb_render for back-to-back frames with HOST buffers. Returns as soon as the frame has been
-// rasterised (arena overflows handled as usual); the tail of ITS read-back may still be in flight on the copy stream,
-// overlapping the next call's upload and geometry stages. On return every EARLIER frame's `out_host` is complete;
-// vb_readback_wait() completes the last one. Use a different out_host for consecutive frames.
+// ---- streaming: vb_render_begin / vb_readback_wait ------------------------------------------------------------------------
+// Back-to-back frames with HOST buffers (a viewer / exporter reading every frame back, examples/headless/src/main.rs:188-210).
+// vb_render_begin(k) uploads frame k's scene into the free scene slot on the upload stream, enqueues its rasterisation and
+// its read-back, and only THEN waits for frame k-1 (whose kernels were running all along) to be complete on the host. In
+// steady state the GPU therefore sees  upload(k+1) | raster(k) | read-back(k-1)  side by side and a frame costs
+// max(raster, read-back, upload) instead of their sum. On return every EARLIER frame's out_host is complete and `stats`
+// describes frame k-1 (zeros on the first call); vb_readback_wait completes the last frame. Consecutive frames must use
+// different out_host buffers. An arena overflow is found when a frame is completed; that frame (and the one enqueued
+// behind it) is then re-run synchronously with grown arenas -- rare (first frames of a new scene size) and exact.
+static int rerun_slot_sync(vb_renderer *r, uint32_t slot, vb_frame_stats *stats) {
+    select_slot(r, slot);
+    r->host_out = r->inflight[slot].out_host;
+    r->use_alt = slot != 0u;
+    const uint32_t bands = r->readback_bands;
+    r->readback_bands = 1;
+    int rc = vb_render_resident(r, &r->inflight[slot].params, nullptr, stats);
+    r->readback_bands = bands;
+    r->host_out = nullptr;
+    r->use_alt = false;
+    cudaError_t e = cudaStreamSynchronize(r->copy_stream);
+    if (rc == VB_OK && e != cudaSuccess) {
+        r->err = std::string("copy stream: ") + cudaGetErrorString(e);
+        rc = VB_E_CUDA;
+    }
+    return rc;
+}
+
+// Complete the in-flight frame of `slot` on the host; `younger` = a frame was enqueued behind it.
+static int complete_slot(vb_renderer *r, uint32_t slot, bool younger, vb_frame_stats *stats) {
+    if (!r->inflight[slot].pending) return VB_OK;
+    const uint32_t keep = r->cur_slot;
+    CK(cudaEventSynchronize(r->raster_done[slot]));
+    const VbBump *hb = slot == r->cur_slot ? r->h_bump : r->other.h_bump;
+    int rc = VB_OK;
+    if (hb->failed != 0u) {
+        // drain, then re-run this frame (and the younger one, which ran with the same too-small arenas) synchronously
+        CK(cudaStreamSynchronize(r->stream));
+        CK(cudaStreamSynchronize(r->copy_stream));
+        select_slot(r, slot);
+        grow_arenas(r);
+        rc = rerun_slot_sync(r, slot, stats);
+        if (rc == VB_OK && younger) {
+            const VbBump *hy = (slot ^ 1u) == r->cur_slot ? r->h_bump : r->other.h_bump;
+            if (hy->failed != 0u) {
+                rc = rerun_slot_sync(r, slot ^ 1u, nullptr);
+                if (rc == VB_OK) {
+                    CK(cudaEventRecord(r->raster_done[slot ^ 1u], r->stream));
+                    CK(cudaEventRecord(r->copy_done[slot ^ 1u], r->copy_stream));
+                }
+            }
+        }
+        select_slot(r, keep);
+    } else {
+        CK(cudaEventSynchronize(r->copy_done[slot]));
+        if (stats) {
+            select_slot(r, slot);
+            r->retries = 0;
+            fill_stats(r, stats);
+            select_slot(r, keep);
+        }
+    }
+    r->inflight[slot].pending = false;
+    return rc;
+}
+
 extern "C" int vb_render_begin(vb_renderer *r, const uint8_t *scene, size_t scene_len, const vb_layout *layout, const uint32_t *ramps,
                                uint32_t ramp_w, uint32_t ramp_h, const uint8_t *atlas, uint32_t atlas_w, uint32_t atlas_h,
                                const vb_params *p, void *out_host, vb_frame_stats *stats) {
     if (!r || !p || !out_host) return VB_E_INVALID;
-    int rc = vb_scene_upload(r, scene, scene_len, layout, ramps, ramp_w, ramp_h, atlas, atlas_w, atlas_h);
+    CK(cudaSetDevice(r->device));
+    if (stats) memset(stats, 0, sizeof *stats);
+    struct Guard {
+        vb_renderer *r;
+        ~Guard() { r->in_stream_call = false; }
+    } guard{r};
+    r->in_stream_call = true;
+    const uint32_t slot = r->stream_parity;
+    // the frame that used this slot two calls ago was completed by the previous call
+    select_slot(r, slot);
+    int rc = upload_on(r, r->upload_stream, scene, scene_len, layout, ramps, ramp_w, ramp_h, atlas, atlas_w, atlas_h);
     if (rc) return rc;
-    const uint32_t par = r->stream_parity;
+    CK(cudaEventRecord(r->upload_done[slot], r->upload_stream));
+    CK(cudaStreamWaitEvent(r->stream, r->upload_done[slot], 0));
     const uint32_t bands = r->readback_bands;
     r->readback_bands = 1; // the whole read-back overlaps the next frame: no reason to split fine
     r->host_out = out_host;
-    r->use_alt = par != 0u;
-    rc = vb_render_resident(r, p, nullptr, stats);
+    r->use_alt = slot != 0u;
+    rc = vb_render_enqueue(r, p, nullptr);
     r->host_out = nullptr;
     r->use_alt = false;
     r->readback_bands = bands;
-    CK(cudaEventRecord(r->copy_done[par], r->copy_stream));
-    if (r->stream_pending) CK(cudaEventSynchronize(r->copy_done[par ^ 1u])); // the previous frame's pixels are on the host
+    if (rc) return rc;
+    r->frame_pending = false;
+    CK(cudaEventRecord(r->raster_done[slot], r->stream));
+    CK(cudaEventRecord(r->copy_done[slot], r->copy_stream));
+    r->inflight[slot].pending = true;
+    r->inflight[slot].params = *p;
+    r->inflight[slot].out_host = out_host;
+    // now complete the previous frame: its kernels ran while this one was being uploaded and enqueued
+    rc = complete_slot(r, slot ^ 1u, true, stats);
     r->stream_pending = true;
-    r->stream_parity = par ^ 1u;
+    r->stream_parity = slot ^ 1u;
     return rc;
 }
 
 extern "C" int vb_readback_wait(vb_renderer *r) {
     if (!r) return VB_E_INVALID;
     CK(cudaSetDevice(r->device));
+    struct Guard {
+        vb_renderer *r;
+        ~Guard() { r->in_stream_call = false; }
+    } guard{r};
+    r->in_stream_call = true;
+    // frames complete in order: the older one is the slot the NEXT begin would use
+    int rc = complete_slot(r, r->stream_parity, r->inflight[r->stream_parity ^ 1u].pending, nullptr);
+    const int rc2 = complete_slot(r, r->stream_parity ^ 1u, false, nullptr);
     CK(cudaStreamSynchronize(r->copy_stream));
     r->stream_pending = false;
-    return VB_OK;
+    return rc ? rc : rc2;
 }
 
 extern "C" int vb_run_stages(vb_renderer *r, const vb_params *p, int first, int last, void *out_device) {
@@ -957,4 +1134,291 @@ extern "C" int vb_debug_upload(vb_renderer *r, const char *name, const void *src
         return VB_OK;
     }
     return VB_E_UNKNOWN_BUFFER;
+}
+
+
+extern "C" float vb_last_frame_ms(vb_renderer *r) {
+    if (!r || !r->frame_timed) return 0.0f;
+    cudaSetDevice(r->device);
+    float ms = 0.0f;
+    if (cudaEventSynchronize(r->frame_ev[1]) != cudaSuccess || cudaEventElapsedTime(&ms, r->frame_ev[0], r->frame_ev[1]) != cudaSuccess) {
+        cudaGetLastError();
+        return 0.0f;
+    }
+    return ms;
+}
+
+// ---- CUDA IPC helpers (one process per GPU: the frame buffer of rank 0 mapped into the other ranks) ----------------------
+extern "C" int vb_frame_alloc(vb_renderer *r, size_t bytes, void **device_ptr) {
+    if (!r || !device_ptr || !bytes) return VB_E_INVALID;
+    CK(cudaSetDevice(r->device));
+    CK(cudaMalloc(device_ptr, bytes));
+    return VB_OK;
+}
+extern "C" int vb_frame_free(vb_renderer *r, void *device_ptr) {
+    if (!r) return VB_E_INVALID;
+    CK(cudaSetDevice(r->device));
+    CK(cudaStreamSynchronize(r->stream));
+    if (device_ptr) CK(cudaFree(device_ptr));
+    return VB_OK;
+}
+extern "C" int vb_ipc_export(vb_renderer *r, void *device_ptr, uint8_t handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    if (!r || !device_ptr || !handle) return VB_E_INVALID;
+    CK(cudaSetDevice(r->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, device_ptr));
+    memcpy(handle, &h, 64);
+    return VB_OK;
+}
+extern "C" int vb_ipc_open(vb_renderer *r, const uint8_t handle[64], void **device_ptr) {
+    if (!r || !handle || !device_ptr) return VB_E_INVALID;
+    CK(cudaSetDevice(r->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CK(cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return VB_OK;
+}
+extern "C" int vb_ipc_close(vb_renderer *r, void *device_ptr) {
+    if (!r || !device_ptr) return VB_E_INVALID;
+    CK(cudaSetDevice(r->device));
+    CK(cudaStreamSynchronize(r->stream));
+    CK(cudaIpcCloseMemHandle(device_ptr));
+    return VB_OK;
+}
+
+// ---- vb_group: one frame on several devices of one box, one host thread ---------------------------------------------------
+struct vb_group {
+    std::vector<vb_renderer *> subs;
+    std::vector<int> devices;
+    std::vector<uint32_t> bounds;   // tile-row boundaries, subs.size() + 1 entries
+    std::vector<float> ms;          // device time of the last frame per renderer
+    std::vector<char> peer_ok;      // renderer i can store into device 0's memory
+    std::vector<cudaEvent_t> done;  // per renderer: its stripe is in the frame
+    void *frame = nullptr;          // assembled frame on devices[0]
+    size_t frame_cap = 0;
+    uint32_t bounds_h = 0;          // height in tiles the boundaries were made for
+    bool balancing = true;
+    std::string err;
+};
+
+extern "C" int vb_group_new(const int32_t *devices, uint32_t n, const vb_options *opt, vb_group **out) {
+    if (!devices || !n || n > 64 || !out) return VB_E_INVALID;
+    vb_group *g = new vb_group();
+    for (uint32_t i = 0; i < n; i++) {
+        vb_options o{};
+        if (opt) o = *opt;
+        o.device = devices[i];
+        vb_renderer *r = nullptr;
+        int rc = vb_renderer_new(&o, &r);
+        if (rc) {
+            vb_group_free(g);
+            return rc;
+        }
+        g->subs.push_back(r);
+        g->devices.push_back(devices[i]);
+        cudaEvent_t ev = nullptr;
+        cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        g->done.push_back(ev);
+        // stores of `fine` on device i land in device 0's frame buffer through peer mapping (NVLink / NVSwitch)
+        char ok = 1;
+        if (devices[i] != devices[0]) {
+            int can = 0;
+            cudaSetDevice(devices[i]);
+            if (cudaDeviceCanAccessPeer(&can, devices[i], devices[0]) != cudaSuccess || !can) ok = 0;
+            else {
+                cudaError_t e = cudaDeviceEnablePeerAccess(devices[0], 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
+                cudaGetLastError();
+            }
+        }
+        g->peer_ok.push_back(ok);
+    }
+    g->ms.assign(n, 0.0f);
+    *out = g;
+    return VB_OK;
+}
+
+extern "C" void vb_group_free(vb_group *g) {
+    if (!g) return;
+    for (vb_renderer *r : g->subs) vb_renderer_free(r);
+    if (!g->devices.empty()) cudaSetDevice(g->devices[0]);
+    if (g->frame) cudaFree(g->frame);
+    for (cudaEvent_t ev : g->done)
+        if (ev) cudaEventDestroy(ev);
+    delete g;
+}
+extern "C" uint32_t vb_group_size(const vb_group *g) { return g ? (uint32_t)g->subs.size() : 0u; }
+extern "C" vb_renderer *vb_group_renderer(vb_group *g, uint32_t i) { return g && i < g->subs.size() ? g->subs[i] : nullptr; }
+extern "C" const char *vb_group_last_error(vb_group *g) { return g ? g->err.c_str() : ""; }
+extern "C" int vb_group_set_balancing(vb_group *g, int on) {
+    if (!g) return VB_E_INVALID;
+    g->balancing = on != 0;
+    return VB_OK;
+}
+extern "C" void *vb_group_frame(vb_group *g, size_t *bytes) {
+    if (!g) return nullptr;
+    if (bytes) *bytes = g->frame_cap;
+    return g->frame;
+}
+extern "C" int vb_group_stripes(vb_group *g, uint32_t *boundaries, float *device_ms) {
+    if (!g) return VB_E_INVALID;
+    if (boundaries)
+        for (size_t i = 0; i < g->bounds.size(); i++) boundaries[i] = g->bounds[i];
+    if (device_ms)
+        for (size_t i = 0; i < g->ms.size(); i++) device_ms[i] = g->ms[i];
+    return VB_OK;
+}
+
+// Move the stripe boundaries so that the device times of the last frame would have been equal, assuming the cost of a stripe is
+// spread evenly over its tile rows (piecewise-linear cumulative cost); damped, every stripe keeps at least one tile row.
+static void group_rebalance(vb_group *g, uint32_t ht) {
+    const size_t n = g->subs.size();
+    if (g->bounds.size() != n + 1 || g->bounds_h != ht) {
+        g->bounds.assign(n + 1, 0u);
+        for (size_t i = 0; i <= n; i++) g->bounds[i] = (uint32_t)((uint64_t)ht * i / n);
+        g->bounds_h = ht;
+        return;
+    }
+    if (!g->balancing || n < 2 || ht < n) return;
+    double total = 0.0, lo = 1e30, hi = 0.0;
+    for (size_t i = 0; i < n; i++) {
+        if (!(g->ms[i] > 0.0f)) return; // no measurement yet
+        total += g->ms[i];
+        lo = std::min<double>(lo, g->ms[i]);
+        hi = std::max<double>(hi, g->ms[i]);
+    }
+    if (hi - lo < 0.06 * (total / n)) return; // balanced within noise: keep the stripes (and the captured graphs)
+    std::vector<uint32_t> nb(n + 1, 0u);
+    nb[n] = ht;
+    size_t seg = 0;
+    double acc = 0.0; // cost of the stripes before `seg`
+    for (size_t k = 1; k < n; k++) {
+        const double want = total * k / n;
+        while (seg + 1 < n && acc + g->ms[seg] < want) acc += g->ms[seg++];
+        const double rows = (double)(g->bounds[seg + 1] - g->bounds[seg]);
+        const double frac = g->ms[seg] > 0.0f ? (want - acc) / g->ms[seg] : 0.0;
+        const double ideal = g->bounds[seg] + rows * frac;
+        const double damped = 0.5 * g->bounds[k] + 0.5 * ideal;
+        nb[k] = (uint32_t)(damped + 0.5);
+    }
+    for (size_t k = 1; k < n; k++) { // monotone, at least one row each
+        if (nb[k] < nb[k - 1] + 1u) nb[k] = nb[k - 1] + 1u;
+    }
+    for (size_t k = n - 1; k >= 1; k--) {
+        if (nb[k] > nb[k + 1] - 1u) nb[k] = nb[k + 1] - 1u;
+    }
+    g->bounds = nb;
+}
+
+#define GCK(call)                                                                                 \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            g->err = std::string(#call) + ": " + cudaGetErrorString(e_);                          \
+            return VB_E_CUDA;                                                                     \
+        }                                                                                         \
+    } while (0)
+
+extern "C" int vb_group_scene_upload(vb_group *g, const uint8_t *scene, size_t scene_len, const vb_layout *layout, const uint32_t *ramps,
+                                     uint32_t ramp_w, uint32_t ramp_h, const uint8_t *atlas, uint32_t atlas_w, uint32_t atlas_h) {
+    if (!g) return VB_E_INVALID;
+    // every device pulls the scene over its own PCIe link (asynchronous per renderer, so the copies run side by side)
+    for (vb_renderer *r : g->subs) {
+        int rc = vb_scene_upload(r, scene, scene_len, layout, ramps, ramp_w, ramp_h, atlas, atlas_w, atlas_h);
+        if (rc) {
+            g->err = r->err;
+            return rc;
+        }
+    }
+    return VB_OK;
+}
+
+// out: nullptr (group frame), a device pointer on devices[0], or (host_out) a host pointer
+static int group_render(vb_group *g, const vb_params *p, void *out_device, void *host_out, vb_frame_stats *stats) {
+    if (!g || !p || p->bin_row1 > p->bin_row0 || p->tile_row1 > p->tile_row0) return VB_E_INVALID;
+    const size_t n = g->subs.size();
+    const uint32_t ht = (p->height + 15u) / 16u;
+    group_rebalance(g, ht);
+    const size_t pitch = (size_t)p->width * 4u;
+    void *frame = out_device;
+    if (!host_out && !frame) {
+        const size_t need = pitch * p->height;
+        if (g->frame_cap < need) {
+            GCK(cudaSetDevice(g->devices[0]));
+            if (g->frame) GCK(cudaFree(g->frame));
+            g->frame = nullptr;
+            g->frame_cap = 0;
+            GCK(cudaMalloc(&g->frame, need));
+            g->frame_cap = need;
+        }
+        frame = g->frame;
+    }
+    // enqueue every device's stripe, then complete them (one host thread; the devices run side by side)
+    std::vector<vb_params> ps(n, *p);
+    for (size_t i = 0; i < n; i++) {
+        vb_renderer *r = g->subs[i];
+        ps[i].tile_row0 = g->bounds[i];
+        ps[i].tile_row1 = g->bounds[i + 1];
+        if (ps[i].tile_row1 <= ps[i].tile_row0) continue; // more devices than tile rows
+        const size_t row0 = (size_t)g->bounds[i] * 16u;
+        void *dst = nullptr; // nullptr: the renderer's own target (then copied)
+        if (host_out) {
+            r->host_out = (char *)host_out + row0 * pitch;
+            r->readback_bands = 1;
+        } else if (g->peer_ok[i]) {
+            dst = (char *)frame + row0 * pitch;
+        }
+        int rc = vb_render_enqueue(r, &ps[i], dst);
+        if (rc) {
+            r->host_out = nullptr;
+            g->err = r->err;
+            return rc;
+        }
+    }
+    int result = VB_OK;
+    for (size_t i = 0; i < n; i++) {
+        vb_renderer *r = g->subs[i];
+        if (ps[i].tile_row1 <= ps[i].tile_row0) {
+            if (stats) memset(&stats[i], 0, sizeof(vb_frame_stats));
+            continue;
+        }
+        const size_t row0 = (size_t)g->bounds[i] * 16u;
+        void *dst = (!host_out && g->peer_ok[i]) ? (char *)frame + row0 * pitch : nullptr;
+        int rc = vb_frame_finish(r, stats ? &stats[i] : nullptr);
+        if (rc == VB_E_BUMP_OVERFLOW) rc = vb_render_resident(r, &ps[i], dst, stats ? &stats[i] : nullptr); // grow and re-run (first frames)
+        g->ms[i] = vb_last_frame_ms(r);
+        if (rc == VB_OK && host_out) {
+            cudaSetDevice(r->device);
+            if (cudaStreamSynchronize(r->copy_stream) != cudaSuccess) rc = VB_E_CUDA;
+        }
+        if (rc == VB_OK && !host_out && !g->peer_ok[i]) {
+            // no peer mapping between these two devices: stage through the renderer's own target
+            const size_t h0 = row0, h1 = std::min<size_t>((size_t)g->bounds[i + 1] * 16u, p->height);
+            cudaSetDevice(r->device);
+            if (cudaMemcpyPeerAsync((char *)frame + row0 * pitch, g->devices[0], r->out_dev, r->device, (h1 - h0) * pitch, r->stream) != cudaSuccess ||
+                cudaStreamSynchronize(r->stream) != cudaSuccess)
+                rc = VB_E_CUDA;
+        }
+        r->host_out = nullptr;
+        if (rc && result == VB_OK) {
+            result = rc;
+            g->err = r->err;
+        }
+    }
+    return result;
+}
+
+extern "C" int vb_group_render_resident(vb_group *g, const vb_params *p, void *out_device, vb_frame_stats *stats) {
+    return group_render(g, p, out_device, nullptr, stats);
+}
+
+extern "C" int vb_group_render(vb_group *g, const uint8_t *scene, size_t scene_len, const vb_layout *layout, const uint32_t *ramps,
+                               uint32_t ramp_w, uint32_t ramp_h, const uint8_t *atlas, uint32_t atlas_w, uint32_t atlas_h, const vb_params *p,
+                               void *out, uint32_t out_is_device, vb_frame_stats *stats) {
+    if (!g || !p) return VB_E_INVALID;
+    int rc = vb_group_scene_upload(g, scene, scene_len, layout, ramps, ramp_w, ramp_h, atlas, atlas_w, atlas_h);
+    if (rc) return rc;
+    if (out && !out_is_device) return group_render(g, p, nullptr, out, stats);
+    return group_render(g, p, out, nullptr, stats);
 }

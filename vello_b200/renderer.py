@@ -39,7 +39,7 @@ class _Layout(C.Structure):
 
 
 class _Params(C.Structure):
-    _fields_ = [(n, C.c_uint32) for n in ("base_color", "width", "height", "aa", "bin_row0", "bin_row1")]
+    _fields_ = [(n, C.c_uint32) for n in ("base_color", "width", "height", "aa", "bin_row0", "bin_row1", "tile_row0", "tile_row1")]
 
 
 class FrameStats(C.Structure):
@@ -95,13 +95,39 @@ def load_library() -> C.CDLL:
     lib.vb_debug_upload.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
     lib.vb_set_occlusion_cull.argtypes = [vp, C.c_int]
     lib.vb_debug_fine_traffic.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.vb_last_frame_ms.restype = C.c_float
+    lib.vb_last_frame_ms.argtypes = [vp]
+    lib.vb_frame_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    lib.vb_frame_free.argtypes = [vp, vp]
+    lib.vb_ipc_export.argtypes = [vp, vp, C.c_char_p]
+    lib.vb_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    lib.vb_ipc_close.argtypes = [vp, vp]
+    lib.vb_group_new.argtypes = [C.POINTER(C.c_int32), C.c_uint32, C.POINTER(_Options), C.POINTER(vp)]
+    lib.vb_group_free.argtypes = [vp]
+    lib.vb_group_size.restype = C.c_uint32
+    lib.vb_group_size.argtypes = [vp]
+    lib.vb_group_renderer.restype = vp
+    lib.vb_group_renderer.argtypes = [vp, C.c_uint32]
+    lib.vb_group_last_error.restype = C.c_char_p
+    lib.vb_group_last_error.argtypes = [vp]
+    lib.vb_group_render.argtypes = [vp, vp, C.c_size_t, C.POINTER(_Layout), vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, C.c_uint32,
+                                    C.POINTER(_Params), vp, C.c_uint32, vp]
+    lib.vb_group_scene_upload.argtypes = [vp, vp, C.c_size_t, C.POINTER(_Layout), vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, C.c_uint32]
+    lib.vb_group_render_resident.argtypes = [vp, C.POINTER(_Params), vp, vp]
+    lib.vb_group_frame.restype = vp
+    lib.vb_group_frame.argtypes = [vp, C.POINTER(C.c_size_t)]
+    lib.vb_group_stripes.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
+    lib.vb_group_set_balancing.argtypes = [vp, C.c_int]
     _lib = lib
     return lib
 
 
 EXPORTED_SYMBOLS = ["vb_renderer_new", "vb_renderer_free", "vb_strerror", "vb_last_error", "vb_scene_upload",
                     "vb_render_resident", "vb_render_enqueue", "vb_frame_finish", "vb_render", "vb_target", "vb_copy_to_host", "vb_stream",
-                    "vb_run_stages", "vb_debug_download", "vb_debug_upload", "vb_debug_fine_traffic", "vb_set_occlusion_cull", "vb_render_begin", "vb_readback_wait", "vb_set_readback_bands", "vb_set_cuda_graph"]
+                    "vb_run_stages", "vb_debug_download", "vb_debug_upload", "vb_debug_fine_traffic", "vb_set_occlusion_cull", "vb_render_begin", "vb_readback_wait", "vb_set_readback_bands", "vb_set_cuda_graph",
+                    "vb_last_frame_ms", "vb_frame_alloc", "vb_frame_free", "vb_ipc_export", "vb_ipc_open", "vb_ipc_close",
+                    "vb_group_new", "vb_group_free", "vb_group_size", "vb_group_renderer", "vb_group_last_error", "vb_group_render",
+                    "vb_group_scene_upload", "vb_group_render_resident", "vb_group_frame", "vb_group_stripes", "vb_group_set_balancing"]
 
 
 @dataclass
@@ -112,9 +138,9 @@ class RendererOptions:
     max_retries: int = 6
 
 
-def _params_struct(p: RenderParams, bin_rows=(0, 0)) -> _Params:
+def _params_struct(p: RenderParams, bin_rows=(0, 0), tile_rows=(0, 0)) -> _Params:
     return _Params(p.base_color.premul_rgba8_u32(), int(p.width), int(p.height), int(p.antialiasing_method),
-                   int(bin_rows[0]), int(bin_rows[1]))
+                   int(bin_rows[0]), int(bin_rows[1]), int(tile_rows[0]), int(tile_rows[1]))
 
 
 class Renderer:
@@ -161,7 +187,7 @@ class Renderer:
         self._check(rc, "vb_scene_upload")
 
     # -- rendering ---------------------------------------------------------------------------------
-    def render_to_texture(self, scene, params: RenderParams, bin_rows=(0, 0)) -> np.ndarray:
+    def render_to_texture(self, scene, params: RenderParams, bin_rows=(0, 0), tile_rows=(0, 0)) -> np.ndarray:
         """Render `scene` (a `Scene`, or an already resolved `Packed`) and return the RGBA8 image
         (h, w, 4) -- un-premultiplied, like the reference's Rgba8Unorm storage texture. Goes through
         the one-call C entry point `vb_render` with host buffers (upload + render + readback)."""
@@ -170,8 +196,8 @@ class Renderer:
         ramps = np.ascontiguousarray(packed.ramps, dtype=np.uint32)
         atlas = np.ascontiguousarray(packed.atlas, dtype=np.uint8)
         lay = _Layout(*[int(v) for v in packed.layout.as_array()])
-        ps = _params_struct(params, bin_rows)
-        h0, h1 = self.stripe_rows(params, bin_rows)
+        ps = _params_struct(params, bin_rows, tile_rows)
+        h0, h1 = self.stripe_rows(params, bin_rows, tile_rows)
         out = np.zeros((h1 - h0, params.width, 4), dtype=np.uint8)
         st = FrameStats()
         rc = self.lib.vb_render(self.handle, scene_w.ctypes.data, scene_w.nbytes, C.byref(lay),
@@ -208,22 +234,24 @@ class Renderer:
             yield prev
 
     @staticmethod
-    def stripe_rows(params: RenderParams, bin_rows=(0, 0)):
+    def stripe_rows(params: RenderParams, bin_rows=(0, 0), tile_rows=(0, 0)):
+        if tile_rows[1] > tile_rows[0]:
+            return min(tile_rows[0] * 16, params.height), min(tile_rows[1] * 16, params.height)
         if bin_rows[1] > bin_rows[0]:
             return min(bin_rows[0] * 256, params.height), min(bin_rows[1] * 256, params.height)
         return 0, params.height
 
-    def render_resident(self, params: RenderParams, out_device_ptr: int = 0, bin_rows=(0, 0)) -> FrameStats:
+    def render_resident(self, params: RenderParams, out_device_ptr: int = 0, bin_rows=(0, 0), tile_rows=(0, 0)) -> FrameStats:
         """Render the uploaded scene into a device buffer (0 = the renderer's own target)."""
-        ps = _params_struct(params, bin_rows)
+        ps = _params_struct(params, bin_rows, tile_rows)
         st = FrameStats()
         rc = self.lib.vb_render_resident(self.handle, C.byref(ps), C.c_void_p(out_device_ptr or None), C.byref(st))
         self.last_stats = st
         self._check(rc, "vb_render_resident")
         return st
 
-    def enqueue(self, params: RenderParams, out_device_ptr: int = 0, bin_rows=(0, 0)):
-        ps = _params_struct(params, bin_rows)
+    def enqueue(self, params: RenderParams, out_device_ptr: int = 0, bin_rows=(0, 0), tile_rows=(0, 0)):
+        ps = _params_struct(params, bin_rows, tile_rows)
         self._check(self.lib.vb_render_enqueue(self.handle, C.byref(ps), C.c_void_p(out_device_ptr or None)), "vb_render_enqueue")
 
     def finish(self) -> FrameStats:
@@ -273,11 +301,98 @@ class Renderer:
         self._check(self.lib.vb_debug_fine_traffic(self.handle, C.byref(a), C.byref(b), C.byref(c)), "vb_debug_fine_traffic")
         return int(a.value), int(b.value), int(c.value)
 
-    def download_target(self, params: RenderParams, bin_rows=(0, 0), device_ptr: int = 0) -> np.ndarray:
+    def download_target(self, params: RenderParams, bin_rows=(0, 0), device_ptr: int = 0, tile_rows=(0, 0)) -> np.ndarray:
         """Copy the last frame's target (or `device_ptr`) to the host."""
-        h0, h1 = self.stripe_rows(params, bin_rows)
+        h0, h1 = self.stripe_rows(params, bin_rows, tile_rows)
         out = np.zeros((h1 - h0, params.width, 4), dtype=np.uint8)
         src = device_ptr or self.target_ptr()
         self._check(self.lib.vb_copy_to_host(self.handle, C.c_void_p(src), C.c_void_p(out.ctypes.data), C.c_size_t(out.nbytes)),
                     "vb_copy_to_host")
         return out
+
+
+class RendererGroup:
+    """One frame on several GPUs of one box from one process (`vb_group`): the frame is cut into cost-balanced stripes of tile
+    rows, every device renders one, and `fine` on device k stores its pixels straight into the frame on devices[0] over
+    NVLink peer mapping (or every device reads its stripe back over its own PCIe link for a host destination)."""
+
+    def __init__(self, devices, options: Optional[RendererOptions] = None):
+        self.lib = load_library()
+        options = options or RendererOptions()
+        self.devices = [int(d) for d in devices]
+        arr = (C.c_int32 * len(self.devices))(*self.devices)
+        opt = _Options(self.devices[0], 1 if options.timing else 0, options.max_retries, 0)
+        self.handle = C.c_void_p()
+        rc = self.lib.vb_group_new(arr, len(self.devices), C.byref(opt), C.byref(self.handle))
+        if rc != 0:
+            raise VelloB200Error(f"vb_group_new failed: {self.lib.vb_strerror(rc).decode()}")
+        self.last_stats = None
+
+    def close(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            self.lib.vb_group_free(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise VelloB200Error(f"{what}: {self.lib.vb_strerror(rc).decode()} [{self.lib.vb_group_last_error(self.handle).decode()}]")
+
+    def set_balancing(self, on: bool):
+        self._check(self.lib.vb_group_set_balancing(self.handle, 1 if on else 0), "vb_group_set_balancing")
+
+    def upload(self, packed: Packed):
+        scene = np.ascontiguousarray(packed.scene, dtype=np.uint32)
+        ramps = np.ascontiguousarray(packed.ramps, dtype=np.uint32)
+        atlas = np.ascontiguousarray(packed.atlas, dtype=np.uint8)
+        lay = _Layout(*[int(v) for v in packed.layout.as_array()])
+        self._keep = (scene, ramps, atlas)
+        self._check(self.lib.vb_group_scene_upload(self.handle, scene.ctypes.data, scene.nbytes, C.byref(lay),
+                                                   ramps.ctypes.data if ramps.size else None, 512, ramps.shape[0],
+                                                   atlas.ctypes.data, atlas.shape[1], atlas.shape[0]), "vb_group_scene_upload")
+
+    def render_resident(self, params: RenderParams, out_device_ptr: int = 0):
+        ps = _params_struct(params)
+        st = (FrameStats * len(self.devices))()
+        self._check(self.lib.vb_group_render_resident(self.handle, C.byref(ps), C.c_void_p(out_device_ptr or None), st), "vb_group_render_resident")
+        self.last_stats = list(st)
+        return self.last_stats
+
+    def render_to_texture(self, scene, params: RenderParams) -> np.ndarray:
+        """ONE call, ONE frame: upload to every device, render the stripes, assemble in the caller's host buffer."""
+        packed = scene if isinstance(scene, Packed) else resolve(scene.encoding)
+        scene_w = np.ascontiguousarray(packed.scene, dtype=np.uint32)
+        ramps = np.ascontiguousarray(packed.ramps, dtype=np.uint32)
+        atlas = np.ascontiguousarray(packed.atlas, dtype=np.uint8)
+        lay = _Layout(*[int(v) for v in packed.layout.as_array()])
+        ps = _params_struct(params)
+        out = np.zeros((params.height, params.width, 4), dtype=np.uint8)
+        st = (FrameStats * len(self.devices))()
+        rc = self.lib.vb_group_render(self.handle, scene_w.ctypes.data, scene_w.nbytes, C.byref(lay),
+                                      ramps.ctypes.data if ramps.size else None, 512, ramps.shape[0],
+                                      atlas.ctypes.data, atlas.shape[1], atlas.shape[0], C.byref(ps), out.ctypes.data, 0, st)
+        self.last_stats = list(st)
+        self._check(rc, "vb_group_render")
+        return out
+
+    def frame_to_host(self, params: RenderParams) -> np.ndarray:
+        """Copy the group's assembled frame (on devices[0]) to the host."""
+        n = C.c_size_t(0)
+        ptr = self.lib.vb_group_frame(self.handle, C.byref(n))
+        out = np.zeros((params.height, params.width, 4), dtype=np.uint8)
+        r0 = self.lib.vb_group_renderer(self.handle, 0)
+        rc = self.lib.vb_copy_to_host(r0, C.c_void_p(ptr), C.c_void_p(out.ctypes.data), C.c_size_t(out.nbytes))
+        self._check(rc, "vb_copy_to_host")
+        return out
+
+    def stripes(self):
+        n = len(self.devices)
+        b = (C.c_uint32 * (n + 1))()
+        ms = (C.c_float * n)()
+        self._check(self.lib.vb_group_stripes(self.handle, b, ms), "vb_group_stripes")
+        return list(b), list(ms)
