@@ -214,31 +214,82 @@ def main():
     from vello_b200.config import RenderParams
     from vello_b200.encoding import BLACK
     from vello_b200.renderer import Renderer, RendererOptions, FrameStats, _Layout, _Params
+    from vello_b200.stripes import even_tile_bounds, rebalance
 
     packed, gen_s = build_scene(args)
     params = RenderParams(BLACK, args.size, H, args.aa)
-    bin_rows = stripe_for(rank, world, H) if world > 1 else (0, 0)
     torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
     r = Renderer(RendererOptions(device=local))
     r.upload(packed)
-    h0, h1 = r.stripe_rows(params, bin_rows)
-    out = torch.empty((max(h1 - h0, 1), args.size, 4), dtype=torch.uint8, device=f"cuda:{local}")
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
-    stream = torch.cuda.ExternalStream(r.stream, device=f"cuda:{local}")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.ExternalStream(r.stream, device=dev)
+    vp = C.c_void_p
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- resident-scene throughput ("value") -------------------------------------------------
-    st = r.render_resident(params, out.data_ptr(), bin_rows)  # sizes the arenas (may retry)
+    def allgather_floats(v):
+        if dist is None:
+            return [list(v)]
+        t = torch.tensor(list(v), dtype=torch.float64, device=dev)
+        outs = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(outs, t)
+        return [o.tolist() for o in outs]
+
+    # ---- the frame buffer. One GPU: a device buffer. N GPUs: the frame lives on rank 0 (allocated by the library, exported
+    # through CUDA IPC) and every rank's `fine` stores its stripe STRAIGHT INTO IT over NVLink peer mapping -- no gather pass.
+    frame_bytes = args.size * H * 4
+    frame_ptr = vp()
+    if rank == 0:
+        assert r.lib.vb_frame_alloc(r.handle, frame_bytes, C.byref(frame_ptr)) == 0
+    if world > 1:
+        handle = C.create_string_buffer(64)
+        if rank == 0:
+            assert r.lib.vb_ipc_export(r.handle, frame_ptr, handle) == 0
+        ht = torch.tensor(list(handle.raw), dtype=torch.uint8, device=dev)
+        dist.broadcast(ht, src=0)
+        if rank != 0:
+            hb = C.create_string_buffer(bytes(ht.cpu().tolist()), 64)
+            rc = r.lib.vb_ipc_open(r.handle, hb, C.byref(frame_ptr))
+            assert rc == 0, f"vb_ipc_open failed on rank {rank}: {r.lib.vb_last_error(r.handle).decode()}"
+    frame_base = int(frame_ptr.value)
+
+    bounds = even_tile_bounds(world, H)
+
+    def my_rows():
+        return (bounds[rank], bounds[rank + 1]) if world > 1 else (0, 0)
+
+    def my_out():
+        return frame_base + (bounds[rank] * 16 * args.size * 4 if world > 1 else 0)
+
+    def render_once():
+        return r.render_resident(params, my_out(), tile_rows=my_rows())
+
+    # ---- warm-up: size the arenas, then (N > 1) move the stripe boundaries until the ranks take equally long
+    st = render_once()
+    balance_log = []
+    if world > 1:
+        for it in range(12):
+            for _ in range(2):
+                render_once()
+            ms = [v[0] for v in allgather_floats([float(r.lib.vb_last_frame_ms(r.handle))])]
+            balance_log.append({"bounds": list(bounds), "ms": [round(m, 4) for m in ms]})
+            nb = rebalance(bounds, ms)
+            if nb == bounds:
+                break
+            bounds = nb
     for _ in range(args.warmup):
-        r.render_resident(params, out.data_ptr(), bin_rows)
+        st = render_once()
     if args.profile_only:
         for _ in range(args.steps):
-            r.render_resident(params, out.data_ptr(), bin_rows)
+            render_once()
         return
+
+    # ---- resident-scene throughput ("value"): exactly K steps, CUDA events per step on the renderer's stream, L2 flushed
+    # between steps; a step of the N-GPU job lasts as long as its slowest rank, so the per-step times are max-reduced over ranks
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -249,8 +300,11 @@ def main():
     for a, b in evs:
         flush.fill_(1)          # L2 flush on the default stream ...
         torch.cuda.synchronize()  # ... finished before the step starts
+        if dist is not None:
+            dist.barrier()      # all ranks start the frame together (one frame = all its stripes)
+            torch.cuda.synchronize()
         a.record(stream)
-        r.enqueue(params, out.data_ptr(), bin_rows)
+        r.enqueue(params, my_out(), tile_rows=my_rows())
         b.record(stream)
         s = r.finish()
         assert s.failed == 0
@@ -258,44 +312,58 @@ def main():
     barrier()
     wall = time.perf_counter() - t_wall
     clocks = sampler.stop() if rank == 0 else None
-    total_ms = sum(a.elapsed_time(b) for a, b in evs)
-    t = torch.tensor([total_ms], dtype=torch.float64, device=f"cuda:{local}")
+    step_ms = torch.tensor([a.elapsed_time(b) for a, b in evs], dtype=torch.float64, device=dev)
+    my_total = float(step_ms.sum().item())
     if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
+        dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(step_ms.sum().item())
     fps = args.steps / (total_ms / 1000.0)
+    rank_totals = [v[0] for v in allgather_floats([my_total])]
 
-    # ---- end-to-end through vb_render with pinned host buffers ("e2e") ---------------------------
+    # ---- the assembled frame: rank 0 renders the whole frame alone and compares (stripes over NVLink == one GPU)
+    stripes_parity = None
+    if world > 1:
+        barrier()
+        if rank == 0:
+            asm = np.zeros((H, args.size, 4), dtype=np.uint8)
+            assert r.lib.vb_copy_to_host(r.handle, vp(frame_base), vp(asm.ctypes.data), C.c_size_t(asm.nbytes)) == 0
+            r.render_resident(params, 0)
+            solo = r.download_target(params)
+            stripes_parity = {"assembled_over_nvlink_equals_single_gpu": bool(np.array_equal(asm, solo)),
+                              "differing_pixels": int((asm != solo).any(axis=2).sum())}
+            del asm, solo
+        barrier()
+
+    # ---- end-to-end through the C ABI with pinned host buffers ("e2e") ---------------------------
+    h0, h1 = r.stripe_rows(params, (0, 0), my_rows())
     scene_h = torch.from_numpy(np.ascontiguousarray(packed.scene)).pin_memory()
     ramps_h = torch.from_numpy(np.ascontiguousarray(packed.ramps.reshape(-1))).pin_memory() if packed.ramps.size else None
     atlas_np = np.ascontiguousarray(packed.atlas)
-    out_h = torch.empty((max(h1 - h0, 1), args.size, 4), dtype=torch.uint8).pin_memory()
+    outs = tuple(torch.empty((max(h1 - h0, 1), args.size, 4), dtype=torch.uint8).pin_memory() for _ in range(3))
     lay = _Layout(*[int(v) for v in packed.layout.as_array()])
-    ps = _Params(BLACK.premul_rgba8_u32(), args.size, H, args.aa, bin_rows[0], bin_rows[1])
+    tr = my_rows()
+    ps = _Params(BLACK.premul_rgba8_u32(), args.size, H, args.aa, 0, 0, tr[0], tr[1])
     fs = FrameStats()
-
-    out_h2 = torch.empty_like(out_h).pin_memory()
-    outs = (out_h, out_h2)
 
     def e2e_args(o):
         return (r.handle, scene_h.data_ptr(), scene_h.numel() * 4, C.byref(lay), ramps_h.data_ptr() if ramps_h is not None else None, 512,
                 packed.ramps.shape[0], atlas_np.ctypes.data, atlas_np.shape[1], atlas_np.shape[0], C.byref(ps), o.data_ptr())
 
     def e2e_sync_step():  # one blocking call per frame: upload + render + read-back
-        rc = r.lib.vb_render(*e2e_args(out_h), 0, C.byref(fs))
+        rc = r.lib.vb_render(*e2e_args(outs[0]), 0, C.byref(fs))
         assert rc == 0 and fs.failed == 0
 
-    def e2e_stream(n):  # streaming form: frame k's read-back tail overlaps frame k+1's upload and geometry stages
+    def e2e_stream(n):  # streaming form: upload(k+1) | raster(k) | read-back(k-1) overlap, three host buffers
         for k in range(n):
-            rc = r.lib.vb_render_begin(*e2e_args(outs[k & 1]), C.byref(fs))
+            rc = r.lib.vb_render_begin(*e2e_args(outs[k % 3]), C.byref(fs))
             assert rc == 0 and fs.failed == 0
         assert r.lib.vb_readback_wait(r.handle) == 0  # every frame's pixels are in host memory when the clock stops
 
-    e2e_steps = max(4, args.steps // 2)
+    e2e_steps = max(6, args.steps // 2)
     e2e_fps_by_mode = {}
     for mode in ("sync", "stream"):
         for _ in range(3):
-            e2e_sync_step() if mode == "sync" else e2e_stream(2)
+            e2e_sync_step() if mode == "sync" else e2e_stream(3)
         barrier()
         t0 = time.perf_counter()
         if mode == "sync":
@@ -305,39 +373,78 @@ def main():
             e2e_stream(e2e_steps)
         barrier()
         e2e_s = time.perf_counter() - t0
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_fps_by_mode[mode] = e2e_steps / float(t.item())
-    assert torch.equal(out_h, out_h2), "streamed frames differ"
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), "streamed frames differ"
     e2e_fps = e2e_fps_by_mode["stream"]
     h2d = int(packed.scene.nbytes + packed.ramps.nbytes + packed.atlas.nbytes)
     d2h = int((h1 - h0) * args.size * 4 + 32)
 
-    if rank != 0:
-        return
-
-    # ---- roofline of the dominant kernel (fine), measured live with per-stage CUDA events ----------
+    # ---- per-stage CUDA events of this rank's stripe (a second renderer with options.timing; launches individually) -----
     rt = Renderer(RendererOptions(device=local, timing=True))
     rt.upload(packed)
-    rt.render_resident(params, out.data_ptr(), bin_rows)
+    rt.render_resident(params, my_out(), tile_rows=my_rows())
     stage_ms = {}
     n_t = 10
     for _ in range(n_t):
         flush.fill_(1)
         torch.cuda.synchronize()
-        sd = rt.render_resident(params, out.data_ptr(), bin_rows).as_dict()
+        sd = rt.render_resident(params, my_out(), tile_rows=my_rows()).as_dict()
         for k, v in sd["stage_ms"].items():
             stage_ms[k] = stage_ms.get(k, 0.0) + v / n_t
     ptcl_words, seg_refs, fill_cmds = rt.fine_traffic()  # what the interpreter reads, from each tile's occlusion start
     rt.set_occlusion_cull(False)
     full_words, full_segs, full_fills = rt.fine_traffic()  # the whole command lists, as the reference executes them
     rt.set_occlusion_cull(True)
-    px = (h1 - h0) * args.size
-    seg_bytes = 24 * seg_refs * (2 if args.aa else 1)  # MSAA reads each segment twice (count + rasterise), fine.wgsl:177,225
-    alg_bytes = 4 * px + 4 * ptcl_words + 24 * seg_refs  # each datum once
-    fine_s = stage_ms["fine"] / 1000.0
+    bump = {k: int(getattr(st, k)) for k in ("lines", "tile", "seg_counts", "segments", "ptcl", "binning")}
+    rt.close()
+    stage_by_rank = None
+    if dist is not None:
+        names = list(stage_ms.keys())
+        allv = allgather_floats([stage_ms[k] for k in names])
+        stage_by_rank = [{k: round(v, 4) for k, v in zip(names, row)} for row in allv]
+    if rank != 0:
+        if world > 1:
+            r.lib.vb_ipc_close(r.handle, vp(frame_base))
+        r.close()
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (fine) and the per-stage table, from algorithmic bytes ----------
     peak, peak_src = measured_peaks()
+    px = (h1 - h0) * args.size
+    L = packed.layout
+    n_tags = int(L.path_data_base - L.path_tag_base) * 4
+    n_tag_words = n_tags // 4
+    n_paths, n_draw, n_clips = int(L.n_paths), int(L.n_draw_objects), int(L.n_clips)
+    points_bytes = int(L.draw_tag_base - L.path_data_base) * 4
+    NL, Nx, Ta, W = bump["lines"], bump["seg_counts"], bump["tile"], ptcl_words
+    alg = {  # minimum traffic, each datum once
+        "pathtag": n_tags + 20 * n_tag_words,
+        "flatten": n_tags + 20 * n_tag_words + points_bytes + 24 * NL,
+        "draw": 4 * n_draw + 16 * n_draw + 24 * n_paths,
+        "clip": 8 * n_clips + 16 * n_clips,
+        "binning": 16 * n_draw + 4 * bump["binning"],
+        "tile_alloc": 32 * n_draw + 8 * Ta,
+        "path_count": 24 * NL + 8 * Nx,
+        "backdrop": 16 * Ta,
+        "coarse": 8 * Ta + 4 * (full_words if world == 1 else W),
+        "path_tiling": 8 * Nx + 24 * Nx + 24 * Nx,
+        "fine": 4 * px + 4 * ptcl_words + 24 * seg_refs,
+    }
+    stages = {k: {"bytes": int(alg[k]), "ms": round(stage_ms[k], 4), "gbs": round(alg[k] / max(stage_ms[k], 1e-9) / 1e6, 1),
+                  "frac_of_hbm": round(alg[k] / max(stage_ms[k], 1e-9) / 1e6 / peak, 4)} for k in alg if k in stage_ms}
+    scans = {"pathtag_words_per_s": n_tag_words / (stage_ms["pathtag"] / 1e3), "pathtag_tags_per_s": n_tags / (stage_ms["pathtag"] / 1e3),
+             "draw_objs_per_s": n_draw / (stage_ms["draw"] / 1e3),
+             "pathtag_frac_of_hbm": stages["pathtag"]["frac_of_hbm"], "draw_frac_of_hbm": stages["draw"]["frac_of_hbm"],
+             "note": "single-pass decoupled look-back scans; bytes = tags in + 20 B monoid per tag word out (pathtag), "
+                     "draw tag + monoid + bbox per object (draw)"}
+    alg_bytes = alg["fine"]
+    fine_s = stage_ms["fine"] / 1000.0
     achieved = alg_bytes / fine_s / 1e9
     roofline = {"kernel": f"k_fine<{args.aa}>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
@@ -346,38 +453,64 @@ def main():
                 "whole_list": {"bytes": 4 * px + 4 * full_words + 24 * full_segs, "fill_cmds": full_fills},
                 "note": "bytes = pixels + the PTCL words and segments fine reads from each tile's occlusion start (last opaque "
                 "full-tile cover, noted by coarse); whole_list = the same count over the complete lists the reference executes. "
-                "MSAA16 fine is shared-memory-atomic / ALU bound (SURVEY.md 8d caveat); segments re-read from L2 by the second "
-                "MSAA pass are not counted"}
-    tp = os.path.join(ROOT, "profiles", "fine_traffic.json")
-    if os.path.exists(tp):
-        try:
-            roofline["traffic"] = json.load(open(tp)).get("dram_bytes_per_launch")
-        except Exception:
-            pass
-    rt.close()
+                "MSAA16 fine is issue / shared-memory-atomic bound, not HBM bound (SURVEY.md 8d caveat): see issue_bound"}
+    # dram traffic and warp-instruction count of k_fine are ncu measurements: they are quoted only when the capture under
+    # profiles/ was made with THIS k_fine.cu at THIS configuration (hash + workload recorded beside the numbers), else null
+    try:
+        import hashlib
+        meta = json.load(open(os.path.join(ROOT, "profiles", "fine_ncu.json")))
+        src_hash = hashlib.sha256(open(os.path.join(ROOT, "vello_b200", "csrc", "k_fine.cu"), "rb").read()).hexdigest()[:16]
+        if meta.get("k_fine_sha16") == src_hash and meta.get("workload") == config["workload"] and world == 1:
+            roofline["traffic"] = meta.get("dram_bytes_per_launch")
+            wi = meta.get("warp_instructions")
+            if wi and clocks and clocks.get("sm_mhz"):
+                issue_peak = 148 * 4 * clocks["sm_mhz"] * 1e6  # warp instructions / s: 4 schedulers per SM, one issue per cycle
+                roofline["issue_bound"] = {"warp_instructions": wi, "achieved_per_s": wi / fine_s, "peak_per_s": issue_peak,
+                                           "frac": wi / fine_s / issue_peak, "source": meta.get("source")}
+    except Exception:
+        pass
 
     cpu_baseline, parity = None, {"checked": False}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # rank 0 at N = 1 only (contract)
         # the CPU arm renders this very frame: keep it and compare the GPU's pixels with it (the oracle is the checker here,
         # after every timed region; it is never on the measured path)
         _, cpu_baseline, _, _, cpu_frame = run_cpu_arm(args, packed, False)
-        r.render_resident(params, out.data_ptr(), bin_rows)
-        gpu_frame = out.cpu().numpy()
-        ref_rows = cpu_frame[h0:h1]
-        d = np.abs(gpu_frame.astype(np.int16) - ref_rows.astype(np.int16))
-        parity = {"checked": True, "against": "oracle (cpu_baseline frame)", "rows": [int(h0), int(h1)], "max_diff": int(d.max()) if d.size else 0,
+        gpu_frame = np.zeros((H, args.size, 4), dtype=np.uint8)
+        if world == 1:
+            r.render_resident(params, frame_base)
+        assert r.lib.vb_copy_to_host(r.handle, vp(frame_base), vp(gpu_frame.ctypes.data), C.c_size_t(gpu_frame.nbytes)) == 0
+        d = np.abs(gpu_frame.astype(np.int16) - cpu_frame.astype(np.int16))
+        parity = {"checked": True, "against": "oracle (cpu_baseline frame)", "rows": [0, int(H)], "max_diff": int(d.max()) if d.size else 0,
                   "differing_channel_values": int((d > 0).sum()), "tolerance": 0 if args.aa else 1}
+        try:  # the named CPU baseline is sparse_strips/vello_cpu; it needs a Rust toolchain
+            has_cargo = subprocess.run(["cargo", "--version"], capture_output=True).returncode == 0
+        except Exception:
+            has_cargo = False
+        cpu_baseline["vello_cpu"] = ("cargo present but the reference tree is not on this box" if has_cargo
+                                     else "not buildable: no cargo / rustc on this box (probed), crates not vendored")
+    if stripes_parity is not None:
+        parity["stripes"] = stripes_parity
 
+    config["parallelism"] = (f"tile-row stripes x{world}, cost-balanced, fine stores into rank 0's frame over NVLink (CUDA IPC)"
+                             if world > 1 else "1 GPU")
     line = {"metric": "frames/sec paris-30k@4K", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "vb_render_begin x steps + vb_readback_wait (host scene in, host pixels out, every frame)",
+                    "api": "vb_render_begin x steps + vb_readback_wait (host scene in, host pixels out, every frame; three frames in flight)",
                     "blocking_vb_render_value": e2e_fps_by_mode["sync"]},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
-            "stage_ms": stage_ms, "bump": {k: int(getattr(st, k)) for k in ("lines", "tile", "seg_counts", "segments", "ptcl", "binning")},
+            "stage_ms": stage_ms, "stages": stages, "scans": scans, "bump": bump,
             "scene_bytes": int(packed.scene.nbytes), "wall_s_timed_region": wall, "scene_build_s": gen_s}
+    if world > 1:
+        slow = int(np.argmax(rank_totals))
+        line["multi_gpu"] = {"tile_row_bounds": list(bounds), "rank_ms_per_step": [round(v / args.steps, 4) for v in rank_totals],
+                             "slowest_rank": slow, "stage_ms_by_rank": stage_by_rank, "balancing": balance_log,
+                             "frame": "assembled on rank 0 by peer stores from every rank's fine kernel"}
     emit(line)
+    if world > 1:
+        dist.barrier()
+    r.lib.vb_frame_free(r.handle, vp(frame_base))
     r.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -112,10 +112,12 @@ int vb_render(vb_renderer *, const uint8_t *scene, size_t scene_len, const vb_la
               uint32_t out_is_device, vb_frame_stats *);
 
 /* Streaming form of vb_render for back-to-back frames with HOST buffers (a viewer / exporter reading every frame back,
- * as vello's headless examples do with a mapped read-back buffer, examples/headless/src/main.rs:188-210). Returns once
- * the frame is rasterised; the tail of its device->host copy may still be in flight and overlaps the next call's upload
- * and geometry stages. On return every EARLIER frame's out_host is complete; vb_readback_wait completes the last one.
- * Consecutive frames must use different out_host buffers. */
+ * as vello's headless examples do with a mapped read-back buffer, examples/headless/src/main.rs:188-210). Three frames are in
+ * flight: the call uploads frame k's scene (its own stream, second scene slot), enqueues its rasterisation and read-back and
+ * returns once frame k-1 is known to have rasterised without an arena overflow and frame k-2's pixels are in ITS out_host, so
+ * upload(k+1), raster(k) and read-back(k-1) overlap and a frame costs max(raster, read-back). `stats` describes frame k-2
+ * (zeros while there is none). vb_readback_wait completes everything still in flight. Use THREE alternating out_host buffers
+ * (a buffer may be reused once the call two frames later has returned). */
 int vb_render_begin(vb_renderer *, const uint8_t *scene, size_t scene_len, const vb_layout *, const uint32_t *ramps, uint32_t ramp_w,
                     uint32_t ramp_h, const uint8_t *atlas_rgba8, uint32_t atlas_w, uint32_t atlas_h, const vb_params *, void *out_host,
                     vb_frame_stats *);

@@ -163,7 +163,7 @@ struct vb_renderer {
     // still be draining while frame n+1 is rasterised
     bool use_alt = false, stream_pending = false;
     uint32_t stream_parity = 0;
-    cudaEvent_t copy_done[2]{};
+    cudaEvent_t copy_done[3]{};
     bool frame_pending = false;
     bool zero_fine_queue = false; // set by vb_run_stages (see enqueue_direct)
     bool in_stream_call = false;  // inside vb_render_begin / vb_readback_wait (their internal calls must not drain)
@@ -182,11 +182,14 @@ struct vb_renderer {
     uint32_t cur_slot = 0;
     cudaStream_t upload_stream = nullptr;
     cudaEvent_t upload_done[2]{}, raster_done[2]{};
-    struct PendingFrame {
-        bool pending = false;
+    struct RingFrame { // a streamed frame between vb_render_begin and its completion on the host
+        bool pending = false, raster_checked = false;
         vb_params params{};
         void *out_host = nullptr;
-    } inflight[2];
+        uint32_t slot = 0;
+        vb_frame_stats stats{};
+    } ring[3];
+    uint64_t stream_seq = 0;
 };
 
 static void swap_slot(vb_renderer *r) {
@@ -875,20 +878,21 @@ extern "C" int vb_render(vb_renderer *r, const uint8_t *scene, size_t scene_len,
 
 // ---- streaming: vb_render_begin / vb_readback_wait ------------------------------------------------------------------------
 // Back-to-back frames with HOST buffers (a viewer / exporter reading every frame back, examples/headless/src/main.rs:188-210).
-// vb_render_begin(k) uploads frame k's scene into the free scene slot on the upload stream, enqueues its rasterisation and
-// its read-back, and only THEN waits for frame k-1 (whose kernels were running all along) to be complete on the host. In
-// steady state the GPU therefore sees  upload(k+1) | raster(k) | read-back(k-1)  side by side and a frame costs
-// max(raster, read-back, upload) instead of their sum. On return every EARLIER frame's out_host is complete and `stats`
-// describes frame k-1 (zeros on the first call); vb_readback_wait completes the last frame. Consecutive frames must use
-// different out_host buffers. An arena overflow is found when a frame is completed; that frame (and the one enqueued
-// behind it) is then re-run synchronously with grown arenas -- rare (first frames of a new scene size) and exact.
-static int rerun_slot_sync(vb_renderer *r, uint32_t slot, vb_frame_stats *stats) {
+// Three frames are in flight: vb_render_begin(k) uploads frame k's scene into the free scene slot on the upload stream and
+// enqueues its rasterisation and read-back; it then makes sure frame k-1 was RASTERISED without an arena overflow and that
+// frame k-2's PIXELS are on the host. In steady state the GPU sees  upload(k+1) | raster(k) | read-back(k-1)  side by side and a
+// frame costs max(raster, read-back) instead of their sum. On return every frame before the previous one is complete in its
+// out_host and `stats` describes frame k-2 (zeros while there is none); vb_readback_wait completes the rest. THREE alternating
+// out_host buffers are needed. An arena overflow is found at the rasterisation check; that frame (and the one enqueued behind
+// it) is then re-run synchronously with grown arenas -- rare (first frames of a new scene size) and exact.
+static int rerun_frame_sync(vb_renderer *r, uint32_t q, vb_frame_stats *stats) {
+    const uint32_t slot = r->ring[q].slot;
     select_slot(r, slot);
-    r->host_out = r->inflight[slot].out_host;
+    r->host_out = r->ring[q].out_host;
     r->use_alt = slot != 0u;
     const uint32_t bands = r->readback_bands;
     r->readback_bands = 1;
-    int rc = vb_render_resident(r, &r->inflight[slot].params, nullptr, stats);
+    int rc = vb_render_resident(r, &r->ring[q].params, nullptr, stats);
     r->readback_bands = bands;
     r->host_out = nullptr;
     r->use_alt = false;
@@ -900,41 +904,45 @@ static int rerun_slot_sync(vb_renderer *r, uint32_t slot, vb_frame_stats *stats)
     return rc;
 }
 
-// Complete the in-flight frame of `slot` on the host; `younger` = a frame was enqueued behind it.
-static int complete_slot(vb_renderer *r, uint32_t slot, bool younger, vb_frame_stats *stats) {
-    if (!r->inflight[slot].pending) return VB_OK;
+// Frame in ring entry q: wait for its kernels, look at its bump counters, re-run on overflow (together with the younger frame
+// enqueued behind it, ring entry `younger`, or -1).
+static int check_raster(vb_renderer *r, uint32_t q, int younger) {
+    vb_renderer::RingFrame &f = r->ring[q];
+    if (!f.pending || f.raster_checked) return VB_OK;
     const uint32_t keep = r->cur_slot;
-    CK(cudaEventSynchronize(r->raster_done[slot]));
-    const VbBump *hb = slot == r->cur_slot ? r->h_bump : r->other.h_bump;
+    CK(cudaEventSynchronize(r->raster_done[f.slot]));
+    select_slot(r, f.slot);
     int rc = VB_OK;
-    if (hb->failed != 0u) {
-        // drain, then re-run this frame (and the younger one, which ran with the same too-small arenas) synchronously
+    if (r->h_bump->failed != 0u) {
         CK(cudaStreamSynchronize(r->stream));
         CK(cudaStreamSynchronize(r->copy_stream));
-        select_slot(r, slot);
         grow_arenas(r);
-        rc = rerun_slot_sync(r, slot, stats);
-        if (rc == VB_OK && younger) {
-            const VbBump *hy = (slot ^ 1u) == r->cur_slot ? r->h_bump : r->other.h_bump;
-            if (hy->failed != 0u) {
-                rc = rerun_slot_sync(r, slot ^ 1u, nullptr);
-                if (rc == VB_OK) {
-                    CK(cudaEventRecord(r->raster_done[slot ^ 1u], r->stream));
-                    CK(cudaEventRecord(r->copy_done[slot ^ 1u], r->copy_stream));
-                }
+        rc = rerun_frame_sync(r, q, &f.stats);
+        CK(cudaEventRecord(r->copy_done[q], r->copy_stream));
+        if (rc == VB_OK && younger >= 0 && r->ring[younger].pending) {
+            select_slot(r, r->ring[younger].slot);
+            if (r->h_bump->failed != 0u) {
+                rc = rerun_frame_sync(r, (uint32_t)younger, &r->ring[younger].stats);
+                CK(cudaEventRecord(r->raster_done[r->ring[younger].slot], r->stream));
+                CK(cudaEventRecord(r->copy_done[younger], r->copy_stream));
             }
         }
-        select_slot(r, keep);
     } else {
-        CK(cudaEventSynchronize(r->copy_done[slot]));
-        if (stats) {
-            select_slot(r, slot);
-            r->retries = 0;
-            fill_stats(r, stats);
-            select_slot(r, keep);
-        }
+        r->retries = 0;
+        fill_stats(r, &f.stats);
     }
-    r->inflight[slot].pending = false;
+    f.raster_checked = true;
+    select_slot(r, keep);
+    return rc;
+}
+
+static int complete_host(vb_renderer *r, uint32_t q, vb_frame_stats *stats) {
+    vb_renderer::RingFrame &f = r->ring[q];
+    if (!f.pending) return VB_OK;
+    int rc = check_raster(r, q, -1);
+    CK(cudaEventSynchronize(r->copy_done[q]));
+    if (stats) *stats = f.stats;
+    f.pending = false;
     return rc;
 }
 
@@ -949,15 +957,17 @@ extern "C" int vb_render_begin(vb_renderer *r, const uint8_t *scene, size_t scen
         ~Guard() { r->in_stream_call = false; }
     } guard{r};
     r->in_stream_call = true;
-    const uint32_t slot = r->stream_parity;
-    // the frame that used this slot two calls ago was completed by the previous call
+    const uint64_t k = r->stream_seq;
+    const uint32_t slot = (uint32_t)(k & 1u), q = (uint32_t)(k % 3u), q1 = (uint32_t)((k + 2u) % 3u), q2 = (uint32_t)((k + 1u) % 3u);
+    // frame k-2 (same scene slot, same device target) was checked by the previous call; frame k-3 (ring entry q) is complete
     select_slot(r, slot);
     int rc = upload_on(r, r->upload_stream, scene, scene_len, layout, ramps, ramp_w, ramp_h, atlas, atlas_w, atlas_h);
     if (rc) return rc;
     CK(cudaEventRecord(r->upload_done[slot], r->upload_stream));
     CK(cudaStreamWaitEvent(r->stream, r->upload_done[slot], 0));
+    if (k >= 2u && r->ring[q2].pending) CK(cudaStreamWaitEvent(r->stream, r->copy_done[q2], 0)); // its read-back still reads this target
     const uint32_t bands = r->readback_bands;
-    r->readback_bands = 1; // the whole read-back overlaps the next frame: no reason to split fine
+    r->readback_bands = 1; // the whole read-back overlaps the next frames: no reason to split fine
     r->host_out = out_host;
     r->use_alt = slot != 0u;
     rc = vb_render_enqueue(r, p, nullptr);
@@ -967,14 +977,21 @@ extern "C" int vb_render_begin(vb_renderer *r, const uint8_t *scene, size_t scen
     if (rc) return rc;
     r->frame_pending = false;
     CK(cudaEventRecord(r->raster_done[slot], r->stream));
-    CK(cudaEventRecord(r->copy_done[slot], r->copy_stream));
-    r->inflight[slot].pending = true;
-    r->inflight[slot].params = *p;
-    r->inflight[slot].out_host = out_host;
-    // now complete the previous frame: its kernels ran while this one was being uploaded and enqueued
-    rc = complete_slot(r, slot ^ 1u, true, stats);
+    CK(cudaEventRecord(r->copy_done[q], r->copy_stream));
+    r->ring[q].pending = true;
+    r->ring[q].raster_checked = false;
+    r->ring[q].params = *p;
+    r->ring[q].out_host = out_host;
+    r->ring[q].slot = slot;
+    memset(&r->ring[q].stats, 0, sizeof(vb_frame_stats));
+    r->stream_seq = k + 1u;
     r->stream_pending = true;
-    r->stream_parity = slot ^ 1u;
+    // frame k-1: rasterised without overflow?  frame k-2: pixels on the host?
+    if (k >= 1u) rc = check_raster(r, q1, (int)q);
+    if (k >= 2u) {
+        const int rc2 = complete_host(r, q2, stats);
+        if (rc == VB_OK) rc = rc2;
+    }
     return rc;
 }
 
@@ -986,12 +1003,18 @@ extern "C" int vb_readback_wait(vb_renderer *r) {
         ~Guard() { r->in_stream_call = false; }
     } guard{r};
     r->in_stream_call = true;
-    // frames complete in order: the older one is the slot the NEXT begin would use
-    int rc = complete_slot(r, r->stream_parity, r->inflight[r->stream_parity ^ 1u].pending, nullptr);
-    const int rc2 = complete_slot(r, r->stream_parity ^ 1u, false, nullptr);
+    int rc = VB_OK;
+    const uint64_t k = r->stream_seq; // the next frame number: complete k-3 .. k-1 in order
+    for (uint64_t j = k >= 3u ? k - 3u : 0u; j < k; j++) {
+        const uint32_t q = (uint32_t)(j % 3u);
+        const int younger = j + 1u < k ? (int)((j + 1u) % 3u) : -1;
+        int rc1 = check_raster(r, q, younger);
+        if (rc1 == VB_OK) rc1 = complete_host(r, q, nullptr);
+        if (rc == VB_OK) rc = rc1;
+    }
     CK(cudaStreamSynchronize(r->copy_stream));
     r->stream_pending = false;
-    return rc ? rc : rc2;
+    return rc;
 }
 
 extern "C" int vb_run_stages(vb_renderer *r, const vb_params *p, int first, int last, void *out_device) {

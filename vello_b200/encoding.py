@@ -219,6 +219,8 @@ class Stroke:
     miter_limit: float = 4.0
     start_cap: int = STYLE_CAP_ROUND
     end_cap: int = STYLE_CAP_ROUND
+    dash_pattern: Tuple[float, ...] = ()  # kurbo Stroke::dash_pattern / dash_offset: expanded on the CPU (scene.rs:411-438)
+    dash_offset: float = 0.0
 
 
 def style_from_fill(fill: int) -> Tuple[int, float]:
@@ -653,7 +655,12 @@ class Scene:
         assert ok
         # non-dashed strokes go through Encoding::encode_shape -> PathEncoder::shape -> path_elements(0.1)
         # (vello/src/scene.rs:417-421, vello_encoding/src/path.rs:655-657); only the dash expansion uses 0.01
-        return e.encode_shape(shape, False)
+        if not stroke.dash_pattern:
+            return e.encode_shape(shape, False)
+        # dashes are not supported by the GPU pipeline: the shape (flattened at SHAPE_TOLERANCE = 0.01) is cut into dashes
+        # on the CPU by kurbo::dash and the dashes are encoded as the path (scene.rs:404,422-437)
+        dashed = _shapes.dash(_shapes.path_elements(shape, 0.01), stroke.dash_offset, stroke.dash_pattern)
+        return e.encode_path_elements(dashed, False)
 
     def stroke(self, stroke: Stroke, transform: Affine, brush, brush_transform: Optional[Affine], shape):
         if stroke.width == 0.0:

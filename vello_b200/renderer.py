@@ -208,9 +208,10 @@ class Renderer:
         return out
 
     def render_stream(self, scenes, params: RenderParams):
-        """Render a sequence of scenes through the streaming entry points (vb_render_begin / vb_readback_wait):
-        a generator of RGBA8 images, each complete when yielded."""
-        bufs, prev = [None, None], None
+        """Render a sequence of scenes through the streaming entry points (vb_render_begin / vb_readback_wait): a generator
+        of RGBA8 images, each complete when yielded. Three frames are in flight (upload | rasterise | read back), so frame k-2
+        is yielded after frame k has been submitted."""
+        outs = []
         for k, scene in enumerate(scenes):
             packed = scene if isinstance(scene, Packed) else resolve(scene.encoding)
             scene_w = np.ascontiguousarray(packed.scene, dtype=np.uint32)
@@ -219,19 +220,21 @@ class Renderer:
             lay = _Layout(*[int(v) for v in packed.layout.as_array()])
             ps = _params_struct(params, (0, 0))
             out = np.zeros((params.height, params.width, 4), dtype=np.uint8)
-            bufs[k & 1] = out
+            outs.append(out)
             st = FrameStats()
             rc = self.lib.vb_render_begin(self.handle, scene_w.ctypes.data, scene_w.nbytes, C.byref(lay),
                                           ramps.ctypes.data if ramps.size else None, 512, ramps.shape[0],
                                           atlas.ctypes.data, atlas.shape[1], atlas.shape[0], C.byref(ps), out.ctypes.data, C.byref(st))
             self.last_stats = st
             self._check(rc, "vb_render_begin")
-            if prev is not None:
-                yield prev  # complete: vb_render_begin returned for a later frame
-            prev = out
-        if prev is not None:
+            if k >= 2:
+                yield outs[k - 2]  # complete: vb_render_begin returned for the frame two later
+                outs[k - 2] = None
+        if outs:
             self._check(self.lib.vb_readback_wait(self.handle), "vb_readback_wait")
-            yield prev
+            for o in outs[-2:]:
+                if o is not None:
+                    yield o
 
     @staticmethod
     def stripe_rows(params: RenderParams, bin_rows=(0, 0), tile_rows=(0, 0)):

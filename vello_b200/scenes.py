@@ -726,3 +726,27 @@ def image_extend_modes(quality: int = QUALITY_MEDIUM) -> Tuple[Scene, int, int]:
         im = Image(px, quality=quality, x_extend=xe, y_extend=ye)
         s.fill(FILL_NON_ZERO, Affine.translate(tx, ty) * Affine.scale(100.0), im, off, Rect(0.0, 0.0, 6.0, 6.0))
     return s, 1500, 1500
+
+
+def longpathdash(cap: int = STYLE_CAP_BUTT) -> Tuple[Scene, int, int]:
+    """test_scenes.rs:779-819: 15 rings of 200 spokes, every spoke a polyline of 21 points, stroked 1 px wide with a
+    [1, 1] dash pattern (the dashes are cut on the CPU by kurbo::dash; ~200 k dashes). Lines only: the dash arithmetic is
+    closed-form."""
+    p = BezPath()
+    x = 32
+    while x < 256:
+        a = 0.0
+        while a < math.pi * 2.0:
+            p0 = (256.0 + math.sin(a) * x, 256.0 + math.cos(a) * x)
+            p1 = (256.0 + math.sin(a + math.pi / 3.0) * (x + 64), 256.0 + math.cos(a + math.pi / 3.0) * (x + 64))
+            p.move_to(p0[0], p0[1])
+            i = 0.0
+            while i < 1.0:
+                p.line_to(p0[0] * (1.0 - i) + p1[0] * i, p0[1] * (1.0 - i) + p1[1] * i)
+                i += 0.05
+            a += math.pi * 0.01
+        x += 16
+    s = Scene()
+    st = Stroke(1.0, join=STYLE_JOIN_BEVEL, start_cap=cap, end_cap=cap, dash_pattern=(1.0, 1.0), dash_offset=0.0)
+    s.stroke(st, Affine.translate(50.0, 50.0), YELLOW, None, p)
+    return s, 612, 612

@@ -438,3 +438,247 @@ def parse_svg_path(d: str) -> List[tuple]:
             raise ValueError(f"unsupported path command {cmd!r}")
         last_cmd = u
     return els
+
+
+# ---------------------------------------------------------------------------------------------
+# kurbo::dash (kurbo 0.13.1 stroke.rs `DashIterator`), which vello applies on the CPU before encoding a dashed stroke
+# (vello/src/scene.rs:404-438). kurbo is a Cargo dependency that is not under /root/reference: the state machine below
+# restates its published algorithm (stash the first dash of a closed subpath so that it can be joined to the last one,
+# walk arc length with `dash_remaining` / `seg_remaining`, split segments with subsegment / inv_arclen). Lines -- the
+# reference's `longpathdash` scene -- use closed forms and are exact; for curves kurbo's arclen / inv_arclen (adaptive
+# Gauss-Legendre, ITP root finding, accuracy 1e-6) are replaced by a fixed-order composite Gauss-Legendre rule and
+# bisection of the same accuracy class, so dash end points on curves agree with kurbo's to ~1e-6, not bit for bit
+# ("parity unpinned" for dashed curves; the C++ front end uses the identical arithmetic, vb_scene.cpp).
+# ---------------------------------------------------------------------------------------------
+_GL8_X = (0.1834346424956498, 0.5255324099163290, 0.7966664774136267, 0.9602898564975363)
+_GL8_W = (0.3626837833783620, 0.3137066458778873, 0.2223810344533745, 0.1012285362903763)
+
+
+def _lerp(a, b, t):
+    return (a[0] + t * (b[0] - a[0]), a[1] + t * (b[1] - a[1]))
+
+
+def _seg_eval(seg, t):
+    k = seg[0]
+    if k == "L":
+        return _lerp(seg[1], seg[2], t)
+    mt = 1.0 - t
+    if k == "Q":
+        p0, p1, p2 = seg[1:]
+        return (mt * mt * p0[0] + 2.0 * mt * t * p1[0] + t * t * p2[0], mt * mt * p0[1] + 2.0 * mt * t * p1[1] + t * t * p2[1])
+    p0, p1, p2, p3 = seg[1:]
+    a, b, c, d = mt * mt * mt, 3.0 * mt * mt * t, 3.0 * mt * t * t, t * t * t
+    return (a * p0[0] + b * p1[0] + c * p2[0] + d * p3[0], a * p0[1] + b * p1[1] + c * p2[1] + d * p3[1])
+
+
+def _seg_deriv(seg, t):
+    k = seg[0]
+    mt = 1.0 - t
+    if k == "Q":
+        p0, p1, p2 = seg[1:]
+        return (2.0 * (mt * (p1[0] - p0[0]) + t * (p2[0] - p1[0])), 2.0 * (mt * (p1[1] - p0[1]) + t * (p2[1] - p1[1])))
+    p0, p1, p2, p3 = seg[1:]
+    a, b, c = 3.0 * mt * mt, 6.0 * mt * t, 3.0 * t * t
+    return (a * (p1[0] - p0[0]) + b * (p2[0] - p1[0]) + c * (p3[0] - p2[0]), a * (p1[1] - p0[1]) + b * (p2[1] - p1[1]) + c * (p3[1] - p2[1]))
+
+
+def _curve_arclen_range(seg, t0, t1, pieces=16):
+    """Arc length of a quad / cubic over [t0, t1]: composite 8-point Gauss-Legendre on `pieces` equal sub-ranges."""
+    total = 0.0
+    h = (t1 - t0) / pieces
+    for i in range(pieces):
+        a = t0 + h * i
+        mid, half = a + 0.5 * h, 0.5 * h
+        acc = 0.0
+        for x, w in zip(_GL8_X, _GL8_W):
+            d0 = _seg_deriv(seg, mid - half * x)
+            d1 = _seg_deriv(seg, mid + half * x)
+            acc += w * (math.sqrt(d0[0] * d0[0] + d0[1] * d0[1]) + math.sqrt(d1[0] * d1[0] + d1[1] * d1[1]))
+        total += acc * half
+    return total
+
+
+def _seg_arclen(seg):
+    if seg[0] == "L":
+        dx, dy = seg[2][0] - seg[1][0], seg[2][1] - seg[1][1]
+        return math.sqrt(dx * dx + dy * dy)
+    return _curve_arclen_range(seg, 0.0, 1.0)
+
+
+def _seg_inv_arclen(seg, s):
+    """t with arclen(seg[0..t]) == s."""
+    if seg[0] == "L":
+        return s / _seg_arclen(seg)
+    lo, hi = 0.0, 1.0
+    for _ in range(48):  # bisection: 2^-48 in t
+        mid = 0.5 * (lo + hi)
+        if _curve_arclen_range(seg, 0.0, mid) < s:
+            lo = mid
+        else:
+            hi = mid
+    return 0.5 * (lo + hi)
+
+
+def _seg_subsegment(seg, t0, t1):
+    k = seg[0]
+    if k == "L":
+        return ("L", _seg_eval(seg, t0), _seg_eval(seg, t1))
+    if k == "Q":  # kurbo QuadBez::subsegment
+        p0, p2 = _seg_eval(seg, t0), _seg_eval(seg, t1)
+        a = (seg[2][0] - seg[1][0], seg[2][1] - seg[1][1])
+        b = (seg[3][0] - seg[2][0], seg[3][1] - seg[2][1])
+        d = _lerp(a, b, t0)
+        return ("Q", p0, (p0[0] + d[0] * (t1 - t0), p0[1] + d[1] * (t1 - t0)), p2)
+    p0, p3 = _seg_eval(seg, t0), _seg_eval(seg, t1)  # kurbo CubicBez::subsegment
+    scale = (t1 - t0) * (1.0 / 3.0)
+    d0, d1 = _seg_deriv(seg, t0), _seg_deriv(seg, t1)
+    return ("C", p0, (p0[0] + scale * d0[0], p0[1] + scale * d0[1]), (p3[0] - scale * d1[0], p3[1] - scale * d1[1]), p3)
+
+
+def _seg_to_el(seg):
+    k = seg[0]
+    if k == "L":
+        return ("L", seg[2][0], seg[2][1])
+    if k == "Q":
+        return ("Q", seg[2][0], seg[2][1], seg[3][0], seg[3][1])
+    return ("C", seg[2][0], seg[2][1], seg[3][0], seg[3][1], seg[4][0], seg[4][1])
+
+
+def dash(elements: Iterable[tuple], dash_offset: float, dashes) -> List[tuple]:
+    """`kurbo::dash(inner, dash_offset, dashes)` collected into a list (as vello does, scene.rs:428-433)."""
+    dashes = [float(d) for d in dashes]
+    if not dashes:
+        return list(elements)
+    NEED_INPUT, TO_STASH, WORKING, FROM_STASH = range(4)
+    inner = iter(list(elements))
+    # place in the dash array for the initial offset
+    dash_ix = 0
+    dash_remaining = dashes[0] - dash_offset
+    is_active = True
+    while dash_remaining < 0.0:
+        dash_ix = (dash_ix + 1) % len(dashes)
+        dash_remaining += dashes[dash_ix]
+        is_active = not is_active
+    S = dict(input_done=False, closepath_pending=False, dash_ix=dash_ix, init_dash_ix=dash_ix, init_dash_remaining=dash_remaining,
+             init_is_active=is_active, is_active=is_active, state=NEED_INPUT, seg=("L", (0.0, 0.0), (0.0, 0.0)), t=0.0,
+             dash_remaining=dash_remaining, seg_remaining=0.0, start_pt=(0.0, 0.0), last_pt=(0.0, 0.0), stash=[], stash_ix=0)
+    out: List[tuple] = []
+
+    def reset_phase():
+        S["dash_ix"], S["dash_remaining"], S["is_active"] = S["init_dash_ix"], S["init_dash_remaining"], S["init_is_active"]
+
+    def handle_closepath():
+        if S["state"] == TO_STASH:
+            S["stash"].append(("Z",))  # looped back without breaking a dash: play it back closed
+        elif S["is_active"]:
+            S["stash_ix"] = 1          # connect with the path in the stash, skip its MoveTo
+        S["state"] = FROM_STASH
+        reset_phase()
+
+    def get_input():
+        while True:
+            if S["closepath_pending"]:
+                handle_closepath()
+                break
+            el = next(inner, None)
+            if el is None:
+                S["input_done"] = True
+                S["state"] = FROM_STASH
+                return
+            p0 = S["last_pt"]
+            k = el[0]
+            if k == "M":
+                if S["stash"]:
+                    S["state"] = FROM_STASH
+                S["start_pt"] = S["last_pt"] = (el[1], el[2])
+                reset_phase()
+                continue
+            if k == "L":
+                S["seg"] = ("L", p0, (el[1], el[2]))
+                S["last_pt"] = (el[1], el[2])
+            elif k == "Q":
+                S["seg"] = ("Q", p0, (el[1], el[2]), (el[3], el[4]))
+                S["last_pt"] = (el[3], el[4])
+            elif k == "C":
+                S["seg"] = ("C", p0, (el[1], el[2]), (el[3], el[4]), (el[5], el[6]))
+                S["last_pt"] = (el[5], el[6])
+            else:  # ClosePath
+                S["closepath_pending"] = True
+                if p0 != S["start_pt"]:
+                    S["seg"] = ("L", p0, S["start_pt"])
+                    S["last_pt"] = S["start_pt"]
+                else:
+                    continue
+            S["seg_remaining"] = _seg_arclen(S["seg"])
+            break
+        S["t"] = 0.0
+
+    def step():
+        result = None
+        if S["state"] == TO_STASH and not S["stash"]:
+            if S["is_active"]:
+                p = S["seg"][1]
+                result = ("M", p[0], p[1])
+            else:
+                S["state"] = WORKING
+        elif S["dash_remaining"] < S["seg_remaining"]:
+            seg = _seg_subsegment(S["seg"], S["t"], 1.0)  # next transition is a dash transition
+            t1 = _seg_inv_arclen(seg, S["dash_remaining"])
+            if S["is_active"]:
+                result = _seg_to_el(_seg_subsegment(seg, 0.0, t1))
+                S["state"] = WORKING
+            else:
+                p = _seg_eval(seg, t1)
+                result = ("M", p[0], p[1])
+            S["is_active"] = not S["is_active"]
+            S["t"] += t1 * (1.0 - S["t"])
+            S["seg_remaining"] -= S["dash_remaining"]
+            S["dash_ix"] += 1
+            if S["dash_ix"] == len(dashes):
+                S["dash_ix"] = 0
+            S["dash_remaining"] = dashes[S["dash_ix"]]
+        else:
+            if S["is_active"]:
+                result = _seg_to_el(_seg_subsegment(S["seg"], S["t"], 1.0))
+            S["dash_remaining"] -= S["seg_remaining"]
+            get_input()
+        return result
+
+    guard = 0
+    while True:
+        guard += 1
+        assert guard < 100_000_000
+        st = S["state"]
+        if st == NEED_INPUT:
+            if S["input_done"]:
+                break
+            get_input()
+            if S["input_done"]:
+                # FROM_STASH drains whatever was stashed (kurbo returns None here only when the stash is empty)
+                if not S["stash"]:
+                    break
+                continue
+            S["state"] = TO_STASH
+        elif st == TO_STASH:
+            el = step()
+            if el is not None:
+                S["stash"].append(el)
+        elif st == WORKING:
+            el = step()
+            if el is not None:
+                out.append(el)
+        else:  # FROM_STASH
+            if S["stash_ix"] < len(S["stash"]):
+                out.append(S["stash"][S["stash_ix"]])
+                S["stash_ix"] += 1
+            else:
+                S["stash"].clear()
+                S["stash_ix"] = 0
+                if S["input_done"]:
+                    break
+                if S["closepath_pending"]:
+                    S["closepath_pending"] = False
+                    S["state"] = NEED_INPUT
+                else:
+                    S["state"] = TO_STASH
+    return out
