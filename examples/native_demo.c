@@ -41,7 +41,7 @@ int main(int argc, char **argv) {
     const uint8_t zig_verbs[] = {'M', 'L', 'L', 'L', 'L'};
     const double zig_coords[] = {40, 340, 140, 300, 240, 350, 340, 290, 470, 345};
     const vb_path zig = {zig_verbs, 5, zig_coords};
-    const vb_stroke pen = {9.0, VB_JOIN_ROUND, VB_CAP_ROUND, VB_CAP_ROUND, 4.0};
+    const vb_stroke pen = {9.0, VB_JOIN_ROUND, VB_CAP_ROUND, VB_CAP_ROUND, 4.0, NULL, 0, 0.0};
     vb_brush white;
     memset(&white, 0, sizeof white);
     white.kind = VB_BRUSH_SOLID;
@@ -58,7 +58,8 @@ int main(int argc, char **argv) {
     vb_pathbuf_clear(pb);
     vb_pathbuf_rounded_rect(pb, 30.0, 30.0, 190.0, 110.0, 18.0, 0.1);
     shape = vb_pathbuf_view(pb);
-    const vb_stroke thin = {3.0, VB_JOIN_MITER, VB_CAP_BUTT, VB_CAP_BUTT, 4.0};
+    static const double dashes[2] = {12.0, 6.0};
+    const vb_stroke thin = {3.0, VB_JOIN_MITER, VB_CAP_BUTT, VB_CAP_BUTT, 4.0, dashes, 2, 0.0}; /* dashed: cut on the CPU like vello (kurbo::dash) */
     if (vb_scene_stroke(scene, &thin, IDENTITY, &white, NULL, &shape)) return 2;
     vb_pathbuf_free(pb);
 

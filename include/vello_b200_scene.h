@@ -84,14 +84,23 @@ typedef struct {
     const vb_image *image;      /* VB_BRUSH_IMAGE */
 } vb_brush;
 
-/* kurbo::Stroke restricted to what the encoding carries (path.rs:70-120): no dashes (vello expands them on the CPU). */
+/* kurbo::Stroke (path.rs:70-120 for the encoded part). A dash pattern is expanded on the CPU exactly where vello does it
+ * (Scene::stroke -> kurbo::dash, vello/src/scene.rs:404-438): the path passed with a dashed stroke should have been flattened at
+ * tolerance 0.01 (SHAPE_TOLERANCE there), an undashed one at 0.1. */
 enum { VB_JOIN_BEVEL = 0, VB_JOIN_MITER = 0x10000000, VB_JOIN_ROUND = 0x20000000 };
 enum { VB_CAP_BUTT = 0, VB_CAP_SQUARE = 0x01000000, VB_CAP_ROUND = 0x02000000 };
 typedef struct {
     double width;
     uint32_t join, start_cap, end_cap;
     double miter_limit;
+    const double *dash_pattern; /* NULL / n_dashes == 0: solid */
+    uint32_t n_dashes;
+    double dash_offset;
 } vb_stroke;
+
+/* kurbo::dash(path, dash_offset, dashes) appended to `out` (kurbo 0.13.1 stroke.rs DashIterator; closed forms for lines, composite
+ * Gauss-Legendre arc length + bisection for curves -- same arithmetic as vello_b200/shapes.py `dash`). */
+int vb_path_dash(const vb_path *path, double dash_offset, const double *dashes, uint32_t n_dashes, vb_pathbuf *out);
 
 enum { VB_FILL_NON_ZERO = 0, VB_FILL_EVEN_ODD = 1 };
 

@@ -84,7 +84,7 @@ def test_property_simple_square_and_empty(renderer):
 # ---- stage-by-stage + pixel parity with the oracle -------------------------------------------------
 SCENES = ["filled_circle", "robust_paths", "funky_paths", "fill_types", "stroke_styles", "many_clips", "deep_blend", "brushes",
           # the reference's own scene recipes (examples/scenes/src/test_scenes.rs), restated in vello_b200/scenes.py
-          "blend_grid", "compose_grid", "tricky_strokes", "gradient_extend", "two_point_radial", "conflation_artifacts"]
+          "blend_grid", "compose_grid", "tricky_strokes", "gradient_extend", "two_point_radial", "conflation_artifacts", "longpathdash"]
 
 
 @pytest.mark.parametrize("name", SCENES)

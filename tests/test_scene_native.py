@@ -337,3 +337,35 @@ def test_invalid_arguments_are_rejected_not_crashed():
     lib.vb_scene_free(s)
     lib.vb_scene_free(None)
     lib.vb_pathbuf_free(None)
+
+
+def test_dash_native_equals_python():
+    """kurbo::dash in both front ends: the native (C++) dash expansion produces the Python statement's stream byte for byte --
+    lines (closed forms), closed subpaths (the stashed first dash joins the last), offsets, odd patterns, quads and cubics."""
+    import ctypes as C
+    from vello_b200 import shapes
+    from vello_b200.encoding import Stroke, Scene, resolve, STYLE_JOIN_BEVEL, STYLE_CAP_BUTT, Color
+    from vello_b200.scene_native import NativeScene
+    from vello_b200.shapes import Affine, BezPath, Circle, Rect
+    rng = np.random.default_rng(3)
+    cases = [(Rect(10, 10, 90, 70), (7.0, 3.0), 0.0), (Rect(10, 10, 90, 70), (7.0, 3.0, 1.0), 4.5), (Circle(50, 50, 30), (5.0, 2.5), 1.0),
+             (BezPath([("M", 0.0, 0.0), ("L", 100.0, 0.0), ("Q", 120.0, 40.0, 60.0, 80.0), ("C", 20.0, 120.0, 10.0, 20.0, 90.0, 90.0)]), (9.0, 4.0), 30.0),
+             (BezPath([("M", 5.0, 5.0), ("L", 50.0, 5.0), ("L", 50.0, 50.0), ("Z",), ("M", 60.0, 60.0), ("L", 90.0, 95.0)]), (4.0, 4.0), 0.0)]
+    p = BezPath()
+    p.move_to(*rng.uniform(0, 100, 2))
+    for _ in range(30):
+        p.line_to(*rng.uniform(0, 100, 2))
+    cases.append((p, (3.0, 1.0, 0.5, 1.0), 2.0))
+    py, nat = Scene(), NativeScene()
+    for shape, pat, off in cases:
+        st = Stroke(2.0, join=STYLE_JOIN_BEVEL, start_cap=STYLE_CAP_BUTT, end_cap=STYLE_CAP_BUTT, dash_pattern=pat, dash_offset=off)
+        for s in (py, nat):
+            s.stroke(st, Affine.translate(3.0, 4.0), Color.from_rgba8(255, 255, 0), None, shape)
+    a, b = resolve(py.encoding), nat.resolve()
+    assert a.scene.tobytes() == b.scene.tobytes()
+    assert a.layout.as_array().tolist() == b.layout.as_array().tolist()
+    # known answers of the state machine on a straight line
+    d = shapes.dash([("M", 0.0, 0.0), ("L", 10.0, 0.0)], 0.0, [1.0, 1.0])
+    assert len(d) == 10 and d[0] == ("M", 2.0, 0.0) and d[-2:] == [("M", 0.0, 0.0), ("L", 1.0, 0.0)]
+    d = shapes.dash([("M", 0.0, 0.0), ("L", 4.0, 0.0), ("L", 4.0, 4.0), ("L", 0.0, 4.0), ("Z",)], 0.5, [3.0, 1.0])
+    assert d[-3:] == [("M", 0.0, 0.5), ("L", 0.0, 0.0), ("L", 2.5, 0.0)]  # last dash joined to the stashed first one

@@ -477,7 +477,20 @@ int encode_brush(Encoding &e, const vb_brush &b, float alpha) {
 bool stroke_inner(Encoding &e, const vb_stroke &st, const Affine &t, const vb_path &p, int *rc) {
     e.encode_transform(t);
     e.encode_stroke_style(st);
-    return encode_path(e, p, false, rc);
+    if (st.n_dashes == 0u || !st.dash_pattern) return encode_path(e, p, false, rc);
+    // dashes are cut on the CPU and encoded as the path (vello/src/scene.rs:422-437)
+    vb_pathbuf *tmp = vb_pathbuf_new();
+    if (!tmp) { *rc = VB_E_INVALID; return false; }
+    bool ok = false;
+    const int drc = vb_path_dash(&p, st.dash_offset, st.dash_pattern, st.n_dashes, tmp);
+    if (drc != VB_OK) {
+        *rc = drc;
+    } else {
+        const vb_path dashed = vb_pathbuf_view(tmp);
+        ok = encode_path(e, dashed, false, rc);
+    }
+    vb_pathbuf_free(tmp);
+    return ok;
 }
 
 int push_layer_inner(vb_scene *s, uint32_t blend_mode, float alpha, uint32_t fill_rule, const vb_stroke *stroke, const double transform[6],
@@ -517,6 +530,270 @@ struct vb_pathbuf {
         coords.insert(coords.end(), c.begin(), c.end());
     }
 };
+
+namespace {
+// ---- kurbo::dash (kurbo 0.13.1 stroke.rs DashIterator); identical arithmetic to vello_b200/shapes.py `dash` ----------------
+struct DSeg { // a path segment in absolute coordinates: k in {'L','Q','C'}, control points p[0..k's degree]
+    char k;
+    double p[4][2];
+};
+const double GL8_X[4] = {0.1834346424956498, 0.5255324099163290, 0.7966664774136267, 0.9602898564975363};
+const double GL8_W[4] = {0.3626837833783620, 0.3137066458778873, 0.2223810344533745, 0.1012285362903763};
+inline void d_lerp(const double a[2], const double b[2], double t, double o[2]) {
+    o[0] = a[0] + t * (b[0] - a[0]);
+    o[1] = a[1] + t * (b[1] - a[1]);
+}
+void dseg_eval(const DSeg &s, double t, double o[2]) {
+    if (s.k == 'L') { d_lerp(s.p[0], s.p[1], t, o); return; }
+    const double mt = 1.0 - t;
+    if (s.k == 'Q') {
+        for (int c = 0; c < 2; c++) o[c] = mt * mt * s.p[0][c] + 2.0 * mt * t * s.p[1][c] + t * t * s.p[2][c];
+        return;
+    }
+    const double a = mt * mt * mt, b = 3.0 * mt * mt * t, cc = 3.0 * mt * t * t, d = t * t * t;
+    for (int c = 0; c < 2; c++) o[c] = a * s.p[0][c] + b * s.p[1][c] + cc * s.p[2][c] + d * s.p[3][c];
+}
+void dseg_deriv(const DSeg &s, double t, double o[2]) {
+    const double mt = 1.0 - t;
+    if (s.k == 'Q') {
+        for (int c = 0; c < 2; c++) o[c] = 2.0 * (mt * (s.p[1][c] - s.p[0][c]) + t * (s.p[2][c] - s.p[1][c]));
+        return;
+    }
+    const double a = 3.0 * mt * mt, b = 6.0 * mt * t, cc = 3.0 * t * t;
+    for (int c = 0; c < 2; c++) o[c] = a * (s.p[1][c] - s.p[0][c]) + b * (s.p[2][c] - s.p[1][c]) + cc * (s.p[3][c] - s.p[2][c]);
+}
+double dseg_curve_arclen(const DSeg &s, double t0, double t1) { // composite 8-point Gauss-Legendre, 16 pieces
+    const int pieces = 16;
+    double total = 0.0;
+    const double h = (t1 - t0) / pieces;
+    for (int i = 0; i < pieces; i++) {
+        const double a = t0 + h * i;
+        const double mid = a + 0.5 * h, half = 0.5 * h;
+        double acc = 0.0;
+        for (int q = 0; q < 4; q++) {
+            double d0[2], d1[2];
+            dseg_deriv(s, mid - half * GL8_X[q], d0);
+            dseg_deriv(s, mid + half * GL8_X[q], d1);
+            acc += GL8_W[q] * (std::sqrt(d0[0] * d0[0] + d0[1] * d0[1]) + std::sqrt(d1[0] * d1[0] + d1[1] * d1[1]));
+        }
+        total += acc * half;
+    }
+    return total;
+}
+double dseg_arclen(const DSeg &s) {
+    if (s.k == 'L') {
+        const double dx = s.p[1][0] - s.p[0][0], dy = s.p[1][1] - s.p[0][1];
+        return std::sqrt(dx * dx + dy * dy);
+    }
+    return dseg_curve_arclen(s, 0.0, 1.0);
+}
+double dseg_inv_arclen(const DSeg &s, double len) {
+    if (s.k == 'L') return len / dseg_arclen(s);
+    double lo = 0.0, hi = 1.0;
+    for (int it = 0; it < 48; it++) {
+        const double mid = 0.5 * (lo + hi);
+        if (dseg_curve_arclen(s, 0.0, mid) < len) lo = mid;
+        else hi = mid;
+    }
+    return 0.5 * (lo + hi);
+}
+DSeg dseg_sub(const DSeg &s, double t0, double t1) {
+    DSeg r;
+    r.k = s.k;
+    for (auto &q : r.p) q[0] = q[1] = 0.0;
+    if (s.k == 'L') {
+        dseg_eval(s, t0, r.p[0]);
+        dseg_eval(s, t1, r.p[1]);
+    } else if (s.k == 'Q') {
+        dseg_eval(s, t0, r.p[0]);
+        dseg_eval(s, t1, r.p[2]);
+        const double a[2] = {s.p[1][0] - s.p[0][0], s.p[1][1] - s.p[0][1]}, b[2] = {s.p[2][0] - s.p[1][0], s.p[2][1] - s.p[1][1]};
+        double d[2];
+        d_lerp(a, b, t0, d);
+        r.p[1][0] = r.p[0][0] + d[0] * (t1 - t0);
+        r.p[1][1] = r.p[0][1] + d[1] * (t1 - t0);
+    } else {
+        dseg_eval(s, t0, r.p[0]);
+        dseg_eval(s, t1, r.p[3]);
+        const double scale = (t1 - t0) * (1.0 / 3.0);
+        double d0[2], d1[2];
+        dseg_deriv(s, t0, d0);
+        dseg_deriv(s, t1, d1);
+        r.p[1][0] = r.p[0][0] + scale * d0[0];
+        r.p[1][1] = r.p[0][1] + scale * d0[1];
+        r.p[2][0] = r.p[3][0] - scale * d1[0];
+        r.p[2][1] = r.p[3][1] - scale * d1[1];
+    }
+    return r;
+}
+struct DEl { char v; double c[6]; };
+DEl dseg_to_el(const DSeg &s) {
+    DEl e{};
+    e.v = s.k;
+    if (s.k == 'L') { e.c[0] = s.p[1][0]; e.c[1] = s.p[1][1]; }
+    else if (s.k == 'Q') { e.c[0] = s.p[1][0]; e.c[1] = s.p[1][1]; e.c[2] = s.p[2][0]; e.c[3] = s.p[2][1]; }
+    else { for (int i = 0; i < 3; i++) { e.c[2 * i] = s.p[i + 1][0]; e.c[2 * i + 1] = s.p[i + 1][1]; } }
+    return e;
+}
+void pb_push(vb_pathbuf &pb, const DEl &e) {
+    switch (e.v) {
+    case 'M': case 'L': pb.el((uint8_t)e.v, {e.c[0], e.c[1]}); break;
+    case 'Q': pb.el('Q', {e.c[0], e.c[1], e.c[2], e.c[3]}); break;
+    case 'C': pb.el('C', {e.c[0], e.c[1], e.c[2], e.c[3], e.c[4], e.c[5]}); break;
+    default: pb.el('Z', {}); break;
+    }
+}
+
+int dash_path(const vb_path &in, double dash_offset, const double *dashes, uint32_t n_dashes, vb_pathbuf &out) {
+    if (!n_dashes) return VB_E_INVALID;
+    enum { NEED_INPUT, TO_STASH, WORKING, FROM_STASH };
+    uint32_t dash_ix = 0;
+    double dash_remaining = dashes[0] - dash_offset;
+    bool is_active = true;
+    for (uint32_t guard = 0; dash_remaining < 0.0; guard++) {
+        if (guard > (1u << 24)) return VB_E_INVALID; // all-zero / negative pattern
+        dash_ix = (dash_ix + 1u) % n_dashes;
+        dash_remaining += dashes[dash_ix];
+        is_active = !is_active;
+    }
+    const uint32_t init_dash_ix = dash_ix;
+    const double init_dash_remaining = dash_remaining;
+    const bool init_is_active = is_active;
+    bool input_done = false, closepath_pending = false;
+    int state = NEED_INPUT;
+    DSeg seg{};
+    seg.k = 'L';
+    double t = 0.0, seg_remaining = 0.0, start_pt[2] = {0, 0}, last_pt[2] = {0, 0};
+    std::vector<DEl> stash;
+    size_t stash_ix = 0;
+    uint32_t vi = 0;
+    size_t ci = 0;
+    auto reset_phase = [&]() { dash_ix = init_dash_ix; dash_remaining = init_dash_remaining; is_active = init_is_active; };
+    auto handle_closepath = [&]() {
+        if (state == TO_STASH) { DEl z{}; z.v = 'Z'; stash.push_back(z); }
+        else if (is_active) stash_ix = 1;
+        state = FROM_STASH;
+        reset_phase();
+    };
+    auto get_input = [&]() -> int {
+        for (;;) {
+            if (closepath_pending) { handle_closepath(); break; }
+            if (vi >= in.n_verbs) { input_done = true; state = FROM_STASH; return VB_OK; }
+            const uint8_t v = in.verbs[vi++];
+            const double *c = in.coords + ci;
+            const double p0[2] = {last_pt[0], last_pt[1]};
+            if (v == 'M') {
+                ci += 2;
+                if (!stash.empty()) state = FROM_STASH;
+                start_pt[0] = last_pt[0] = c[0];
+                start_pt[1] = last_pt[1] = c[1];
+                reset_phase();
+                continue;
+            } else if (v == 'L') {
+                ci += 2;
+                seg.k = 'L';
+                seg.p[0][0] = p0[0]; seg.p[0][1] = p0[1]; seg.p[1][0] = c[0]; seg.p[1][1] = c[1];
+                last_pt[0] = c[0]; last_pt[1] = c[1];
+            } else if (v == 'Q') {
+                ci += 4;
+                seg.k = 'Q';
+                seg.p[0][0] = p0[0]; seg.p[0][1] = p0[1];
+                for (int i = 0; i < 2; i++) { seg.p[i + 1][0] = c[2 * i]; seg.p[i + 1][1] = c[2 * i + 1]; }
+                last_pt[0] = c[2]; last_pt[1] = c[3];
+            } else if (v == 'C') {
+                ci += 6;
+                seg.k = 'C';
+                seg.p[0][0] = p0[0]; seg.p[0][1] = p0[1];
+                for (int i = 0; i < 3; i++) { seg.p[i + 1][0] = c[2 * i]; seg.p[i + 1][1] = c[2 * i + 1]; }
+                last_pt[0] = c[4]; last_pt[1] = c[5];
+            } else if (v == 'Z') {
+                closepath_pending = true;
+                if (p0[0] != start_pt[0] || p0[1] != start_pt[1]) {
+                    seg.k = 'L';
+                    seg.p[0][0] = p0[0]; seg.p[0][1] = p0[1]; seg.p[1][0] = start_pt[0]; seg.p[1][1] = start_pt[1];
+                    last_pt[0] = start_pt[0]; last_pt[1] = start_pt[1];
+                } else {
+                    continue;
+                }
+            } else {
+                return VB_E_INVALID;
+            }
+            seg_remaining = dseg_arclen(seg);
+            break;
+        }
+        t = 0.0;
+        return VB_OK;
+    };
+    int rc = VB_OK;
+    auto step = [&](DEl &result) -> bool {
+        bool have = false;
+        if (state == TO_STASH && stash.empty()) {
+            if (is_active) { result = DEl{}; result.v = 'M'; result.c[0] = seg.p[0][0]; result.c[1] = seg.p[0][1]; have = true; }
+            else state = WORKING;
+        } else if (dash_remaining < seg_remaining) {
+            const DSeg rest = dseg_sub(seg, t, 1.0);
+            const double t1 = dseg_inv_arclen(rest, dash_remaining);
+            if (is_active) {
+                result = dseg_to_el(dseg_sub(rest, 0.0, t1));
+                state = WORKING;
+            } else {
+                double pt[2];
+                dseg_eval(rest, t1, pt);
+                result = DEl{};
+                result.v = 'M'; result.c[0] = pt[0]; result.c[1] = pt[1];
+            }
+            have = true;
+            is_active = !is_active;
+            t += t1 * (1.0 - t);
+            seg_remaining -= dash_remaining;
+            dash_ix += 1;
+            if (dash_ix == n_dashes) dash_ix = 0;
+            dash_remaining = dashes[dash_ix];
+        } else {
+            if (is_active) { result = dseg_to_el(dseg_sub(seg, t, 1.0)); have = true; }
+            dash_remaining -= seg_remaining;
+            const int r2 = get_input();
+            if (r2) rc = r2;
+        }
+        return have;
+    };
+    for (uint64_t guard = 0;; guard++) {
+        if (guard > (1ull << 33) || rc) return rc ? rc : VB_E_INVALID;
+        if (state == NEED_INPUT) {
+            if (input_done) break;
+            const int r2 = get_input();
+            if (r2) return r2;
+            if (input_done) {
+                if (stash.empty()) break;
+                continue;
+            }
+            state = TO_STASH;
+        } else if (state == TO_STASH) {
+            DEl e;
+            if (step(e)) stash.push_back(e);
+        } else if (state == WORKING) {
+            DEl e;
+            if (step(e)) pb_push(out, e);
+        } else {
+            if (stash_ix < stash.size()) {
+                pb_push(out, stash[stash_ix++]);
+            } else {
+                stash.clear();
+                stash_ix = 0;
+                if (input_done) break;
+                if (closepath_pending) { closepath_pending = false; state = NEED_INPUT; }
+                else state = TO_STASH;
+            }
+        }
+    }
+    return rc;
+}
+} // namespace
+
+extern "C" int vb_path_dash(const vb_path *path, double dash_offset, const double *dashes, uint32_t n_dashes, vb_pathbuf *out) {
+    if (!path || !dashes || !n_dashes || !out || (path->n_verbs && (!path->verbs || !path->coords))) return VB_E_INVALID;
+    return dash_path(*path, dash_offset, dashes, n_dashes, *out);
+}
 
 namespace {
 const double PI = 3.141592653589793;

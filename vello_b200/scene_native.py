@@ -39,7 +39,8 @@ class _Brush(C.Structure):
 
 
 class _Stroke(C.Structure):
-    _fields_ = [("width", C.c_double), ("join", C.c_uint32), ("start_cap", C.c_uint32), ("end_cap", C.c_uint32), ("miter_limit", C.c_double)]
+    _fields_ = [("width", C.c_double), ("join", C.c_uint32), ("start_cap", C.c_uint32), ("end_cap", C.c_uint32), ("miter_limit", C.c_double),
+                ("dash_pattern", C.c_void_p), ("n_dashes", C.c_uint32), ("dash_offset", C.c_double)]
 
 
 class _Packed(C.Structure):
@@ -168,7 +169,13 @@ class NativeScene:
 
     @staticmethod
     def _stroke(s: Stroke) -> _Stroke:
-        return _Stroke(float(s.width), s.join, s.start_cap, s.end_cap, float(s.miter_limit))
+        st = _Stroke(float(s.width), s.join, s.start_cap, s.end_cap, float(s.miter_limit), None, 0, float(s.dash_offset))
+        if s.dash_pattern:
+            arr = (C.c_double * len(s.dash_pattern))(*[float(d) for d in s.dash_pattern])
+            st._keep = arr  # keeps the pattern alive as long as the struct
+            st.dash_pattern = C.cast(arr, C.c_void_p)
+            st.n_dashes = len(s.dash_pattern)
+        return st
 
     def _check(self, rc):
         if rc != 0:
@@ -182,7 +189,7 @@ class NativeScene:
         self._check(self.lib.vb_scene_fill(self.handle, style, _affine(transform), C.byref(b), bt, C.byref(p)))
 
     def stroke(self, stroke: Stroke, transform: Affine, brush, brush_transform: Optional[Affine], shape):
-        p, hold = self._path(shape, 0.1)  # scene.rs:417-421: encode_shape -> path_elements(0.1); 0.01 is the dash path only
+        p, hold = self._path(shape, 0.01 if stroke.dash_pattern else 0.1)  # scene.rs:404-437: 0.01 only for the dash expansion
         b, hb = self._brush(brush)
         st = self._stroke(stroke)
         bt = _affine(brush_transform) if brush_transform is not None else None
@@ -191,7 +198,7 @@ class NativeScene:
     def _clip_args(self, clip_style, clip):
         if isinstance(clip_style, Stroke):
             st = self._stroke(clip_style)
-            p, hold = self._path(clip, 0.1)
+            p, hold = self._path(clip, 0.01 if clip_style.dash_pattern else 0.1)
             return 0, C.byref(st), p, (st, hold)
         p, hold = self._path(clip, 0.1)
         return int(clip_style), None, p, hold
