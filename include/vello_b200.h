@@ -156,6 +156,41 @@ int vb_set_occlusion_cull(vb_renderer *, int on);
 
 int vb_debug_fine_traffic(vb_renderer *, uint64_t *ptcl_words, uint64_t *segment_refs, uint64_t *fill_cmds);
 
+/* ---- Resolver::resolve on the DEVICE (vello_encoding/src/resolve.rs:183-399, ramp_cache.rs:119-155) ----
+ * Instead of a packed scene the caller hands over the six streams of a vello_encoding::Encoding (encoding.rs:22-48) and its
+ * late-bound patches (resolve.rs:560-590): each stream is copied straight to its Layout offset inside the packed buffer in
+ * device memory, and a kernel finishes the job there -- tag padding, the trailing PATH / END_CLIP tags of unclosed clips, the
+ * ramp-id and atlas-position patches, and the gradient ramps themselves (one thread per texel). The images go into the atlas
+ * with one 2-D copy each. Only sizes, the ramp de-duplication and the atlas shelf placement stay on the host. The resulting
+ * device buffers are byte-identical to what vb_scene_upload receives from the host-side resolve (tests/test_gpu_parity.py).
+ * Glyph runs are not part of this path (they are resolved to outlines above the boundary). */
+typedef struct { float offset, r, g, b, a; } vb_ramp_stop; /* straight-alpha colour */
+typedef struct {
+    uint32_t draw_data_offset; /* word in the draw-data stream that receives (ramp id << 2) | extend */
+    uint32_t extend, premul_interp, n_stops;
+    const vb_ramp_stop *stops;
+} vb_ramp_patch;
+typedef struct {
+    uint32_t draw_data_offset; /* word that receives (atlas x << 16) | atlas y */
+    uint32_t width, height;
+    const uint8_t *pixels; /* RGBA8 / BGRA8 rows, width * 4 bytes each; identical pointers share one atlas slot */
+} vb_image_patch;
+typedef struct {
+    const uint8_t *path_tags; uint32_t n_path_tags;
+    const uint32_t *path_data; uint32_t n_path_data;   /* 32-bit words */
+    const uint32_t *draw_tags; uint32_t n_draw_tags;
+    const uint32_t *draw_data; uint32_t n_draw_data;
+    const float *transforms; uint32_t n_transforms;    /* 6 floats each (math.rs:9-17) */
+    const uint32_t *styles; uint32_t n_styles;         /* 2 words each (path.rs:11-69) */
+    uint32_t n_paths, n_clips, n_open_clips;
+    const vb_ramp_patch *ramp_patches; uint32_t n_ramp_patches;
+    const vb_image_patch *image_patches; uint32_t n_image_patches;
+} vb_encoding_streams;
+/* Resolve + upload; afterwards the renderer holds the scene exactly as after vb_scene_upload. *layout_out (optional) = the Layout. */
+int vb_scene_upload_streams(vb_renderer *, const vb_encoding_streams *, vb_layout *layout_out);
+/* Render the uploaded scene and deliver the pixels like vb_render does (host pointer with out_is_device == 0, device otherwise). */
+int vb_render_uploaded(vb_renderer *, const vb_params *, void *out, uint32_t out_is_device, vb_frame_stats *);
+
 /* ---- one frame on several GPUs of one box (north_star: "a single frame shards across the GPUs by stripes") ----
  * The frame is cut into horizontal stripes of tile rows, one per device; every device runs the element stages on the scene and
  * the tile stages on its stripe (no winding seam exists between horizontal stripes), and `fine` on device k stores

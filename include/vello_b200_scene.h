@@ -154,6 +154,8 @@ int vb_scene_resolve(vb_scene *, vb_packed *out);
 
 /* Renderer::render_to_texture (vello/src/lib.rs:474-515) for a vb_scene: resolve + vb_render. */
 int vb_render_scene(vb_renderer *, vb_scene *, const vb_params *, void *out, uint32_t out_is_device, vb_frame_stats *);
+/* The first half of vb_render_scene: resolve the scene's streams on the device (vb_scene_upload_streams) and leave them uploaded. */
+int vb_scene_upload_device(vb_renderer *, vb_scene *, vb_layout *layout_out);
 
 #ifdef __cplusplus
 }

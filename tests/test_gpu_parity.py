@@ -602,3 +602,45 @@ def test_group_one_call_one_frame(oracle, n):
     got = g.render_to_texture(other, p2)
     assert_pixels(got, oracle.render(other, 700, 500, BLACK.premul_rgba8_u32(), AA_AREA), AA_AREA)
     g.close()
+
+
+def test_device_resolve_equals_host_resolve(renderer, oracle):
+    """Resolver::resolve on the device (vb_scene_upload_streams: stream copies to their Layout offsets + the patch / padding /
+    ramp kernels, k_resolve.cu): packed scene, gradient ramps and image atlas are byte-identical to the host-side resolve --
+    all brush kinds, duplicated gradients (one ramp) and images (one atlas slot), premultiplied and straight interpolation,
+    unclosed clips (trailing PATH / END_CLIP tags), dashed strokes -- and so are the pixels."""
+    from vello_b200.scene_native import NativeScene
+    from vello_b200.shapes import Affine, Circle, Rect, RoundedRect
+    from vello_b200.encoding import FILL_NON_ZERO, FILL_EVEN_ODD, Gradient, Image, Stroke, EXTEND_REPEAT, MIX_SCREEN, COMPOSE_SRC_OVER
+    rng = np.random.default_rng(8)
+    stops = [(0.0, Color.from_rgba8(255, 40, 0)), (0.3, Color.from_rgba8(0, 200, 90, 100)), (0.31, Color.from_rgba8(20, 0, 255)), (1.0, Color.from_rgba8(250, 250, 0, 30))]
+    img_a = rng.integers(0, 256, (9, 14, 4), dtype=np.uint8)
+    img_b = rng.integers(0, 256, (30, 5, 4), dtype=np.uint8)
+    nat = NativeScene()
+    for k in range(3):
+        g = Gradient.linear((0, 0), (300, 200), stops, EXTEND_REPEAT, premul_interp=(k != 1))
+        nat.fill(FILL_NON_ZERO, Affine.translate(10.0 * k, 0.0), g, None, Rect(10, 10, 290, 190))
+    nat.fill(FILL_EVEN_ODD, Affine.IDENTITY, Gradient.radial((150, 100), 5.0, (160, 110), 80.0, stops[:2]), None, Circle(150.0, 100.0, 90.0))
+    nat.fill(FILL_NON_ZERO, Affine.scale(1.2), Gradient.sweep((80, 60), 0.0, 6.0, stops), None, RoundedRect(30, 20, 150, 110, 9.0))
+    for im in (img_a, img_b, img_a):
+        nat.draw_image(Image(im), Affine.translate(float(rng.uniform(0, 200)), float(rng.uniform(0, 100))) * Affine.scale(3.0))
+    nat.stroke(Stroke(3.0, dash_pattern=(9.0, 4.0, 2.0), dash_offset=3.0), Affine.IDENTITY, Color.from_rgba8(255, 255, 255), None, Circle(200.0, 120.0, 60.0))
+    nat.push_layer(FILL_NON_ZERO, MIX_SCREEN, COMPOSE_SRC_OVER, 0.7, Affine.IDENTITY, Circle(100.0, 100.0, 80.0))
+    nat.fill(FILL_NON_ZERO, Affine.IDENTITY, Color.from_rgba8(30, 90, 200, 180), None, Rect(40, 40, 260, 160))
+    nat.push_clip_layer(FILL_NON_ZERO, Affine.IDENTITY, Rect(60, 60, 200, 140))  # both layers left open on purpose
+    nat.fill(FILL_NON_ZERO, Affine.IDENTITY, Gradient.linear((0, 0), (300, 200), stops, EXTEND_REPEAT), None, Rect(0, 0, 300, 200))
+    host = nat.resolve()
+    layout = nat.upload_device(renderer)
+    assert layout.as_array().tolist() == host.layout.as_array().tolist()
+    assert renderer.download("scene", np.uint32).tobytes() == host.scene.tobytes()
+    assert renderer.download("ramps", np.uint32).tobytes() == host.ramps.tobytes()
+    assert host.ramps.shape[0] == 3  # (stops, premultiplied), (stops, straight), (first two stops): de-duplicated by (stops, space)
+    assert renderer.download("atlas", np.uint8).tobytes() == host.atlas.tobytes()
+    w, h = 300, 200
+    for aa in (AA_MSAA16, AA_AREA):
+        p = RenderParams(Color.from_rgba8(12, 12, 12), w, h, aa)
+        want = renderer.render_to_texture(host, p)
+        nat.upload_device(renderer)
+        got = renderer.render_resident(p) and renderer.download_target(p)
+        assert np.array_equal(got, want)
+        assert_pixels(got, oracle.render(host, w, h, p.base_color.premul_rgba8_u32(), aa), aa)

@@ -50,6 +50,8 @@ void vb_launch_fine(const VbConfig *, int, const VbBump *, const VbSegment *, co
 }
 
 extern "C" int vb_fine_init_constants(void);
+extern "C" void vb_launch_resolve_finish(uint32_t *, uint32_t, uint32_t, uint32_t, uint32_t, const void *, uint32_t, cudaStream_t);
+extern "C" void vb_launch_make_ramps(const void *, const void *, uint32_t, uint32_t *, cudaStream_t);
 
 // path_tiling_setup.wgsl:21-26 flags a failed frame to fine through ptcl[0] = ~0. That word is also tile 0's blend offset
 // and is only rewritten when coarse visits tile 0 -- which a stripe window with bin_row0 > 0 never does, so the flag of a
@@ -133,6 +135,7 @@ struct vb_renderer {
     DevBuf tag_monoids, path_bboxes, draw_monoids, info_bin_data, clip_inp, clip_bboxes, clip_scratch, draw_bboxes, bin_headers, paths,
         ctl, target, target_alt, tile_start;
     // bump arenas (capacities in elements live in cap_*)
+    DevBuf resolve_tmp; // patches, ramp descriptors and stops of vb_scene_upload_streams
     DevBuf lines, line_scratch, flatten_jobs, flatten_parts, tiles, seg_counts, segments, ptcl, blend_spill;
     uint32_t cap_lines = 0, cap_binning = 0, cap_tiles = 0, cap_seg_counts = 0, cap_segments = 0, cap_blend = 0, cap_ptcl = 0;
 
@@ -331,7 +334,7 @@ extern "C" void vb_renderer_free(vb_renderer *r) {
                      &r->ctl, &r->target, &r->target_alt, &r->tile_start, &r->lines, &r->line_scratch, &r->flatten_jobs, &r->flatten_parts, &r->tiles, &r->seg_counts, &r->segments, &r->ptcl, &r->blend_spill};
     for (auto b : all)
         if (b->p) cudaFree(b->p);
-    for (DevBuf *b : {&r->other.scene, &r->other.ramps, &r->other.atlas})
+    for (DevBuf *b : {&r->other.scene, &r->other.ramps, &r->other.atlas, &r->resolve_tmp})
         if (b->p) cudaFree(b->p);
     if (r->h_bump) cudaFreeHost(r->h_bump);
     if (r->other.h_bump) cudaFreeHost(r->other.h_bump);
@@ -856,14 +859,10 @@ extern "C" int vb_render_resident(vb_renderer *r, const vb_params *p, void *out_
     return VB_OK;
 }
 
-extern "C" int vb_render(vb_renderer *r, const uint8_t *scene, size_t scene_len, const vb_layout *layout, const uint32_t *ramps,
-                         uint32_t ramp_w, uint32_t ramp_h, const uint8_t *atlas, uint32_t atlas_w, uint32_t atlas_h, const vb_params *p,
-                         void *out, uint32_t out_is_device, vb_frame_stats *stats) {
+extern "C" int vb_render_uploaded(vb_renderer *r, const vb_params *p, void *out, uint32_t out_is_device, vb_frame_stats *stats) {
     if (!r || !p || !out) return VB_E_INVALID;
-    int rc = vb_scene_upload(r, scene, scene_len, layout, ramps, ramp_w, ramp_h, atlas, atlas_w, atlas_h);
-    if (rc) return rc;
     r->host_out = out_is_device ? nullptr : out;
-    rc = vb_render_resident(r, p, out_is_device ? out : nullptr, stats);
+    int rc = vb_render_resident(r, p, out_is_device ? out : nullptr, stats);
     r->host_out = nullptr;
     if (!out_is_device) {
         // the band copies were queued behind the fine bands; a re-run after an arena overflow simply copies again
@@ -874,6 +873,15 @@ extern "C" int vb_render(vb_renderer *r, const uint8_t *scene, size_t scene_len,
         }
     }
     return rc;
+}
+
+extern "C" int vb_render(vb_renderer *r, const uint8_t *scene, size_t scene_len, const vb_layout *layout, const uint32_t *ramps,
+                         uint32_t ramp_w, uint32_t ramp_h, const uint8_t *atlas, uint32_t atlas_w, uint32_t atlas_h, const vb_params *p,
+                         void *out, uint32_t out_is_device, vb_frame_stats *stats) {
+    if (!r || !p || !out) return VB_E_INVALID;
+    int rc = vb_scene_upload(r, scene, scene_len, layout, ramps, ramp_w, ramp_h, atlas, atlas_w, atlas_h);
+    if (rc) return rc;
+    return vb_render_uploaded(r, p, out, out_is_device, stats);
 }
 
 // ---- streaming: vb_render_begin / vb_readback_wait ------------------------------------------------------------------------
@@ -1080,6 +1088,14 @@ extern "C" int vb_debug_download(vb_renderer *r, const char *name, void *dst, si
     if (!strcmp(name, "seg_holes")) { // reserved-but-unused segment slots of the last frame (k_coarse.cu)
         if (bytes) *bytes = 4;
         if (dst && cap >= 4) CK(cudaMemcpy(dst, (const uint32_t *)r->ctl.p + VB_CTL_SEG_HOLES, 4, cudaMemcpyDeviceToHost));
+        return VB_OK;
+    }
+    if (!strcmp(name, "scene") || !strcmp(name, "ramps") || !strcmp(name, "atlas")) { // the uploaded / device-resolved inputs
+        const DevBuf &b = name[0] == 's' ? r->scene : (name[0] == 'r' ? r->ramps : r->atlas);
+        const size_t n = name[0] == 's' ? r->scene_words * 4 : (name[0] == 'r' ? (size_t)r->n_ramps * 512 * 4 : (size_t)r->atlas_w * r->atlas_h * 4);
+        if (bytes) *bytes = n;
+        const size_t c = n < cap ? n : cap;
+        if (dst && c) CK(cudaMemcpy(dst, b.p, c, cudaMemcpyDeviceToHost));
         return VB_OK;
     }
     if (!strcmp(name, "config")) {
@@ -1444,4 +1460,124 @@ extern "C" int vb_group_render(vb_group *g, const uint8_t *scene, size_t scene_l
     if (rc) return rc;
     if (out && !out_is_device) return group_render(g, p, nullptr, out, stats);
     return group_render(g, p, out, nullptr, stats);
+}
+
+
+// ---- Resolver::resolve on the device (resolve.rs:183-399): see include/vello_b200.h and k_resolve.cu ---------------------------
+extern "C" int vb_scene_upload_streams(vb_renderer *r, const vb_encoding_streams *e, vb_layout *layout_out) {
+    if (!r || !e) return VB_E_INVALID;
+    if ((e->n_path_tags && !e->path_tags) || (e->n_path_data && !e->path_data) || (e->n_draw_tags && !e->draw_tags) ||
+        (e->n_draw_data && !e->draw_data) || (e->n_transforms && !e->transforms) || (e->n_styles && !e->styles) ||
+        (e->n_ramp_patches && !e->ramp_patches) || (e->n_image_patches && !e->image_patches))
+        return VB_E_INVALID;
+    int rc = drain_stream(r);
+    if (rc) return rc;
+    CK(cudaSetDevice(r->device));
+    cudaStream_t st = r->stream;
+    struct Patch { uint32_t word, value; };
+    struct Ramp { uint32_t first_stop, n_stops, premul, pad; };
+    std::vector<Patch> patches;
+    std::vector<Ramp> ramps;
+    std::vector<vb_ramp_stop> stops;
+    std::vector<const vb_ramp_patch *> ramp_of;
+    // layout: sizes only (resolve.rs:107-154)
+    VbLayout L;
+    memset(&L, 0, sizeof L);
+    L.n_paths = e->n_paths;
+    L.n_clips = e->n_clips;
+    L.n_draw_objects = e->n_paths;
+    const uint32_t n_tags = e->n_path_tags + e->n_open_clips;
+    const uint32_t padded = (n_tags + 1023u) & ~1023u; // 4 * PATH_REDUCE_WG bytes (resolve.rs:625, config.rs:237)
+    uint32_t off = padded / 4u;
+    L.path_tag_base = 0;
+    L.path_data_base = off; off += e->n_path_data;
+    L.draw_tag_base = off; off += e->n_draw_tags + e->n_open_clips;
+    L.draw_data_base = off; off += e->n_draw_data;
+    L.transform_base = off; off += e->n_transforms * 6u;
+    L.style_base = off; off += e->n_styles * 2u;
+    const size_t total_words = off;
+    uint32_t info = 0;
+    for (uint32_t i = 0; i < e->n_draw_tags; i++) info += (e->draw_tags[i] >> 6) & 0xFu;
+    L.bin_data_start = info;
+    // late-bound gradient ramps, de-duplicated by (stops, interpolation space) as the ramp cache does
+    for (uint32_t i = 0; i < e->n_ramp_patches; i++) {
+        const vb_ramp_patch &p = e->ramp_patches[i];
+        if (!p.n_stops || !p.stops || p.draw_data_offset >= e->n_draw_data) return VB_E_INVALID;
+        uint32_t rid = (uint32_t)ramp_of.size();
+        for (uint32_t k = 0; k < ramp_of.size(); k++) {
+            const vb_ramp_patch &q = *ramp_of[k];
+            if ((q.premul_interp != 0u) == (p.premul_interp != 0u) && q.n_stops == p.n_stops &&
+                memcmp(q.stops, p.stops, sizeof(vb_ramp_stop) * p.n_stops) == 0) { rid = k; break; }
+        }
+        if (rid == ramp_of.size()) {
+            ramp_of.push_back(&p);
+            ramps.push_back(Ramp{(uint32_t)stops.size(), p.n_stops, p.premul_interp ? 1u : 0u, 0u});
+            stops.insert(stops.end(), p.stops, p.stops + p.n_stops);
+        }
+        patches.push_back(Patch{L.draw_data_base + p.draw_data_offset, (rid << 2) | p.extend});
+    }
+    // late-bound images: shelf placement (ours; only the (x, y) written into the draw data matters to the pipeline)
+    struct Placed { const uint8_t *key; uint32_t w, h, x, y; };
+    std::vector<Placed> placed;
+    uint32_t atlas_w = 1, x = 0, y = 0, shelf_h = 0;
+    const uint32_t MAXW = 2048;
+    for (uint32_t i = 0; i < e->n_image_patches; i++) {
+        const vb_image_patch &im = e->image_patches[i];
+        if (im.draw_data_offset >= e->n_draw_data) return VB_E_INVALID;
+        const Placed *hit = nullptr;
+        for (const Placed &q : placed)
+            if (q.key == im.pixels && q.w == im.width && q.h == im.height) { hit = &q; break; }
+        uint32_t px, py;
+        if (!hit) {
+            if (x + im.width > MAXW) { y += shelf_h; x = 0; shelf_h = 0; }
+            placed.push_back(Placed{im.pixels, im.width, im.height, x, y});
+            px = x; py = y;
+            x += im.width;
+            if (im.height > shelf_h) shelf_h = im.height;
+            if (x > atlas_w) atlas_w = x;
+        } else {
+            px = hit->x; py = hit->y;
+        }
+        patches.push_back(Patch{L.draw_data_base + im.draw_data_offset, (px << 16) | py});
+    }
+    const uint32_t atlas_h = (y + shelf_h) > 1u ? (y + shelf_h) : 1u;
+
+    // the six streams go straight to their places in the packed buffer
+    if ((rc = ensure(r, r->scene, total_words * 4 + 64))) return rc;
+    char *base = (char *)r->scene.p;
+    if (e->n_path_tags) CK(cudaMemcpyAsync(base, e->path_tags, e->n_path_tags, cudaMemcpyHostToDevice, st));
+    if (e->n_path_data) CK(cudaMemcpyAsync(base + (size_t)L.path_data_base * 4, e->path_data, (size_t)e->n_path_data * 4, cudaMemcpyHostToDevice, st));
+    if (e->n_draw_tags) CK(cudaMemcpyAsync(base + (size_t)L.draw_tag_base * 4, e->draw_tags, (size_t)e->n_draw_tags * 4, cudaMemcpyHostToDevice, st));
+    if (e->n_draw_data) CK(cudaMemcpyAsync(base + (size_t)L.draw_data_base * 4, e->draw_data, (size_t)e->n_draw_data * 4, cudaMemcpyHostToDevice, st));
+    if (e->n_transforms) CK(cudaMemcpyAsync(base + (size_t)L.transform_base * 4, e->transforms, (size_t)e->n_transforms * 24, cudaMemcpyHostToDevice, st));
+    if (e->n_styles) CK(cudaMemcpyAsync(base + (size_t)L.style_base * 4, e->styles, (size_t)e->n_styles * 8, cudaMemcpyHostToDevice, st));
+    // patches, ramp descriptors and stops in one staging buffer
+    const size_t pb = patches.size() * sizeof(Patch), rb = ramps.size() * sizeof(Ramp), sb = stops.size() * sizeof(vb_ramp_stop);
+    const size_t o_r = (pb + 15) & ~(size_t)15, o_s = (o_r + rb + 15) & ~(size_t)15;
+    if ((rc = ensure(r, r->resolve_tmp, o_s + sb + 16))) return rc;
+    char *tmp = (char *)r->resolve_tmp.p;
+    if (pb) CK(cudaMemcpyAsync(tmp, patches.data(), pb, cudaMemcpyHostToDevice, st));
+    if (rb) CK(cudaMemcpyAsync(tmp + o_r, ramps.data(), rb, cudaMemcpyHostToDevice, st));
+    if (sb) CK(cudaMemcpyAsync(tmp + o_s, stops.data(), sb, cudaMemcpyHostToDevice, st));
+    vb_launch_resolve_finish((uint32_t *)r->scene.p, e->n_path_tags, e->n_open_clips, padded, L.draw_tag_base + e->n_draw_tags, tmp,
+                             (uint32_t)patches.size(), st);
+    r->n_ramps = (uint32_t)ramps.size();
+    if ((rc = ensure(r, r->ramps, (size_t)r->n_ramps * 512 * 4))) return rc;
+    vb_launch_make_ramps(tmp + o_r, tmp + o_s, r->n_ramps, (uint32_t *)r->ramps.p, st);
+    r->atlas_w = atlas_w;
+    r->atlas_h = atlas_h;
+    if ((rc = ensure(r, r->atlas, (size_t)atlas_w * atlas_h * 4))) return rc;
+    CK(cudaMemsetAsync(r->atlas.p, 0, (size_t)atlas_w * atlas_h * 4, st));
+    for (const Placed &q : placed)
+        if (q.key && q.w && q.h)
+            CK(cudaMemcpy2DAsync((char *)r->atlas.p + ((size_t)q.y * atlas_w + q.x) * 4, (size_t)atlas_w * 4, q.key, (size_t)q.w * 4, (size_t)q.w * 4, q.h,
+                                 cudaMemcpyHostToDevice, st));
+    CK(cudaGetLastError());
+    // the host vectors above are read by the asynchronous copies: they must outlive them
+    CK(cudaStreamSynchronize(st));
+    r->layout = L;
+    r->scene_words = total_words;
+    r->have_scene = true;
+    if (layout_out) memcpy(layout_out, &L, sizeof(vb_layout));
+    return VB_OK;
 }

@@ -1393,12 +1393,36 @@ int vb_scene_resolve(vb_scene *s, vb_packed *out) {
     return VB_OK;
 }
 
+// Shapes to pixels: the scene's streams are resolved ON THE DEVICE (vb_scene_upload_streams: stream copies to their Layout offsets,
+// patch / padding / ramp kernels), then rendered.
+int vb_scene_upload_device(vb_renderer *r, vb_scene *s, vb_layout *layout_out) {
+    if (!r || !s) return VB_E_INVALID;
+    const Encoding &e = s->e;
+    static_assert(sizeof(Stop) == sizeof(vb_ramp_stop) && sizeof(Xform) == 24 && sizeof(Style) == 8, "stream record layouts");
+    std::vector<vb_ramp_patch> rps;
+    for (const RampPatch &p : e.ramp_patches)
+        rps.push_back(vb_ramp_patch{p.draw_data_offset, p.extend, p.premul ? 1u : 0u, (uint32_t)p.stops.size(),
+                                    reinterpret_cast<const vb_ramp_stop *>(p.stops.data())});
+    std::vector<vb_image_patch> ips;
+    for (const ImagePatch &p : e.image_patches) ips.push_back(vb_image_patch{p.draw_data_offset, p.image.width, p.image.height, p.image.pixels});
+    vb_encoding_streams st;
+    std::memset(&st, 0, sizeof st);
+    st.path_tags = e.path_tags.data(); st.n_path_tags = (uint32_t)e.path_tags.size();
+    st.path_data = reinterpret_cast<const uint32_t *>(e.path_data.data()); st.n_path_data = (uint32_t)e.path_data.size();
+    st.draw_tags = e.draw_tags.data(); st.n_draw_tags = (uint32_t)e.draw_tags.size();
+    st.draw_data = e.draw_data.data(); st.n_draw_data = (uint32_t)e.draw_data.size();
+    st.transforms = reinterpret_cast<const float *>(e.transforms.data()); st.n_transforms = (uint32_t)e.transforms.size();
+    st.styles = reinterpret_cast<const uint32_t *>(e.styles.data()); st.n_styles = (uint32_t)e.styles.size();
+    st.n_paths = e.n_paths; st.n_clips = e.n_clips; st.n_open_clips = e.n_open_clips;
+    st.ramp_patches = rps.data(); st.n_ramp_patches = (uint32_t)rps.size();
+    st.image_patches = ips.data(); st.n_image_patches = (uint32_t)ips.size();
+    return vb_scene_upload_streams(r, &st, layout_out);
+}
+
 int vb_render_scene(vb_renderer *r, vb_scene *s, const vb_params *p, void *out, uint32_t out_is_device, vb_frame_stats *stats) {
-    vb_packed pk;
-    const int rc = vb_scene_resolve(s, &pk);
+    const int rc = vb_scene_upload_device(r, s, nullptr);
     if (rc) return rc;
-    return vb_render(r, pk.scene, pk.scene_len, &pk.layout, pk.ramps, pk.ramp_w, pk.ramp_h, pk.atlas, pk.atlas_w, pk.atlas_h, p, out,
-                     out_is_device, stats);
+    return vb_render_uploaded(r, p, out, out_is_device, stats);
 }
 
 } // extern "C"

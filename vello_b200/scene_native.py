@@ -53,7 +53,7 @@ PATHBUF_SYMBOLS = ["vb_pathbuf_new", "vb_pathbuf_free", "vb_pathbuf_clear", "vb_
                    "vb_pathbuf_svg", "vb_pathbuf_view"]
 SCENE_SYMBOLS = ["vb_scene_new", "vb_scene_free", "vb_scene_reset", "vb_scene_fill", "vb_scene_stroke", "vb_scene_push_layer",
                  "vb_scene_push_luminance_mask_layer", "vb_scene_push_clip_layer", "vb_scene_pop_layer", "vb_scene_draw_image",
-                 "vb_scene_draw_blurred_rounded_rect", "vb_scene_draw_blurred_rounded_rect_in", "vb_scene_append", "vb_scene_resolve", "vb_render_scene"]
+                 "vb_scene_draw_blurred_rounded_rect", "vb_scene_draw_blurred_rounded_rect_in", "vb_scene_append", "vb_scene_resolve", "vb_render_scene", "vb_scene_upload_device", "vb_path_dash"]
 
 _bound = False
 
@@ -78,6 +78,8 @@ def _lib():
         lib.vb_scene_append.argtypes = [vp, vp, vp]
         lib.vb_scene_resolve.argtypes = [vp, vp]
         lib.vb_render_scene.argtypes = [vp, vp, vp, vp, C.c_uint32, vp]
+        lib.vb_scene_upload_device.argtypes = [vp, vp, vp]
+        lib.vb_path_dash.argtypes = [vp, C.c_double, vp, C.c_uint32, vp]
         d = C.c_double
         lib.vb_pathbuf_new.restype = vp
         lib.vb_pathbuf_free.argtypes = [vp]
@@ -237,6 +239,14 @@ class NativeScene:
         self._check(self.lib.vb_scene_append(self.handle, other.handle, _affine(transform) if transform is not None else None))
 
     # -- Resolver::resolve ---------------------------------------------------------------------------
+    def upload_device(self, renderer) -> Layout:
+        """Resolve this scene ON THE DEVICE of `renderer` (vb_scene_upload_streams: the six streams are copied to their Layout
+        offsets, kernels apply the patches / padding and generate the gradient ramps) and leave it uploaded there."""
+        L = _Layout()
+        self._check(self.lib.vb_scene_upload_device(renderer.handle, self.handle, C.byref(L)))
+        return Layout(L.n_draw_objects, L.n_paths, L.n_clips, L.bin_data_start, L.path_tag_base, L.path_data_base, L.draw_tag_base,
+                      L.draw_data_base, L.transform_base, L.style_base)
+
     def resolve(self) -> Packed:
         pk = _Packed()
         self._check(self.lib.vb_scene_resolve(self.handle, C.byref(pk)))
