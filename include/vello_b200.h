@@ -137,7 +137,13 @@ int vb_copy_to_host(vb_renderer *, const void *src_device, void *dst_host, size_
 /* cudaStream_t the renderer enqueues on (for event timing by the caller). */
 void *vb_stream(vb_renderer *);
 
-/* ---- stage-level access (parity tests; mirrors the reference's CPU-shader operator seam) ---- */
+/* ---- stage-level access (parity tests; mirrors the reference's CPU-shader operator seam) ----
+ * SURVEY.md 8(b) sketched one entry point per stage, `vb_stage_<name>(renderer, n_wg, bindings, n)`, 1:1 with the reference's
+ * `fn(u32 n_wg, &[CpuBinding])` (wgpu_engine.rs:57-61). That shape does not fit this implementation -- stages are fused
+ * (pathtag_reduce / reduce2 / scan1 / scan are ONE kernel, draw_reduce + draw_leaf another), grids are derived on the device,
+ * and the bindings are renderer-owned arenas -- so the seam is instead: vb_run_stages(first..last) over the renderer's own
+ * buffers + vb_debug_download / vb_debug_upload of any buffer by its Appendix-B name. A stage range may be run once per
+ * zeroing of the control block (i.e. once after a range that started at stage 0). */
 /* Run stages first..last (VB_STAGE_ID_*) of the uploaded scene, one attempt, synchronously. */
 int vb_run_stages(vb_renderer *, const vb_params *, int first, int last, void *out_device);
 /* Copy an intermediate buffer to the host: "tag_monoids","path_bboxes","lines","draw_monoids",

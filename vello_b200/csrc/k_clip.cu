@@ -16,35 +16,46 @@
 
 #define CL_THREADS 1024
 
+// Depth sequence B (exclusive scan of +1 / -1) and its 32 / 1024 minima. One CTA per 1024 clip ops; the carry between CTAs
+// comes from the single-pass decoupled look-back of vb_device.cuh (K = 1), so a million clip ops are a thousand CTAs, not a
+// thousand passes of one CTA (round 1: k_clip_depth<<<1, 1024>>>).
 __global__ void __launch_bounds__(CL_THREADS)
-k_clip_depth(uint32_t n_clips, const VbClipInp *__restrict__ clip_inp, int32_t *B, int32_t *min32, int32_t *min1024) {
+k_clip_depth(uint32_t n_clips, const VbClipInp *__restrict__ clip_inp, int32_t *B, int32_t *min32, int32_t *min1024, uint32_t *lb_mem,
+             uint32_t n_parts) {
     __shared__ uint32_t sh_scan[CL_THREADS / 32 + 2];
     __shared__ int32_t sh_min[CL_THREADS / 32];
-    uint32_t carry = 0;
-    for (uint32_t base = 0; base < n_clips; base += CL_THREADS) {
-        uint32_t i = base + threadIdx.x;
-        uint32_t v = 0;
-        if (i < n_clips) v = clip_inp[i].path_ix >= 0 ? 1u : 0xffffffffu;
-        uint32_t total;
-        uint32_t ex = vb_block_excl_scan(v, sh_scan, &total);
-        int32_t b = (int32_t)(carry + ex);
-        if (i < n_clips) B[i] = b;
-        int32_t m = i < n_clips ? b : 0x7fffffff;
+    __shared__ uint32_t sh_ticket;
+    __shared__ uint32_t sh_carry;
+    const VbLookback lb = vb_lookback_view(lb_mem, n_parts, 1);
+    const uint32_t part = vb_take_ticket(lb, &sh_ticket);
+    if (part >= n_parts) return;
+    const uint32_t base = part * CL_THREADS;
+    const uint32_t i = base + threadIdx.x;
+    uint32_t v = 0;
+    if (i < n_clips) v = clip_inp[i].path_ix >= 0 ? 1u : 0xffffffffu;
+    uint32_t total;
+    const uint32_t ex = vb_block_excl_scan(v, sh_scan, &total);
+    if (threadIdx.x < 32u) {
+        uint32_t agg[1] = {total}, excl[1];
+        vb_lookback<1>(lb, part, agg, excl);
+        if (threadIdx.x == 0u) sh_carry = excl[0];
+    }
+    __syncthreads();
+    const int32_t b = (int32_t)(sh_carry + ex);
+    if (i < n_clips) B[i] = b;
+    int32_t m = i < n_clips ? b : 0x7fffffff;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(VB_FULL, m, o));
-        if (vb_lane() == 0) {
-            if (base + (threadIdx.x & ~31u) < n_clips) min32[(base + threadIdx.x) >> 5] = m;
-            sh_min[threadIdx.x >> 5] = m;
-        }
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            int32_t mm = sh_min[threadIdx.x];
+    for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(VB_FULL, m, o));
+    if (vb_lane() == 0) {
+        if (base + (threadIdx.x & ~31u) < n_clips) min32[(base + threadIdx.x) >> 5] = m;
+        sh_min[threadIdx.x >> 5] = m;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int32_t mm = sh_min[threadIdx.x];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) mm = min(mm, __shfl_xor_sync(VB_FULL, mm, o));
-            if (threadIdx.x == 0) min1024[base / CL_THREADS] = mm;
-        }
-        carry += total;
-        __syncthreads();
+        for (int o = 16; o > 0; o >>= 1) mm = min(mm, __shfl_xor_sync(VB_FULL, mm, o));
+        if (threadIdx.x == 0) min1024[part] = mm;
     }
 }
 
@@ -123,14 +134,17 @@ __global__ void k_clip_bbox(uint32_t n_clips, const VbClipInp *__restrict__ clip
     }
 }
 
+extern "C" uint32_t vb_clip_parts(uint32_t n_clips) { return (n_clips + CL_THREADS - 1u) / CL_THREADS; }
 extern "C" void vb_launch_clip(uint32_t n_clips, const VbClipInp *clip_inp, const VbPathBbox *pbs, VbDrawMonoid *draw_monoids,
-                               VbBbox4 *clip_bboxes, int32_t *scratch /* B | min32 | min1024 | link */, cudaStream_t st) {
+                               VbBbox4 *clip_bboxes, int32_t *scratch /* B | min32 | min1024 | link */, uint32_t *lb_mem /* zeroed */,
+                               cudaStream_t st) {
     if (n_clips == 0) return;
     int32_t *B = scratch;
     int32_t *min32 = B + n_clips;
     int32_t *min1024 = min32 + (n_clips + 31) / 32;
     int32_t *link = min1024 + (n_clips + 1023) / 1024;
-    k_clip_depth<<<1, CL_THREADS, 0, st>>>(n_clips, clip_inp, B, min32, min1024);
+    const uint32_t n_parts = vb_clip_parts(n_clips);
+    k_clip_depth<<<n_parts, CL_THREADS, 0, st>>>(n_clips, clip_inp, B, min32, min1024, lb_mem, n_parts);
     k_clip_link<<<(n_clips + 255) / 256, 256, 0, st>>>(n_clips, clip_inp, B, min32, min1024, link);
     k_clip_bbox<<<(n_clips + 255) / 256, 256, 0, st>>>(n_clips, clip_inp, pbs, link, draw_monoids, clip_bboxes);
 }

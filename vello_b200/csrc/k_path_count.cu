@@ -16,11 +16,14 @@
 #ifndef PC_THREADS
 #define PC_THREADS 256
 #endif
+#ifndef PC_MINB
+#define PC_MINB 8
+#endif
 #define ONE_MINUS_ULP 0.99999994f
 #define ROBUST_EPSILON 2e-7f
 #define TILE_SCALE 0.0625f
 
-__global__ void __launch_bounds__(PC_THREADS)
+__global__ void __launch_bounds__(PC_THREADS, PC_MINB)
 k_path_count(VbConfig cfg, VbBump *bump, const VbLineSoup *__restrict__ lines, const VbPath *__restrict__ paths, VbTile *tile,
              VbSegmentCount *seg_counts) {
     __shared__ uint32_t sh_scan[PC_THREADS / 32 + 2];

@@ -7,12 +7,17 @@
 // read, 24 written (scattered into the tile's slice).
 #include "vb_device.cuh"
 
+#ifndef PTI_THREADS
 #define PTI_THREADS 256
+#endif
+#ifndef PTI_MINB
+#define PTI_MINB 8
+#endif
 #define ONE_MINUS_ULP 0.99999994f
 #define ROBUST_EPSILON 2e-7f
 #define TILE_SCALE 0.0625f
 
-__global__ void __launch_bounds__(PTI_THREADS)
+__global__ void __launch_bounds__(PTI_THREADS, PTI_MINB)
 k_path_tiling(VbConfig cfg, const VbBump *__restrict__ bump, const VbSegmentCount *__restrict__ seg_counts,
               const VbLineSoup *__restrict__ lines, const VbPath *__restrict__ paths, const VbTile *__restrict__ tiles,
               VbSegment *segments) {

@@ -30,7 +30,8 @@ void vb_flatten_arena_bytes(uint32_t, size_t *, size_t *);
 void vb_launch_draw(const VbConfig *, const uint32_t *, const VbPathBbox *, VbDrawMonoid *, uint32_t *, VbClipInp *, uint32_t *, uint32_t,
                     cudaStream_t);
 uint32_t vb_draw_parts(uint32_t);
-void vb_launch_clip(uint32_t, const VbClipInp *, const VbPathBbox *, VbDrawMonoid *, VbBbox4 *, int32_t *, cudaStream_t);
+void vb_launch_clip(uint32_t, const VbClipInp *, const VbPathBbox *, VbDrawMonoid *, VbBbox4 *, int32_t *, uint32_t *, cudaStream_t);
+uint32_t vb_clip_parts(uint32_t);
 size_t vb_clip_scratch_words(uint32_t);
 void vb_launch_binning(const VbConfig *, const VbDrawMonoid *, const VbPathBbox *, const VbBbox4 *, VbBbox4 *, VbBump *, uint32_t *,
                        VbBinHeader *, cudaStream_t);
@@ -153,7 +154,7 @@ struct vb_renderer {
     uint32_t readback_bands = 8; // fine launches per frame when the pixels go to the host (vb_render); 1 while streaming
     uint32_t occlusion_cull = 1; // fine starts each tile at its last opaque full-tile cover
     uint32_t parts_pathtag = 0, parts_flatten = 0, parts_draw = 0, parts_tile = 0;
-    size_t off_lb_pathtag = 0, off_lb_flatten = 0, off_lb_draw = 0, off_lb_tile = 0;
+    size_t off_lb_pathtag = 0, off_lb_flatten = 0, off_lb_draw = 0, off_lb_tile = 0, off_lb_clip = 0;
     cudaEvent_t ev[VB_N_STAGE_IDS + 1]{};
     cudaEvent_t frame_ev[2]{}; // around every whole frame (vb_last_frame_ms: the signal stripe balancing uses)
     bool frame_timed = false;
@@ -533,6 +534,7 @@ static int prepare(vb_renderer *r, const vb_params *p) {
     r->off_lb_flatten = off; off += 4; // flatten: [0] literal-record counter, [1] job counter
     r->off_lb_draw = off; off += vb_lookback_words(r->parts_draw, 4);
     r->off_lb_tile = off; off += vb_lookback_words(r->parts_tile, 1);
+    r->off_lb_clip = off; off += vb_lookback_words(vb_clip_parts(n_clips), 1);
     r->ctl_words = off;
     if ((rc = ensure(r, r->ctl, off * 4))) return rc;
     if ((rc = ensure(r, r->flatten_parts, ((size_t)r->parts_flatten * 34 + 8) * 4))) return rc;
@@ -581,7 +583,8 @@ static int enqueue_direct(vb_renderer *r, int first, int last, void *out_dev) {
             break;
         case VB_STAGE_ID_CLIP:
             vb_launch_clip(c.layout.n_clips, (const VbClipInp *)r->clip_inp.p, (const VbPathBbox *)r->path_bboxes.p,
-                           (VbDrawMonoid *)r->draw_monoids.p, (VbBbox4 *)r->clip_bboxes.p, (int32_t *)r->clip_scratch.p, st);
+                           (VbDrawMonoid *)r->draw_monoids.p, (VbBbox4 *)r->clip_bboxes.p, (int32_t *)r->clip_scratch.p,
+                           ctl + r->off_lb_clip, st);
             launches += c.layout.n_clips ? 3 : 0;
             break;
         case VB_STAGE_ID_BINNING:
