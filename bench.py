@@ -320,6 +320,30 @@ def main():
     fps = args.steps / (total_ms / 1000.0)
     rank_totals = [v[0] for v in allgather_floats([my_total])]
 
+    # ---- the same K steps with the stripes LEFT ON THEIR GPUS (every rank paints into its own buffer, no NVLink traffic): at
+    # 16384^2 the assembly of 1 GiB per frame on one GPU is bound by that GPU's NVLink ingest (~0.8 TB/s), SURVEY.md 8e asks
+    # for both figures
+    distributed = None
+    if world > 1:
+        for _ in range(3):
+            r.render_resident(params, 0, tile_rows=my_rows())
+        barrier()
+        evs2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for a, b in evs2:
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            a.record(stream)
+            r.enqueue(params, 0, tile_rows=my_rows())
+            b.record(stream)
+            assert r.finish().failed == 0
+        barrier()
+        sm2 = torch.tensor([a.elapsed_time(b) for a, b in evs2], dtype=torch.float64, device=dev)
+        dist.all_reduce(sm2, op=dist.ReduceOp.MAX)
+        distributed = {"value": args.steps / (float(sm2.sum().item()) / 1000.0), "unit": "frames/s",
+                       "ms_per_step": float(sm2.sum().item()) / args.steps, "note": "stripes left in each GPU's own memory"}
+
     # ---- the assembled frame: rank 0 renders the whole frame alone and compares (stripes over NVLink == one GPU)
     stripes_parity = None
     if world > 1:
@@ -506,7 +530,7 @@ def main():
         slow = int(np.argmax(rank_totals))
         line["multi_gpu"] = {"tile_row_bounds": list(bounds), "rank_ms_per_step": [round(v / args.steps, 4) for v in rank_totals],
                              "slowest_rank": slow, "stage_ms_by_rank": stage_by_rank, "balancing": balance_log,
-                             "frame": "assembled on rank 0 by peer stores from every rank's fine kernel"}
+                             "frame": "assembled on rank 0 by peer stores from every rank's fine kernel", "distributed": distributed}
     emit(line)
     if world > 1:
         dist.barrier()

@@ -228,6 +228,27 @@ void *vb_group_frame(vb_group *, size_t *bytes);
 int vb_group_stripes(vb_group *, uint32_t *boundaries, float *device_ms);
 int vb_group_set_balancing(vb_group *, int on); /* default on */
 
+/* ---- flatten sharded across the GPUs (SURVEY.md 8e option B) ----
+ * By default every GPU of a multi-GPU frame flattens the whole scene (culled to its stripe). With the exchange enabled GPU k
+ * flattens only its 1/G share of the tag stream and the GPUs trade results through peer memory inside the frame, without host
+ * or NCCL involvement: lines are routed to the stripes they touch and PULLED by their owners, partial path boxes are combined,
+ * the GPUs synchronise through epoch flags in each other's exchange arena (k_exchange.cu). Set-up, per renderer, after the
+ * scene has been uploaded:
+ *   vb_exchange_configure(r, rank, world, &arena, &bytes)   allocate my arena (fixed size; export it with vb_ipc_export across processes)
+ *   vb_exchange_attach(r, peer, peer_arena)                 for every other rank: its arena as seen from this device
+ *   vb_exchange_set_bounds(r, rows)                         the world + 1 tile-row boundaries of the stripes (same on every rank)
+ *   vb_exchange_enable(r, 1)
+ * then render with tile_row0/1 = rows[rank], rows[rank + 1] as before. All ranks must render the SAME sequence of frames
+ * (every attempt advances an epoch): a frame that overflows an arena returns VB_E_BUMP_OVERFLOW after growing it instead of
+ * re-running on its own, and the caller re-issues that frame on EVERY rank. A peer that never shows up turns into a failed
+ * frame after ~2 s (VB_STAGE_EXCHANGE in stats.failed), never into a hung GPU. vb_group does all of this itself
+ * (vb_group_set_exchange). */
+int vb_exchange_configure(vb_renderer *, uint32_t rank, uint32_t world, void **arena, size_t *arena_bytes);
+int vb_exchange_attach(vb_renderer *, uint32_t peer_rank, void *peer_arena);
+int vb_exchange_set_bounds(vb_renderer *, const uint32_t *tile_row_bounds);
+int vb_exchange_enable(vb_renderer *, int on);
+int vb_group_set_exchange(vb_group *, int on);
+
 /* CUDA IPC helpers for the one-process-per-GPU arrangement (64-byte handles, exchanged by the caller, e.g. over torch.distributed) */
 int vb_frame_alloc(vb_renderer *, size_t bytes, void **device_ptr);  /* cudaMalloc on the renderer's device */
 int vb_frame_free(vb_renderer *, void *device_ptr);

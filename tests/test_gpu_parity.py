@@ -644,3 +644,37 @@ def test_device_resolve_equals_host_resolve(renderer, oracle):
         got = renderer.render_resident(p) and renderer.download_target(p)
         assert np.array_equal(got, want)
         assert_pixels(got, oracle.render(host, w, h, p.base_color.premul_rgba8_u32(), aa), aa)
+
+
+@pytest.mark.parametrize("n", [2, 3, 5])
+def test_group_with_sharded_flatten(oracle, n):
+    """SURVEY.md 8(e) option B: every renderer of the group flattens only its share of the tag stream; lines (routed by the
+    stripes they touch) and partial path boxes are exchanged through peer memory with epoch flags (k_exchange.cu). The
+    assembled frame is the oracle's, for a host destination and for the device frame, across re-balanced stripes, new scenes
+    (arenas rebuilt) and frames whose first attempt overflows an arena (re-issued on every renderer together)."""
+    from vello_b200.renderer import RendererGroup
+    packed = resolve(scenes.paris_like(2500, 1024, seed=4).encoding)
+    p = RenderParams(BLACK, 1024, 1024, AA_MSAA16)
+    ref = oracle.render(packed, 1024, 1024, BLACK.premul_rgba8_u32(), AA_MSAA16)
+    g = RendererGroup([0] * n)
+    g.set_exchange(True)
+    assert np.array_equal(g.render_to_texture(packed, p), ref)
+    g.upload(packed)
+    for k in range(5):
+        st = g.render_resident(p)
+        assert all(int(s.failed) == 0 for s in st)
+        assert np.array_equal(g.frame_to_host(p), ref), k
+    total = sum(int(s.lines) for s in st)
+    assert total >= int(oracle.buffer("bump")["lines"][0])  # every line reached at least one stripe
+    # strokes with round joins / caps (arcs), curves, clips and blends; area AA within 1 LSB
+    for name in ("stroke_styles", "many_clips", "blend_grid"):
+        s, w, h = getattr(scenes, name)()
+        pk = resolve(s.encoding)
+        for aa in (AA_MSAA16, AA_AREA):
+            got = g.render_to_texture(pk, RenderParams(BLACK, w, h, aa))
+            assert_pixels(got, oracle.render(pk, w, h, BLACK.premul_rgba8_u32(), aa), aa)
+    big = resolve(scenes.paris_like(9000, 1024, seed=5).encoding)  # much larger: arenas overflow and the frame is re-issued
+    assert np.array_equal(g.render_to_texture(big, p), oracle.render(big, 1024, 1024, BLACK.premul_rgba8_u32(), AA_MSAA16))
+    g.set_exchange(False)
+    assert np.array_equal(g.render_to_texture(packed, p), ref)
+    g.close()

@@ -38,4 +38,10 @@ def test_group_across_devices(oracle, n):
     for k in range(5):                                              # device frame on devices[0]: fine stores over NVLink
         g.render_resident(p)
         assert np.array_equal(g.frame_to_host(p), ref), k
+    g.set_exchange(True)                                            # flatten sharded by tag range, lines exchanged over NVLink
+    g.upload(packed)
+    for k in range(5):
+        g.render_resident(p)
+        assert np.array_equal(g.frame_to_host(p), ref), ("exchange", k)
+    assert np.array_equal(g.render_to_texture(packed, p), ref)
     g.close()

@@ -51,8 +51,9 @@ __device__ __forceinline__ bool co_tag_writes_path(uint32_t tag) { // the draw t
 
 // Returns the PTCL offset of the CMD_SOLID it wrote, or 0 when it wrote a CMD_FILL.
 __device__ __forceinline__ uint32_t co_write_path(TileState &s, const VbTile &tile, uint32_t tile_ix, uint32_t draw_flags, const VbConfig &cfg,
-                                                  VbBump *bump, uint32_t *ptcl, VbTile *tiles, uint32_t &seg_next) {
+                                                  VbBump *bump, uint32_t *ptcl, VbTile *tiles, uint32_t &seg_next, uint32_t &cost) {
     const uint32_t n_segs = tile.segment_count_or_ix;
+    cost += n_segs != 0u ? 8u + n_segs : 1u; // what fine will spend on it, in rough units (a fill: set-up + its segments)
     if (n_segs != 0u) {
         const uint32_t seg_ix = seg_next; // reserved for this tile by the coverage pass
         seg_next += n_segs;
@@ -74,7 +75,7 @@ __device__ __forceinline__ uint32_t co_write_path(TileState &s, const VbTile &ti
 __global__ void __launch_bounds__(CO_THREADS)
 k_coarse(VbConfig cfg, const uint32_t *__restrict__ scene, const VbDrawMonoid *__restrict__ draw_monoids,
          const VbBinHeader *__restrict__ bin_headers, const uint32_t *__restrict__ info_bin_data, const VbPath *__restrict__ paths,
-         VbTile *tiles, VbBump *bump, uint32_t *ptcl, uint32_t *tile_start) {
+         VbTile *tiles, VbBump *bump, uint32_t *ptcl, uint32_t *tile_start, uint2 *cls_list, uint32_t cls_stride) {
     __shared__ uint32_t sh_bitmaps[CO_N_SLICE][VB_N_TILE];
     __shared__ uint32_t sh_part_count[CO_THREADS];
     __shared__ uint32_t sh_part_offsets[CO_THREADS];
@@ -120,6 +121,7 @@ k_coarse(VbConfig cfg, const uint32_t *__restrict__ scene, const VbDrawMonoid *_
     uint32_t partition_ix = 0u, rd_ix = 0u, wr_ix = 0u, part_start_ix = 0u, ready_ix = 0u;
     uint32_t render_blend_depth = 0u, max_blend_depth = 0u;
     uint32_t cull_start = 0u; // PTCL offset of the CMD_SOLID of this tile's last opaque full-tile cover (0: none)
+    uint32_t cost = 0u;       // estimated work of fine on this tile from its occlusion start (orders fine's tile queue)
     const uint32_t blend_offset = st.cmd_offset;
     st.cmd_offset += 1u;
 
@@ -295,43 +297,50 @@ k_coarse(VbConfig cfg, const uint32_t *__restrict__ scene, const VbDrawMonoid *_
             if (clip_zero_depth == 0u) {
                 switch (drawtag) {
                 case VB_DRAWTAG_FILL_COLOR: {
-                    const uint32_t solid_at = co_write_path(st, tile, tile_ix, draw_flags, cfg, bump, ptcl, tiles, seg_next);
+                    const uint32_t solid_at = co_write_path(st, tile, tile_ix, draw_flags, cfg, bump, ptcl, tiles, seg_next, cost);
                     const uint32_t rgba = vb_scene(scene, cfg, dd);
                     co_alloc_cmd(st, 2u, cfg, bump, ptcl);
                     ptcl[st.cmd_offset] = VB_CMD_COLOR;
                     ptcl[st.cmd_offset + 1u] = rgba;
                     st.cmd_offset += 2u;
                     // an opaque colour over the whole tile, outside any clip: nothing emitted so far can show through
-                    if (solid_at != 0u && (rgba >> 24) == 0xffu && render_blend_depth == 0u) cull_start = solid_at;
+                    cost += 2u;
+                    if (solid_at != 0u && (rgba >> 24) == 0xffu && render_blend_depth == 0u) {
+                        cull_start = solid_at;
+                        cost = 3u; // fine starts here: everything before is never executed
+                    }
                     break;
                 }
                 case VB_DRAWTAG_BLURRED_ROUNDED_RECT:
-                    co_write_path(st, tile, tile_ix, draw_flags, cfg, bump, ptcl, tiles, seg_next);
+                    co_write_path(st, tile, tile_ix, draw_flags, cfg, bump, ptcl, tiles, seg_next, cost);
                     co_alloc_cmd(st, 3u, cfg, bump, ptcl);
                     ptcl[st.cmd_offset] = VB_CMD_BLUR_RECT;
                     ptcl[st.cmd_offset + 1u] = di + 1u;
                     ptcl[st.cmd_offset + 2u] = vb_scene(scene, cfg, dd);
                     st.cmd_offset += 3u;
+                    cost += 24u;
                     break;
                 case VB_DRAWTAG_FILL_LIN_GRADIENT:
                 case VB_DRAWTAG_FILL_RAD_GRADIENT:
                 case VB_DRAWTAG_FILL_SWEEP_GRADIENT: {
                     const uint32_t ty = drawtag == VB_DRAWTAG_FILL_LIN_GRADIENT ? VB_CMD_LIN_GRAD
                                         : drawtag == VB_DRAWTAG_FILL_RAD_GRADIENT ? VB_CMD_RAD_GRAD : VB_CMD_SWEEP_GRAD;
-                    co_write_path(st, tile, tile_ix, draw_flags, cfg, bump, ptcl, tiles, seg_next);
+                    co_write_path(st, tile, tile_ix, draw_flags, cfg, bump, ptcl, tiles, seg_next, cost);
                     co_alloc_cmd(st, 3u, cfg, bump, ptcl);
                     ptcl[st.cmd_offset] = ty;
                     ptcl[st.cmd_offset + 1u] = vb_scene(scene, cfg, dd);
                     ptcl[st.cmd_offset + 2u] = di + 1u;
                     st.cmd_offset += 3u;
+                    cost += 8u;
                     break;
                 }
                 case VB_DRAWTAG_FILL_IMAGE:
-                    co_write_path(st, tile, tile_ix, draw_flags, cfg, bump, ptcl, tiles, seg_next);
+                    co_write_path(st, tile, tile_ix, draw_flags, cfg, bump, ptcl, tiles, seg_next, cost);
                     co_alloc_cmd(st, 2u, cfg, bump, ptcl);
                     ptcl[st.cmd_offset] = VB_CMD_IMAGE;
                     ptcl[st.cmd_offset + 1u] = di + 1u;
                     st.cmd_offset += 2u;
+                    cost += 16u;
                     break;
                 case VB_DRAWTAG_BEGIN_CLIP: {
                     const bool even_odd = (draw_flags & 1u) != 0u;
@@ -344,19 +353,21 @@ k_coarse(VbConfig cfg, const uint32_t *__restrict__ scene, const VbDrawMonoid *_
                         st.cmd_offset += 1u;
                         render_blend_depth += 1u;
                         max_blend_depth = max(max_blend_depth, render_blend_depth);
+                        cost += 4u;
                     }
                     clip_depth += 1u;
                     break;
                 }
                 case VB_DRAWTAG_END_CLIP:
                     clip_depth -= 1u;
-                    co_write_path(st, tile, tile_ix, draw_flags, cfg, bump, ptcl, tiles, seg_next);
+                    co_write_path(st, tile, tile_ix, draw_flags, cfg, bump, ptcl, tiles, seg_next, cost);
                     co_alloc_cmd(st, 3u, cfg, bump, ptcl);
                     ptcl[st.cmd_offset] = VB_CMD_END_CLIP;
                     ptcl[st.cmd_offset + 1u] = vb_scene(scene, cfg, dd);
                     ptcl[st.cmd_offset + 2u] = vb_scene(scene, cfg, dd + 1u);
                     st.cmd_offset += 3u;
                     render_blend_depth -= 1u;
+                    cost += 8u;
                     break;
                 default: break;
                 }
@@ -385,21 +396,38 @@ k_coarse(VbConfig cfg, const uint32_t *__restrict__ scene, const VbDrawMonoid *_
         ptcl[blend_offset] = blend_ix;
         tile_start[this_tile_ix] = cull_start;
     }
+    // fine's tile queue, heaviest first: every tile of the window goes into one of VB_FINE_CLASSES lists by its estimated cost
+    // (one atomic per warp and class; fine walks the lists in class order, so the long tiles start at time zero instead of
+    // turning up at the tail of a persistent kernel that has nothing left to overlap them with)
+    if (lid < 64u) { // the two owner warps, whole
+        const uint32_t ty = bin_tile_y + tile_y, tx = bin_tile_x + tile_x;
+        const bool in_win = tx < cfg.width_in_tiles && ty >= cfg.win_ty0 && ty < cfg.win_ty1 && ty < cfg.height_in_tiles;
+        const uint32_t cls = cost >= 256u ? 0u : (cost >= 96u ? 1u : (cost >= 32u ? 2u : 3u));
+        const uint32_t lane = lid & 31u;
+#pragma unroll
+        for (uint32_t k = 0; k < VB_FINE_CLASSES; k++) {
+            const uint32_t m = __ballot_sync(VB_FULL, in_win && cls == k);
+            if (m == 0u) continue;
+            uint32_t base = 0u;
+            if (lane == (uint32_t)(__ffs((int)m) - 1)) base = atomicAdd(reinterpret_cast<uint32_t *>(bump) + VB_CTL_FINE_CLASS + k, (uint32_t)__popc(m));
+            base = __shfl_sync(VB_FULL, base, __ffs((int)m) - 1);
+            if (in_win && cls == k) {
+                const uint32_t slot = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+                if (slot < cls_stride) cls_list[(size_t)k * cls_stride + slot] = make_uint2((ty - cfg.win_ty0) * cfg.width_in_tiles + tx, cull_start);
+            }
+        }
+    }
 }
 
-// After coarse: segments arena overflow check (the reference sizes `segments` statically and
-// never checks; path_tiling would write out of bounds).
-__global__ void k_coarse_check(VbConfig cfg, VbBump *bump) {
-    if (bump->segments > cfg.segments_size) atomicOr(&bump->failed, VB_STAGE_FINE_SEGMENTS);
-}
+// The segments-arena overflow check (the reference sizes `segments` statically and never checks) lives at the top of
+// k_path_tiling, the next kernel.
 
 extern "C" void vb_launch_coarse(const VbConfig *cfg, const uint32_t *scene, const VbDrawMonoid *draw_monoids,
                                  const VbBinHeader *bin_headers, const uint32_t *info_bin_data, const VbPath *paths, VbTile *tiles,
-                                 VbBump *bump, uint32_t *ptcl, uint32_t *tile_start, cudaStream_t st) {
+                                 VbBump *bump, uint32_t *ptcl, uint32_t *tile_start, void *cls_list, uint32_t cls_stride, cudaStream_t st) {
     uint32_t width_in_bins = (cfg->width_in_tiles + 15u) / 16u;
     uint32_t rows = cfg->win_by1 - cfg->win_by0;
     if (width_in_bins == 0 || rows == 0) return;
     dim3 grid(width_in_bins * 2u, rows * 2u); // four quadrant CTAs per bin
-    k_coarse<<<grid, CO_THREADS, 0, st>>>(*cfg, scene, draw_monoids, bin_headers, info_bin_data, paths, tiles, bump, ptcl, tile_start);
-    k_coarse_check<<<1, 1, 0, st>>>(*cfg, bump);
+    k_coarse<<<grid, CO_THREADS, 0, st>>>(*cfg, scene, draw_monoids, bin_headers, info_bin_data, paths, tiles, bump, ptcl, tile_start, (uint2 *)cls_list, cls_stride);
 }

@@ -78,6 +78,9 @@ struct FineArgs {
     const VbBump *bump;         // bump.failed != 0: an upstream stage overflowed an arena, nothing to paint (fine.wgsl:1070)
     const uint32_t *tile_start; // per tile: PTCL offset of its last opaque full-tile cover, or 0 (written by coarse)
     uint32_t *queue;            // tile queue of this launch (zero at launch; see the tile loop)
+    const uint2 *cls_list;      // cost-ordered tile lists written by coarse: VB_FINE_CLASSES x cls_stride entries {tile, start}
+    const uint32_t *cls_count;  // their fill counts (control block); NULL: natural tile order
+    uint32_t cls_stride;
     uint32_t cull;              // 1: start each tile there
 };
 
@@ -795,34 +798,61 @@ k_fine(VbConfig cfg, FineArgs A) {
     const uint32_t n_tiles = wt * (cfg.win_ty1 - cfg.win_ty0);
     const uint32_t G = gridDim.x * n_warps, g = blockIdx.x * n_warps + warp;
     const uint32_t first_tile = cfg.win_ty0 * wt;
-#define START_OF(t, s0) ((s0) != 0u ? (s0) : (first_tile + (t)) * VB_PTCL_INITIAL_ALLOC + 1u)
-    uint32_t t_cur = g, t_nxt = g + G;
+#define START_OF(t, s0) ((s0) != 0u && A.cull != 0u ? (s0) : (first_tile + (t)) * VB_PTCL_INITIAL_ALLOC + 1u)
+    // Queue position -> {tile of the window, occlusion start}. coarse sorted the window's tiles into VB_FINE_CLASSES lists by
+    // estimated cost; walking them in class order makes the heavy tiles the FIRST ones every warp takes (longest-processing-
+    // time-first), which is what bounds a persistent kernel's tail when a stripe has only a few tiles per warp.
+    uint32_t cpre[VB_FINE_CLASSES]; // first queue position of each class
+    bool ordered = A.cls_count != nullptr;
+    if (ordered) {
+        uint32_t acc = 0u;
+#pragma unroll
+        for (uint32_t k = 0; k < VB_FINE_CLASSES; k++) {
+            cpre[k] = acc;
+            acc += min(__ldg(A.cls_count + k), A.cls_stride);
+        }
+        ordered = acc == n_tiles; // a launch over part of the window (read-back bands) keeps the natural order
+    }
+    auto entry_of = [&](uint32_t pos) -> uint2 {
+        if (ordered) {
+            uint32_t k = 0u;
+#pragma unroll
+            for (uint32_t q = 1; q < VB_FINE_CLASSES; q++)
+                if (pos >= cpre[q]) k = q;
+            return __ldg(A.cls_list + (size_t)k * A.cls_stride + (pos - cpre[k]));
+        }
+        return make_uint2(pos, A.cull != 0u ? __ldg(A.tile_start + first_tile + pos) : 0u);
+    };
+    uint32_t p_cur = g, p_nxt = g + G; // queue positions
     uint32_t buf = 0u, phase = 0u; // phase: bit b = parity to wait for on mbar[b]
-    uint32_t start_cur = 0u, s0_nxt = 0u, ticket = 0u;
-    if (t_cur < n_tiles) {
-        const uint32_t s0 = A.cull != 0u ? __ldg(A.tile_start + first_tile + t_cur) : 0u;
-        start_cur = START_OF(t_cur, s0);
+    uint32_t t_cur = 0u, start_cur = 0u, ticket = 0u;
+    uint2 e_nxt = make_uint2(0u, 0u);
+    if (p_cur < n_tiles) {
+        const uint2 e = entry_of(p_cur);
+        t_cur = e.x;
+        start_cur = START_OF(e.x, e.y);
         if (lane == 0u) {
             mbar_expect_tx(&io.mbar[0], WIN_WORDS * 4u);
             bulk_g2s(io.ptcl[0], ptcl + (start_cur & ~3u), WIN_WORDS * 4u, &io.mbar[0]);
             ticket = atomicAdd(A.queue, 1u);
         }
-        if (t_nxt < n_tiles && A.cull != 0u) s0_nxt = __ldg(A.tile_start + first_tile + t_nxt);
+        if (p_nxt < n_tiles) e_nxt = entry_of(p_nxt);
     }
     if (AA != 0) mbar_wait(lut_bar, 0u); // every thread of the CTA observes the LUT copy before its first use
 
     const uint32_t ly = lane >> 1, h = lane & 1u;
-    while (t_cur < n_tiles) {
+    while (p_cur < n_tiles) {
         // ---- pipeline bookkeeping for the tiles after this one
-        const uint32_t start_nxt = START_OF(t_nxt, s0_nxt);
-        if (t_nxt < n_tiles && lane == 0u) {
+        const uint32_t t_nxt = e_nxt.x;
+        const uint32_t start_nxt = START_OF(e_nxt.x, e_nxt.y);
+        if (p_nxt < n_tiles && lane == 0u) {
             mbar_expect_tx(&io.mbar[buf ^ 1u], WIN_WORDS * 4u);
             bulk_g2s(io.ptcl[buf ^ 1u], ptcl + (start_nxt & ~3u), WIN_WORDS * 4u, &io.mbar[buf ^ 1u]);
         }
-        const uint32_t t_nn = 2u * G + __shfl_sync(VB_FULL, ticket, 0);
-        uint32_t s0_nn = 0u;
-        if (t_nn < n_tiles) {
-            if (A.cull != 0u) s0_nn = __ldg(A.tile_start + first_tile + t_nn);
+        const uint32_t p_nn = 2u * G + __shfl_sync(VB_FULL, ticket, 0);
+        uint2 e_nn = make_uint2(0u, 0u);
+        if (p_nn < n_tiles) {
+            e_nn = entry_of(p_nn);
             if (lane == 0u) ticket = atomicAdd(A.queue, 1u);
         }
 
@@ -1161,8 +1191,8 @@ k_fine(VbConfig cfg, FineArgs A) {
             }
         }
         __syncwarp();
-        t_cur = t_nxt; start_cur = start_nxt;
-        t_nxt = t_nn; s0_nxt = s0_nn;
+        p_cur = p_nxt; t_cur = t_nxt; start_cur = start_nxt;
+        p_nxt = p_nn; e_nxt = e_nn;
         buf ^= 1u;
     }
 #undef START_OF
@@ -1183,7 +1213,7 @@ extern "C" int vb_fine_init_constants(void) {
 extern "C" void vb_launch_fine(const VbConfig *cfg, int aa, const VbBump *bump, const VbSegment *segments, const uint32_t *ptcl, const uint32_t *info,
                                uint32_t *blend_spill, uint32_t *out, const uint32_t *ramps, const uint8_t *atlas,
                                const uint32_t *mask_lut8, const uint32_t *mask_lut16, const uint32_t *tile_start, uint32_t cull, uint32_t *queue,
-                               int sm_count, cudaStream_t st) {
+                               const void *cls_list, const uint32_t *cls_count, uint32_t cls_stride, int sm_count, cudaStream_t st) {
     uint32_t rows = cfg->win_ty1 - cfg->win_ty0;
     uint32_t n = cfg->width_in_tiles * rows;
     if (n == 0) return;
@@ -1200,6 +1230,9 @@ extern "C" void vb_launch_fine(const VbConfig *cfg, int aa, const VbBump *bump, 
     A.tile_start = tile_start;
     A.bump = bump;
     A.queue = queue;
+    A.cls_list = (const uint2 *)cls_list;
+    A.cls_count = cls_count;
+    A.cls_stride = cls_stride;
     if (aa == 0) k_fine<0><<<grid, 32u * warps, FineSmem<0>::bytes(warps), st>>>(*cfg, A);
     else if (aa == 1) k_fine<1><<<grid, 32u * warps, FineSmem<1>::bytes(warps), st>>>(*cfg, A);
     else k_fine<2><<<grid, 32u * warps, FineSmem<2>::bytes(warps), st>>>(*cfg, A);

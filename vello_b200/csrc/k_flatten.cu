@@ -868,10 +868,12 @@ __device__ __forceinline__ int fl_ceil_i(float v) { return v != v ? (int)0x80000
 // thrashed the instruction cache, ncu r1_f: no_instruction = top stall.)
 __global__ void __launch_bounds__(FL_THREADS, FL_MINB)
 k_flatten(VbConfig cfg, const uint32_t *__restrict__ scene, const VbTagMonoid *__restrict__ tag_monoids,
-          VbPathBbox *path_bboxes, FlCtx ctx, uint32_t *part_count, uint32_t *tag_off, uint32_t n_parts) {
+          VbPathBbox *path_bboxes, FlCtx ctx, uint32_t *part_count, uint32_t *tag_off, uint32_t part_base, uint32_t part_end) {
+    // [part_base, part_end): the partitions (32 tags each) this launch covers -- all of them, or this GPU's share of a
+    // frame whose flatten is sharded by tag range (k_exchange.cu); every array is indexed by the GLOBAL partition / tag
     const uint32_t lane = vb_lane();
-    const uint32_t part = blockIdx.x * (FL_THREADS / 32) + (threadIdx.x >> 5);
-    if (part >= n_parts) return;
+    const uint32_t part = part_base + blockIdx.x * (FL_THREADS / 32) + (threadIdx.x >> 5);
+    if (part >= part_end) return;
     const uint32_t ix = part * 32u + lane;
     const uint32_t n_tags = cfg.n_tag_words * 4u;
     const uint32_t n_paths = cfg.layout.n_paths;
@@ -936,47 +938,60 @@ k_flatten(VbConfig cfg, const uint32_t *__restrict__ scene, const VbTagMonoid *_
     }
 }
 
-// B: exclusive scan of part_count -> destination offsets; publishes bump.lines. One CTA, 8 values per thread per pass.
+// B: exclusive scan of part_count -> destination offsets; publishes bump.lines. One CTA per 8192 partitions (8 values per
+// thread, 128-bit accesses); the carry between CTAs is the single-pass look-back of vb_device.cuh (round 1 walked the whole
+// array with ONE CTA: 17 us on the critical path of every frame and of every rank of a multi-GPU frame).
 #define FS_THREADS 1024
 #define FS_PER_THREAD 8
 static_assert(FS_PER_THREAD == 8, "k_flatten_scan is written for 8 values per thread");
 __global__ void __launch_bounds__(FS_THREADS)
-k_flatten_scan(VbConfig cfg, uint32_t n_parts, const uint32_t *__restrict__ part_count, uint32_t *part_dst, VbBump *bump) {
+k_flatten_scan(VbConfig cfg, uint32_t n_parts, const uint32_t *__restrict__ part_count, uint32_t *part_dst, VbBump *bump, uint32_t *lb_mem,
+               uint32_t n_blocks) {
     __shared__ uint32_t sh_scan[FS_THREADS / 32 + 2];
-    uint32_t carry = 0u;
-    for (uint32_t base = 0u; base < n_parts; base += FS_THREADS * FS_PER_THREAD) {
-        const uint32_t i0 = base + threadIdx.x * FS_PER_THREAD;
-        uint32_t v[FS_PER_THREAD], sum = 0u;
-        if (i0 + FS_PER_THREAD <= n_parts) { // two 128-bit loads (the arrays are 16-byte aligned, i0 is a multiple of 8):
-            const uint4 a = *reinterpret_cast<const uint4 *>(part_count + i0); // one CTA issuing 8 scalar loads per thread
-            const uint4 b = *reinterpret_cast<const uint4 *>(part_count + i0 + 4); // stalls on its own LSU queue (lg_throttle)
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        } else {
+    __shared__ uint32_t sh_ticket;
+    __shared__ uint32_t sh_carry;
+    const VbLookback lb = vb_lookback_view(lb_mem, n_blocks, 1);
+    const uint32_t blk = vb_take_ticket(lb, &sh_ticket);
+    if (blk >= n_blocks) return;
+    const uint32_t i0 = blk * (FS_THREADS * FS_PER_THREAD) + threadIdx.x * FS_PER_THREAD;
+    uint32_t v[FS_PER_THREAD], sum = 0u;
+    if (i0 + FS_PER_THREAD <= n_parts) { // two 128-bit loads (the arrays are 16-byte aligned, i0 is a multiple of 8)
+        const uint4 a = *reinterpret_cast<const uint4 *>(part_count + i0);
+        const uint4 b = *reinterpret_cast<const uint4 *>(part_count + i0 + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
 #pragma unroll
-            for (int k = 0; k < FS_PER_THREAD; k++) v[k] = i0 + k < n_parts ? part_count[i0 + k] : 0u;
-        }
-#pragma unroll
-        for (int k = 0; k < FS_PER_THREAD; k++) sum += v[k];
-        uint32_t total;
-        uint32_t run = carry + vb_block_excl_scan(sum, sh_scan, &total);
-        if (i0 + FS_PER_THREAD <= n_parts) {
-            uint4 a, b;
-            a.x = run; a.y = a.x + v[0]; a.z = a.y + v[1]; a.w = a.z + v[2];
-            b.x = a.w + v[3]; b.y = b.x + v[4]; b.z = b.y + v[5]; b.w = b.z + v[6];
-            *reinterpret_cast<uint4 *>(part_dst + i0) = a;
-            *reinterpret_cast<uint4 *>(part_dst + i0 + 4) = b;
-        } else {
-#pragma unroll
-            for (int k = 0; k < FS_PER_THREAD; k++) {
-                if (i0 + k < n_parts) part_dst[i0 + k] = run;
-                run += v[k];
-            }
-        }
-        carry += total;
+        for (int k = 0; k < FS_PER_THREAD; k++) v[k] = i0 + k < n_parts ? part_count[i0 + k] : 0u;
     }
-    if (threadIdx.x == 0) {
-        bump->lines = carry;
-        if (carry > cfg.lines_size) atomicOr(&bump->failed, VB_STAGE_FLATTEN);
+#pragma unroll
+    for (int k = 0; k < FS_PER_THREAD; k++) sum += v[k];
+    uint32_t total;
+    const uint32_t ex = vb_block_excl_scan(sum, sh_scan, &total);
+    if (threadIdx.x < 32u) {
+        uint32_t agg[1] = {total}, excl[1];
+        vb_lookback<1>(lb, blk, agg, excl);
+        if (threadIdx.x == 0u) sh_carry = excl[0];
+    }
+    __syncthreads();
+    const uint32_t carry = sh_carry;
+    uint32_t run = carry + ex;
+    if (i0 + FS_PER_THREAD <= n_parts) {
+        uint4 a, b;
+        a.x = run; a.y = a.x + v[0]; a.z = a.y + v[1]; a.w = a.z + v[2];
+        b.x = a.w + v[3]; b.y = b.x + v[4]; b.z = b.y + v[5]; b.w = b.z + v[6];
+        *reinterpret_cast<uint4 *>(part_dst + i0) = a;
+        *reinterpret_cast<uint4 *>(part_dst + i0 + 4) = b;
+    } else {
+#pragma unroll
+        for (int k = 0; k < FS_PER_THREAD; k++) {
+            if (i0 + k < n_parts) part_dst[i0 + k] = run;
+            run += v[k];
+        }
+    }
+    if (blk == n_blocks - 1u && threadIdx.x == 0u) { // the block holding the end of the array knows the grand total
+        const uint32_t lines = carry + total;
+        bump->lines = lines;
+        if (lines > cfg.lines_size) atomicOr(&bump->failed, VB_STAGE_FLATTEN);
     }
 }
 
@@ -1100,9 +1115,11 @@ k_flatten_place(VbConfig cfg, const uint32_t *__restrict__ scene, FlCtx ctx, con
 
 extern "C" void vb_launch_flatten(const VbConfig *cfg, const uint32_t *scene, const VbTagMonoid *tag_monoids,
                                   VbPathBbox *path_bboxes, VbBump *bump, VbLineSoup *lines, void *lit_arena, void *job_arena,
-                                  uint32_t *part_mem /* 34 * n_parts + 8 words */, uint32_t *ctrs, uint32_t n_parts, cudaStream_t st) {
+                                  uint32_t *part_mem /* 34 * n_parts + 8 words */, uint32_t *ctrs, uint32_t n_parts, int clear_bboxes,
+                                  uint32_t part_base, uint32_t part_end /* 0, n_parts: everything */, cudaStream_t st) {
     uint32_t n_paths = cfg->layout.n_paths;
-    if (n_paths) k_bbox_clear<<<(n_paths + 255) / 256, 256, 0, st>>>(n_paths, path_bboxes);
+    // whole frames reset the boxes in k_frame_init (vb_api.cu); a stage range that starts later does it here
+    if (n_paths && clear_bboxes) k_bbox_clear<<<(n_paths + 255) / 256, 256, 0, st>>>(n_paths, path_bboxes);
     if (n_parts) {
         const size_t np4 = ((size_t)n_parts + 3u) & ~(size_t)3u; // 16-byte aligned sub-arrays (k_flatten_scan uses 128-bit accesses)
         uint32_t *part_count = part_mem, *part_dst = part_mem + np4, *tag_off = part_mem + 2 * np4;
@@ -1113,9 +1130,15 @@ extern "C" void vb_launch_flatten(const VbConfig *cfg, const uint32_t *scene, co
         ctx.jobs_cap = cfg->lines_size / FL_DEFER_MIN + 1u;
         ctx.ctrs = ctrs;
         const uint32_t warps_per_cta = FL_THREADS / 32;
-        k_flatten<<<(n_parts + warps_per_cta - 1) / warps_per_cta, FL_THREADS, 0, st>>>(*cfg, scene, tag_monoids, path_bboxes, ctx, part_count,
-                                                                                       tag_off, n_parts);
-        k_flatten_scan<<<1, FS_THREADS, 0, st>>>(*cfg, n_parts, part_count, part_dst, bump);
+        if (part_end > n_parts) part_end = n_parts;
+        if (part_base >= part_end) { // an empty share still has to publish bump.lines = 0
+            part_base = part_end = 0u;
+        }
+        const uint32_t n_own = part_end - part_base; // part_base is a multiple of 8: the scan's 128-bit accesses stay aligned
+        if (n_own) k_flatten<<<(n_own + warps_per_cta - 1) / warps_per_cta, FL_THREADS, 0, st>>>(*cfg, scene, tag_monoids, path_bboxes, ctx,
+                                                                                             part_count, tag_off, part_base, part_end);
+        const uint32_t n_blocks = n_own ? (n_own + FS_THREADS * FS_PER_THREAD - 1u) / (FS_THREADS * FS_PER_THREAD) : 1u;
+        k_flatten_scan<<<n_blocks, FS_THREADS, 0, st>>>(*cfg, n_own, part_count + part_base, part_dst + part_base, bump, ctrs + 4, n_blocks);
         k_flatten_place<<<148 * 4, FP_THREADS, 0, st>>>(*cfg, scene, ctx, part_dst, tag_off, path_bboxes, lines);
     }
 }

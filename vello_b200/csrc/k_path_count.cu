@@ -164,14 +164,10 @@ k_path_count(VbConfig cfg, VbBump *bump, const VbLineSoup *__restrict__ lines, c
     }
 }
 
-// Runs after path_count: flag seg_counts overflow (the WGSL does this at the top of coarse).
-__global__ void k_path_count_check(VbConfig cfg, VbBump *bump) {
-    if (bump->seg_counts > cfg.seg_counts_size) atomicOr(&bump->failed, VB_STAGE_PATH_COUNT);
-}
+// The seg_counts overflow check (the WGSL does it at the top of coarse) lives at the top of k_backdrop, the next kernel.
 
 extern "C" void vb_launch_path_count(const VbConfig *cfg, VbBump *bump, const VbLineSoup *lines, const VbPath *paths, VbTile *tile,
                                      VbSegmentCount *seg_counts, uint32_t grid, cudaStream_t st) {
     if (grid == 0) return;
     k_path_count<<<grid, PC_THREADS, 0, st>>>(*cfg, bump, lines, paths, tile, seg_counts);
-    k_path_count_check<<<1, 1, 0, st>>>(*cfg, bump);
 }

@@ -18,10 +18,13 @@
 #define TILE_SCALE 0.0625f
 
 __global__ void __launch_bounds__(PTI_THREADS, PTI_MINB)
-k_path_tiling(VbConfig cfg, const VbBump *__restrict__ bump, const VbSegmentCount *__restrict__ seg_counts,
+k_path_tiling(VbConfig cfg, VbBump *bump, const VbSegmentCount *__restrict__ seg_counts,
               const VbLineSoup *__restrict__ lines, const VbPath *__restrict__ paths, const VbTile *__restrict__ tiles,
               VbSegment *segments) {
-    if (bump->failed != 0u) return;
+    // coarse reserved more segment slots than the arena holds: flagged here (one thread), decided by every CTA alike
+    const bool seg_overflow = bump->segments > cfg.segments_size;
+    if (seg_overflow && blockIdx.x == 0u && threadIdx.x == 0u) atomicOr(&bump->failed, VB_STAGE_FINE_SEGMENTS);
+    if (bump->failed != 0u || seg_overflow) return;
     const uint32_t n_segments = min(bump->seg_counts, cfg.seg_counts_size);
     for (uint32_t g = blockIdx.x * PTI_THREADS + threadIdx.x; g < n_segments; g += gridDim.x * PTI_THREADS) {
         const VbSegmentCount sc = seg_counts[g];
@@ -129,7 +132,7 @@ k_path_tiling(VbConfig cfg, const VbBump *__restrict__ bump, const VbSegmentCoun
     }
 }
 
-extern "C" void vb_launch_path_tiling(const VbConfig *cfg, const VbBump *bump, const VbSegmentCount *seg_counts,
+extern "C" void vb_launch_path_tiling(const VbConfig *cfg, VbBump *bump, const VbSegmentCount *seg_counts,
                                       const VbLineSoup *lines, const VbPath *paths, const VbTile *tiles, VbSegment *segments,
                                       uint32_t grid, cudaStream_t st) {
     if (grid == 0) return;

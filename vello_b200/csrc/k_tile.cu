@@ -85,10 +85,14 @@ __global__ void __launch_bounds__(256) k_tile_zero(VbConfig cfg, const VbBump *_
 #define BD_WARPS (BD_THREADS / 32)
 #define BD_PATHS 32u // paths per CTA
 __global__ void __launch_bounds__(BD_THREADS)
-k_backdrop(VbConfig cfg, const VbBump *__restrict__ bump, const VbPath *__restrict__ paths, VbTile *tiles) {
+k_backdrop(VbConfig cfg, VbBump *bump, const VbPath *__restrict__ paths, VbTile *tiles) {
     __shared__ uint32_t sh_start[BD_PATHS + 1]; // first tile of each path, then the end of the range
     __shared__ uint32_t sh_width[BD_PATHS];
-    if (bump->failed != 0u) return;
+    // path_count's worklist overflow (the WGSL checks it at the top of coarse) is detected here, by every CTA alike, and
+    // published by one thread: a separate one-thread check kernel used to sit on the frame's critical path
+    const bool pc_overflow = bump->seg_counts > cfg.seg_counts_size;
+    if (pc_overflow && blockIdx.x == 0u && blockIdx.y == 0u && threadIdx.x == 0u) atomicOr(&bump->failed, VB_STAGE_PATH_COUNT);
+    if (bump->failed != 0u || pc_overflow) return;
     const uint32_t n_draw = cfg.layout.n_draw_objects;
     const uint32_t p0 = blockIdx.x * BD_PATHS;
     const uint32_t arena_end = min(bump->tile, cfg.tiles_size);
@@ -166,7 +170,7 @@ extern "C" void vb_launch_tile_alloc(const VbConfig *cfg, const uint32_t *scene,
     k_tile_zero<<<148 * 4, 256, 0, st>>>(*cfg, bump, tiles);
 }
 extern "C" uint32_t vb_tile_alloc_parts(uint32_t n_draw) { return (n_draw + TA_THREADS - 1) / TA_THREADS; }
-extern "C" void vb_launch_backdrop(const VbConfig *cfg, const VbBump *bump, const VbPath *paths, VbTile *tiles, cudaStream_t st) {
+extern "C" void vb_launch_backdrop(const VbConfig *cfg, VbBump *bump, const VbPath *paths, VbTile *tiles, cudaStream_t st) {
     uint32_t n = cfg->layout.n_draw_objects;
     if (n == 0) return;
     const uint32_t groups = (n + BD_PATHS - 1) / BD_PATHS;

@@ -24,7 +24,7 @@ extern "C" {
 void vb_launch_pathtag(const VbConfig *, const uint32_t *, VbTagMonoid *, uint32_t *, uint32_t, cudaStream_t);
 uint32_t vb_pathtag_parts(uint32_t);
 void vb_launch_flatten(const VbConfig *, const uint32_t *, const VbTagMonoid *, VbPathBbox *, VbBump *, VbLineSoup *, void *, void *, uint32_t *,
-                       uint32_t *, uint32_t, cudaStream_t);
+                       uint32_t *, uint32_t, int, uint32_t, uint32_t, cudaStream_t);
 uint32_t vb_flatten_parts(uint32_t);
 void vb_flatten_arena_bytes(uint32_t, size_t *, size_t *);
 void vb_launch_draw(const VbConfig *, const uint32_t *, const VbPathBbox *, VbDrawMonoid *, uint32_t *, VbClipInp *, uint32_t *, uint32_t,
@@ -38,19 +38,30 @@ void vb_launch_binning(const VbConfig *, const VbDrawMonoid *, const VbPathBbox 
 void vb_launch_tile_alloc(const VbConfig *, const uint32_t *, const VbBbox4 *, VbBump *, VbPath *, VbTile *, uint32_t *, uint32_t,
                           cudaStream_t);
 uint32_t vb_tile_alloc_parts(uint32_t);
-void vb_launch_backdrop(const VbConfig *, const VbBump *, const VbPath *, VbTile *, cudaStream_t);
+void vb_launch_backdrop(const VbConfig *, VbBump *, const VbPath *, VbTile *, cudaStream_t);
 void vb_launch_path_count(const VbConfig *, VbBump *, const VbLineSoup *, const VbPath *, VbTile *, VbSegmentCount *, uint32_t,
                           cudaStream_t);
 void vb_launch_coarse(const VbConfig *, const uint32_t *, const VbDrawMonoid *, const VbBinHeader *, const uint32_t *, const VbPath *,
-                      VbTile *, VbBump *, uint32_t *, uint32_t *, cudaStream_t);
-void vb_launch_path_tiling(const VbConfig *, const VbBump *, const VbSegmentCount *, const VbLineSoup *, const VbPath *, const VbTile *,
+                      VbTile *, VbBump *, uint32_t *, uint32_t *, void *, uint32_t, cudaStream_t);
+void vb_launch_path_tiling(const VbConfig *, VbBump *, const VbSegmentCount *, const VbLineSoup *, const VbPath *, const VbTile *,
                            VbSegment *, uint32_t, cudaStream_t);
 void vb_launch_fine(const VbConfig *, int, const VbBump *, const VbSegment *, const uint32_t *, const uint32_t *, uint32_t *, uint32_t *,
-                    const uint32_t *, const uint8_t *, const uint32_t *, const uint32_t *, const uint32_t *, uint32_t, uint32_t *, int,
-                    cudaStream_t);
+                    const uint32_t *, const uint8_t *, const uint32_t *, const uint32_t *, const uint32_t *, uint32_t, uint32_t *, const void *,
+                    const uint32_t *, uint32_t, int, cudaStream_t);
 }
 
 extern "C" int vb_fine_init_constants(void);
+// k_exchange.cu: flatten sharded by tag range, lines / path boxes exchanged through peer memory
+struct XPeersHost { // == XPeers in k_exchange.cu
+    unsigned char *base[8];
+    uint32_t rows[9];
+    uint32_t world, rank, n_paths, lines_cap;
+    unsigned long long half_bytes;
+};
+extern "C" size_t vb_exchange_half_bytes(uint32_t n_paths, uint32_t lines_cap);
+extern "C" size_t vb_exchange_peers_bytes(void);
+extern "C" uint32_t vb_exchange_epoch_word(void);
+extern "C" void vb_launch_exchange(const void *, VbBump *, uint32_t, VbLineSoup *, uint32_t *, VbPathBbox *, int, cudaStream_t);
 extern "C" void vb_launch_resolve_finish(uint32_t *, uint32_t, uint32_t, uint32_t, uint32_t, const void *, uint32_t, cudaStream_t);
 extern "C" void vb_launch_make_ramps(const void *, const void *, uint32_t, uint32_t *, cudaStream_t);
 
@@ -89,8 +100,21 @@ __global__ void k_ptcl_stats(VbConfig cfg, const uint32_t *__restrict__ ptcl, co
     atomicAdd(out + 2, fills);
 }
 
-__global__ void k_ctl_zero(uint32_t *ctl, uint32_t words) {
-    for (uint32_t i = blockIdx.x * 1024u + threadIdx.x; i < min(words, (blockIdx.x + 1u) * 1024u); i += 256u) ctl[i] = 0u;
+// Frame start: zero the control block (bump counters, look-back descriptors, fine's tile queues) and reset the path bounding
+// boxes (bbox_clear.wgsl: (+INT_MAX, -INT_MAX)) -- one launch; blocks past the control block clear 256 boxes each.
+__global__ void k_frame_init(uint32_t *ctl, uint32_t words, uint32_t ctl_blocks, VbPathBbox *path_bboxes, uint32_t n_paths, uint32_t *xepoch) {
+    if (xepoch != nullptr && blockIdx.x == 0u && threadIdx.x == 0u) *xepoch += 1u; // multi-GPU exchange: this attempt's epoch
+    if (blockIdx.x < ctl_blocks) {
+        for (uint32_t i = blockIdx.x * 1024u + threadIdx.x; i < min(words, (blockIdx.x + 1u) * 1024u); i += 256u) ctl[i] = 0u;
+    } else {
+        const uint32_t i = (blockIdx.x - ctl_blocks) * 256u + threadIdx.x;
+        if (i < n_paths) {
+            VbPathBbox b;
+            b.x0 = 0x7fffffff; b.y0 = 0x7fffffff; b.x1 = (int32_t)0x80000000; b.y1 = (int32_t)0x80000000;
+            b.draw_flags = 0; b.trans_ix = 0;
+            path_bboxes[i] = b;
+        }
+    }
 }
 __global__ void k_publish_bump(const VbBump *bump, VbBump *host) {
     if (threadIdx.x < sizeof(VbBump) / 4u) {
@@ -110,6 +134,8 @@ struct GraphKey {
     const void *ptrs[32];
     uint64_t ctl_words;
     uint32_t aa, cull, last;
+    uint32_t xen, xrows[9];
+    const void *xpeer[8];
 };
 struct GraphSlot {
     GraphKey key;
@@ -134,7 +160,7 @@ struct vb_renderer {
 
     // fixed-size intermediates
     DevBuf tag_monoids, path_bboxes, draw_monoids, info_bin_data, clip_inp, clip_bboxes, clip_scratch, draw_bboxes, bin_headers, paths,
-        ctl, target, target_alt, tile_start;
+        ctl, target, target_alt, tile_start, cls_list;
     // bump arenas (capacities in elements live in cap_*)
     DevBuf resolve_tmp; // patches, ramp descriptors and stops of vb_scene_upload_streams
     DevBuf lines, line_scratch, flatten_jobs, flatten_parts, tiles, seg_counts, segments, ptcl, blend_spill;
@@ -194,6 +220,16 @@ struct vb_renderer {
         vb_frame_stats stats{};
     } ring[3];
     uint64_t stream_seq = 0;
+
+    // multi-GPU exchange (flatten sharded by tag range; k_exchange.cu)
+    struct Exchange {
+        bool configured = false, enabled = false;
+        uint32_t rank = 0, world = 1, lines_cap = 0, n_paths = 0;
+        size_t half_bytes = 0;
+        DevBuf arena;
+        void *peer[8] = {};
+        uint32_t rows[9] = {};
+    } xc;
 };
 
 static void swap_slot(vb_renderer *r) {
@@ -237,7 +273,7 @@ static int ensure(vb_renderer *r, DevBuf &b, size_t bytes) {
 static size_t arena_bytes(const vb_renderer *r) {
     const DevBuf *all[] = {&r->scene, &r->ramps, &r->atlas, &r->mask8, &r->mask16, &r->tag_monoids, &r->path_bboxes, &r->draw_monoids,
                            &r->info_bin_data, &r->clip_inp, &r->clip_bboxes, &r->clip_scratch, &r->draw_bboxes, &r->bin_headers, &r->paths,
-                           &r->ctl, &r->target, &r->target_alt, &r->tile_start, &r->lines, &r->line_scratch, &r->flatten_jobs, &r->flatten_parts, &r->tiles, &r->seg_counts, &r->segments, &r->ptcl, &r->blend_spill};
+                           &r->ctl, &r->target, &r->target_alt, &r->tile_start, &r->cls_list, &r->lines, &r->line_scratch, &r->flatten_jobs, &r->flatten_parts, &r->tiles, &r->seg_counts, &r->segments, &r->ptcl, &r->blend_spill};
     size_t s = r->other.scene.cap + r->other.ramps.cap + r->other.atlas.cap;
     for (auto b : all) s += b->cap;
     return s;
@@ -332,10 +368,10 @@ extern "C" void vb_renderer_free(vb_renderer *r) {
     if (r->stream) cudaStreamSynchronize(r->stream);
     DevBuf *all[] = {&r->scene, &r->ramps, &r->atlas, &r->mask8, &r->mask16, &r->tag_monoids, &r->path_bboxes, &r->draw_monoids,
                      &r->info_bin_data, &r->clip_inp, &r->clip_bboxes, &r->clip_scratch, &r->draw_bboxes, &r->bin_headers, &r->paths,
-                     &r->ctl, &r->target, &r->target_alt, &r->tile_start, &r->lines, &r->line_scratch, &r->flatten_jobs, &r->flatten_parts, &r->tiles, &r->seg_counts, &r->segments, &r->ptcl, &r->blend_spill};
+                     &r->ctl, &r->target, &r->target_alt, &r->tile_start, &r->cls_list, &r->lines, &r->line_scratch, &r->flatten_jobs, &r->flatten_parts, &r->tiles, &r->seg_counts, &r->segments, &r->ptcl, &r->blend_spill};
     for (auto b : all)
         if (b->p) cudaFree(b->p);
-    for (DevBuf *b : {&r->other.scene, &r->other.ramps, &r->other.atlas, &r->resolve_tmp})
+    for (DevBuf *b : {&r->other.scene, &r->other.ramps, &r->other.atlas, &r->resolve_tmp, &r->xc.arena})
         if (b->p) cudaFree(b->p);
     if (r->h_bump) cudaFreeHost(r->h_bump);
     if (r->other.h_bump) cudaFreeHost(r->other.h_bump);
@@ -487,6 +523,7 @@ static int prepare(vb_renderer *r, const vb_params *p) {
     if ((rc = ensure(r, r->bin_headers, (size_t)((n_draw + 255u) / 256u) * aligned_n_bins * sizeof(VbBinHeader)))) return rc;
     if ((rc = ensure(r, r->paths, (size_t)((n_draw + 255u) & ~255u) * sizeof(VbPath)))) return rc;
     if ((rc = ensure(r, r->tile_start, ((size_t)n_tiles + 256) * 4))) return rc;
+    if ((rc = ensure(r, r->cls_list, (size_t)VB_FINE_CLASSES * n_tiles * 8))) return rc; // fine's cost-ordered tile lists
 
     // first-guess arena capacities (elements); they only ever grow
     const uint32_t n_tags = c.n_tag_words * 4u;
@@ -531,7 +568,8 @@ static int prepare(vb_renderer *r, const vb_params *p) {
     r->parts_tile = vb_tile_alloc_parts(n_draw);
     size_t off = VB_CTL_HEADER_WORDS;
     r->off_lb_pathtag = off; off += vb_lookback_words(r->parts_pathtag, 5);
-    r->off_lb_flatten = off; off += 4; // flatten: [0] literal-record counter, [1] job counter
+    r->off_lb_flatten = off; // flatten: [0] literal-record counter, [1] job counter, [4..] look-back state of its partition scan
+    off += 4 + vb_lookback_words((r->parts_flatten + 8191u) / 8192u, 1);
     r->off_lb_draw = off; off += vb_lookback_words(r->parts_draw, 4);
     r->off_lb_tile = off; off += vb_lookback_words(r->parts_tile, 1);
     r->off_lb_clip = off; off += vb_lookback_words(vb_clip_parts(n_clips), 1);
@@ -556,12 +594,18 @@ static int enqueue_direct(vb_renderer *r, int first, int last, void *out_dev) {
     if (first == 0) {
         // a kernel, not cudaMemsetAsync: small memsets / copies are served by a copy engine and would queue behind a
         // 64 MiB read-back still draining from the previous frame (measured: +1.2 ms per streamed frame)
-        k_ctl_zero<<<(unsigned)((r->ctl_words + 1023) / 1024), 256, 0, st>>>(ctl, (uint32_t)r->ctl_words);
+        const unsigned ctl_blocks = (unsigned)((r->ctl_words + 1023) / 1024), bb_blocks = (c.layout.n_paths + 255u) / 256u;
+        uint32_t *xepoch = r->xc.enabled ? (uint32_t *)r->xc.arena.p + vb_exchange_epoch_word() : nullptr;
+        k_frame_init<<<ctl_blocks + bb_blocks, 256, 0, st>>>(ctl, (uint32_t)r->ctl_words, ctl_blocks, (VbPathBbox *)r->path_bboxes.p, c.layout.n_paths,
+                                                             xepoch);
         launches++;
     }
-    else if (last >= VB_STAGE_ID_FINE && r->zero_fine_queue) {
-        // vb_run_stages starting after stage 0: the control block is not zeroed, but fine's tile queues must start at 0
-        CK(cudaMemsetAsync(ctl + VB_CTL_FINE_QUEUE, 0, 8 * sizeof(uint32_t), st));
+    else if (r->zero_fine_queue) {
+        // vb_run_stages starting after stage 0: the control block is not zeroed, but fine's tile queues must start at 0 and
+        // coarse must append to empty class lists
+        if (last >= VB_STAGE_ID_FINE) CK(cudaMemsetAsync(ctl + VB_CTL_FINE_QUEUE, 0, 8 * sizeof(uint32_t), st));
+        if (first <= VB_STAGE_ID_COARSE && last >= VB_STAGE_ID_COARSE)
+            CK(cudaMemsetAsync(ctl + VB_CTL_FINE_CLASS, 0, VB_FINE_CLASSES * sizeof(uint32_t), st));
     }
     rec(r, 0);
     for (int s = first; s <= last; s++) {
@@ -571,10 +615,31 @@ static int enqueue_direct(vb_renderer *r, int first, int last, void *out_dev) {
             launches += r->parts_pathtag ? 1 : 0;
             break;
         case VB_STAGE_ID_FLATTEN:
+            if (r->xc.enabled) {
+                // this GPU flattens its share of the tag stream (no stripe culling: the lines are for everybody), then the
+                // lines and path boxes are exchanged through peer memory (k_exchange.cu)
+                VbConfig cx = c;
+                cx.win_cull = 0u;
+                const uint32_t P = r->parts_flatten, G = r->xc.world, k = r->xc.rank;
+                const uint32_t p0 = (uint32_t)((uint64_t)P * k / G) & ~7u;
+                const uint32_t p1 = k + 1u == G ? P : ((uint32_t)((uint64_t)P * (k + 1u) / G) & ~7u);
+                vb_launch_flatten(&cx, (const uint32_t *)r->scene.p, (const VbTagMonoid *)r->tag_monoids.p, (VbPathBbox *)r->path_bboxes.p, bump,
+                                  (VbLineSoup *)r->lines.p, r->line_scratch.p, r->flatten_jobs.p, (uint32_t *)r->flatten_parts.p,
+                                  ctl + r->off_lb_flatten, r->parts_flatten, first != 0 ? 1 : 0, p0, p1, st);
+                XPeersHost X;
+                memset(&X, 0, sizeof X);
+                for (uint32_t i = 0; i < G; i++) X.base[i] = (unsigned char *)r->xc.peer[i];
+                for (uint32_t i = 0; i <= G; i++) X.rows[i] = r->xc.rows[i];
+                X.world = G; X.rank = k; X.n_paths = r->xc.n_paths; X.lines_cap = r->xc.lines_cap; X.half_bytes = r->xc.half_bytes;
+                vb_launch_exchange(&X, bump, c.lines_size, (VbLineSoup *)r->lines.p, ctl + VB_CTL_XCHG_SCRATCH, (VbPathBbox *)r->path_bboxes.p,
+                                   r->sm_count, st);
+                launches += (r->parts_flatten ? 3 : 0) + 7;
+                break;
+            }
             vb_launch_flatten(&c, (const uint32_t *)r->scene.p, (const VbTagMonoid *)r->tag_monoids.p, (VbPathBbox *)r->path_bboxes.p, bump,
                               (VbLineSoup *)r->lines.p, r->line_scratch.p, r->flatten_jobs.p, (uint32_t *)r->flatten_parts.p,
-                              ctl + r->off_lb_flatten, r->parts_flatten, st);
-            launches += (c.layout.n_paths ? 1 : 0) + (r->parts_flatten ? 3 : 0);
+                              ctl + r->off_lb_flatten, r->parts_flatten, first != 0 ? 1 : 0, 0u, r->parts_flatten, st);
+            launches += (first != 0 && c.layout.n_paths ? 1 : 0) + (r->parts_flatten ? 3 : 0);
             break;
         case VB_STAGE_ID_DRAW:
             vb_launch_draw(&c, (const uint32_t *)r->scene.p, (const VbPathBbox *)r->path_bboxes.p, (VbDrawMonoid *)r->draw_monoids.p,
@@ -604,7 +669,7 @@ static int enqueue_direct(vb_renderer *r, int first, int last, void *out_dev) {
             uint32_t grid = (uint32_t)(blocks < (uint64_t)r->sm_count * 16 ? blocks : (uint64_t)r->sm_count * 16);
             vb_launch_path_count(&c, bump, (const VbLineSoup *)r->lines.p, (const VbPath *)r->paths.p, (VbTile *)r->tiles.p,
                                  (VbSegmentCount *)r->seg_counts.p, grid, st);
-            launches += 2;
+            launches += 1;
             break;
         }
         case VB_STAGE_ID_BACKDROP:
@@ -614,8 +679,8 @@ static int enqueue_direct(vb_renderer *r, int first, int last, void *out_dev) {
         case VB_STAGE_ID_COARSE:
             vb_launch_coarse(&c, (const uint32_t *)r->scene.p, (const VbDrawMonoid *)r->draw_monoids.p, (const VbBinHeader *)r->bin_headers.p,
                              (const uint32_t *)r->info_bin_data.p, (const VbPath *)r->paths.p, (VbTile *)r->tiles.p, bump,
-                             (uint32_t *)r->ptcl.p, (uint32_t *)r->tile_start.p, st);
-            launches += 2;
+                             (uint32_t *)r->ptcl.p, (uint32_t *)r->tile_start.p, r->cls_list.p, c.width_in_tiles * c.height_in_tiles, st);
+            launches += 1;
             break;
         case VB_STAGE_ID_PATH_TILING: {
             uint64_t blocks = ((uint64_t)c.seg_counts_size + 255) / 256;
@@ -641,7 +706,8 @@ static int enqueue_direct(vb_renderer *r, int first, int last, void *out_dev) {
                                (const uint32_t *)r->info_bin_data.p, (uint32_t *)r->blend_spill.p, (uint32_t *)out_dev,
                                (const uint32_t *)r->ramps.p, (const uint8_t *)r->atlas.p, (const uint32_t *)r->mask8.p,
                                (const uint32_t *)r->mask16.p, (const uint32_t *)r->tile_start.p, r->occlusion_cull,
-                               ctl + VB_CTL_FINE_QUEUE + b, r->sm_count, st);
+                               ctl + VB_CTL_FINE_QUEUE + b, r->cls_list.p, n_bands == 1u ? ctl + VB_CTL_FINE_CLASS : nullptr,
+                               c.width_in_tiles * c.height_in_tiles, r->sm_count, st);
                 launches += 1;
                 if (r->host_out) {
                     size_t y0 = (size_t)cb.win_ty0 * 16u, y1 = (size_t)cb.win_ty1 * 16u;
@@ -679,7 +745,7 @@ static void graph_key(const vb_renderer *r, int last, const void *out_dev, Graph
     k->cfg = r->cfg;
     const DevBuf *bufs[] = {&r->scene, &r->ramps, &r->atlas, &r->mask8, &r->mask16, &r->tag_monoids, &r->path_bboxes, &r->draw_monoids,
                             &r->info_bin_data, &r->clip_inp, &r->clip_bboxes, &r->clip_scratch, &r->draw_bboxes, &r->bin_headers, &r->paths,
-                            &r->ctl, &r->tile_start, &r->lines, &r->line_scratch, &r->flatten_jobs, &r->flatten_parts, &r->tiles,
+                            &r->ctl, &r->tile_start, &r->cls_list, &r->lines, &r->line_scratch, &r->flatten_jobs, &r->flatten_parts, &r->tiles,
                             &r->seg_counts, &r->segments, &r->ptcl, &r->blend_spill};
     size_t n = 0;
     for (const DevBuf *b : bufs) k->ptrs[n++] = b->p;
@@ -689,6 +755,11 @@ static void graph_key(const vb_renderer *r, int last, const void *out_dev, Graph
     k->aa = r->params.aa;
     k->cull = r->occlusion_cull;
     k->last = (uint32_t)last;
+    k->xen = r->xc.enabled ? 1u + r->xc.rank + (r->xc.world << 8) : 0u;
+    if (r->xc.enabled) {
+        memcpy(k->xrows, r->xc.rows, sizeof k->xrows);
+        memcpy(k->xpeer, r->xc.peer, sizeof k->xpeer);
+    }
 }
 
 static int queue_readback(vb_renderer *r, const VbConfig &c, uint32_t ty0, uint32_t ty1, void *out_dev, uint32_t band) {
@@ -850,6 +921,14 @@ extern "C" int vb_render_resident(vb_renderer *r, const vb_params *p, void *out_
         CK(cudaStreamSynchronize(r->stream));
         r->frame_pending = false;
         if (r->h_bump->failed == 0) break;
+        if (r->xc.enabled) {
+            // every attempt of an exchanged frame is a collective step (all GPUs advance their epoch together): grow what
+            // overflowed here and let the caller re-issue the frame on every GPU
+            grow_arenas(r);
+            fill_stats(r, stats);
+            r->err = "bump overflow in an exchanged frame: re-issue the frame on every GPU";
+            return VB_E_BUMP_OVERFLOW;
+        }
         if (attempt >= r->max_retries) {
             fill_stats(r, stats);
             r->err = "bump overflow persisted";
@@ -1241,6 +1320,7 @@ struct vb_group {
     size_t frame_cap = 0;
     uint32_t bounds_h = 0;          // height in tiles the boundaries were made for
     bool balancing = true;
+    bool exchange = false;          // flatten sharded by tag range, lines exchanged through peer memory (k_exchange.cu)
     std::string err;
 };
 
@@ -1362,6 +1442,58 @@ static void group_rebalance(vb_group *g, uint32_t ht) {
         }                                                                                         \
     } while (0)
 
+// (re)build the exchange arenas for the uploaded scene and introduce the renderers to each other
+static int group_setup_exchange(vb_group *g) {
+    const uint32_t n = (uint32_t)g->subs.size();
+    if (n > 8u) return VB_E_INVALID;
+    std::vector<void *> arenas(n, nullptr);
+    for (uint32_t i = 0; i < n; i++) {
+        int rc = vb_exchange_configure(g->subs[i], i, n, &arenas[i], nullptr);
+        if (rc) {
+            g->err = g->subs[i]->err;
+            return rc;
+        }
+    }
+    for (uint32_t i = 0; i < n; i++) {
+        for (uint32_t j = 0; j < n; j++) {
+            if (i == j) continue;
+            if (g->devices[i] != g->devices[j]) { // every GPU reads every other GPU's arena
+                int can = 0;
+                cudaSetDevice(g->devices[i]);
+                if (cudaDeviceCanAccessPeer(&can, g->devices[i], g->devices[j]) != cudaSuccess || !can) {
+                    g->err = "exchange needs peer access between all devices of the group";
+                    return VB_E_CUDA;
+                }
+                cudaError_t e = cudaDeviceEnablePeerAccess(g->devices[j], 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                    g->err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e);
+                    return VB_E_CUDA;
+                }
+                cudaGetLastError();
+            }
+            int rc = vb_exchange_attach(g->subs[i], j, arenas[j]);
+            if (rc) return rc;
+        }
+    }
+    for (uint32_t i = 0; i < n; i++) {
+        int rc = vb_exchange_enable(g->subs[i], 1);
+        if (rc) return rc;
+    }
+    return VB_OK;
+}
+
+extern "C" int vb_group_set_exchange(vb_group *g, int on) {
+    if (!g) return VB_E_INVALID;
+    g->exchange = on != 0;
+    if (!g->exchange) {
+        for (vb_renderer *r : g->subs) vb_exchange_enable(r, 0);
+        return VB_OK;
+    }
+    for (vb_renderer *r : g->subs)
+        if (!r->have_scene) return VB_OK; // arenas are built by the next vb_group_scene_upload
+    return group_setup_exchange(g);
+}
+
 extern "C" int vb_group_scene_upload(vb_group *g, const uint8_t *scene, size_t scene_len, const vb_layout *layout, const uint32_t *ramps,
                                      uint32_t ramp_w, uint32_t ramp_h, const uint8_t *atlas, uint32_t atlas_w, uint32_t atlas_h) {
     if (!g) return VB_E_INVALID;
@@ -1373,7 +1505,7 @@ extern "C" int vb_group_scene_upload(vb_group *g, const uint8_t *scene, size_t s
             return rc;
         }
     }
-    return VB_OK;
+    return g->exchange ? group_setup_exchange(g) : VB_OK;
 }
 
 // out: nullptr (group frame), a device pointer on devices[0], or (host_out) a host pointer
@@ -1381,6 +1513,10 @@ static int group_render(vb_group *g, const vb_params *p, void *out_device, void 
     if (!g || !p || p->bin_row1 > p->bin_row0 || p->tile_row1 > p->tile_row0) return VB_E_INVALID;
     const size_t n = g->subs.size();
     const uint32_t ht = (p->height + 15u) / 16u;
+    if (g->exchange && ht < n) {
+        g->err = "exchange needs at least one tile row per device";
+        return VB_E_INVALID;
+    }
     group_rebalance(g, ht);
     const size_t pitch = (size_t)p->width * 4u;
     void *frame = out_device;
@@ -1398,54 +1534,73 @@ static int group_render(vb_group *g, const vb_params *p, void *out_device, void 
     }
     // enqueue every device's stripe, then complete them (one host thread; the devices run side by side)
     std::vector<vb_params> ps(n, *p);
-    for (size_t i = 0; i < n; i++) {
-        vb_renderer *r = g->subs[i];
-        ps[i].tile_row0 = g->bounds[i];
-        ps[i].tile_row1 = g->bounds[i + 1];
-        if (ps[i].tile_row1 <= ps[i].tile_row0) continue; // more devices than tile rows
-        const size_t row0 = (size_t)g->bounds[i] * 16u;
-        void *dst = nullptr; // nullptr: the renderer's own target (then copied)
-        if (host_out) {
-            r->host_out = (char *)host_out + row0 * pitch;
-            r->readback_bands = 1;
-        } else if (g->peer_ok[i]) {
-            dst = (char *)frame + row0 * pitch;
-        }
-        int rc = vb_render_enqueue(r, &ps[i], dst);
-        if (rc) {
-            r->host_out = nullptr;
-            g->err = r->err;
-            return rc;
-        }
-    }
     int result = VB_OK;
-    for (size_t i = 0; i < n; i++) {
-        vb_renderer *r = g->subs[i];
-        if (ps[i].tile_row1 <= ps[i].tile_row0) {
-            if (stats) memset(&stats[i], 0, sizeof(vb_frame_stats));
-            continue;
+    for (uint32_t attempt = 0;; attempt++) {
+        if (g->exchange)
+            for (vb_renderer *r : g->subs) vb_exchange_set_bounds(r, g->bounds.data());
+        for (size_t i = 0; i < n; i++) {
+            vb_renderer *r = g->subs[i];
+            ps[i].tile_row0 = g->bounds[i];
+            ps[i].tile_row1 = g->bounds[i + 1];
+            if (ps[i].tile_row1 <= ps[i].tile_row0) continue; // more devices than tile rows (never with the exchange on)
+            const size_t row0 = (size_t)g->bounds[i] * 16u;
+            void *dst = nullptr; // nullptr: the renderer's own target (then copied)
+            if (host_out) {
+                r->host_out = (char *)host_out + row0 * pitch;
+                r->readback_bands = 1;
+            } else if (g->peer_ok[i]) {
+                dst = (char *)frame + row0 * pitch;
+            }
+            int rc = vb_render_enqueue(r, &ps[i], dst);
+            if (rc) {
+                r->host_out = nullptr;
+                g->err = r->err;
+                return rc;
+            }
         }
-        const size_t row0 = (size_t)g->bounds[i] * 16u;
-        void *dst = (!host_out && g->peer_ok[i]) ? (char *)frame + row0 * pitch : nullptr;
-        int rc = vb_frame_finish(r, stats ? &stats[i] : nullptr);
-        if (rc == VB_E_BUMP_OVERFLOW) rc = vb_render_resident(r, &ps[i], dst, stats ? &stats[i] : nullptr); // grow and re-run (first frames)
-        g->ms[i] = vb_last_frame_ms(r);
-        if (rc == VB_OK && host_out) {
-            cudaSetDevice(r->device);
-            if (cudaStreamSynchronize(r->copy_stream) != cudaSuccess) rc = VB_E_CUDA;
+        result = VB_OK;
+        bool redo = false;
+        for (size_t i = 0; i < n; i++) {
+            vb_renderer *r = g->subs[i];
+            if (ps[i].tile_row1 <= ps[i].tile_row0) {
+                if (stats) memset(&stats[i], 0, sizeof(vb_frame_stats));
+                continue;
+            }
+            const size_t row0 = (size_t)g->bounds[i] * 16u;
+            void *dst = (!host_out && g->peer_ok[i]) ? (char *)frame + row0 * pitch : nullptr;
+            int rc = vb_frame_finish(r, stats ? &stats[i] : nullptr);
+            if (rc == VB_E_BUMP_OVERFLOW) {
+                if (g->exchange) { // an exchanged frame is re-issued on EVERY device (epochs advance together)
+                    grow_arenas(r);
+                    redo = true;
+                    rc = VB_OK;
+                } else {
+                    rc = vb_render_resident(r, &ps[i], dst, stats ? &stats[i] : nullptr); // grow and re-run (first frames)
+                }
+            }
+            g->ms[i] = vb_last_frame_ms(r);
+            if (rc == VB_OK && host_out) {
+                cudaSetDevice(r->device);
+                if (cudaStreamSynchronize(r->copy_stream) != cudaSuccess) rc = VB_E_CUDA;
+            }
+            if (rc == VB_OK && !host_out && !g->peer_ok[i]) {
+                // no peer mapping between these two devices: stage through the renderer's own target
+                const size_t h0 = row0, h1 = std::min<size_t>((size_t)g->bounds[i + 1] * 16u, p->height);
+                cudaSetDevice(r->device);
+                if (h1 > h0 && (cudaMemcpyPeerAsync((char *)frame + row0 * pitch, g->devices[0], r->out_dev, r->device, (h1 - h0) * pitch, r->stream) != cudaSuccess ||
+                                cudaStreamSynchronize(r->stream) != cudaSuccess))
+                    rc = VB_E_CUDA;
+            }
+            r->host_out = nullptr;
+            if (rc && result == VB_OK) {
+                result = rc;
+                g->err = r->err;
+            }
         }
-        if (rc == VB_OK && !host_out && !g->peer_ok[i]) {
-            // no peer mapping between these two devices: stage through the renderer's own target
-            const size_t h0 = row0, h1 = std::min<size_t>((size_t)g->bounds[i + 1] * 16u, p->height);
-            cudaSetDevice(r->device);
-            if (cudaMemcpyPeerAsync((char *)frame + row0 * pitch, g->devices[0], r->out_dev, r->device, (h1 - h0) * pitch, r->stream) != cudaSuccess ||
-                cudaStreamSynchronize(r->stream) != cudaSuccess)
-                rc = VB_E_CUDA;
-        }
-        r->host_out = nullptr;
-        if (rc && result == VB_OK) {
-            result = rc;
-            g->err = r->err;
+        if (!redo || result != VB_OK) break;
+        if (attempt >= 8u) {
+            g->err = "bump overflow persisted in an exchanged frame";
+            return VB_E_BUMP_OVERFLOW;
         }
     }
     return result;
@@ -1582,5 +1737,60 @@ extern "C" int vb_scene_upload_streams(vb_renderer *r, const vb_encoding_streams
     r->scene_words = total_words;
     r->have_scene = true;
     if (layout_out) memcpy(layout_out, &L, sizeof(vb_layout));
+    return VB_OK;
+}
+
+
+// ---- multi-GPU exchange set-up (k_exchange.cu) ----------------------------------------------------------------------------
+// grow_arenas() is declared above; these entry points only manage the arena and the peer table.
+extern "C" int vb_exchange_configure(vb_renderer *r, uint32_t rank, uint32_t world, void **arena, size_t *arena_bytes) {
+    if (!r || world < 1u || world > 8u || rank >= world) return VB_E_INVALID;
+    if (!r->have_scene) return VB_E_NO_SCENE;
+    CK(cudaSetDevice(r->device));
+    CK(cudaStreamSynchronize(r->stream));
+    vb_renderer::Exchange &x = r->xc;
+    x.enabled = false;
+    const uint32_t n_tags = (r->layout.path_data_base - r->layout.path_tag_base) * 4u;
+    // my outbox holds my share of the lines (+ the ones needed by two stripes): generous and fixed, so that the arena -- which
+    // the peers have mapped -- never moves
+    const uint64_t cap = (uint64_t)n_tags * 4u / world * 2u + 262144u;
+    x.lines_cap = cap > 0x7fffffffull ? 0x7fffffffu : (uint32_t)cap;
+    x.n_paths = r->layout.n_paths;
+    x.half_bytes = vb_exchange_half_bytes(x.n_paths, x.lines_cap);
+    const size_t bytes = 256 + 2 * x.half_bytes;
+    int rc = ensure(r, x.arena, bytes);
+    if (rc) return rc;
+    CK(cudaMemset(x.arena.p, 0, 256)); // flags and epoch start at 0
+    x.rank = rank;
+    x.world = world;
+    memset(x.peer, 0, sizeof x.peer);
+    x.peer[rank] = x.arena.p;
+    for (uint32_t i = 0; i <= world; i++) x.rows[i] = 0;
+    x.configured = true;
+    if (arena) *arena = x.arena.p;
+    if (arena_bytes) *arena_bytes = bytes;
+    return VB_OK;
+}
+extern "C" int vb_exchange_attach(vb_renderer *r, uint32_t peer_rank, void *peer_arena) {
+    if (!r || !r->xc.configured || peer_rank >= r->xc.world || !peer_arena) return VB_E_INVALID;
+    r->xc.peer[peer_rank] = peer_arena;
+    return VB_OK;
+}
+extern "C" int vb_exchange_set_bounds(vb_renderer *r, const uint32_t *tile_rows) {
+    if (!r || !r->xc.configured || !tile_rows) return VB_E_INVALID;
+    for (uint32_t i = 0; i <= r->xc.world; i++) {
+        if (i && tile_rows[i] < tile_rows[i - 1]) return VB_E_INVALID;
+        r->xc.rows[i] = tile_rows[i];
+    }
+    return VB_OK;
+}
+extern "C" int vb_exchange_enable(vb_renderer *r, int on) {
+    if (!r) return VB_E_INVALID;
+    if (on) {
+        if (!r->xc.configured) return VB_E_INVALID;
+        for (uint32_t i = 0; i < r->xc.world; i++)
+            if (!r->xc.peer[i]) return VB_E_INVALID;
+    }
+    r->xc.enabled = on != 0;
     return VB_OK;
 }

@@ -27,7 +27,12 @@ typedef struct { uint32_t failed, binning, ptcl, tile, seg_counts, segments, ble
 #define VB_CTL_SEG_HOLES 8
 /* words 16..23: fine's tile queues, one per launch of a frame (up to 8 read-back bands); the header is 32 words */
 #define VB_CTL_FINE_QUEUE 16
-#define VB_CTL_HEADER_WORDS 32
+/* words 24..27: fill counts of fine's cost-class tile lists (written by coarse) */
+#define VB_CTL_FINE_CLASS 24
+#define VB_FINE_CLASSES 4
+/* words 32..47: per-destination counts and cursors of the multi-GPU line routing (k_exchange.cu) */
+#define VB_CTL_XCHG_SCRATCH 32
+#define VB_CTL_HEADER_WORDS 64
 
 typedef struct {
     uint32_t n_draw_objects, n_paths, n_clips, bin_data_start;
@@ -57,6 +62,7 @@ typedef struct {
 #define VB_STAGE_PATH_COUNT 0x8u
 #define VB_STAGE_COARSE 0x10u
 #define VB_STAGE_FINE_SEGMENTS 0x20u /* extension: segments arena too small (checked in coarse) */
+#define VB_STAGE_EXCHANGE 0x40u      /* extension: multi-GPU line exchange (outbox too small, or a peer never signalled) */
 
 #define VB_TILE_WIDTH 16u
 #define VB_TILE_HEIGHT 16u

@@ -118,6 +118,11 @@ def load_library() -> C.CDLL:
     lib.vb_group_frame.argtypes = [vp, C.POINTER(C.c_size_t)]
     lib.vb_group_stripes.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
     lib.vb_group_set_balancing.argtypes = [vp, C.c_int]
+    lib.vb_group_set_exchange.argtypes = [vp, C.c_int]
+    lib.vb_exchange_configure.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    lib.vb_exchange_attach.argtypes = [vp, C.c_uint32, vp]
+    lib.vb_exchange_set_bounds.argtypes = [vp, C.POINTER(C.c_uint32)]
+    lib.vb_exchange_enable.argtypes = [vp, C.c_int]
     _lib = lib
     return lib
 
@@ -127,7 +132,8 @@ EXPORTED_SYMBOLS = ["vb_renderer_new", "vb_renderer_free", "vb_strerror", "vb_la
                     "vb_run_stages", "vb_debug_download", "vb_debug_upload", "vb_debug_fine_traffic", "vb_set_occlusion_cull", "vb_render_begin", "vb_readback_wait", "vb_set_readback_bands", "vb_set_cuda_graph",
                     "vb_scene_upload_streams", "vb_render_uploaded", "vb_last_frame_ms", "vb_frame_alloc", "vb_frame_free", "vb_ipc_export", "vb_ipc_open", "vb_ipc_close",
                     "vb_group_new", "vb_group_free", "vb_group_size", "vb_group_renderer", "vb_group_last_error", "vb_group_render",
-                    "vb_group_scene_upload", "vb_group_render_resident", "vb_group_frame", "vb_group_stripes", "vb_group_set_balancing"]
+                    "vb_group_scene_upload", "vb_group_render_resident", "vb_group_frame", "vb_group_stripes", "vb_group_set_balancing",
+                    "vb_group_set_exchange", "vb_exchange_configure", "vb_exchange_attach", "vb_exchange_set_bounds", "vb_exchange_enable"]
 
 
 @dataclass
@@ -348,6 +354,11 @@ class RendererGroup:
 
     def set_balancing(self, on: bool):
         self._check(self.lib.vb_group_set_balancing(self.handle, 1 if on else 0), "vb_group_set_balancing")
+
+    def set_exchange(self, on: bool):
+        """Shard `flatten` by tag range across the devices and exchange lines / path boxes through peer memory
+        (k_exchange.cu) instead of flattening the whole scene on every device."""
+        self._check(self.lib.vb_group_set_exchange(self.handle, 1 if on else 0), "vb_group_set_exchange")
 
     def upload(self, packed: Packed):
         scene = np.ascontiguousarray(packed.scene, dtype=np.uint32)
