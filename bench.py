@@ -186,6 +186,7 @@ def main():
     ap.add_argument("--scene", default="paris", choices=["paris", "tiger", "beziers"], help="paris = the headline workload")
     ap.add_argument("--height", type=int, default=0, help="frame height (default: --size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-exchange", action="store_true", help="N > 1: every rank flattens the whole scene (round-1 behaviour)")
     ap.add_argument("--profile-only", action="store_true", help="just run warmup+steps resident frames (for ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if not args.profile_only else args.warmup
@@ -281,6 +282,95 @@ def main():
             if nb == bounds:
                 break
             bounds = nb
+    # ---- N > 1: shard flatten by tag range and exchange lines / path boxes through peer memory (k_exchange.cu). The frames
+    # above (every rank flattening everything) are the `replicated` figure reported beside `value`.
+    replicated = None
+    exchange_on = world > 1 and not args.no_exchange
+    xinfo = None
+
+    def render_collective():
+        """One frame on every rank; re-issued on every rank while any rank's arenas overflow (exchanged frames advance an
+        epoch on all GPUs together)."""
+        nonlocal st
+        for attempt in range(10):
+            ps_ = _Params(BLACK.premul_rgba8_u32(), args.size, H, args.aa, 0, 0, my_rows()[0], my_rows()[1])
+            fs_ = FrameStats()
+            rc = r.lib.vb_render_resident(r.handle, C.byref(ps_), vp(my_out()), C.byref(fs_))
+            bad = torch.tensor([1.0 if rc != 0 else 0.0], device=dev)
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+            if bad.item() == 0.0:
+                st = fs_
+                return attempt
+            assert rc in (0, -3), f"rank {rank}: vb_render_resident rc={rc} [{r.lib.vb_last_error(r.handle).decode()}]"
+        raise RuntimeError("exchanged frame kept overflowing")
+
+    if exchange_on:
+        # the replicated mode's K steps first (same protocol as the main loop below)
+        for _ in range(args.warmup):
+            render_once()
+        barrier()
+        evs0 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for a, b in evs0:
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            a.record(stream)
+            r.enqueue(params, my_out(), tile_rows=my_rows())
+            b.record(stream)
+            assert r.finish().failed == 0
+        barrier()
+        sm0 = torch.tensor([a.elapsed_time(b) for a, b in evs0], dtype=torch.float64, device=dev)
+        dist.all_reduce(sm0, op=dist.ReduceOp.MAX)
+        replicated = {"value": args.steps / (float(sm0.sum().item()) / 1000.0), "unit": "frames/s", "ms_per_step": float(sm0.sum().item()) / args.steps,
+                      "tile_row_bounds": list(bounds), "note": "every rank flattens the whole scene (culled to its stripe); no exchange"}
+        # arenas, CUDA IPC handles all-gathered, peers mapped
+        arena, nbytes = vp(), C.c_size_t(0)
+        assert r.lib.vb_exchange_configure(r.handle, rank, world, C.byref(arena), C.byref(nbytes)) == 0
+        hb = C.create_string_buffer(64)
+        assert r.lib.vb_ipc_export(r.handle, arena, hb) == 0
+        mine = torch.tensor(list(hb.raw), dtype=torch.uint8, device=dev)
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        peer_ptrs = []
+        for k in range(world):
+            if k == rank:
+                continue
+            hk = C.create_string_buffer(bytes(allh[k].cpu().tolist()), 64)
+            pk = vp()
+            rc = r.lib.vb_ipc_open(r.handle, hk, C.byref(pk))
+            assert rc == 0, f"vb_ipc_open(exchange arena of rank {k}) failed on rank {rank}: {r.lib.vb_last_error(r.handle).decode()}"
+            assert r.lib.vb_exchange_attach(r.handle, k, pk) == 0
+            peer_ptrs.append(pk)
+
+        def set_bounds():
+            arr = (C.c_uint32 * (world + 1))(*bounds)
+            assert r.lib.vb_exchange_set_bounds(r.handle, arr) == 0
+
+        set_bounds()
+        assert r.lib.vb_exchange_enable(r.handle, 1) == 0
+        barrier()
+        retries = render_collective()
+        xbal = []
+        for it in range(12):  # re-balance: the replicated flatten is gone, the stripes weigh differently now
+            for _ in range(2):
+                render_collective()
+            ms = [v[0] for v in allgather_floats([float(r.lib.vb_last_frame_ms(r.handle))])]
+            xbal.append({"bounds": list(bounds), "ms": [round(m, 4) for m in ms]})
+            nb = rebalance(bounds, ms)
+            if nb == bounds:
+                break
+            bounds = nb
+            set_bounds()
+        xinfo = {"arena_bytes": int(nbytes.value), "first_frame_reissues": retries, "balancing": xbal,
+                 "how": "rank k flattens partitions [P*k/N, P*(k+1)/N) of the tag stream; lines are routed by the stripes they touch into an "
+                        "outbox in peer-mapped memory and pulled by their owners, partial path boxes are min/max-combined; the ranks "
+                        "synchronise through epoch flags in each other's arenas (no host, no NCCL on the data path)"}
+
+        def render_once():  # noqa: F811  (from here on every frame is an exchanged one)
+            render_collective()
+            return st
+
     for _ in range(args.warmup):
         st = render_once()
     if args.profile_only:
@@ -351,8 +441,12 @@ def main():
         if rank == 0:
             asm = np.zeros((H, args.size, 4), dtype=np.uint8)
             assert r.lib.vb_copy_to_host(r.handle, vp(frame_base), vp(asm.ctypes.data), C.c_size_t(asm.nbytes)) == 0
+            if exchange_on:
+                assert r.lib.vb_exchange_enable(r.handle, 0) == 0  # a frame of rank 0 alone: nobody to exchange with
             r.render_resident(params, 0)
             solo = r.download_target(params)
+            if exchange_on:
+                assert r.lib.vb_exchange_enable(r.handle, 1) == 0
             stripes_parity = {"assembled_over_nvlink_equals_single_gpu": bool(np.array_equal(asm, solo)),
                               "differing_pixels": int((asm != solo).any(axis=2).sum())}
             del asm, solo
@@ -406,24 +500,28 @@ def main():
     h2d = int(packed.scene.nbytes + packed.ramps.nbytes + packed.atlas.nbytes)
     d2h = int((h1 - h0) * args.size * 4 + 32)
 
-    # ---- per-stage CUDA events of this rank's stripe (a second renderer with options.timing; launches individually) -----
-    rt = Renderer(RendererOptions(device=local, timing=True))
-    rt.upload(packed)
-    rt.render_resident(params, my_out(), tile_rows=my_rows())
+    # ---- per-stage CUDA events of this rank's stripe (the same renderer with timing switched on: plain launches, an event
+    # between stages; at N > 1 these are collective frames like all the others, so `flatten` includes the exchange and the wait
+    # for the slowest peer)
+    assert r.lib.vb_set_timing(r.handle, 1) == 0
+    render_once()
     stage_ms = {}
     n_t = 10
     for _ in range(n_t):
         flush.fill_(1)
         torch.cuda.synchronize()
-        sd = rt.render_resident(params, my_out(), tile_rows=my_rows()).as_dict()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+        sd = render_once().as_dict()
         for k, v in sd["stage_ms"].items():
             stage_ms[k] = stage_ms.get(k, 0.0) + v / n_t
-    ptcl_words, seg_refs, fill_cmds = rt.fine_traffic()  # what the interpreter reads, from each tile's occlusion start
-    rt.set_occlusion_cull(False)
-    full_words, full_segs, full_fills = rt.fine_traffic()  # the whole command lists, as the reference executes them
-    rt.set_occlusion_cull(True)
+    assert r.lib.vb_set_timing(r.handle, 0) == 0
+    ptcl_words, seg_refs, fill_cmds = r.fine_traffic()  # what the interpreter reads, from each tile's occlusion start
+    r.set_occlusion_cull(False)
+    full_words, full_segs, full_fills = r.fine_traffic()  # the whole command lists, as the reference executes them
+    r.set_occlusion_cull(True)
     bump = {k: int(getattr(st, k)) for k in ("lines", "tile", "seg_counts", "segments", "ptcl", "binning")}
-    rt.close()
     stage_by_rank = None
     if dist is not None:
         names = list(stage_ms.keys())
@@ -528,7 +626,9 @@ def main():
             "scene_bytes": int(packed.scene.nbytes), "wall_s_timed_region": wall, "scene_build_s": gen_s}
     if world > 1:
         slow = int(np.argmax(rank_totals))
-        line["multi_gpu"] = {"tile_row_bounds": list(bounds), "rank_ms_per_step": [round(v / args.steps, 4) for v in rank_totals],
+        line["multi_gpu"] = {"flatten": "sharded by tag range, peer-memory exchange" if exchange_on else "replicated", "exchange": xinfo,
+                             "replicated": replicated,
+                             "tile_row_bounds": list(bounds), "rank_ms_per_step": [round(v / args.steps, 4) for v in rank_totals],
                              "slowest_rank": slow, "stage_ms_by_rank": stage_by_rank, "balancing": balance_log,
                              "frame": "assembled on rank 0 by peer stores from every rank's fine kernel", "distributed": distributed}
     emit(line)

@@ -129,6 +129,8 @@ int vb_set_readback_bands(vb_renderer *, uint32_t n);
  * the scene layout, the frame size or the window changes). On by default; 0 launches every kernel individually.
  * Environment: VELLO_B200_NO_GRAPH=1 disables it at renderer creation. */
 int vb_set_cuda_graph(vb_renderer *, int on);
+/* Switch the per-stage CUDA events of vb_options.timing on or off for the following frames (on: plain launches, no graph). */
+int vb_set_timing(vb_renderer *, int on);
 
 /* The renderer-owned target of the last frame (device pointer) and its size in bytes. */
 void *vb_target(vb_renderer *, size_t *bytes);

@@ -402,7 +402,9 @@ k_coarse(VbConfig cfg, const uint32_t *__restrict__ scene, const VbDrawMonoid *_
     if (lid < 64u) { // the two owner warps, whole
         const uint32_t ty = bin_tile_y + tile_y, tx = bin_tile_x + tile_x;
         const bool in_win = tx < cfg.width_in_tiles && ty >= cfg.win_ty0 && ty < cfg.win_ty1 && ty < cfg.height_in_tiles;
-        const uint32_t cls = cost >= 256u ? 0u : (cost >= 96u ? 1u : (cost >= 32u ? 2u : 3u));
+        // classes by powers of two of the estimate: >= 1024, 512, 256, 128, 64, 32, 16, rest
+        const uint32_t lg = 31u - (uint32_t)__clz((int)max(cost, 1u));
+        const uint32_t cls = lg >= 10u ? 0u : (lg <= 3u ? 7u : 10u - lg);
         const uint32_t lane = lid & 31u;
 #pragma unroll
         for (uint32_t k = 0; k < VB_FINE_CLASSES; k++) {

@@ -1195,6 +1195,12 @@ extern "C" int vb_debug_download(vb_renderer *r, const char *name, void *dst, si
     return VB_E_UNKNOWN_BUFFER;
 }
 
+extern "C" int vb_set_timing(vb_renderer *r, int on) {
+    if (!r) return VB_E_INVALID;
+    r->timing = on != 0;
+    return VB_OK;
+}
+
 extern "C" int vb_set_cuda_graph(vb_renderer *r, int on) {
     if (!r) return VB_E_INVALID;
     r->use_graph = on != 0;

@@ -27,9 +27,9 @@ typedef struct { uint32_t failed, binning, ptcl, tile, seg_counts, segments, ble
 #define VB_CTL_SEG_HOLES 8
 /* words 16..23: fine's tile queues, one per launch of a frame (up to 8 read-back bands); the header is 32 words */
 #define VB_CTL_FINE_QUEUE 16
-/* words 24..27: fill counts of fine's cost-class tile lists (written by coarse) */
+/* words 24..31: fill counts of fine's cost-class tile lists (written by coarse) */
 #define VB_CTL_FINE_CLASS 24
-#define VB_FINE_CLASSES 4
+#define VB_FINE_CLASSES 8
 /* words 32..47: per-destination counts and cursors of the multi-GPU line routing (k_exchange.cu) */
 #define VB_CTL_XCHG_SCRATCH 32
 #define VB_CTL_HEADER_WORDS 64

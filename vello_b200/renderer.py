@@ -85,6 +85,7 @@ def load_library() -> C.CDLL:
     lib.vb_readback_wait.argtypes = [vp]
     lib.vb_set_readback_bands.argtypes = [vp, C.c_uint32]
     lib.vb_set_cuda_graph.argtypes = [vp, C.c_int]
+    lib.vb_set_timing.argtypes = [vp, C.c_int]
     lib.vb_target.restype = vp
     lib.vb_target.argtypes = [vp, C.POINTER(C.c_size_t)]
     lib.vb_copy_to_host.argtypes = [vp, vp, vp, C.c_size_t]
@@ -129,7 +130,7 @@ def load_library() -> C.CDLL:
 
 EXPORTED_SYMBOLS = ["vb_renderer_new", "vb_renderer_free", "vb_strerror", "vb_last_error", "vb_scene_upload",
                     "vb_render_resident", "vb_render_enqueue", "vb_frame_finish", "vb_render", "vb_target", "vb_copy_to_host", "vb_stream",
-                    "vb_run_stages", "vb_debug_download", "vb_debug_upload", "vb_debug_fine_traffic", "vb_set_occlusion_cull", "vb_render_begin", "vb_readback_wait", "vb_set_readback_bands", "vb_set_cuda_graph",
+                    "vb_run_stages", "vb_debug_download", "vb_debug_upload", "vb_debug_fine_traffic", "vb_set_occlusion_cull", "vb_render_begin", "vb_readback_wait", "vb_set_readback_bands", "vb_set_cuda_graph", "vb_set_timing",
                     "vb_scene_upload_streams", "vb_render_uploaded", "vb_last_frame_ms", "vb_frame_alloc", "vb_frame_free", "vb_ipc_export", "vb_ipc_open", "vb_ipc_close",
                     "vb_group_new", "vb_group_free", "vb_group_size", "vb_group_renderer", "vb_group_last_error", "vb_group_render",
                     "vb_group_scene_upload", "vb_group_render_resident", "vb_group_frame", "vb_group_stripes", "vb_group_set_balancing",
