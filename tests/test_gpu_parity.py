@@ -664,8 +664,8 @@ def test_group_with_sharded_flatten(oracle, n):
         st = g.render_resident(p)
         assert all(int(s.failed) == 0 for s in st)
         assert np.array_equal(g.frame_to_host(p), ref), k
-    total = sum(int(s.lines) for s in st)
-    assert total >= int(oracle.buffer("bump")["lines"][0])  # every line reached at least one stripe
+    total = sum(int(s.lines) for s in st)  # lines pulled by the stripes: all lines that touch the frame's rows (some twice)
+    assert 0.8 * int(oracle.buffer("bump")["lines"][0]) < total < 1.3 * int(oracle.buffer("bump")["lines"][0])
     # strokes with round joins / caps (arcs), curves, clips and blends; area AA within 1 LSB
     for name in ("stroke_styles", "many_clips", "blend_grid"):
         s, w, h = getattr(scenes, name)()

@@ -61,7 +61,8 @@ struct XPeersHost { // == XPeers in k_exchange.cu
 extern "C" size_t vb_exchange_half_bytes(uint32_t n_paths, uint32_t lines_cap);
 extern "C" size_t vb_exchange_peers_bytes(void);
 extern "C" uint32_t vb_exchange_epoch_word(void);
-extern "C" void vb_launch_exchange(const void *, VbBump *, uint32_t, VbLineSoup *, uint32_t *, VbPathBbox *, int, cudaStream_t);
+extern "C" void vb_launch_exchange_send(const void *, VbBump *, uint32_t, VbLineSoup *, uint32_t *, VbPathBbox *, int, cudaStream_t);
+extern "C" void vb_launch_exchange_recv(const void *, VbBump *, uint32_t, VbLineSoup *, VbPathBbox *, int, cudaStream_t);
 extern "C" void vb_launch_resolve_finish(uint32_t *, uint32_t, uint32_t, uint32_t, uint32_t, const void *, uint32_t, cudaStream_t);
 extern "C" void vb_launch_make_ramps(const void *, const void *, uint32_t, uint32_t *, cudaStream_t);
 
@@ -579,6 +580,13 @@ static int prepare(vb_renderer *r, const vb_params *p) {
     return VB_OK;
 }
 
+static void xpeers_of(const vb_renderer *r, XPeersHost *X) {
+    memset(X, 0, sizeof *X);
+    for (uint32_t i = 0; i < r->xc.world; i++) X->base[i] = (unsigned char *)r->xc.peer[i];
+    for (uint32_t i = 0; i <= r->xc.world; i++) X->rows[i] = r->xc.rows[i];
+    X->world = r->xc.world; X->rank = r->xc.rank; X->n_paths = r->xc.n_paths; X->lines_cap = r->xc.lines_cap; X->half_bytes = r->xc.half_bytes;
+}
+
 static void rec(vb_renderer *r, int i) {
     if (r->timing) cudaEventRecord(r->ev[i], r->stream);
 }
@@ -627,13 +635,10 @@ static int enqueue_direct(vb_renderer *r, int first, int last, void *out_dev) {
                                   (VbLineSoup *)r->lines.p, r->line_scratch.p, r->flatten_jobs.p, (uint32_t *)r->flatten_parts.p,
                                   ctl + r->off_lb_flatten, r->parts_flatten, first != 0 ? 1 : 0, p0, p1, st);
                 XPeersHost X;
-                memset(&X, 0, sizeof X);
-                for (uint32_t i = 0; i < G; i++) X.base[i] = (unsigned char *)r->xc.peer[i];
-                for (uint32_t i = 0; i <= G; i++) X.rows[i] = r->xc.rows[i];
-                X.world = G; X.rank = k; X.n_paths = r->xc.n_paths; X.lines_cap = r->xc.lines_cap; X.half_bytes = r->xc.half_bytes;
-                vb_launch_exchange(&X, bump, c.lines_size, (VbLineSoup *)r->lines.p, ctl + VB_CTL_XCHG_SCRATCH, (VbPathBbox *)r->path_bboxes.p,
-                                   r->sm_count, st);
-                launches += (r->parts_flatten ? 3 : 0) + 7;
+                xpeers_of(r, &X);
+                vb_launch_exchange_send(&X, bump, c.lines_size, (VbLineSoup *)r->lines.p, ctl + VB_CTL_XCHG_SCRATCH,
+                                        (VbPathBbox *)r->path_bboxes.p, r->sm_count, st);
+                launches += (r->parts_flatten ? 3 : 0) + 4;
                 break;
             }
             vb_launch_flatten(&c, (const uint32_t *)r->scene.p, (const VbTagMonoid *)r->tag_monoids.p, (VbPathBbox *)r->path_bboxes.p, bump,
@@ -642,6 +647,12 @@ static int enqueue_direct(vb_renderer *r, int first, int last, void *out_dev) {
             launches += (first != 0 && c.layout.n_paths ? 1 : 0) + (r->parts_flatten ? 3 : 0);
             break;
         case VB_STAGE_ID_DRAW:
+            if (r->xc.enabled) { // second half of the exchange: my lines and the complete path boxes arrive before draw_leaf reads them
+                XPeersHost X;
+                xpeers_of(r, &X);
+                vb_launch_exchange_recv(&X, bump, c.lines_size, (VbLineSoup *)r->lines.p, (VbPathBbox *)r->path_bboxes.p, r->sm_count, st);
+                launches += 3;
+            }
             vb_launch_draw(&c, (const uint32_t *)r->scene.p, (const VbPathBbox *)r->path_bboxes.p, (VbDrawMonoid *)r->draw_monoids.p,
                            (uint32_t *)r->info_bin_data.p, (VbClipInp *)r->clip_inp.p, ctl + r->off_lb_draw, r->parts_draw, st);
             launches += r->parts_draw ? 1 : 0;
@@ -852,7 +863,11 @@ static int pick_out(vb_renderer *r, void *out_device, void **out) {
     return rc;
 }
 
-extern "C" int vb_render_enqueue(vb_renderer *r, const vb_params *p, void *out_device) {
+// A frame is enqueued in two steps: everything that may allocate, free or otherwise synchronise with the device (config,
+// arenas, the output target), then the launches. vb_group runs step 1 for ALL its renderers before step 2 of any: with the
+// exchange on, a renderer's frame contains a kernel that waits for its peers, and a peer that shares the device (tests)
+// must not be stuck in a cudaFree behind that kernel.
+static int frame_prepare(vb_renderer *r, const vb_params *p, void *out_device) {
     if (!r || !p) return VB_E_INVALID;
     if (!r->have_scene) return VB_E_NO_SCENE;
     CK(cudaSetDevice(r->device));
@@ -861,12 +876,40 @@ extern "C" int vb_render_enqueue(vb_renderer *r, const vb_params *p, void *out_d
     void *out;
     if ((rc = pick_out(r, out_device, &out))) return rc;
     r->out_dev = out;
+    return VB_OK;
+}
+static int frame_launch(vb_renderer *r) {
+    CK(cudaSetDevice(r->device));
     CK(cudaEventRecord(r->frame_ev[0], r->stream));
-    rc = enqueue(r, 0, VB_N_STAGE_IDS - 1, out);
+    int rc = enqueue(r, 0, VB_N_STAGE_IDS - 1, r->out_dev);
     if (rc == VB_OK) CK(cudaEventRecord(r->frame_ev[1], r->stream));
     r->frame_timed = rc == VB_OK;
     r->frame_pending = rc == VB_OK;
     return rc;
+}
+
+// The same frame in two submissions (plain launches): up to and including flatten + the sending half of the exchange, then
+// the rest. Used by vb_group when renderers share a device, see k_exchange.cu.
+static int frame_launch_half(vb_renderer *r, int half) {
+    CK(cudaSetDevice(r->device));
+    if (half == 0) {
+        CK(cudaEventRecord(r->frame_ev[0], r->stream));
+        return enqueue_direct(r, 0, VB_STAGE_ID_FLATTEN, r->out_dev);
+    }
+    uint32_t first_half = r->launches;
+    int rc = enqueue_direct(r, VB_STAGE_ID_DRAW, VB_N_STAGE_IDS - 1, r->out_dev);
+    r->launches += first_half;
+    // (with a host destination enqueue_direct queues the read-back behind fine itself)
+    if (rc == VB_OK) CK(cudaEventRecord(r->frame_ev[1], r->stream));
+    r->frame_timed = rc == VB_OK;
+    r->frame_pending = rc == VB_OK;
+    return rc;
+}
+
+extern "C" int vb_render_enqueue(vb_renderer *r, const vb_params *p, void *out_device) {
+    int rc = frame_prepare(r, p, out_device);
+    if (rc) return rc;
+    return frame_launch(r);
 }
 
 static void fill_stats(vb_renderer *r, vb_frame_stats *s) {
@@ -1327,6 +1370,7 @@ struct vb_group {
     uint32_t bounds_h = 0;          // height in tiles the boundaries were made for
     bool balancing = true;
     bool exchange = false;          // flatten sharded by tag range, lines exchanged through peer memory (k_exchange.cu)
+    bool shared_device = false;     // two renderers on one GPU (tests)
     std::string err;
 };
 
@@ -1481,9 +1525,15 @@ static int group_setup_exchange(vb_group *g) {
             if (rc) return rc;
         }
     }
+    bool shared_device = false;
+    for (uint32_t i = 0; i < n; i++)
+        for (uint32_t j = i + 1; j < n; j++) shared_device = shared_device || g->devices[i] == g->devices[j];
+    g->shared_device = shared_device;
     for (uint32_t i = 0; i < n; i++) {
         int rc = vb_exchange_enable(g->subs[i], 1);
         if (rc) return rc;
+        // renderers that share a GPU (tests): no graph (re-)instantiation while a peer's wait kernel is resident on that GPU
+        if (shared_device) g->subs[i]->use_graph = false;
     }
     return VB_OK;
 }
@@ -1544,24 +1594,27 @@ static int group_render(vb_group *g, const vb_params *p, void *out_device, void 
     for (uint32_t attempt = 0;; attempt++) {
         if (g->exchange)
             for (vb_renderer *r : g->subs) vb_exchange_set_bounds(r, g->bounds.data());
-        for (size_t i = 0; i < n; i++) {
-            vb_renderer *r = g->subs[i];
-            ps[i].tile_row0 = g->bounds[i];
-            ps[i].tile_row1 = g->bounds[i + 1];
-            if (ps[i].tile_row1 <= ps[i].tile_row0) continue; // more devices than tile rows (never with the exchange on)
-            const size_t row0 = (size_t)g->bounds[i] * 16u;
-            void *dst = nullptr; // nullptr: the renderer's own target (then copied)
-            if (host_out) {
-                r->host_out = (char *)host_out + row0 * pitch;
-                r->readback_bands = 1;
-            } else if (g->peer_ok[i]) {
-                dst = (char *)frame + row0 * pitch;
-            }
-            int rc = vb_render_enqueue(r, &ps[i], dst);
-            if (rc) {
-                r->host_out = nullptr;
-                g->err = r->err;
-                return rc;
+        const bool halves = g->exchange && g->shared_device;
+        for (int phase = 0; phase < (halves ? 3 : 2); phase++) { // 0: configs and arenas of every renderer, 1 (and 2): the launches
+            for (size_t i = 0; i < n; i++) {
+                vb_renderer *r = g->subs[i];
+                ps[i].tile_row0 = g->bounds[i];
+                ps[i].tile_row1 = g->bounds[i + 1];
+                if (ps[i].tile_row1 <= ps[i].tile_row0) continue; // more devices than tile rows (never with the exchange on)
+                const size_t row0 = (size_t)g->bounds[i] * 16u;
+                void *dst = nullptr; // nullptr: the renderer's own target (then copied)
+                if (host_out) {
+                    r->host_out = (char *)host_out + row0 * pitch;
+                    r->readback_bands = 1;
+                } else if (g->peer_ok[i]) {
+                    dst = (char *)frame + row0 * pitch;
+                }
+                const int rc = phase == 0 ? frame_prepare(r, &ps[i], dst) : (halves ? frame_launch_half(r, phase - 1) : frame_launch(r));
+                if (rc) {
+                    for (vb_renderer *q : g->subs) q->host_out = nullptr;
+                    g->err = r->err;
+                    return rc;
+                }
             }
         }
         result = VB_OK;
@@ -1605,7 +1658,8 @@ static int group_render(vb_group *g, const vb_params *p, void *out_device, void 
         }
         if (!redo || result != VB_OK) break;
         if (attempt >= 8u) {
-            g->err = "bump overflow persisted in an exchanged frame";
+            g->err = "bump overflow persisted in an exchanged frame; failed bits per renderer:";
+            for (vb_renderer *q : g->subs) g->err += " 0x" + std::to_string(q->h_bump->failed);
             return VB_E_BUMP_OVERFLOW;
         }
     }
