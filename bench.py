@@ -367,9 +367,31 @@ def main():
                         "outbox in peer-mapped memory and pulled by their owners, partial path boxes are min/max-combined; the ranks "
                         "synchronise through epoch flags in each other's arenas (no host, no NCCL on the data path)"}
 
-        def render_once():  # noqa: F811  (from here on every frame is an exchanged one)
+        # which mode is faster depends on N and on the scene (the exchange moves every line once more; it pays when the
+        # replicated flatten is a large part of a rank's frame: many GPUs, curve-heavy scenes): calibrate, keep the better one
+        cal = []
+        for _ in range(8):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
             render_collective()
-            return st
+            cal.append(float(r.lib.vb_last_frame_ms(r.handle)))
+        tcal = torch.tensor([sum(cal[2:]) / len(cal[2:])], dtype=torch.float64, device=dev)
+        dist.all_reduce(tcal, op=dist.ReduceOp.MAX)
+        xinfo["calibration_ms"] = float(tcal.item())
+        xinfo["replicated_ms"] = replicated["ms_per_step"]
+        if float(tcal.item()) > replicated["ms_per_step"]:
+            exchange_on = False
+            assert r.lib.vb_exchange_enable(r.handle, 0) == 0
+            bounds = list(replicated["tile_row_bounds"])
+            xinfo["chosen"] = "replicated"
+        else:
+            xinfo["chosen"] = "exchange"
+
+            def render_once():  # noqa: F811  (from here on every frame is an exchanged one)
+                render_collective()
+                return st
 
     for _ in range(args.warmup):
         st = render_once()

@@ -61,28 +61,35 @@ __device__ __forceinline__ uint32_t x_dest_mask(const XPeers &X, float y0, float
     return m;
 }
 
-// counts[d] += lines of mine that destination d needs
+// counts[d] += lines of mine that destination d needs (ballots per destination: one shared-memory atomic per warp and stripe)
 __global__ void __launch_bounds__(256)
 k_route_count(XPeers X, const VbBump *__restrict__ bump, uint32_t lines_size, const VbLineSoup *__restrict__ lines, uint32_t *counts) {
     __shared__ uint32_t sh[XG_MAX];
     if (threadIdx.x < XG_MAX) sh[threadIdx.x] = 0u;
     __syncthreads();
     const uint32_t n = min(bump->lines, lines_size);
-    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
-        const uint2 *lp = reinterpret_cast<const uint2 *>(lines + i);
-        const uint2 a = __ldg(lp + 1), b = __ldg(lp + 2);
-        uint32_t m = x_dest_mask(X, __uint_as_float(a.y), __uint_as_float(b.y));
-        while (m) {
-            const uint32_t d = (uint32_t)__ffs((int)m) - 1u;
-            m &= m - 1u;
-            atomicAdd(&sh[d], 1u);
+    const uint32_t lane = vb_lane();
+    uint32_t acc = 0u; // lane d accumulates destination d's count of this warp
+    for (uint32_t base = blockIdx.x * 256u; base < n; base += gridDim.x * 256u) {
+        const uint32_t i = base + threadIdx.x;
+        uint32_t m = 0u;
+        if (i < n) {
+            const uint2 *lp = reinterpret_cast<const uint2 *>(lines + i);
+            const uint2 a = __ldg(lp + 1), b = __ldg(lp + 2);
+            m = x_dest_mask(X, __uint_as_float(a.y), __uint_as_float(b.y));
+        }
+        for (uint32_t d = 0; d < X.world; d++) {
+            const uint32_t c = (uint32_t)__popc(__ballot_sync(VB_FULL, (m >> d) & 1u));
+            if (lane == d) acc += c;
         }
     }
+    if (lane < X.world && acc != 0u) atomicAdd(&sh[lane], acc);
     __syncthreads();
     if (threadIdx.x < X.world && sh[threadIdx.x] != 0u) atomicAdd(&counts[threadIdx.x], sh[threadIdx.x]);
 }
 
-// outbox[off[d] + ...] = my lines for destination d (off = exclusive prefix of counts)
+// outbox[off[d] + ...] = my lines for destination d (off = exclusive prefix of counts). Slots: rank inside the warp from a
+// ballot, warp base from one shared-memory atomic per (warp, stripe), block base from one global atomic per (block, stripe).
 __global__ void __launch_bounds__(256)
 k_route_scatter(XPeers X, VbBump *bump, uint32_t lines_size, const VbLineSoup *__restrict__ lines, const uint32_t *__restrict__ counts,
                 uint32_t *cursors) {
@@ -95,21 +102,27 @@ k_route_scatter(XPeers X, VbBump *bump, uint32_t lines_size, const VbLineSoup *_
         if (acc > X.lines_cap && blockIdx.x == 0u) atomicOr(&bump->failed, VB_STAGE_EXCHANGE);
     }
     const uint32_t n = min(bump->lines, lines_size);
+    const uint32_t lane = vb_lane();
     for (uint32_t base = blockIdx.x * 256u; base < n; base += gridDim.x * 256u) {
         if (threadIdx.x < XG_MAX) sh_cnt[threadIdx.x] = 0u;
         __syncthreads();
         const uint32_t i = base + threadIdx.x;
-        uint32_t m = 0u, slot[XG_MAX];
+        uint32_t m = 0u;
         uint2 w0 = make_uint2(0u, 0u), w1 = w0, w2 = w0;
         if (i < n) {
             const uint2 *lp = reinterpret_cast<const uint2 *>(lines + i);
             w0 = __ldg(lp); w1 = __ldg(lp + 1); w2 = __ldg(lp + 2);
             m = x_dest_mask(X, __uint_as_float(w1.y), __uint_as_float(w2.y));
-            for (uint32_t mm = m; mm;) {
-                const uint32_t d = (uint32_t)__ffs((int)mm) - 1u;
-                mm &= mm - 1u;
-                slot[d] = atomicAdd(&sh_cnt[d], 1u);
-            }
+        }
+        // pass 1: slot of each (line, destination) inside the block
+        uint32_t slot_lo = 0u, slot_hi = 0u; // 8 destinations x 8 bits: my slot inside the block for each of them (< 256)
+        for (uint32_t d = 0; d < X.world; d++) {
+            const uint32_t b = __ballot_sync(VB_FULL, (m >> d) & 1u);
+            uint32_t wbase = 0u;
+            if (b != 0u && lane == (uint32_t)(__ffs((int)b) - 1)) wbase = atomicAdd(&sh_cnt[d], (uint32_t)__popc(b));
+            wbase = __shfl_sync(VB_FULL, wbase, b != 0u ? __ffs((int)b) - 1 : 0);
+            const uint32_t sl = (wbase + (uint32_t)__popc(b & ((1u << lane) - 1u))) & 0xffu;
+            if (d < 4u) slot_lo |= sl << (8u * d); else slot_hi |= sl << (8u * (d - 4u));
         }
         __syncthreads();
         if (threadIdx.x < X.world) sh_base[threadIdx.x] = sh_cnt[threadIdx.x] ? atomicAdd(&cursors[threadIdx.x], sh_cnt[threadIdx.x]) : 0u;
@@ -117,7 +130,8 @@ k_route_scatter(XPeers X, VbBump *bump, uint32_t lines_size, const VbLineSoup *_
         for (uint32_t mm = m; mm;) {
             const uint32_t d = (uint32_t)__ffs((int)mm) - 1u;
             mm &= mm - 1u;
-            const uint32_t o = sh_off[d] + sh_base[d] + slot[d];
+            const uint32_t sl = d < 4u ? (slot_lo >> (8u * d)) & 0xffu : (slot_hi >> (8u * (d - 4u))) & 0xffu;
+            const uint32_t o = sh_off[d] + sh_base[d] + sl;
             if (o < X.lines_cap) {
                 uint2 *dst = reinterpret_cast<uint2 *>(outbox + o);
                 dst[0] = w0; dst[1] = w1; dst[2] = w2;
@@ -208,15 +222,17 @@ __global__ void __launch_bounds__(256) k_lines_pull(XPeers X, VbBump *bump, uint
     }
     __syncthreads();
     const uint32_t total = min(sh_pre[X.world], lines_size);
-    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < total; i += gridDim.x * 256u) {
+    // a line is three 8-byte words: consecutive threads move consecutive words, so every warp reads and writes 256
+    // contiguous bytes whether the source is local or behind NVLink
+    uint2 *dflat = reinterpret_cast<uint2 *>(lines);
+    for (uint64_t j = (uint64_t)blockIdx.x * 256u + threadIdx.x; j < (uint64_t)total * 3u; j += (uint64_t)gridDim.x * 256u) {
+        const uint32_t i = (uint32_t)(j / 3u), part = (uint32_t)(j - (uint64_t)i * 3u);
         uint32_t s = 0u;
         for (uint32_t q = 1; q < X.world; q++)
             if (i >= sh_pre[q]) s = q;
-        const VbLineSoup *src = reinterpret_cast<const VbLineSoup *>(x_half(X, s, epoch) + x_lines_off(X.n_paths)) + sh_src0[s] + (i - sh_pre[s]);
-        const uint2 *sp = reinterpret_cast<const uint2 *>(src);
-        const uint2 a = sp[0], b = sp[1], c = sp[2];
-        uint2 *dp = reinterpret_cast<uint2 *>(lines + i);
-        dp[0] = a; dp[1] = b; dp[2] = c;
+        const uint2 *src = reinterpret_cast<const uint2 *>(reinterpret_cast<const VbLineSoup *>(x_half(X, s, epoch) + x_lines_off(X.n_paths)) + sh_src0[s] +
+                                                           (i - sh_pre[s]));
+        dflat[j] = src[part];
     }
 }
 

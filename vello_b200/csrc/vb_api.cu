@@ -1595,23 +1595,30 @@ static int group_render(vb_group *g, const vb_params *p, void *out_device, void 
         if (g->exchange)
             for (vb_renderer *r : g->subs) vb_exchange_set_bounds(r, g->bounds.data());
         const bool halves = g->exchange && g->shared_device;
-        for (int phase = 0; phase < (halves ? 3 : 2); phase++) { // 0: configs and arenas of every renderer, 1 (and 2): the launches
+        // phases: 0 = configs and arenas of every renderer, 1 (and 2) = the launches, last = the read-backs of a host
+        // destination. A copy into pageable host memory blocks the host until it is done, so it must not be issued before
+        // every renderer's frame has been launched (with the exchange on, a frame waits for its peers).
+        const int n_launch = halves ? 2 : 1;
+        for (int phase = 0; phase < 1 + n_launch + (host_out ? 1 : 0); phase++) {
             for (size_t i = 0; i < n; i++) {
                 vb_renderer *r = g->subs[i];
                 ps[i].tile_row0 = g->bounds[i];
                 ps[i].tile_row1 = g->bounds[i + 1];
                 if (ps[i].tile_row1 <= ps[i].tile_row0) continue; // more devices than tile rows (never with the exchange on)
                 const size_t row0 = (size_t)g->bounds[i] * 16u;
-                void *dst = nullptr; // nullptr: the renderer's own target (then copied)
-                if (host_out) {
-                    r->host_out = (char *)host_out + row0 * pitch;
-                    r->readback_bands = 1;
-                } else if (g->peer_ok[i]) {
-                    dst = (char *)frame + row0 * pitch;
+                // device destination: straight into the frame on devices[0] when peer-mapped; otherwise (and for a host
+                // destination) the renderer's own target
+                void *dst = (!host_out && g->peer_ok[i]) ? (char *)frame + row0 * pitch : nullptr;
+                int rc = VB_OK;
+                if (phase == 0) rc = frame_prepare(r, &ps[i], dst);
+                else if (phase <= n_launch) rc = halves ? frame_launch_half(r, phase - 1) : frame_launch(r);
+                else {
+                    const size_t h1 = std::min<size_t>((size_t)g->bounds[i + 1] * 16u, p->height);
+                    cudaSetDevice(r->device);
+                    if (h1 > row0 && cudaMemcpyAsync((char *)host_out + row0 * pitch, r->out_dev, (h1 - row0) * pitch, cudaMemcpyDeviceToHost, r->stream) != cudaSuccess)
+                        rc = VB_E_CUDA;
                 }
-                const int rc = phase == 0 ? frame_prepare(r, &ps[i], dst) : (halves ? frame_launch_half(r, phase - 1) : frame_launch(r));
                 if (rc) {
-                    for (vb_renderer *q : g->subs) q->host_out = nullptr;
                     g->err = r->err;
                     return rc;
                 }
@@ -1635,13 +1642,16 @@ static int group_render(vb_group *g, const vb_params *p, void *out_device, void 
                     rc = VB_OK;
                 } else {
                     rc = vb_render_resident(r, &ps[i], dst, stats ? &stats[i] : nullptr); // grow and re-run (first frames)
+                    if (rc == VB_OK && host_out) { // the stripe copied above was the failed attempt's
+                        const size_t h1 = std::min<size_t>((size_t)g->bounds[i + 1] * 16u, p->height);
+                        cudaSetDevice(r->device);
+                        if (h1 > row0 && (cudaMemcpyAsync((char *)host_out + row0 * pitch, r->out_dev, (h1 - row0) * pitch, cudaMemcpyDeviceToHost, r->stream) != cudaSuccess ||
+                                          cudaStreamSynchronize(r->stream) != cudaSuccess))
+                            rc = VB_E_CUDA;
+                    }
                 }
             }
             g->ms[i] = vb_last_frame_ms(r);
-            if (rc == VB_OK && host_out) {
-                cudaSetDevice(r->device);
-                if (cudaStreamSynchronize(r->copy_stream) != cudaSuccess) rc = VB_E_CUDA;
-            }
             if (rc == VB_OK && !host_out && !g->peer_ok[i]) {
                 // no peer mapping between these two devices: stage through the renderer's own target
                 const size_t h0 = row0, h1 = std::min<size_t>((size_t)g->bounds[i + 1] * 16u, p->height);
@@ -1650,7 +1660,6 @@ static int group_render(vb_group *g, const vb_params *p, void *out_device, void 
                                 cudaStreamSynchronize(r->stream) != cudaSuccess))
                     rc = VB_E_CUDA;
             }
-            r->host_out = nullptr;
             if (rc && result == VB_OK) {
                 result = rc;
                 g->err = r->err;
