@@ -1599,7 +1599,8 @@ static int group_render(vb_group *g, const vb_params *p, void *out_device, void 
         // destination. A copy into pageable host memory blocks the host until it is done, so it must not be issued before
         // every renderer's frame has been launched (with the exchange on, a frame waits for its peers).
         const int n_launch = halves ? 2 : 1;
-        for (int phase = 0; phase < 1 + n_launch + (host_out ? 1 : 0); phase++) {
+        const bool late_copy = host_out != nullptr && g->exchange; // without the exchange every frame queues its own read-back
+        for (int phase = 0; phase < 1 + n_launch + (late_copy ? 1 : 0); phase++) {
             for (size_t i = 0; i < n; i++) {
                 vb_renderer *r = g->subs[i];
                 ps[i].tile_row0 = g->bounds[i];
@@ -1609,6 +1610,10 @@ static int group_render(vb_group *g, const vb_params *p, void *out_device, void 
                 // device destination: straight into the frame on devices[0] when peer-mapped; otherwise (and for a host
                 // destination) the renderer's own target
                 void *dst = (!host_out && g->peer_ok[i]) ? (char *)frame + row0 * pitch : nullptr;
+                if (host_out && !late_copy) { // the frame copies its stripe to the host itself, on the renderer's copy stream
+                    r->host_out = (char *)host_out + row0 * pitch;
+                    r->readback_bands = 1;
+                }
                 int rc = VB_OK;
                 if (phase == 0) rc = frame_prepare(r, &ps[i], dst);
                 else if (phase <= n_launch) rc = halves ? frame_launch_half(r, phase - 1) : frame_launch(r);
@@ -1619,6 +1624,7 @@ static int group_render(vb_group *g, const vb_params *p, void *out_device, void 
                         rc = VB_E_CUDA;
                 }
                 if (rc) {
+                    for (vb_renderer *q : g->subs) q->host_out = nullptr;
                     g->err = r->err;
                     return rc;
                 }
@@ -1641,17 +1647,16 @@ static int group_render(vb_group *g, const vb_params *p, void *out_device, void 
                     redo = true;
                     rc = VB_OK;
                 } else {
-                    rc = vb_render_resident(r, &ps[i], dst, stats ? &stats[i] : nullptr); // grow and re-run (first frames)
-                    if (rc == VB_OK && host_out) { // the stripe copied above was the failed attempt's
-                        const size_t h1 = std::min<size_t>((size_t)g->bounds[i + 1] * 16u, p->height);
-                        cudaSetDevice(r->device);
-                        if (h1 > row0 && (cudaMemcpyAsync((char *)host_out + row0 * pitch, r->out_dev, (h1 - row0) * pitch, cudaMemcpyDeviceToHost, r->stream) != cudaSuccess ||
-                                          cudaStreamSynchronize(r->stream) != cudaSuccess))
-                            rc = VB_E_CUDA;
-                    }
+                    // grow and re-run (first frames); with a host destination the re-run queues its read-back again
+                    rc = vb_render_resident(r, &ps[i], dst, stats ? &stats[i] : nullptr);
                 }
             }
             g->ms[i] = vb_last_frame_ms(r);
+            if (rc == VB_OK && host_out && !late_copy) {
+                cudaSetDevice(r->device);
+                if (cudaStreamSynchronize(r->copy_stream) != cudaSuccess) rc = VB_E_CUDA;
+            }
+            r->host_out = nullptr;
             if (rc == VB_OK && !host_out && !g->peer_ok[i]) {
                 // no peer mapping between these two devices: stage through the renderer's own target
                 const size_t h0 = row0, h1 = std::min<size_t>((size_t)g->bounds[i + 1] * 16u, p->height);
