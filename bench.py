@@ -252,11 +252,19 @@ def main():
             assert r.lib.vb_ipc_export(r.handle, frame_ptr, handle) == 0
         ht = torch.tensor(list(handle.raw), dtype=torch.uint8, device=dev)
         dist.broadcast(ht, src=0)
+        ok = 1.0
         if rank != 0:
             hb = C.create_string_buffer(bytes(ht.cpu().tolist()), 64)
             rc = r.lib.vb_ipc_open(r.handle, hb, C.byref(frame_ptr))
-            assert rc == 0, f"vb_ipc_open failed on rank {rank}: {r.lib.vb_last_error(r.handle).decode()}"
-    frame_base = int(frame_ptr.value)
+            if rc != 0:
+                print(f"rank {rank}: vb_ipc_open failed ({r.lib.vb_last_error(r.handle).decode()}): stripes stay on their GPUs", file=sys.stderr)
+                ok = 0.0
+        okt = torch.tensor([ok], device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        p2p_frame = okt.item() > 0.0
+    else:
+        p2p_frame = True
+    frame_base = int(frame_ptr.value or 0)
 
     bounds = even_tile_bounds(world, H)
 
@@ -264,6 +272,8 @@ def main():
         return (bounds[rank], bounds[rank + 1]) if world > 1 else (0, 0)
 
     def my_out():
+        if world > 1 and not p2p_frame:
+            return 0  # no peer mapping of rank 0's frame on this box: every rank keeps its stripe (the renderer's own target)
         return frame_base + (bounds[rank] * 16 * args.size * 4 if world > 1 else 0)
 
     def render_once():
@@ -324,24 +334,35 @@ def main():
         dist.all_reduce(sm0, op=dist.ReduceOp.MAX)
         replicated = {"value": args.steps / (float(sm0.sum().item()) / 1000.0), "unit": "frames/s", "ms_per_step": float(sm0.sum().item()) / args.steps,
                       "tile_row_bounds": list(bounds), "note": "every rank flattens the whole scene (culled to its stripe); no exchange"}
-        # arenas, CUDA IPC handles all-gathered, peers mapped
+        # arenas, CUDA IPC handles all-gathered, peers mapped (any failure on any rank: everybody stays in replicated mode)
         arena, nbytes = vp(), C.c_size_t(0)
-        assert r.lib.vb_exchange_configure(r.handle, rank, world, C.byref(arena), C.byref(nbytes)) == 0
+        xok = 1.0 if r.lib.vb_exchange_configure(r.handle, rank, world, C.byref(arena), C.byref(nbytes)) == 0 else 0.0
         hb = C.create_string_buffer(64)
-        assert r.lib.vb_ipc_export(r.handle, arena, hb) == 0
+        if xok and r.lib.vb_ipc_export(r.handle, arena, hb) != 0:
+            xok = 0.0
         mine = torch.tensor(list(hb.raw), dtype=torch.uint8, device=dev)
         allh = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(allh, mine)
+        okt = torch.tensor([xok], device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
         peer_ptrs = []
-        for k in range(world):
-            if k == rank:
-                continue
-            hk = C.create_string_buffer(bytes(allh[k].cpu().tolist()), 64)
-            pk = vp()
-            rc = r.lib.vb_ipc_open(r.handle, hk, C.byref(pk))
-            assert rc == 0, f"vb_ipc_open(exchange arena of rank {k}) failed on rank {rank}: {r.lib.vb_last_error(r.handle).decode()}"
-            assert r.lib.vb_exchange_attach(r.handle, k, pk) == 0
-            peer_ptrs.append(pk)
+        if okt.item() > 0.0:
+            for k in range(world):
+                if k == rank:
+                    continue
+                hk = C.create_string_buffer(bytes(allh[k].cpu().tolist()), 64)
+                pk = vp()
+                if r.lib.vb_ipc_open(r.handle, hk, C.byref(pk)) != 0 or r.lib.vb_exchange_attach(r.handle, k, pk) != 0:
+                    print(f"rank {rank}: could not map the exchange arena of rank {k}: {r.lib.vb_last_error(r.handle).decode()}", file=sys.stderr)
+                    xok = 0.0
+                    break
+                peer_ptrs.append(pk)
+            okt = torch.tensor([xok], device=dev)
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        exchange_on = okt.item() > 0.0
+        if not exchange_on:
+            xinfo = {"chosen": "replicated", "why": "exchange arenas could not be set up on this box"}
+    if exchange_on:
 
         def set_bounds():
             arr = (C.c_uint32 * (world + 1))(*bounds)
@@ -458,7 +479,7 @@ def main():
 
     # ---- the assembled frame: rank 0 renders the whole frame alone and compares (stripes over NVLink == one GPU)
     stripes_parity = None
-    if world > 1:
+    if world > 1 and p2p_frame:
         barrier()
         if rank == 0:
             asm = np.zeros((H, args.size, 4), dtype=np.uint8)

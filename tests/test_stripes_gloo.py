@@ -71,3 +71,35 @@ def test_stripes_over_gloo(tmp_path, world):
     packed = resolve(scenes.paris_like(400, h, seed=5).encoding)
     full = Oracle().render(packed, w, h, BLACK.premul_rgba8_u32(), aa)
     assert np.array_equal(np.load(out), full)
+
+
+def test_tile_row_bounds_and_rebalance():
+    """The cost-balanced tile-row split (vello_b200.stripes.rebalance == group_rebalance in vb_api.cu): boundaries stay
+    monotone with at least one row per stripe, move towards the slower stripes, stop inside the tolerance, and converge on a
+    synthetic cost profile."""
+    from vello_b200.stripes import even_tile_bounds, n_tile_rows, rebalance
+    for h in (16, 100, 1080, 4096, 16384):
+        for w in (1, 2, 3, 8):
+            b = even_tile_bounds(w, h)
+            assert b[0] == 0 and b[-1] == n_tile_rows(h) and all(x <= y for x, y in zip(b, b[1:]))
+    b = even_tile_bounds(8, 4096)
+    assert rebalance(b, [1.0] * 8) == b                       # balanced: unchanged
+    assert rebalance(b, [1.0, 1.02, 0.99, 1.0, 1.01, 1.0, 0.98, 1.0]) == b   # inside the 6 % tolerance
+    assert rebalance(b, [0.0] * 8) == b                       # no measurement yet
+    nb = rebalance(b, [2.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0])
+    assert nb[1] < b[1] and nb[0] == 0 and nb[-1] == b[-1] and all(x < y for x, y in zip(nb, nb[1:]))
+    # a cost density that falls linearly over the rows: iterate with the "true" cost of each stripe
+    import numpy as np
+    dens = np.linspace(3.0, 1.0, 256)
+    cum = np.concatenate([[0.0], np.cumsum(dens)])
+    b = even_tile_bounds(8, 4096)
+    for _ in range(40):
+        ms = [float(cum[b[i + 1]] - cum[b[i]]) for i in range(8)]
+        nb = rebalance(b, ms)
+        if nb == b:
+            break
+        b = nb
+    ms = [float(cum[b[i + 1]] - cum[b[i]]) for i in range(8)]
+    assert (max(ms) - min(ms)) / (sum(ms) / 8) < 0.12
+    # tiny frames: more stripes than rows cannot be balanced and are returned unchanged
+    assert rebalance([0, 1, 1, 2], [1.0, 0.0, 1.0]) == [0, 1, 1, 2]

@@ -27,5 +27,23 @@ for s, w, h in cases:
 packed = resolve(scenes.paris_like(300, 512, seed=1).encoding)
 ref = o.render(packed, 512, 512, BLACK.premul_rgba8_u32(), 2)
 assert np.array_equal(r.render_to_texture(packed, RenderParams(BLACK, 512, 512, 2), bin_rows=(1, 2)), ref[256:512])
+# one frame on three renderers with the sharded flatten + peer-memory exchange (k_exchange.cu), device frame and host destination
+from vello_b200.renderer import RendererGroup  # noqa: E402
+g = RendererGroup([0, 0, 0])
+g.set_exchange(True)
+assert np.array_equal(g.render_to_texture(packed, RenderParams(BLACK, 512, 512, 2)), ref)
+g.upload(packed)
+for _ in range(2):
+    g.render_resident(RenderParams(BLACK, 512, 512, 2))
+    assert np.array_equal(g.frame_to_host(RenderParams(BLACK, 512, 512, 2)), ref)
+g.close()
+# Resolver::resolve on the device (k_resolve.cu)
+from vello_b200.scene_native import NativeScene  # noqa: E402
+from vello_b200.encoding import FILL_NON_ZERO, Gradient  # noqa: E402
+from vello_b200.shapes import Affine, Rect  # noqa: E402
+nat = NativeScene()
+nat.fill(FILL_NON_ZERO, Affine.IDENTITY, Gradient.linear((0, 0), (200, 100), [(0.0, BLACK), (1.0, BLACK.with_alpha(0.3))]), None, Rect(5, 5, 190, 120))
+nat.upload_device(r)
+r.render_resident(RenderParams(BLACK, 200, 128, 2))
 print("sanitize_frame: all frames match the oracle; launches of the last frame:", r.last_stats.as_dict()["kernel_launches"])
 r.close()
