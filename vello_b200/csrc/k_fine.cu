@@ -6,7 +6,7 @@
 // (MSAA: integer sample counts -> exact; area: float sums in slice order).
 //
 // B200 design (v3): PERSISTENT WARPS, ONE WARP PER TILE, TMA-STAGED COMMAND WINDOWS.
-//  * The grid is sized to the machine (2 CTAs of up to 16 warps per SM) and every warp pulls tile indices from a
+//  * The grid is sized to the machine (2 CTAs of FI_MAX_WARPS warps per SM) and every warp pulls tile indices from a
 //    global queue (one atomic per tile, issued two tiles ahead), so a long tile no longer idles the other warp
 //    slots of its CTA (v2: 32,768 two-warp CTAs, 36 % achieved occupancy against 50 % theoretical).
 //  * The half-plane mask LUT (8 KB for MSAA16) is copied ONCE per CTA into shared memory with one bulk copy
@@ -23,6 +23,10 @@
 //    pixels through a divergent branch -- and untouched pixels are decided 4 at a time with SWAR byte compares on
 //    the winding words. The integer arithmetic per touched pixel is the WGSL's, word for word.
 //  * Each tile starts at its occlusion start (the last opaque full-tile cover, noted by coarse).
+//  * The lane's 8 pixels (rgba[8], area[8]: 40 registers) are only ever indexed by compile-time constants, so they live in
+//    registers for the whole tile; the rarely used brushes that loop over them without unrolling work on a copy. (Until
+//    round 2 build k a dynamically indexed loop kept them in local memory: 132 M L2 sectors of local traffic per frame,
+//    ncu `memory_l2_theoretical_sectors_local`, against 6.5 M sectors of global traffic -- the top stall of the kernel.)
 // Conventions fixed where WGSL leaves latitude: see oracle/vbo_fine.c.
 // Algorithmic bytes: 4 B/pixel stored + 4 B per PTCL word + 24 B per segment referenced.
 #include <cuda_fp16.h>
@@ -31,7 +35,8 @@
 #include "vb_device.cuh"
 
 #ifndef FI_MAX_WARPS
-#define FI_MAX_WARPS 12 // warps (= tiles in flight) per CTA; the launcher picks 2..FI_MAX_WARPS by frame size
+#define FI_MAX_WARPS 10 // warps (= tiles in flight) per CTA; the launcher picks 2..FI_MAX_WARPS by frame size. 2 CTAs x 10 warps leave
+                        // 102 registers per thread: the 8 pixels of a lane (32 colour + 8 coverage registers) stay in registers
 #endif
 #ifndef FI_MINB
 #define FI_MINB 2
@@ -458,8 +463,8 @@ __device__ void fill_path_ms(const FineArgs &A, WarpMs<AA> &S, const uint32_t *_
             }
         }
         uint32_t packed_w[2];
-        packed_w[0] = pw[h * 2u];
-        packed_w[1] = pw[h * 2u + 1u];
+        packed_w[0] = h == 1u ? pw[2] : pw[0]; // selects, not pw[h * 2]: a dynamically indexed array would live in local memory
+        packed_w[1] = h == 1u ? pw[3] : pw[1];
         if (h == 1u) { packed_w[0] += pfx[0]; packed_w[0] += pfx[1]; packed_w[1] += pfx[0]; packed_w[1] += pfx[1]; packed_w[1] += pfx[2]; }
         else { packed_w[1] += pfx[0]; }
         uint32_t wind_y;
@@ -474,8 +479,12 @@ __device__ void fill_path_ms(const FineArgs &A, WarpMs<AA> &S, const uint32_t *_
                 w += (w - 0x8080u) << 16;
                 py[k] = w;
             }
-            wind_y = (py[ly >> 2] >> ((ly & 3u) << 3)) - 0x80u;
-            for (uint32_t k = 0; k < (ly >> 2); k++) wind_y += (py[k] >> 24) - 0x80u;
+            const uint32_t yq = ly >> 2;
+            const uint32_t py_sel = yq == 0u ? py[0] : (yq == 1u ? py[1] : (yq == 2u ? py[2] : py[3]));
+            wind_y = (py_sel >> ((ly & 3u) << 3)) - 0x80u;
+            if (yq > 0u) wind_y += (py[0] >> 24) - 0x80u;
+            if (yq > 1u) wind_y += (py[1] >> 24) - 0x80u;
+            if (yq > 2u) wind_y += (py[2] >> 24) - 0x80u;
         }
         // t = ((packed_w >> 8i) + wind_y) & 0xff for my 8 pixels (fine.wgsl:447); expected_zero = t - backdrop
         const uint32_t wy = (wind_y & 0xffu) * 0x1010101u;
@@ -877,12 +886,18 @@ k_fine(VbConfig cfg, FineArgs A) {
         // (Do not turn this into a register array updated through `d == clip_depth ? new : old` selects without
         // initialising it: the optimiser folds selects on undefined values and clobbers live levels.)
         uint32_t blend_stack[VB_BLEND_STACK_SPLIT][PX];
+        rgba_t t_rgba[PX]; // see PIX_TO_LOCAL
+        float t_area[PX];
         uint32_t clip_depth = 0u;
         uint32_t cmd_ix = start_cur;
         uint32_t win_base = start_cur & ~3u;
         mbar_wait(&io.mbar[buf], (phase >> buf) & 1u);
         phase ^= 1u << buf;
 #define PXX(i) ((((i) < 4) ? xyx0 : xyx1) + (float)((i) & 3))
+        // The rarely used brushes loop over the lane's pixels WITHOUT unrolling (code size); they work on a copy in local
+        // memory so that rgba[] / area[] themselves are only ever indexed by constants and live in registers.
+#define PIX_TO_LOCAL() _Pragma("unroll") for (int q_ = 0; q_ < PX; q_++) { t_rgba[q_] = rgba[q_]; t_area[q_] = area[q_]; }
+#define PIX_FROM_LOCAL() _Pragma("unroll") for (int q_ = 0; q_ < PX; q_++) rgba[q_] = t_rgba[q_]
         for (;;) {
             // the command word and its (up to 3) operands come from the staged window; when the pointer leaves the
             // window (a list longer than the window, CMD_JUMP into another chunk) the window is staged again there
@@ -994,7 +1009,8 @@ k_fine(VbConfig cfg, FineArgs A) {
                 const float width = bw + fminf(delta, 0.0f);
                 const float height = bh - fmaxf(delta, 0.0f);
                 const float scale = 0.5f * erf7(inv_std_dev * 0.5f * (fmaxf(width, height) - 0.5f * bradius));
-    #pragma unroll 1
+                PIX_TO_LOCAL();
+#pragma unroll 1
                 for (int i = 0; i < PX; i++) {
                     const float px = PXX(i), py = xyy;
                     const float x = (m0 * px + m2 * py) + tx;
@@ -1007,8 +1023,9 @@ k_fine(VbConfig cfg, FineArgs A) {
                     const float d_neg = fminf(fmaxf(x0, y0), 0.0f);
                     const float d = d_pos + d_neg - r1;
                     const float alpha = scale * (erf7(inv_std_dev * (min_edge + d)) - erf7(inv_std_dev * d));
-                    rgba[i] = over(rgba[i], rg_scale(rg_scale(blur_rgba, alpha), area[i]));
+                    t_rgba[i] = over(t_rgba[i], rg_scale(rg_scale(blur_rgba, alpha), t_area[i]));
                 }
+                PIX_FROM_LOCAL();
                 cmd_ix += 3u;
                 break;
             }
@@ -1041,7 +1058,8 @@ k_fine(VbConfig cfg, FineArgs A) {
                 const float r1_recip = is_circular ? 0.0f : 1.0f / radius;
                 const float less_scale = (is_swapped || (1.0f - focal_x) < 0.0f) ? -1.0f : 1.0f;
                 const float t_sign = vb_signf(1.0f - focal_x);
-    #pragma unroll 1
+                PIX_TO_LOCAL();
+#pragma unroll 1
                 for (int i = 0; i < PX; i++) {
                     const float px = PXX(i), py = xyy;
                     const float x = (m0 * px + m2 * py) + tx;
@@ -1067,9 +1085,10 @@ k_fine(VbConfig cfg, FineArgs A) {
                         tt = extend_mode_normalized(focal_x + t_sign * tt, ext);
                         if (is_swapped) tt = 1.0f - tt;
                         const int32_t rx = vb_f2i_sat(rintf(tt * (float)(GRADIENT_WIDTH - 1)));
-                        rgba[i] = over(rgba[i], rg_scale(ramp_load(A, cfg, rx, index), area[i]));
+                        t_rgba[i] = over(t_rgba[i], rg_scale(ramp_load(A, cfg, rx, index), t_area[i]));
                     }
                 }
+                PIX_FROM_LOCAL();
                 cmd_ix += 3u;
                 break;
             }
@@ -1081,7 +1100,8 @@ k_fine(VbConfig cfg, FineArgs A) {
                 const float tx = __uint_as_float(info[io + 4]), ty = __uint_as_float(info[io + 5]);
                 const float t0 = __uint_as_float(info[io + 6]), t1 = __uint_as_float(info[io + 7]);
                 const float scale = 1.0f / (t1 - t0);
-    #pragma unroll 1
+                PIX_TO_LOCAL();
+#pragma unroll 1
                 for (int i = 0; i < PX; i++) {
                     const float px = PXX(i), py = xyy;
                     const float x = (m0 * px + m2 * py) + tx;
@@ -1099,8 +1119,9 @@ k_fine(VbConfig cfg, FineArgs A) {
                     phi = (phi - t0) * scale;
                     const float tt = extend_mode_normalized(phi, ext);
                     const int32_t rx = vb_f2i_sat(rintf(tt * (float)(GRADIENT_WIDTH - 1)));
-                    rgba[i] = over(rgba[i], rg_scale(ramp_load(A, cfg, rx, index), area[i]));
+                    t_rgba[i] = over(t_rgba[i], rg_scale(ramp_load(A, cfg, rx, index), t_area[i]));
                 }
+                PIX_FROM_LOCAL();
                 cmd_ix += 3u;
                 break;
             }
@@ -1116,9 +1137,10 @@ k_fine(VbConfig cfg, FineArgs A) {
                 const float ox = (float)(xy >> 16), oy = (float)(xy & 0xffffu);
                 const float ew = (float)(wh >> 16), eh = (float)(wh & 0xffffu);
                 const float mx = ox + ew - 1.0f, my = oy + eh - 1.0f;
-    #pragma unroll 1
+                PIX_TO_LOCAL();
+#pragma unroll 1
                 for (int i = 0; i < PX; i++) {
-                    if (area[i] == 0.0f) continue;
+                    if (t_area[i] == 0.0f) continue;
                     const float px = PXX(i) + 0.5f, py = xyy + 0.5f;
                     float u = (m0 * px + m2 * py) + tx;
                     float v = (m1 * px + m3 * py) + ty;
@@ -1144,9 +1166,10 @@ k_fine(VbConfig cfg, FineArgs A) {
                         const rgba_t cd = RG(mixf(c.r, d.r, fv), mixf(c.g, d.g, fv), mixf(c.b, d.b, fv), mixf(c.a, d.a, fv));
                         fg = RG(mixf(ab.r, cd.r, fu), mixf(ab.g, cd.g, fu), mixf(ab.b, cd.b, fu), mixf(ab.a, cd.a, fu));
                     }
-                    const rgba_t fg_i = pixel_format(rg_scale(rg_scale(fg, area[i]), alpha), format);
-                    rgba[i] = over(rgba[i], fg_i);
+                    const rgba_t fg_i = pixel_format(rg_scale(rg_scale(fg, t_area[i]), alpha), format);
+                    t_rgba[i] = over(t_rgba[i], fg_i);
                 }
+                PIX_FROM_LOCAL();
                 cmd_ix += 2u;
                 break;
             }
@@ -1156,6 +1179,8 @@ k_fine(VbConfig cfg, FineArgs A) {
             }
         }
 #undef PXX
+#undef PIX_TO_LOCAL
+#undef PIX_FROM_LOCAL
 #undef xyy
 #undef xyx0
 #undef xyx1
