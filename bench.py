@@ -4,7 +4,7 @@ fine-stage HBM roofline, next to the CPU baseline (the oracle = restated referen
 
     python bench.py --gpus 1 --steps 20 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-        bench.py --gpus N --steps K --warmup W          (one rank per GPU, bin-row stripes, no data-path collective)
+        bench.py --gpus N --steps K --warmup W          (one rank per GPU, tile-row stripes assembled over NVLink)
     python bench.py --impl reference ...                (the CPU arm: oracle on the host cores)
 
 One step = one frame of the hot path (pathtag .. fine) over the synthetic scene.
@@ -194,7 +194,7 @@ def main():
     H = args.height or args.size
     wl = {"paris": f"paris-like-{args.paths // 1000}k", "tiger": "Ghostscript tiger", "beziers": f"beziers-{args.paths // 1000}k+clips"}[args.scene]
     config = {"workload": f"{wl} {args.size}x{H} " + ["Area", "MSAA8", "MSAA16"][args.aa],
-              "n_paths": args.paths, "seed": args.seed, "parallelism": f"bin-row stripes x{args.gpus}",
+              "n_paths": args.paths, "seed": args.seed, "parallelism": f"tile-row stripes x{args.gpus}",
               "l2": "flushed between steps (256 MiB write) outside the per-step CUDA-event pairs"}
 
     if args.impl == "reference":
