@@ -20,11 +20,42 @@ def test_f16_known_answers():
     assert f32_to_f16(1e6) == 0x7C00  # overflow clamps to infinity
 
 
+def test_f16_reference_vectors():
+    """The exact inputs / outputs of the reference's own unit tests, vello_encoding/src/math.rs:151-281."""
+    import math
+    import struct
+
+    def bits(u):
+        return struct.unpack("<f", struct.pack("<I", u))[0]
+
+    assert f32_to_f16(math.pi) == 0x4248                      # test_f32_to_f16_simple
+    assert f32_to_f16(bits(0x7F800001)) == 0x7E00             # signalling NaN -> quiet NaN, not infinity
+    assert f32_to_f16(bits(0x7F800000)) == 0x7C00             # +inf
+    assert f32_to_f16(0.00003051758) == 0x0200                # exponent rebias (a half denormal)
+    assert f32_to_f16(1.701412e38) == 0x7C00 and f32_to_f16(-1.701412e38) == 0xFC00
+    assert f16_to_f32(0x4248) == np.float32(3.140625)
+    assert np.isinf(f16_to_f32(0x7C00)) and np.isinf(f16_to_f32(0xFC00)) and f16_to_f32(0xFC00) < 0
+    assert np.isnan(f16_to_f32(0x7C01)) and np.isnan(f16_to_f32(f32_to_f16(f16_to_f32(0x7C01))))
+    for h in (0x7C00, 0xFC00, 0x7BFF, 0xFBFF, 0x0001, 0x8001):  # the *_roundtrip tests
+        assert f32_to_f16(f16_to_f32(h)) == h, hex(h)
+    assert abs(math.pi - float(f16_to_f32(f32_to_f16(math.pi)))) < 0.001
+
+
+def test_extend_and_quality_values():
+    # vello_encoding/src/encoding.rs:623-645: the numeric values the shaders decode
+    from vello_b200.encoding import EXTEND_PAD, EXTEND_REFLECT, EXTEND_REPEAT, QUALITY_HIGH, QUALITY_LOW, QUALITY_MEDIUM
+    assert (EXTEND_PAD, EXTEND_REPEAT, EXTEND_REFLECT) == (0, 1, 2)
+    assert (QUALITY_LOW, QUALITY_MEDIUM, QUALITY_HIGH) == (0, 1, 2)
+
+
 def test_draw_color_is_premultiplied_little_endian():
     # draw.rs:281-297: premultiplied, r in the low byte
     assert Color.from_rgba8(255, 0, 0, 255).premul_rgba8_u32() == 0xFF0000FF
     assert Color.from_rgba8(0, 255, 0, 255).premul_rgba8_u32() == 0xFF00FF00
     assert Color(1.0, 1.0, 1.0, 0.5).premul_rgba8_u32() == 0x80808080
+    # the reference's own vectors (draw_color_endianness, draw_color_premultiplied)
+    assert Color.from_rgba8(0x00, 0xCA, 0xFE, 0xFF).premul_rgba8_u32().to_bytes(4, "little") == bytes([0x00, 0xCA, 0xFE, 0xFF])
+    assert Color.from_rgba8(0x00, 0xCA, 0xFE, 0x00).premul_rgba8_u32() == 0
 
 
 def test_stroke_style_flags_roundtrip():
@@ -33,6 +64,26 @@ def test_stroke_style_flags_roundtrip():
     assert st[0] & STYLE_FLAGS_STYLE_BIT and st[1] == 3.5
     assert f16_to_f32(st[0] & 0xFFFF) == 4.0
     assert style_from_stroke(Stroke(0.0)) is None
+
+
+def test_fill_and_stroke_style_fields():
+    """path.rs:846-877 (test_fill_style, test_stroke_style): every cap x cap x join combination decodes through the masks the
+    shaders use (flatten.wgsl:20-32)."""
+    from vello_b200.encoding import (FILL_EVEN_ODD, STYLE_CAP_BUTT, STYLE_CAP_ROUND, STYLE_CAP_SQUARE, STYLE_FLAGS_FILL_BIT, STYLE_JOIN_BEVEL,
+                                     STYLE_JOIN_MITER, STYLE_JOIN_ROUND, style_from_fill)
+    assert style_from_fill(FILL_NON_ZERO)[0] == 0 and style_from_fill(FILL_EVEN_ODD)[0] == STYLE_FLAGS_FILL_BIT
+    assert not style_from_fill(FILL_NON_ZERO)[0] & STYLE_FLAGS_STYLE_BIT  # a fill has no stroke width
+    assert style_from_stroke(Stroke(1.0))[0] & STYLE_FLAGS_STYLE_BIT      # and a stroke is not a fill
+    caps, joins = (STYLE_CAP_BUTT, STYLE_CAP_SQUARE, STYLE_CAP_ROUND), (STYLE_JOIN_BEVEL, STYLE_JOIN_MITER, STYLE_JOIN_ROUND)
+    for start in caps:
+        for end in caps:
+            for join in joins:
+                flags, width = style_from_stroke(Stroke(1.0, join=join, miter_limit=0.0, start_cap=start, end_cap=end))
+                assert width == 1.0
+                assert flags & 0x3000_0000 == join
+                assert (flags & 0x0C00_0000) >> 2 == start
+                assert flags & 0x0300_0000 == end
+                assert flags & 0xFFFF == 0
 
 
 def test_tag_stream_of_a_fill_and_an_open_stroke():
