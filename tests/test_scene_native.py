@@ -369,3 +369,41 @@ def test_dash_native_equals_python():
     assert len(d) == 10 and d[0] == ("M", 2.0, 0.0) and d[-2:] == [("M", 0.0, 0.0), ("L", 1.0, 0.0)]
     d = shapes.dash([("M", 0.0, 0.0), ("L", 4.0, 0.0), ("L", 4.0, 4.0), ("L", 0.0, 4.0), ("Z",)], 0.5, [3.0, 1.0])
     assert d[-3:] == [("M", 0.0, 0.5), ("L", 0.0, 0.0), ("L", 2.5, 0.0)]  # last dash joined to the stashed first one
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_dash_fuzz_native_equals_python(seed):
+    """Random subpaths (lines, quads, cubics, closes, degenerate segments), random patterns and offsets (also negative and
+    longer than the pattern): the C++ dash expansion and the Python one produce the same byte stream."""
+    from vello_b200.encoding import Stroke, Scene, resolve, STYLE_JOIN_MITER, STYLE_CAP_SQUARE, Color
+    from vello_b200.scene_native import NativeScene
+    from vello_b200.shapes import Affine, BezPath
+    rng = np.random.default_rng(1000 + seed)
+    py, nat = Scene(), NativeScene()
+    for _ in range(6):
+        p = BezPath()
+        for _sub in range(int(rng.integers(1, 4))):
+            p.move_to(*rng.uniform(0, 200, 2))
+            for _seg in range(int(rng.integers(1, 8))):
+                k = int(rng.integers(0, 8))
+                if k < 4:
+                    p.line_to(*rng.uniform(0, 200, 2))
+                elif k < 5:
+                    last = p.els[-1]
+                    p.line_to(last[-2], last[-1])  # zero-length segment
+                elif k < 6:
+                    p.quad_to(*rng.uniform(0, 200, 4))
+                else:
+                    p.curve_to(*rng.uniform(0, 200, 6))
+            if rng.random() < 0.4:
+                p.close_path()
+        n = int(rng.integers(1, 6))
+        pat = tuple(float(v) for v in np.round(rng.uniform(0.5, 25.0, n), 3))
+        off = float(np.round(rng.uniform(-40.0, 80.0), 3))
+        st = Stroke(float(np.round(rng.uniform(0.5, 6.0), 2)), join=STYLE_JOIN_MITER, start_cap=STYLE_CAP_SQUARE, end_cap=STYLE_CAP_SQUARE,
+                    dash_pattern=pat, dash_offset=off)
+        for s in (py, nat):
+            s.stroke(st, Affine.IDENTITY, Color.from_rgba8(10, 200, 90), None, p)
+    a, b = resolve(py.encoding), nat.resolve()
+    assert a.layout.as_array().tolist() == b.layout.as_array().tolist()
+    assert a.scene.tobytes() == b.scene.tobytes()
