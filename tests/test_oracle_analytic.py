@@ -1,0 +1,377 @@
+"""Analytic ground truth for the oracle (and, through the GPU parity tests, for the CUDA path), independent of the restated
+shader code: what the pixels SHOULD be by geometry and by the W3C compositing definitions.
+
+The reference's golden images pin fills, one circle, linear gradients and nearest images only. These
+tests tie the rows the goldens do not reach -- partial MSAA coverage, sloped edges, strokes, clips, the 16 mix modes and 14
+Porter-Duff operators, radial and sweep gradients, luminance masks -- to first principles:
+
+* area AA of a simple polygon == the exact area of polygon n pixel (sloped edges: 1.5 LSB; axis-aligned edges inside a pixel
+  go through fine.wgsl's `xmin - 1e-6` division, whose f32 rounding is worth up to 7 % of a pixel: a property of the
+  reference's formula, asserted loosely);
+* MSAA8 / MSAA16: the sample patterns are n-rooks, so an axis-aligned edge at k/n of a pixel covers exactly k/n; sloped
+  edges are the LUT-quantised half planes, asserted within 2 samples of the exact area;
+* a stroke's total coverage == width x length (+ the caps' area);
+* a clipped fill == clip coverage x fill coverage;
+* every blend mode == the W3C `Compositing and Blending Level 1` formula evaluated in float64 here (restated from the
+  specification text, not from blend.wgsl), within 2 LSB (the backdrop passes through one 8-bit store on the blend stack);
+* radial / sweep gradients == the ramp colour at the analytically computed parameter.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from vello_b200.config import AA_AREA, AA_MSAA8, AA_MSAA16
+from vello_b200.encoding import (BLACK, COMPOSE_SRC_OVER, FILL_EVEN_ODD, FILL_NON_ZERO, MIX_NORMAL, STYLE_CAP_BUTT, STYLE_CAP_ROUND,
+                                 STYLE_CAP_SQUARE, STYLE_JOIN_BEVEL, TRANSPARENT, Color, Gradient, Scene, Stroke, resolve)
+from vello_b200.shapes import Affine, BezPath, Line, Rect
+
+WHITE = Color.from_rgba8(255, 255, 255)
+
+
+def render(oracle, scene, w, h, aa, base=BLACK):
+    return oracle.render(resolve(scene.encoding), w, h, base.premul_rgba8_u32(), aa)
+
+
+def coverage(oracle, shape, w, h, aa, rule=FILL_NON_ZERO):
+    """White `shape` on black: the red channel / 255 is the coverage the rasteriser assigned to each pixel."""
+    s = Scene()
+    s.fill(rule, Affine.IDENTITY, WHITE, None, shape)
+    return render(oracle, s, w, h, aa)[..., 0].astype(np.float64) / 255.0
+
+
+# ---- exact polygon-pixel intersection areas (Sutherland-Hodgman against the four pixel edges) ------------------------------
+def _clip_poly(poly, axis, bound, keep_less):
+    out = []
+    n = len(poly)
+    for i in range(n):
+        a, b = poly[i], poly[(i + 1) % n]
+        ina = (a[axis] <= bound) if keep_less else (a[axis] >= bound)
+        inb = (b[axis] <= bound) if keep_less else (b[axis] >= bound)
+        if ina:
+            out.append(a)
+        if ina != inb:
+            t = (bound - a[axis]) / (b[axis] - a[axis])
+            out.append((a[0] + t * (b[0] - a[0]), a[1] + t * (b[1] - a[1])))
+    return out
+
+
+def _area(poly):
+    return 0.5 * abs(sum(poly[i][0] * poly[(i + 1) % len(poly)][1] - poly[(i + 1) % len(poly)][0] * poly[i][1] for i in range(len(poly))))
+
+
+def exact_coverage(poly, w, h):
+    cov = np.zeros((h, w))
+    xs = [p[0] for p in poly]
+    ys = [p[1] for p in poly]
+    for y in range(max(0, int(math.floor(min(ys)))), min(h, int(math.ceil(max(ys))))):
+        for x in range(max(0, int(math.floor(min(xs)))), min(w, int(math.ceil(max(xs))))):
+            p = _clip_poly(poly, 0, x, False)
+            p = _clip_poly(p, 0, x + 1, True) if p else p
+            p = _clip_poly(p, 1, y, False) if p else p
+            p = _clip_poly(p, 1, y + 1, True) if p else p
+            cov[y, x] = _area(p) if len(p) >= 3 else 0.0
+    return cov
+
+
+def poly_path(poly):
+    p = BezPath()
+    p.move_to(*poly[0])
+    for q in poly[1:]:
+        p.line_to(*q)
+    p.close_path()
+    return p
+
+
+def random_convex(rng, cx, cy, r, n):
+    ang = np.sort(rng.uniform(0, 2 * math.pi, n))
+    rad = rng.uniform(0.6 * r, r, n)
+    return [(float(cx + rad[i] * math.cos(ang[i])), float(cy + rad[i] * math.sin(ang[i]))) for i in range(n)]
+
+
+# ---- coverage ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", range(6))
+def test_area_aa_of_sloped_polygons_is_the_exact_area(oracle, seed):
+    rng = np.random.default_rng(seed)
+    poly = random_convex(rng, 24.3, 23.1, 19.0, int(rng.integers(3, 9)))
+    got = coverage(oracle, poly_path(poly), 48, 48, AA_AREA)
+    want = exact_coverage(poly, 48, 48)
+    assert np.abs(got - want).max() <= 1.5 / 255 + 1e-6, np.abs(got - want).max()
+
+
+def test_area_aa_of_a_concave_even_odd_star(oracle):
+    # a pentagram under the even-odd rule: the inner pentagon is a hole; compare the TOTAL area (pixelwise the self-
+    # intersections make area AA approximate: two edges of one path in one pixel)
+    pts = [(24 + 20 * math.sin(2 * math.pi * k * 2 / 5), 24 - 20 * math.cos(2 * math.pi * k * 2 / 5)) for k in range(5)]
+    eo = coverage(oracle, poly_path(pts), 48, 48, AA_AREA, FILL_EVEN_ODD).sum()
+    nz = coverage(oracle, poly_path(pts), 48, 48, AA_AREA, FILL_NON_ZERO).sum()
+    r = 20.0
+    outer = 5 * r * r * math.sin(math.radians(36)) * math.sin(math.radians(18)) / math.sin(math.radians(126))  # area of the {5/2} star's hull of points
+    inner_r = r * math.sin(math.radians(18)) / math.sin(math.radians(126))
+    pentagon = 2.5 * inner_r * inner_r * math.sin(math.radians(72))
+    assert abs(nz - outer) / outer < 0.01
+    assert abs(eo - (outer - pentagon)) / outer < 0.01
+
+
+def test_area_aa_of_axis_aligned_edges(oracle):
+    got = coverage(oracle, Rect(3.25, 2.5, 10.75, 9.125), 16, 16, AA_AREA)
+    xs = np.arange(16)
+    cx = np.clip(np.minimum(xs + 1, 10.75) - np.maximum(xs, 3.25), 0, 1)
+    cy = np.clip(np.minimum(xs + 1, 9.125) - np.maximum(xs, 2.5), 0, 1)
+    # the vertical edges go through `(..) / (xmax - xmin)` with xmin = x - 1e-6 in f32 (fine.wgsl:1046-1052)
+    assert np.abs(got - np.outer(cy, cx)).max() <= 0.07
+    assert np.abs(got - np.outer(cy, cx))[:, 4:10].max() <= 1.0 / 255  # columns without a vertical edge: exact
+
+
+@pytest.mark.parametrize("aa,n", [(AA_MSAA8, 8), (AA_MSAA16, 16)])
+def test_msaa_patterns_are_n_rooks(oracle, aa, n):
+    """An axis-aligned edge at k/n of a pixel covers exactly k of the n samples, horizontally and vertically."""
+    for k in range(n + 1):
+        f = k / n
+        got = coverage(oracle, Rect(2.0 + f, 1.0, 9.0, 7.0), 12, 8, aa)
+        assert got[3, 2] == pytest.approx(round(255 * (1 - f)) / 255, abs=1e-9), (k, got[3, 2])
+        assert (got[3, 3:9] == 1.0).all() and got[3, 1] == 0.0
+        got = coverage(oracle, Rect(2.0, 1.0 + f, 9.0, 7.0), 12, 8, aa)
+        assert got[1, 4] == pytest.approx(round(255 * (1 - f)) / 255, abs=1e-9), (k, got[1, 4])
+
+
+@pytest.mark.parametrize("aa,n", [(AA_MSAA8, 8), (AA_MSAA16, 16)])
+@pytest.mark.parametrize("seed", range(3))
+def test_msaa_of_sloped_polygons_is_near_the_exact_area(oracle, aa, n, seed):
+    rng = np.random.default_rng(100 + seed)
+    poly = random_convex(rng, 24.3, 23.1, 19.0, int(rng.integers(3, 9)))
+    got = coverage(oracle, poly_path(poly), 48, 48, aa)
+    want = exact_coverage(poly, 48, 48)
+    # every value is a whole number of samples
+    assert np.abs(got * 255 - np.round(np.round(got * n) / n * 255)).max() <= 0.5
+    assert np.abs(got - want).max() <= 2.0 / n + 1e-3
+    assert abs(got.sum() - want.sum()) / want.sum() < 0.01
+
+
+@pytest.mark.parametrize("aa", [AA_AREA, AA_MSAA16])
+def test_stroke_coverage_is_width_times_length(oracle, aa):
+    def total(stroke, shape):
+        s = Scene()
+        s.stroke(stroke, Affine.IDENTITY, WHITE, None, shape)
+        return render(oracle, s, 64, 64, aa)[..., 0].astype(np.float64).sum() / 255.0
+    line = Line(10.3, 12.6, 50.8, 41.2)
+    length = math.hypot(50.8 - 10.3, 41.2 - 12.6)
+    w = 5.0
+    tol = 0.012 if aa == AA_AREA else 0.02
+    assert abs(total(Stroke(w, join=STYLE_JOIN_BEVEL, start_cap=STYLE_CAP_BUTT, end_cap=STYLE_CAP_BUTT), line) - w * length) / (w * length) < tol
+    sq = w * length + w * w
+    assert abs(total(Stroke(w, join=STYLE_JOIN_BEVEL, start_cap=STYLE_CAP_SQUARE, end_cap=STYLE_CAP_SQUARE), line) - sq) / sq < tol
+    rd = w * length + math.pi * (w / 2) ** 2
+    assert abs(total(Stroke(w, join=STYLE_JOIN_BEVEL, start_cap=STYLE_CAP_ROUND, end_cap=STYLE_CAP_ROUND), line) - rd) / rd < tol
+
+
+def test_clip_is_the_product_of_coverages(oracle):
+    clip, rect = Rect(4.5, 3.25, 20.5, 14.75), Rect(8.0, 1.0, 30.0, 12.5)
+    s = Scene()
+    s.push_clip_layer(FILL_NON_ZERO, Affine.IDENTITY, clip)
+    s.fill(FILL_NON_ZERO, Affine.IDENTITY, WHITE, None, rect)
+    s.pop_layer()
+    got = render(oracle, s, 32, 16, AA_MSAA16)[..., 0].astype(np.float64) / 255
+    a = coverage(oracle, clip, 32, 16, AA_MSAA16)
+    b = coverage(oracle, rect, 32, 16, AA_MSAA16)
+    assert np.abs(got - a * b).max() <= 1.5 / 255
+
+
+# ---- W3C compositing and blending, restated from the specification ----------------------------------------------------------------
+def _lum(c):
+    return 0.3 * c[0] + 0.59 * c[1] + 0.11 * c[2]
+
+
+def _clip_color(c):
+    l, n, x = _lum(c), min(c), max(c)
+    if n < 0:
+        c = [l + (v - l) * l / (l - n) for v in c]
+    if x > 1:
+        c = [l + (v - l) * (1 - l) / (x - l) for v in c]
+    return c
+
+
+def _set_lum(c, l):
+    d = l - _lum(c)
+    return _clip_color([v + d for v in c])
+
+
+def _sat(c):
+    return max(c) - min(c)
+
+
+def _set_sat(c, s):
+    order = sorted(range(3), key=lambda i: c[i])  # spec: Cmin, Cmid, Cmax
+    lo, mid, hi = order
+    out = [0.0, 0.0, 0.0]
+    if c[hi] > c[lo]:
+        out[mid] = (c[mid] - c[lo]) * s / (c[hi] - c[lo])
+        out[hi] = s
+    return out
+
+
+def _sep(mode, cb, cs):
+    if mode == "multiply":
+        return cb * cs
+    if mode == "screen":
+        return cb + cs - cb * cs
+    if mode == "hard_light":
+        return cb * 2 * cs if cs <= 0.5 else _sep("screen", cb, 2 * cs - 1)
+    if mode == "overlay":
+        return _sep("hard_light", cs, cb)
+    if mode == "darken":
+        return min(cb, cs)
+    if mode == "lighten":
+        return max(cb, cs)
+    if mode == "color_dodge":
+        return 0.0 if cb == 0 else (1.0 if cs == 1 else min(1.0, cb / (1 - cs)))
+    if mode == "color_burn":
+        return 1.0 if cb == 1 else (0.0 if cs == 0 else 1 - min(1.0, (1 - cb) / cs))
+    if mode == "soft_light":
+        if cs <= 0.5:
+            return cb - (1 - 2 * cs) * cb * (1 - cb)
+        d = ((16 * cb - 12) * cb + 4) * cb if cb <= 0.25 else math.sqrt(cb)
+        return cb + (2 * cs - 1) * (d - cb)
+    if mode == "difference":
+        return abs(cb - cs)
+    if mode == "exclusion":
+        return cb + cs - 2 * cb * cs
+    raise KeyError(mode)
+
+
+MIXES = ["normal", "multiply", "screen", "overlay", "darken", "lighten", "color_dodge", "color_burn", "hard_light", "soft_light",
+         "difference", "exclusion", "hue", "saturation", "color", "luminosity"]  # peniko::Mix values 0..15
+
+
+def w3c_mix(mode, cb, cs):
+    if mode == "normal":
+        return list(cs)
+    if mode == "hue":
+        return _set_lum(_set_sat(cs, _sat(cb)), _lum(cb))
+    if mode == "saturation":
+        return _set_lum(_set_sat(cb, _sat(cs)), _lum(cb))
+    if mode == "color":
+        return _set_lum(cs, _lum(cb))
+    if mode == "luminosity":
+        return _set_lum(cb, _lum(cs))
+    return [_sep(mode, cb[i], cs[i]) for i in range(3)]
+
+
+# peniko::Compose values 0..13 -> Porter-Duff (Fa, Fb) as functions of (alpha_s, alpha_b)
+PD = [lambda s, b: (0, 0), lambda s, b: (1, 0), lambda s, b: (0, 1), lambda s, b: (1, 1 - s), lambda s, b: (1 - b, 1), lambda s, b: (b, 0),
+      lambda s, b: (0, s), lambda s, b: (1 - b, 0), lambda s, b: (0, 1 - s), lambda s, b: (b, 1 - s), lambda s, b: (1 - b, s),
+      lambda s, b: (1 - b, 1 - s), lambda s, b: (1, 1), lambda s, b: (1, 1)]
+
+
+def w3c_composite(mix, compose, cb, ab, cs, as_):
+    """Unpremultiplied backdrop / source colours and alphas -> premultiplied result (r, g, b, a)."""
+    bm = w3c_mix(MIXES[mix], cb, cs)
+    cm = [(1 - ab) * cs[i] + ab * bm[i] for i in range(3)]
+    fa, fb = PD[compose](as_, ab)
+    co = [as_ * fa * cm[i] + ab * fb * cb[i] for i in range(3)]
+    ao = as_ * fa + ab * fb
+    if compose == 13:  # plus-lighter: clamped sum
+        co = [min(1.0, v) for v in co]
+    return co + [min(1.0, ao)]
+
+
+def _blend_scene(mix, compose, backdrop: Color, source: Color, layer_alpha=1.0):
+    s = Scene()
+    r = Rect(0.0, 0.0, 16.0, 16.0)
+    s.fill(FILL_NON_ZERO, Affine.IDENTITY, backdrop, None, r)
+    s.push_layer(FILL_NON_ZERO, mix, compose, layer_alpha, Affine.IDENTITY, r)
+    s.fill(FILL_NON_ZERO, Affine.IDENTITY, source, None, r)
+    s.pop_layer()
+    return s
+
+
+def _unpremul8(px):
+    return px.astype(np.float64) / 255.0
+
+
+BLEND_COLOURS = [(Color.from_rgba8(200, 90, 40, 255), Color.from_rgba8(30, 160, 220, 255)),
+                 (Color.from_rgba8(200, 90, 40, 255), Color.from_rgba8(30, 160, 220, 140)),
+                 (Color.from_rgba8(64, 220, 130, 180), Color.from_rgba8(240, 70, 200, 110)),
+                 (Color.from_rgba8(20, 40, 230, 90), Color.from_rgba8(250, 240, 30, 255))]
+
+
+def _channels(c: Color):
+    return [c.r, c.g, c.b], c.a
+
+
+@pytest.mark.parametrize("mix", range(16))
+def test_mix_modes_match_the_w3c_formulas(oracle, mix):
+    for backdrop, source in BLEND_COLOURS:
+        img = render(oracle, _blend_scene(mix, COMPOSE_SRC_OVER, backdrop, source), 16, 16, AA_AREA, TRANSPARENT)
+        cb, ab = _channels(backdrop)
+        cs, as_ = _channels(source)
+        want = w3c_composite(mix, COMPOSE_SRC_OVER, cb, ab, cs, as_)
+        got = _unpremul8(img[8, 8])
+        a = want[3]
+        want_stored = [want[i] / a if a > 0 else 0.0 for i in range(3)] + [a]  # the target stores separated alpha
+        assert np.abs(got - np.clip(want_stored, 0, 1)).max() <= 2.5 / 255, (MIXES[mix], got * 255, np.array(want_stored) * 255)
+        assert (img == img[8, 8]).all()  # flat everywhere
+
+
+@pytest.mark.parametrize("compose", range(14))
+@pytest.mark.parametrize("mix", [0, 1, 15])
+def test_compose_operators_match_porter_duff(oracle, compose, mix):
+    for backdrop, source in BLEND_COLOURS:
+        img = render(oracle, _blend_scene(mix, compose, backdrop, source), 16, 16, AA_AREA, TRANSPARENT)
+        cb, ab = _channels(backdrop)
+        cs, as_ = _channels(source)
+        want = w3c_composite(mix, compose, cb, ab, cs, as_)
+        a = want[3]
+        got = _unpremul8(img[8, 8])
+        assert abs(got[3] - a) <= 2.0 / 255, (compose, got[3] * 255, a * 255)
+        if a > 0.02:  # colour of a (nearly) transparent pixel is not meaningful after the division
+            tol = 2.5 / 255 / max(a, 0.25)
+            assert np.abs(got[:3] - np.clip([want[i] / a for i in range(3)], 0, 1)).max() <= tol, (compose, mix, got * 255, want)
+
+
+def test_layer_alpha_and_luminance_mask(oracle):
+    backdrop, source = Color.from_rgba8(200, 90, 40, 255), Color.from_rgba8(30, 160, 220, 255)
+    img = render(oracle, _blend_scene(MIX_NORMAL, COMPOSE_SRC_OVER, backdrop, source, 0.4), 16, 16, AA_AREA, TRANSPARENT)
+    want = [0.4 * s + 0.6 * b for s, b in zip((30, 160, 220), (200, 90, 40))]
+    assert np.abs(img[8, 8, :3].astype(np.float64) - want).max() <= 1.5 and img[8, 8, 3] == 255
+    # luminance mask (scene.rs:208-236): the backdrop is multiplied by the layer's luminance (sRGB coefficients) x alpha
+    s = Scene()
+    r = Rect(0.0, 0.0, 16.0, 16.0)
+    s.fill(FILL_NON_ZERO, Affine.IDENTITY, backdrop, None, r)
+    s.push_luminance_mask_layer(FILL_NON_ZERO, 1.0, Affine.IDENTITY, r)
+    s.fill(FILL_NON_ZERO, Affine.IDENTITY, source, None, r)
+    s.pop_layer()
+    img = render(oracle, s, 16, 16, AA_AREA, TRANSPARENT)
+    lum = 0.2125 * 30 / 255 + 0.7154 * 160 / 255 + 0.0721 * 220 / 255
+    # premultiplied backdrop x lum, stored with separated alpha: colour unchanged, alpha = lum
+    assert abs(int(img[8, 8, 3]) - 255 * lum) <= 1.5
+    assert np.abs(img[8, 8, :3].astype(np.float64) - (200, 90, 40)).max() <= 2.0
+
+
+# ---- gradients ------------------------------------------------------------------------------------------------------------------
+def _lerp_colour(c0, c1, t):
+    return np.array([c0[i] + (c1[i] - c0[i]) * t for i in range(3)])
+
+
+def test_radial_and_sweep_gradients_follow_their_parameter(oracle):
+    c0, c1 = (255, 32, 16), (16, 64, 255)
+    stops = [(0.0, Color.from_rgba8(*c0)), (1.0, Color.from_rgba8(*c1))]
+    r = Rect(0.0, 0.0, 64.0, 64.0)
+    s = Scene()
+    s.fill(FILL_NON_ZERO, Affine.IDENTITY, Gradient.radial((32.0, 32.0), 0.0, (32.0, 32.0), 30.0, stops), None, r)
+    img = render(oracle, s, 64, 64, AA_AREA).astype(np.float64)
+    ys, xs = np.mgrid[0:64, 0:64]
+    t = np.clip(np.hypot(xs - 32.0, ys - 32.0) / 30.0, 0, 1)  # gradients are evaluated at the pixel's integer coordinates (fine.wgsl:1283)
+    want = np.stack([c0[i] + (c1[i] - c0[i]) * t for i in range(3)], axis=-1)
+    assert np.abs(img[..., :3] - want).max() <= 2.0
+    s = Scene()
+    s.fill(FILL_NON_ZERO, Affine.IDENTITY, Gradient.sweep((32.0, 32.0), 0.0, 2 * math.pi, stops), None, r)
+    img = render(oracle, s, 64, 64, AA_AREA).astype(np.float64)
+    ang = np.arctan2(ys - 32.0, xs - 32.0)
+    t = np.where(ang < 0, ang + 2 * math.pi, ang) / (2 * math.pi)
+    want = np.stack([c0[i] + (c1[i] - c0[i]) * t for i in range(3)], axis=-1)
+    far = np.hypot(xs - 32.0, ys - 32.0) > 3  # the parameter is discontinuous at the centre and along the seam
+    seam = (np.abs(ys - 32.0) < 1.5) & (xs >= 32)
+    ok = far & ~seam
+    # the shader's atan2 is a degree-7 polynomial (fine.wgsl:1346-1366): 1e-3 of a turn
+    assert np.abs(img[..., :3] - want)[ok].max() <= 2.5
