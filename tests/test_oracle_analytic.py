@@ -375,3 +375,232 @@ def test_radial_and_sweep_gradients_follow_their_parameter(oracle):
     ok = far & ~seam
     # the shader's atan2 is a degree-7 polynomial (fine.wgsl:1346-1366): 1e-3 of a turn
     assert np.abs(img[..., :3] - want)[ok].max() <= 2.5
+
+
+# ---- joins, curves ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("join", ["bevel", "miter", "round"])
+@pytest.mark.parametrize("phi_deg", [35.0, 90.0, 130.0])
+def test_join_area(oracle, join, phi_deg):
+    """Two segments meeting at exterior angle phi, butt caps. Union area = w (L1 + L2) - inner overlap + join wedge, with the
+    inner overlap a kite of (w/2)^2 tan(phi/2) and the wedge a triangle (bevel), a sector (round) or the same kite (miter)."""
+    from vello_b200.encoding import STYLE_JOIN_MITER, STYLE_JOIN_ROUND
+    w, l1, l2 = 8.0, 60.0, 55.0
+    phi = math.radians(phi_deg)
+    p0 = (20.0, 100.0)
+    p1 = (p0[0] + l1, p0[1])
+    p2 = (p1[0] + l2 * math.cos(phi), p1[1] - l2 * math.sin(phi))
+    path = BezPath([("M",) + p0, ("L",) + p1, ("L",) + p2])
+    jn = {"bevel": STYLE_JOIN_BEVEL, "miter": STYLE_JOIN_MITER, "round": STYLE_JOIN_ROUND}[join]
+    s = Scene()
+    s.stroke(Stroke(w, join=jn, miter_limit=10.0, start_cap=STYLE_CAP_BUTT, end_cap=STYLE_CAP_BUTT), Affine.IDENTITY, WHITE, None, path)
+    got = render(oracle, s, 160, 160, AA_AREA)[..., 0].astype(np.float64).sum() / 255
+    h = w / 2
+    kite = h * h * math.tan(phi / 2)
+    wedge = {"bevel": 0.5 * h * h * math.sin(phi), "round": 0.5 * h * h * phi, "miter": kite}[join]
+    want = w * (l1 + l2) - kite + wedge
+    assert abs(got - want) / want < 0.004, (got, want)
+
+
+def _cubic_area(p0, p1, p2, p3):
+    """Signed area contribution  1/2 * integral (x dy - y dx)  of one cubic Bezier (closed form, from the Bernstein products)."""
+    x0, y0 = p0; x1, y1 = p1; x2, y2 = p2; x3, y3 = p3
+    return (x0 * (6 * y1 + 3 * y2 + y3) + 3 * x1 * (-2 * y0 + y2 + y3) + 3 * x2 * (-y0 - y1 + 2 * y3) - x3 * (y0 + 3 * y1 + 6 * y2)) / 20.0
+
+
+def test_flattened_curves_keep_their_area(oracle):
+    """flatten's Euler-spiral subdivision replaces a curve by chords no further than the tolerance (0.25 px) from the spiral, so
+    for arcs (which the spiral fits exactly) the rendered area differs from the closed form by at most 2/3 x perimeter x
+    tolerance (a chord of sagitta e cuts off 2/3 e x its length) and the chords lie inside; for general cubics the spiral fit
+    may use another `tol`, and every point of every emitted line stays within 2 tol of the true curve."""
+    from vello_b200.shapes import Circle, Ellipse
+    tol = 0.25
+    got = coverage(oracle, Circle(40.3, 39.6, 30.0), 80, 80, AA_AREA).sum()
+    loss = math.pi * 900.0 - got
+    assert -1.0 <= loss <= (2.0 / 3.0) * 2 * math.pi * 30.0 * tol, loss
+    a_, b_ = 33.0, 14.0
+    got = coverage(oracle, Ellipse(40.3, 39.6, a_, b_, 0.6), 80, 80, AA_AREA).sum()
+    perim = math.pi * (3 * (a_ + b_) - math.sqrt((3 * a_ + b_) * (a_ + 3 * b_)))  # Ramanujan
+    loss = math.pi * a_ * b_ - got
+    assert -1.0 <= loss <= (2.0 / 3.0) * perim * tol, loss
+    rng = np.random.default_rng(5)
+    for _ in range(4):
+        # a closed loop of 4 cubics around a centre (simple, no self-intersection: control points stay in their angular sector)
+        k = 4
+        ang = np.linspace(0, 2 * math.pi, k + 1)
+        pts = []
+        for i in range(k):
+            a0, a1 = ang[i], ang[i + 1]
+            r = rng.uniform(22, 34, 4)
+            aa = [a0, a0 + (a1 - a0) / 3, a0 + 2 * (a1 - a0) / 3, a1]
+            pts.append([(50 + r[j] * math.cos(aa[j]), 50 + r[j] * math.sin(aa[j])) for j in range(4)])
+        for i in range(k):  # make it closed and continuous
+            pts[i][3] = pts[(i + 1) % k][0]
+        path = BezPath([("M",) + pts[0][0]] + [("C",) + pts[i][1] + pts[i][2] + pts[i][3] for i in range(k)] + [("Z",)])
+        want = abs(sum(_cubic_area(*pts[i]) for i in range(k)))
+        ts = np.linspace(0, 1, 2001)
+        curve = []
+        for q in pts:
+            bern = ((1 - ts) ** 3, 3 * (1 - ts) ** 2 * ts, 3 * (1 - ts) * ts ** 2, ts ** 3)
+            curve.append(np.stack([sum(c * q[j][0] for j, c in enumerate(bern)), sum(c * q[j][1] for j, c in enumerate(bern))], -1))
+        curve = np.concatenate(curve)
+        perim = float(np.hypot(np.diff(curve[:, 0]), np.diff(curve[:, 1])).sum())
+        got = coverage(oracle, path, 100, 100, AA_AREA).sum()
+        # a general cubic has two error terms of `tol` each: the Euler-spiral fit (flatten.wgsl:420-450) and the chords
+        assert abs(got - want) <= (2.0 / 3.0) * perim * 2 * tol, (got, want, perim)
+        lines = oracle.buffer("lines")[:int(oracle.buffer("bump")["lines"][0])]
+        assert 8 <= len(lines) <= 64
+        for ln in lines:
+            for f in (0.0, 0.25, 0.5, 0.75):
+                m = ln["p0"] * (1 - f) + ln["p1"] * f
+                assert np.sqrt(((curve - m) ** 2).sum(1).min()) <= 2 * tol + 0.01
+
+
+# ---- images ----------------------------------------------------------------------------------------------------------------------
+def _img(rng, h, w):
+    d = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    d[..., 3] = 255
+    return d
+
+
+def test_image_nearest_is_texel_replication(oracle):
+    from vello_b200.encoding import Image, QUALITY_LOW
+    rng = np.random.default_rng(9)
+    d = _img(rng, 5, 7)
+    s = Scene()
+    s.draw_image(Image(d, quality=QUALITY_LOW), Affine.scale(4.0))
+    got = render(oracle, s, 28, 20, AA_AREA)
+    assert np.array_equal(got, np.repeat(np.repeat(d, 4, axis=0), 4, axis=1))
+
+
+def _mitchell(x, b=1.0 / 3.0, c=1.0 / 3.0):
+    """Mitchell-Netravali reconstruction filter (Mitchell & Netravali 1988), the kernel fine.wgsl's bicubic uses with B = C = 1/3."""
+    x = abs(x)
+    if x < 1:
+        return ((12 - 9 * b - 6 * c) * x ** 3 + (-18 + 12 * b + 6 * c) * x ** 2 + (6 - 2 * b)) / 6
+    if x < 2:
+        return ((-b - 6 * c) * x ** 3 + (6 * b + 30 * c) * x ** 2 + (-12 * b - 48 * c) * x + (8 * b + 24 * c)) / 6
+    return 0.0
+
+
+def test_image_bilinear_and_bicubic_reconstruction(oracle):
+    from vello_b200.encoding import Image, QUALITY_HIGH, QUALITY_MEDIUM
+    rng = np.random.default_rng(10)
+    d = _img(rng, 6, 8)
+    f = d.astype(np.float64)
+    scale = 3.0
+    H, W = int(6 * scale), int(8 * scale)
+
+    def texel(ix, iy):  # pad extend
+        return f[min(max(iy, 0), 5), min(max(ix, 0), 7)]
+
+    for quality in (QUALITY_MEDIUM, QUALITY_HIGH):
+        s = Scene()
+        s.draw_image(Image(d, quality=quality), Affine.scale(scale))
+        got = render(oracle, s, W, H, AA_AREA).astype(np.float64)
+        want = np.zeros((H, W, 4))
+        for y in range(H):
+            for x in range(W):
+                u, v = (x + 0.5) / scale, (y + 0.5) / scale  # image-space position of the pixel centre
+                if quality == QUALITY_MEDIUM:
+                    uu, vv = u - 0.5, v - 0.5
+                    x0, y0 = math.floor(uu), math.floor(vv)
+                    fx, fy = uu - x0, vv - y0
+                    want[y, x] = ((1 - fy) * ((1 - fx) * texel(x0, y0) + fx * texel(x0 + 1, y0))
+                                  + fy * ((1 - fx) * texel(x0, y0 + 1) + fx * texel(x0 + 1, y0 + 1)))
+                else:
+                    uu, vv = u - 0.5, v - 0.5
+                    x0, y0 = math.floor(uu), math.floor(vv)
+                    acc = np.zeros(4)
+                    for j in range(-1, 3):
+                        for i in range(-1, 3):
+                            acc += _mitchell(uu - (x0 + i)) * _mitchell(vv - (y0 + j)) * texel(x0 + i, y0 + j)
+                    want[y, x] = np.clip(acc, 0, 255)
+        tol = 1.5 if quality == QUALITY_MEDIUM else 2.5
+        assert np.abs(got - want).max() <= tol, (quality, np.abs(got - want).max())
+
+
+# ---- gradient extend modes and the two-point radial kinds ------------------------------------------------------------------------------
+def test_linear_gradient_extend_modes(oracle):
+    from vello_b200.encoding import EXTEND_PAD, EXTEND_REFLECT, EXTEND_REPEAT
+    c0, c1 = np.array([255.0, 32.0, 16.0]), np.array([16.0, 64.0, 255.0])
+    stops = [(0.0, Color.from_rgba8(255, 32, 16)), (1.0, Color.from_rgba8(16, 64, 255))]
+    xs = np.arange(128, dtype=np.float64)
+    t = (xs - 40.0) / 24.0  # gradient line from x = 40 to x = 64, evaluated at integer pixel coordinates
+    for ext, tt in ((EXTEND_PAD, np.clip(t, 0, 1)), (EXTEND_REPEAT, t - np.floor(t)), (EXTEND_REFLECT, np.abs(t - 2 * np.round(0.5 * t)))):
+        s = Scene()
+        s.fill(FILL_NON_ZERO, Affine.IDENTITY, Gradient.linear((40.0, 0.0), (64.0, 0.0), stops, ext), None, Rect(0.0, 0.0, 128.0, 8.0))
+        got = render(oracle, s, 128, 8, AA_AREA)[4, :, :3].astype(np.float64)
+        want = c0[None, :] + (c1 - c0)[None, :] * tt[:, None]
+        # at the wrap of `repeat` the 512-entry ramp index jumps: skip the pixels within one ramp step of a discontinuity
+        ok = np.ones(128, bool) if ext != EXTEND_REPEAT else (np.abs(tt - 0.5) < 0.49)
+        assert np.abs(got - want)[ok].max() <= 2.0, (ext, np.abs(got - want)[ok].max())
+
+
+@pytest.mark.parametrize("c0,r0,c1,r1", [((40.0, 48.0), 6.0, (56.0, 48.0), 40.0),    # one circle inside the other
+                                         ((30.0, 48.0), 10.0, (70.0, 48.0), 10.0),   # strip (equal radii)
+                                         ((30.0, 48.0), 4.0, (64.0, 50.0), 22.0)])   # cone, circles apart
+def test_two_point_radial_gradient(oracle, c0, r0, c1, r1):
+    """Two-point conical gradient (the HTML canvas / PDF definition): the colour at p is the stop at the LARGEST t with
+    |p - c(t)| = r(t), r(t) >= 0, c(t) = c0 + t (c1 - c0), r(t) = r0 + t (r1 - r0); pixels with no solution stay unpainted."""
+    col0, col1 = np.array([250.0, 40.0, 20.0]), np.array([10.0, 90.0, 240.0])
+    stops = [(0.0, Color.from_rgba8(250, 40, 20)), (1.0, Color.from_rgba8(10, 90, 240))]
+    s = Scene()
+    s.fill(FILL_NON_ZERO, Affine.IDENTITY, Gradient.radial(c0, r0, c1, r1, stops), None, Rect(0.0, 0.0, 96.0, 96.0))
+    got = render(oracle, s, 96, 96, AA_AREA, TRANSPARENT).astype(np.float64)
+    cdx, cdy, dr = c1[0] - c0[0], c1[1] - c0[1], r1 - r0
+    a = cdx * cdx + cdy * cdy - dr * dr
+    checked = 0
+    for y in range(0, 96, 3):
+        for x in range(0, 96, 3):
+            px, py = x - c0[0], y - c0[1]
+            b = px * cdx + py * cdy + r0 * dr
+            c = px * px + py * py - r0 * r0
+            ts = []
+            if abs(a) < 1e-9:
+                if abs(b) > 1e-9:
+                    ts = [c / (2 * b)]
+            else:
+                disc = b * b - a * c
+                if disc >= 0:
+                    ts = [(b + math.sqrt(disc)) / a, (b - math.sqrt(disc)) / a]
+            ts = [t for t in ts if r0 + t * dr >= 0]
+            if not ts:
+                if abs(a) >= 1e-9 and b * b - a * c < -40.0:  # clearly outside the cone: nothing is painted
+                    assert got[y, x, 3] == 0, (x, y)
+                continue
+            t = max(ts)
+            # stay away from the parameter's discontinuities (cone boundary, the focal point) where one pixel decides
+            if abs(a) >= 1e-9 and b * b - a * c < 40.0:
+                continue
+            want = col0 + (col1 - col0) * min(max(t, 0.0), 1.0)
+            assert got[y, x, 3] == 255 and np.abs(got[y, x, :3] - want).max() <= 3.0, (x, y, t, got[y, x], want)
+            checked += 1
+    assert checked > 150
+
+
+# ---- blurred rounded rectangle ---------------------------------------------------------------------------------------------------------
+def test_blurred_rounded_rect_is_a_gaussian_blur_of_the_shape(oracle):
+    """scene.rs:256-314 / fine.wgsl:1290-1330 approximate (closed form, no convolution) the Gaussian blur of a rounded
+    rectangle. Ground truth: the 4x supersampled rounded rectangle convolved with a Gaussian by scipy. The approximation is
+    documented as visually close, not exact: 4 % of full scale, and the total light within 1 %. The edge profile of the
+    reference is erf(x / std_dev) (fine.wgsl:1217), i.e. the Gaussian of the comparison has sigma = std_dev / sqrt(2)."""
+    from scipy.ndimage import gaussian_filter
+    w, h, radius, sigma = 60.0, 36.0, 9.0, 5.0
+    size = 128
+    s = Scene()
+    s.draw_blurred_rounded_rect(Affine.translate(64.0, 64.0), Rect(-w / 2, -h / 2, w / 2, h / 2), WHITE, radius, sigma)
+    got = render(oracle, s, size, size, AA_AREA)[..., 0].astype(np.float64) / 255
+    ss = 4
+    ys, xs = (np.mgrid[0:size * ss, 0:size * ss] + 0.5) / ss
+    qx, qy = np.abs(xs - 64.0) - (w / 2 - radius), np.abs(ys - 64.0) - (h / 2 - radius)
+    d = np.hypot(np.maximum(qx, 0), np.maximum(qy, 0)) + np.minimum(np.maximum(qx, qy), 0) - radius
+    mask = (d <= 0).astype(np.float64)
+    blurred = gaussian_filter(mask, sigma / math.sqrt(2.0) * ss, mode="constant")
+    # the shader evaluates at integer pixel coordinates: sample the truth there (supersample index x * ss)
+    want = blurred[::ss, ::ss]
+    want = 0.25 * (blurred[np.ix_(np.arange(size) * ss, np.arange(size) * ss)] + blurred[np.ix_(np.maximum(np.arange(size) * ss - 1, 0), np.arange(size) * ss)]
+                   + blurred[np.ix_(np.arange(size) * ss, np.maximum(np.arange(size) * ss - 1, 0))]
+                   + blurred[np.ix_(np.maximum(np.arange(size) * ss - 1, 0), np.maximum(np.arange(size) * ss - 1, 0))])
+    inside = (np.abs(xs[::ss, ::ss] - 64.0) < w / 2 + 2.5 * sigma - 1) & (np.abs(ys[::ss, ::ss] - 64.0) < h / 2 + 2.5 * sigma - 1)
+    assert np.abs(got - want)[inside].max() < 0.04, np.abs(got - want)[inside].max()
+    assert abs(got[inside].sum() - want[inside].sum()) / want[inside].sum() < 0.01

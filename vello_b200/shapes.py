@@ -219,9 +219,10 @@ def path_elements(shape, tolerance: float = 0.1) -> Iterator[tuple]:
         a, b = shape.rx * math.cos(shape.x_rotation), shape.rx * math.sin(shape.x_rotation)
         c, d = -shape.ry * math.sin(shape.x_rotation), shape.ry * math.cos(shape.x_rotation)
         a2, b2, c2, d2 = a * a, b * b, c * c, d * d
-        rot = 0.5 * math.atan2(2.0 * (a * c + b * d), a2 - b2 + c2 - d2)
+        # kurbo Affine::svd on coefficients [a, b, c, d] (x' = a x + c y, y' = b x + d y): the off-diagonal of M M^T is ab + cd
+        rot = 0.5 * math.atan2(2.0 * (a * b + c * d), a2 - b2 + c2 - d2)
         s1 = a2 + b2 + c2 + d2
-        s2 = math.sqrt((a2 - b2 + c2 - d2) ** 2 + 4.0 * (a * c + b * d) ** 2)
+        s2 = math.sqrt((a2 - b2 + c2 - d2) ** 2 + 4.0 * (a * b + c * d) ** 2)
         rx, ry = math.sqrt(0.5 * (s1 + s2)), math.sqrt(max(0.5 * (s1 - s2), 0.0))
         cr, sr = math.cos(rot), math.sin(rot)
         yield ("M", shape.cx + cr * rx, shape.cy + sr * rx)
