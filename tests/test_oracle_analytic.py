@@ -604,3 +604,74 @@ def test_blurred_rounded_rect_is_a_gaussian_blur_of_the_shape(oracle):
     inside = (np.abs(xs[::ss, ::ss] - 64.0) < w / 2 + 2.5 * sigma - 1) & (np.abs(ys[::ss, ::ss] - 64.0) < h / 2 + 2.5 * sigma - 1)
     assert np.abs(got - want)[inside].max() < 0.04, np.abs(got - want)[inside].max()
     assert abs(got[inside].sum() - want[inside].sum()) / want[inside].sum() < 0.01
+
+
+# ---- invariances ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("aa", [AA_AREA, AA_MSAA16])
+def test_whole_pixel_translation_invariance_across_tiles_and_bins(oracle, aa):
+    """The same shapes moved by whole pixels across 16-pixel tile and 256-pixel bin boundaries give the same pixels, moved:
+    nothing in binning / tiling / backdrop propagation may depend on where the tile grid falls."""
+    rng = np.random.default_rng(21)
+    polys = [random_convex(rng, 40 + 30 * k, 45 + 11 * k, 26.0, 5 + k) for k in range(3)]
+
+    def scene(dx, dy):
+        s = Scene()
+        for k, poly in enumerate(polys):
+            shifted = [(x + dx, y + dy) for x, y in poly]
+            s.fill(FILL_NON_ZERO if k != 1 else FILL_EVEN_ODD, Affine.IDENTITY, Color.from_rgba8(60 + 90 * k, 200 - 70 * k, 40 + 100 * k, 200), None, poly_path(shifted))
+        s.stroke(Stroke(3.0), Affine.translate(dx, dy), Color.from_rgba8(250, 250, 20), None, Line(12.0, 15.0, 120.0, 70.0))
+        return s
+    ref = render(oracle, scene(0, 0), 160, 110, aa)
+    for dx, dy in ((16, 0), (7, 13), (243, 201), (256, 256), (301, 199)):
+        img = render(oracle, scene(dx, dy), 160 + dx, 110 + dy, aa)
+        d = np.abs(img[dy:dy + 110, dx:dx + 160].astype(np.int32) - ref.astype(np.int32))
+        if aa == AA_AREA:
+            assert d.max() <= 1, (dx, dy, d.max())
+        else:
+            # a vertex at 280.3 is a different f32 than 24.3 + 256: an edge that grazes a sample point may flip that ONE sample
+            flipped = int((d.max(axis=2) > 0).sum())
+            assert d.max() <= 17 and flipped <= 8, (dx, dy, d.max(), flipped)
+        outside = img.copy()
+        outside[dy:dy + 110, dx:dx + 160] = 0
+        assert (outside[..., :3] == 0).all()  # nothing leaks outside the moved bounding box (black base)
+
+
+def test_shapes_hanging_over_the_frame_are_cut_not_distorted(oracle):
+    rng = np.random.default_rng(22)
+    poly = random_convex(rng, 40.0, 40.0, 36.0, 7)
+    full = coverage(oracle, poly_path(poly), 96, 96, AA_MSAA16)
+    for (ox, oy, w, h) in ((20, 0, 50, 96), (0, 30, 96, 40), (25, 25, 30, 30)):
+        moved = [(x - ox, y - oy) for x, y in poly]
+        part = coverage(oracle, poly_path(moved), w, h, AA_MSAA16)
+        assert np.array_equal(part, full[oy:oy + h, ox:ox + w])
+
+
+def test_even_odd_ring_is_the_difference_of_the_areas(oracle):
+    outer = [(10.3, 8.7), (70.2, 12.4), (64.9, 61.3), (14.6, 57.8)]
+    inner = [(28.1, 24.2), (50.7, 26.9), (47.3, 44.4), (30.9, 41.0)]
+    p = BezPath()
+    for poly in (outer, inner):
+        p.move_to(*poly[0])
+        for q in poly[1:]:
+            p.line_to(*q)
+        p.close_path()
+    got = coverage(oracle, p, 80, 72, AA_AREA, FILL_EVEN_ODD)
+    want = exact_coverage(outer, 80, 72) - exact_coverage(inner, 80, 72)
+    assert np.abs(got - want).max() <= 1.5 / 255
+    # nonzero with the inner contour reversed is the same ring; with the same orientation it is the full outer polygon
+    rev = BezPath(list(poly_path(outer).els) + list(poly_path(inner[::-1]).els))
+    same = BezPath(list(poly_path(outer).els) + list(poly_path(inner).els))
+    assert np.abs(coverage(oracle, rev, 80, 72, AA_AREA) - want).max() <= 1.5 / 255
+    assert np.abs(coverage(oracle, same, 80, 72, AA_AREA) - exact_coverage(outer, 80, 72)).max() <= 1.5 / 255
+
+
+def test_affine_transform_of_a_fill_is_the_transformed_polygon(oracle):
+    rng = np.random.default_rng(23)
+    poly = random_convex(rng, 0.0, 0.0, 10.0, 6)
+    a = Affine.translate(50.3, 41.7) * Affine.rotate(0.7) * Affine.scale(2.5)
+    s = Scene()
+    s.fill(FILL_NON_ZERO, a, WHITE, None, poly_path(poly))
+    got = render(oracle, s, 100, 90, AA_AREA)[..., 0].astype(np.float64) / 255
+    c, sn = math.cos(0.7), math.sin(0.7)
+    moved = [(50.3 + 2.5 * (c * x - sn * y), 41.7 + 2.5 * (sn * x + c * y)) for x, y in poly]
+    assert np.abs(got - exact_coverage(moved, 100, 90)).max() <= 1.5 / 255
