@@ -675,3 +675,46 @@ def test_affine_transform_of_a_fill_is_the_transformed_polygon(oracle):
     c, sn = math.cos(0.7), math.sin(0.7)
     moved = [(50.3 + 2.5 * (c * x - sn * y), 41.7 + 2.5 * (sn * x + c * y)) for x, y in poly]
     assert np.abs(got - exact_coverage(moved, 100, 90)).max() <= 1.5 / 255
+
+
+# ---- whole scenes: the painter's algorithm over exact coverages ------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", range(4))
+def test_random_scene_is_the_painters_algorithm_over_exact_areas(oracle, seed):
+    """Twelve overlapping translucent polygons, a clip layer with alpha in the middle of the list: every pixel must equal
+    src-over compositing (premultiplied, float64 here) of the shapes' exact polygon-pixel areas, in order."""
+    rng = np.random.default_rng(300 + seed)
+    W = H = 72
+    s = Scene()
+    acc = np.zeros((H, W, 4))
+    acc[..., 3] = 1.0  # opaque black base
+
+    def over(dst, colour, cov):
+        src_a = colour[3] * cov
+        for c in range(3):
+            dst[..., c] = dst[..., c] * (1 - src_a) + colour[c] * src_a
+        dst[..., 3] = dst[..., 3] * (1 - src_a) + src_a
+
+    def add(target_scene, target_acc):
+        poly = random_convex(rng, rng.uniform(15, 57), rng.uniform(15, 57), rng.uniform(8, 26), int(rng.integers(3, 8)))
+        rgba = [int(v) for v in rng.integers(0, 256, 3)] + [int(rng.integers(60, 256))]
+        target_scene.fill(FILL_NON_ZERO, Affine.IDENTITY, Color.from_rgba8(*rgba), None, poly_path(poly))
+        over(target_acc, [v / 255 for v in rgba], exact_coverage(poly, W, H))
+
+    for _ in range(5):
+        add(s, acc)
+    # a layer: clip polygon, alpha 0.6, three shapes inside; composited as one group (src-over, normal)
+    clip = random_convex(rng, 36.0, 36.0, 27.0, 6)
+    s.push_layer(FILL_NON_ZERO, MIX_NORMAL, COMPOSE_SRC_OVER, 0.6, Affine.IDENTITY, poly_path(clip))
+    layer = np.zeros((H, W, 4))
+    for _ in range(3):
+        add(s, layer)
+    s.pop_layer()
+    k = 0.6 * exact_coverage(clip, W, H)
+    for c in range(3):
+        acc[..., c] = acc[..., c] * (1 - layer[..., 3] * k) + layer[..., c] * k  # layer[] is premultiplied already
+    acc[..., 3] = acc[..., 3] * (1 - layer[..., 3] * k) + layer[..., 3] * k
+    for _ in range(4):
+        add(s, acc)
+    got = render(oracle, s, W, H, AA_AREA).astype(np.float64)
+    assert (got[..., 3] == 255).all()
+    assert np.abs(got[..., :3] - 255 * acc[..., :3]).max() <= 2.5, np.abs(got[..., :3] - 255 * acc[..., :3]).max()
