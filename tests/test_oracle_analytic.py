@@ -718,3 +718,93 @@ def test_random_scene_is_the_painters_algorithm_over_exact_areas(oracle, seed):
     got = render(oracle, s, W, H, AA_AREA).astype(np.float64)
     assert (got[..., 3] == 255).all()
     assert np.abs(got[..., :3] - 255 * acc[..., :3]).max() <= 2.5, np.abs(got[..., :3] - 255 * acc[..., :3]).max()
+
+
+# ---- more stroke / image / layer semantics --------------------------------------------------------------------------------------------------
+def test_miter_limit_falls_back_to_bevel(oracle):
+    """kurbo / SVG: a miter join whose length exceeds miter_limit x half-width... ratio 1 / sin(theta / 2) (theta = interior
+    angle) is drawn as a bevel. Interior angle 20 degrees has ratio 5.76: a bevel under limit 4, a miter under limit 10."""
+    from vello_b200.encoding import STYLE_JOIN_MITER
+    w, l1, l2 = 6.0, 70.0, 70.0
+    phi = math.radians(160.0)  # exterior (turning) angle
+    p0 = (20.0, 60.0)
+    p1 = (p0[0] + l1, p0[1])
+    p2 = (p1[0] + l2 * math.cos(phi), p1[1] - l2 * math.sin(phi))
+    path = BezPath([("M",) + p0, ("L",) + p1, ("L",) + p2])
+    h = w / 2
+    kite = h * h * math.tan(phi / 2)
+    # the two rectangles overlap along most of their length here (narrow angle): count the union by the exact formula for the
+    # difference between the two renderings instead: miter - bevel = kite - triangle
+    def area(limit):
+        s = Scene()
+        s.stroke(Stroke(w, join=STYLE_JOIN_MITER, miter_limit=limit, start_cap=STYLE_CAP_BUTT, end_cap=STYLE_CAP_BUTT), Affine.IDENTITY, WHITE, None, path)
+        return render(oracle, s, 128, 128, AA_AREA)[..., 0].astype(np.float64).sum() / 255
+    bevel_only = Scene()
+    bevel_only.stroke(Stroke(w, join=STYLE_JOIN_BEVEL, start_cap=STYLE_CAP_BUTT, end_cap=STYLE_CAP_BUTT), Affine.IDENTITY, WHITE, None, path)
+    bevel = render(oracle, bevel_only, 128, 128, AA_AREA)[..., 0].astype(np.float64).sum() / 255
+    assert abs(area(4.0) - bevel) < 0.05                       # limit exceeded: identical to a bevel join
+    want_extra = kite - 0.5 * h * h * math.sin(phi)
+    assert abs((area(10.0) - bevel) - want_extra) / want_extra < 0.03
+
+
+def test_dashed_stroke_area_is_width_times_the_on_length(oracle):
+    length, w = 100.0, 4.0
+    for pattern, offset in (((7.0, 3.0), 0.0), ((5.0, 2.0, 1.0), 0.0), ((6.0, 6.0), 4.0)):
+        pat = list(pattern) * (2 if len(pattern) % 2 else 1)  # an odd pattern repeats with the roles swapped
+        period = sum(pat)
+        on = 0.0
+        pos, i, t = offset % period, 0, 0.0  # kurbo: the pattern is entered `dash_offset` along
+        # walk the pattern from the offset
+        acc = 0.0
+        while acc + pat[i] <= pos:
+            acc += pat[i]
+            i = (i + 1) % len(pat)
+        rem = acc + pat[i] - pos
+        while t < length:
+            step = min(rem, length - t)
+            if i % 2 == 0:
+                on += step
+            t += step
+            i = (i + 1) % len(pat)
+            rem = pat[i]
+        s = Scene()
+        st = Stroke(w, join=STYLE_JOIN_BEVEL, start_cap=STYLE_CAP_BUTT, end_cap=STYLE_CAP_BUTT, dash_pattern=tuple(pattern), dash_offset=offset)
+        s.stroke(st, Affine.IDENTITY, WHITE, None, Line(10.0, 20.3, 10.0 + length, 20.3))
+        got = render(oracle, s, 128, 40, AA_AREA)[..., 0].astype(np.float64).sum() / 255
+        assert abs(got - w * on) / (w * on) < 0.02, (pattern, offset, got, w * on)  # area AA's vertical-edge term: see above
+
+
+def test_image_alpha_format_and_alpha_type(oracle):
+    from vello_b200.encoding import ALPHA_PREMULTIPLIED, ALPHA_STRAIGHT, FORMAT_BGRA8, FORMAT_RGBA8, Image, QUALITY_LOW
+    px = np.array([[[200, 100, 50, 128]]], dtype=np.uint8)
+    def one(**kw):
+        s = Scene()
+        s.draw_image(Image(np.repeat(np.repeat(px, 4, 0), 4, 1), quality=QUALITY_LOW, **kw), Affine.IDENTITY)
+        return render(oracle, s, 4, 4, AA_AREA, TRANSPARENT)[1, 1].astype(np.float64)
+    a = 128 / 255
+    # straight alpha: stored separated -> the colour comes back, alpha = a
+    assert np.abs(one(format=FORMAT_RGBA8, alpha_type=ALPHA_STRAIGHT) - (200, 100, 50, 128)).max() <= 1.0
+    # BGRA: the channels swap
+    assert np.abs(one(format=FORMAT_BGRA8, alpha_type=ALPHA_STRAIGHT) - (50, 100, 200, 128)).max() <= 1.0
+    # premultiplied input: the stored texel IS colour x alpha; un-premultiplying on store divides it out
+    assert np.abs(one(format=FORMAT_RGBA8, alpha_type=ALPHA_PREMULTIPLIED) - (min(255, 200 / a), min(255, 100 / a), 50 / a, 128)).max() <= 1.5
+    # the brush alpha multiplies everything
+    got = one(format=FORMAT_RGBA8, alpha_type=ALPHA_STRAIGHT, alpha=0.5)
+    assert abs(got[3] - 64) <= 1.0 and np.abs(got[:3] - (200, 100, 50)).max() <= 2.0
+
+
+def test_deeply_nested_layers_multiply_their_alphas(oracle):
+    """Seven nested layers (more than the four blend-stack levels kept in registers: the deeper ones spill to memory,
+    fine.wgsl:1097-1130), each with alpha 0.8 and its own clip: the innermost fill arrives with 0.8^7."""
+    s = Scene()
+    depth = 7
+    for k in range(depth):
+        s.push_layer(FILL_NON_ZERO, MIX_NORMAL, COMPOSE_SRC_OVER, 0.8, Affine.IDENTITY, Rect(2.0 + k, 2.0 + k, 60.0 - k, 60.0 - k))
+    s.fill(FILL_NON_ZERO, Affine.IDENTITY, WHITE, None, Rect(0.0, 0.0, 64.0, 64.0))
+    for _ in range(depth):
+        s.pop_layer()
+    got = render(oracle, s, 64, 64, AA_AREA)[..., 0].astype(np.float64)
+    assert abs(got[32, 32] - 255 * 0.8 ** depth) <= 3.0  # one 8-bit store per level on the way out
+    # the clips nest: only the innermost rectangle (8 .. 54) is painted
+    assert got[1, 1] == 0 and got[5, 32] == 0 and got[32, 56] == 0
+    assert got[9, 32] == pytest.approx(got[32, 32], abs=1.0) and got[53, 9] == pytest.approx(got[32, 32], abs=1.0)
