@@ -51,6 +51,11 @@ int vb_pathbuf_rect(vb_pathbuf *, double x0, double y0, double x1, double y1);
 int vb_pathbuf_line(vb_pathbuf *, double x0, double y0, double x1, double y1);
 int vb_pathbuf_circle(vb_pathbuf *, double cx, double cy, double r, double tolerance);
 int vb_pathbuf_rounded_rect(vb_pathbuf *, double x0, double y0, double x1, double y1, double radius, double tolerance);
+/* kurbo Ellipse::new(center, radii, x_rotation) (ellipse.rs) and Arc { center, radii, start_angle, sweep_angle, x_rotation }
+ * (arc.rs): the closed ellipse, and the open arc starting with a MoveTo; angles in radians. */
+int vb_pathbuf_ellipse(vb_pathbuf *, double cx, double cy, double rx, double ry, double x_rotation, double tolerance);
+int vb_pathbuf_arc(vb_pathbuf *, double cx, double cy, double rx, double ry, double start_angle, double sweep_angle, double x_rotation,
+                   double tolerance);
 /* kurbo::BezPath::from_svg (kurbo svg.rs): SVG path data with the commands MmLlHhVvCcSsQqTtAaZz, appended to the buffer;
  * elliptical arcs become cubics. VB_E_INVALID on a syntax error (elements parsed before it stay in the buffer). */
 int vb_pathbuf_svg(vb_pathbuf *, const char *path_data);

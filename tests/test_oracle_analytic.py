@@ -808,3 +808,14 @@ def test_deeply_nested_layers_multiply_their_alphas(oracle):
     # the clips nest: only the innermost rectangle (8 .. 54) is painted
     assert got[1, 1] == 0 and got[5, 32] == 0 and got[32, 56] == 0
     assert got[9, 32] == pytest.approx(got[32, 32], abs=1.0) and got[53, 9] == pytest.approx(got[32, 32], abs=1.0)
+
+
+def test_arc_stroke_is_width_times_arc_length(oracle):
+    from vello_b200.shapes import Arc
+    r, w = 30.0, 4.0
+    for start, sweep in ((0.3, 2.0), (1.0, -4.5), (-2.0, 5.9)):
+        s = Scene()
+        s.stroke(Stroke(w, join=STYLE_JOIN_BEVEL, start_cap=STYLE_CAP_BUTT, end_cap=STYLE_CAP_BUTT), Affine.IDENTITY, WHITE, None, Arc(48.0, 47.0, r, r, start, sweep))
+        got = render(oracle, s, 96, 96, AA_AREA)[..., 0].astype(np.float64).sum() / 255
+        want = w * r * abs(sweep)  # the annular sector: 1/2 (R^2 - r^2) |sweep| = w r |sweep|
+        assert abs(got - want) / want < 0.015, (start, sweep, got, want)  # two flattened offset curves, 0.25 px each

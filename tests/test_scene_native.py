@@ -237,11 +237,11 @@ def test_append(mirror, oracle):
 
 
 def test_native_shapes_equal_python_statement_of_kurbo():
-    """vb_pathbuf's Rect / Line / Circle / RoundedRect -> Bezier conversions (kurbo `Shape::path_elements`) produce exactly
+    """vb_pathbuf's Rect / Line / Circle / RoundedRect / Ellipse / Arc -> Bezier conversions (kurbo `Shape::path_elements`) produce exactly
     the doubles vello_b200.shapes does, over radii that take every branch of the subdivision-count formulas."""
     from vello_b200.scene_native import NativePath, PATHBUF_SYMBOLS
     from vello_b200.renderer import load_library
-    from vello_b200.shapes import Circle, Line, Rect, RoundedRect, BezPath, path_elements
+    from vello_b200.shapes import Arc, Circle, Ellipse, Line, Rect, RoundedRect, BezPath, path_elements
     lib = load_library()
     for s in PATHBUF_SYMBOLS:
         assert hasattr(lib, s), s
@@ -253,6 +253,9 @@ def test_native_shapes_equal_python_statement_of_kurbo():
         x0, y0 = (float(v) for v in rng.normal(0, 50, 2))
         w, h = (float(v) for v in 10 ** rng.uniform(-1, 5, 2))
         shapes.append(RoundedRect(x0, y0, x0 + w, y0 + h, float(10 ** rng.uniform(-2, 5))))
+        rx, ry = (float(v) for v in 10 ** rng.uniform(-1, 4, 2))
+        shapes.append(Ellipse(x0, y0, rx, ry, float(rng.uniform(-4, 4))))
+        shapes.append(Arc(x0, y0, rx, ry, float(rng.uniform(-7, 7)), float(rng.uniform(-7, 7)), float(rng.uniform(-4, 4))))
     for tol in (0.1, 0.01, 3.0):
         for sh in shapes:
             want = [tuple(float(v) if not isinstance(v, str) else v for v in e) for e in path_elements(sh, tol)]

@@ -898,6 +898,32 @@ int vb_pathbuf_circle(vb_pathbuf *p, double cx, double cy, double radius, double
     p->el('Z', {});
     return VB_OK;
 }
+// kurbo Ellipse::new(center, radii, x_rotation).path_elements(tolerance): the radii and the rotation are recovered from the
+// ellipse's affine map (rotate(x_rotation) * scale(rx, ry)) by Affine::svd, then Arc { start 0, sweep 2 pi } + ClosePath.
+int vb_pathbuf_ellipse(vb_pathbuf *p, double cx, double cy, double rx, double ry, double x_rotation, double tolerance) {
+    if (!p || !(tolerance > 0.0)) return VB_E_INVALID;
+    const double a = rx * std::cos(x_rotation), b = rx * std::sin(x_rotation);
+    const double c = -ry * std::sin(x_rotation), d = ry * std::cos(x_rotation);
+    const double a2 = a * a, b2 = b * b, c2 = c * c, d2 = d * d;
+    const double rot = 0.5 * std::atan2(2.0 * (a * b + c * d), a2 - b2 + c2 - d2);
+    const double s1 = a2 + b2 + c2 + d2;
+    const double s2 = std::sqrt((a2 - b2 + c2 - d2) * (a2 - b2 + c2 - d2) + 4.0 * (a * b + c * d) * (a * b + c * d));
+    const double r0 = std::sqrt(0.5 * (s1 + s2)), r1 = std::sqrt(std::fmax(0.5 * (s1 - s2), 0.0));
+    p->el('M', {cx + std::cos(rot) * r0, cy + std::sin(rot) * r0});
+    arc_elements(*p, cx, cy, r0, r1, 0.0, 2.0 * PI, rot, tolerance);
+    p->el('Z', {});
+    return VB_OK;
+}
+// kurbo Arc { center, radii, start_angle, sweep_angle, x_rotation }.path_elements(tolerance): MoveTo(start) + the cubics (open)
+int vb_pathbuf_arc(vb_pathbuf *p, double cx, double cy, double rx, double ry, double start_angle, double sweep_angle, double x_rotation,
+                   double tolerance) {
+    if (!p || !(tolerance > 0.0)) return VB_E_INVALID;
+    const double cr = std::cos(x_rotation), sr = std::sin(x_rotation);
+    const double x = rx * std::cos(start_angle), y = ry * std::sin(start_angle);
+    p->el('M', {cx + cr * x - sr * y, cy + sr * x + cr * y});
+    arc_elements(*p, cx, cy, rx, ry, start_angle, sweep_angle, x_rotation, tolerance);
+    return VB_OK;
+}
 int vb_pathbuf_rounded_rect(vb_pathbuf *p, double x0, double y0, double x1, double y1, double radius, double tolerance) {
     if (!p || !(tolerance > 0.0)) return VB_E_INVALID;
     const double rad = std::fmin(std::fabs(radius), std::fmin(0.5 * std::fabs(x1 - x0), 0.5 * std::fabs(y1 - y0)));

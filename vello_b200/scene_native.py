@@ -50,6 +50,7 @@ class _Packed(C.Structure):
 
 PATHBUF_SYMBOLS = ["vb_pathbuf_new", "vb_pathbuf_free", "vb_pathbuf_clear", "vb_pathbuf_move_to", "vb_pathbuf_line_to", "vb_pathbuf_quad_to",
                    "vb_pathbuf_curve_to", "vb_pathbuf_close", "vb_pathbuf_rect", "vb_pathbuf_line", "vb_pathbuf_circle", "vb_pathbuf_rounded_rect",
+                   "vb_pathbuf_ellipse", "vb_pathbuf_arc",
                    "vb_pathbuf_svg", "vb_pathbuf_view"]
 SCENE_SYMBOLS = ["vb_scene_new", "vb_scene_free", "vb_scene_reset", "vb_scene_fill", "vb_scene_stroke", "vb_scene_push_layer",
                  "vb_scene_push_luminance_mask_layer", "vb_scene_push_clip_layer", "vb_scene_pop_layer", "vb_scene_draw_image",
@@ -93,6 +94,8 @@ def _lib():
         lib.vb_pathbuf_line.argtypes = [vp, d, d, d, d]
         lib.vb_pathbuf_circle.argtypes = [vp, d, d, d, d]
         lib.vb_pathbuf_rounded_rect.argtypes = [vp, d, d, d, d, d, d]
+        lib.vb_pathbuf_ellipse.argtypes = [vp, d, d, d, d, d, d]
+        lib.vb_pathbuf_arc.argtypes = [vp, d, d, d, d, d, d, d, d]
         lib.vb_pathbuf_svg.argtypes = [vp, C.c_char_p]
         lib.vb_pathbuf_view.restype = _Path
         lib.vb_pathbuf_view.argtypes = [vp]
@@ -285,6 +288,10 @@ class NativePath:
             L.vb_pathbuf_circle(self.handle, shape.cx, shape.cy, shape.r, tolerance)
         elif isinstance(shape, _shapes.RoundedRect):
             L.vb_pathbuf_rounded_rect(self.handle, shape.x0, shape.y0, shape.x1, shape.y1, shape.radius, tolerance)
+        elif isinstance(shape, _shapes.Ellipse):
+            L.vb_pathbuf_ellipse(self.handle, shape.cx, shape.cy, shape.rx, shape.ry, shape.x_rotation, tolerance)
+        elif isinstance(shape, _shapes.Arc):
+            L.vb_pathbuf_arc(self.handle, shape.cx, shape.cy, shape.rx, shape.ry, shape.start_angle, shape.sweep_angle, shape.x_rotation, tolerance)
         else:
             for e in _shapes.path_elements(shape, tolerance):
                 {"M": L.vb_pathbuf_move_to, "L": L.vb_pathbuf_line_to, "Q": L.vb_pathbuf_quad_to, "C": L.vb_pathbuf_curve_to}.get(

@@ -97,6 +97,18 @@ class Ellipse:
 
 
 @dataclass(frozen=True)
+class Arc:
+    """kurbo `Arc { center, radii, start_angle, sweep_angle, x_rotation }` (arc.rs): an open elliptical arc."""
+    cx: float
+    cy: float
+    rx: float
+    ry: float
+    start_angle: float
+    sweep_angle: float
+    x_rotation: float = 0.0
+
+
+@dataclass(frozen=True)
 class RoundedRect:
     x0: float
     y0: float
@@ -228,6 +240,12 @@ def path_elements(shape, tolerance: float = 0.1) -> Iterator[tuple]:
         yield ("M", shape.cx + cr * rx, shape.cy + sr * rx)
         yield from _arc_elements(shape.cx, shape.cy, rx, ry, 0.0, 2.0 * math.pi, rot, tolerance)
         yield ("Z",)
+    elif isinstance(shape, Arc):
+        # Arc::path_elements: MoveTo(start point) + append_iter
+        cr, sr = math.cos(shape.x_rotation), math.sin(shape.x_rotation)
+        x, y = shape.rx * math.cos(shape.start_angle), shape.ry * math.sin(shape.start_angle)
+        yield ("M", shape.cx + cr * x - sr * y, shape.cy + sr * x + cr * y)
+        yield from _arc_elements(shape.cx, shape.cy, shape.rx, shape.ry, shape.start_angle, shape.sweep_angle, shape.x_rotation, tolerance)
     elif isinstance(shape, RoundedRect):
         x0, y0, x1, y1 = shape.x0, shape.y0, shape.x1, shape.y1
         rad = min(abs(shape.radius), 0.5 * abs(x1 - x0), 0.5 * abs(y1 - y0))
