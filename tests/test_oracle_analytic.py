@@ -819,3 +819,23 @@ def test_arc_stroke_is_width_times_arc_length(oracle):
         got = render(oracle, s, 96, 96, AA_AREA)[..., 0].astype(np.float64).sum() / 255
         want = w * r * abs(sweep)  # the annular sector: 1/2 (R^2 - r^2) |sweep| = w r |sweep|
         assert abs(got - want) / want < 0.015, (start, sweep, got, want)  # two flattened offset curves, 0.25 px each
+
+
+def test_rounded_rect_and_svg_arc_areas(oracle):
+    from vello_b200.shapes import RoundedRect
+    w, h, r = 61.0, 37.0, 11.5
+    got = coverage(oracle, RoundedRect(9.3, 14.2, 9.3 + w, 14.2 + h, r), 96, 72, AA_AREA).sum()
+    want = w * h - (4 - math.pi) * r * r
+    assert -1.0 <= want - got <= (2.0 / 3.0) * 2 * math.pi * r * 0.25 + 1.0  # the four corners: chords within flatten's 0.25 px
+    # SVG elliptical arcs (kurbo svg.rs + SVG implementation notes F.6): half an ellipse closed by its diameter, and a
+    # "pac-man": the large arc of a circle closed through the centre
+    half = BezPath.from_svg("M 20 50 A 35 20 0 0 1 90 50 Z")
+    got = coverage(oracle, half, 110, 90, AA_AREA).sum()
+    assert -1.0 <= 0.5 * math.pi * 35 * 20 - got <= (2.0 / 3.0) * math.pi * 35 * 0.25 + 1.0
+    a = math.radians(40.0)
+    x0, y0 = 50 + 30 * math.cos(a), 50 - 30 * math.sin(a)
+    x1, y1 = 50 + 30 * math.cos(a), 50 + 30 * math.sin(a)
+    pac = BezPath.from_svg(f"M 50 50 L {x0} {y0} A 30 30 0 1 0 {x1} {y1} Z")  # large-arc, sweep 0: counter-clockwise on screen
+    got = coverage(oracle, pac, 100, 100, AA_AREA).sum()
+    want = math.pi * 900 * (360 - 80) / 360
+    assert -1.0 <= want - got <= (2.0 / 3.0) * 2 * math.pi * 30 * 0.25 + 1.0
