@@ -839,3 +839,34 @@ def test_rounded_rect_and_svg_arc_areas(oracle):
     got = coverage(oracle, pac, 100, 100, AA_AREA).sum()
     want = math.pi * 900 * (360 - 80) / 360
     assert -1.0 <= want - got <= (2.0 / 3.0) * 2 * math.pi * 30 * 0.25 + 1.0
+
+
+def test_multi_stop_gradient_and_alpha_interpolation_spaces(oracle):
+    """Three opaque stops at unequal offsets == the piecewise lerp; two stops with different alphas under the two
+    interpolation alpha spaces of peniko (`InterpolationAlphaSpace`): premultiplied lerps colour x alpha, separate lerps
+    the straight components."""
+    r = Rect(0.0, 0.0, 128.0, 4.0)
+    cols = [np.array([250.0, 30.0, 10.0]), np.array([20.0, 230.0, 40.0]), np.array([30.0, 50.0, 245.0])]
+    offs = [0.0, 0.3, 1.0]
+    stops = [(o, Color.from_rgba8(*[int(v) for v in c])) for o, c in zip(offs, cols)]
+    s = Scene()
+    s.fill(FILL_NON_ZERO, Affine.IDENTITY, Gradient.linear((8.0, 0.0), (120.0, 0.0), stops), None, r)
+    got = render(oracle, s, 128, 4, AA_AREA)[2, :, :3].astype(np.float64)
+    t = np.clip((np.arange(128) - 8.0) / 112.0, 0, 1)
+    want = np.where((t < 0.3)[:, None], cols[0] + (cols[1] - cols[0]) * (t / 0.3)[:, None], cols[1] + (cols[2] - cols[1]) * ((t - 0.3) / 0.7)[:, None])
+    assert np.abs(got - want).max() <= 2.5
+    c0, a0, c1, a1 = np.array([255.0, 40.0, 0.0]), 1.0, np.array([0.0, 80.0, 255.0]), 0.2
+    stops = [(0.0, Color.from_rgba8(255, 40, 0, 255)), (1.0, Color.from_rgba8(0, 80, 255, 51))]
+    t = np.clip((np.arange(128) - 8.0) / 112.0, 0, 1)[:, None]
+    for premul in (True, False):
+        s = Scene()
+        s.fill(FILL_NON_ZERO, Affine.IDENTITY, Gradient.linear((8.0, 0.0), (120.0, 0.0), stops, premul_interp=premul), None, r)
+        got = render(oracle, s, 128, 4, AA_AREA, TRANSPARENT)[2].astype(np.float64)
+        alpha = a0 + (a1 - a0) * t
+        if premul:
+            colour = ((c0 * a0) + (c1 * a1 - c0 * a0) * t) / alpha
+        else:
+            colour = c0 + (c1 - c0) * t
+        assert np.abs(got[:, 3:4] - 255 * alpha).max() <= 1.5
+        # the stored colour is premultiplied 8-bit ramp texel / alpha: at alpha 0.2 one LSB of the texel is 5 of the quotient
+        assert (np.abs(got[:, :3] - colour) * alpha).max() <= 2.0, premul
